@@ -1,0 +1,334 @@
+// curves.cuh -- group law on register-resident points, branch-free.
+//
+//  * short Weierstrass curves in Jacobian coordinates (secp256k1: a=0, P-256: a=-3):
+//    doubling and mixed addition.  Replaces the per-bit `r0+r1 / 2r0 / 2r1` ladder of
+//    forge-ec-curves/src/secp256k1.rs:2635-2692 (+ Add :1447-1497, double :1502-1540) and the
+//    secret-branching double-and-add of p256.rs:2120-2156 (+ double :1869-1912, Add :1941-2006).
+//  * twisted Edwards curve Ed25519 in extended coordinates with Niels-form table entries
+//    (replaces ed25519.rs:1864-1927 `Add`, :1828-1832 `double`, :2062-2097 `multiply`).
+//  * Montgomery x-only ladder step for X25519 (replaces curve25519.rs:1671-1701).
+//  * block-level Montgomery-trick inversion (replaces the per-point Fermat inversion inside
+//    every `to_affine`: secp256k1.rs:1342-1363, p256.rs:1835-1857, ed25519.rs:1793-1811,
+//    curve25519.rs:1711-1713).
+#pragma once
+#include "fields.cuh"
+
+namespace fec {
+
+struct CurveK1 {
+  typedef FeK1 F;
+  static constexpr int CURVE_ID = 0;
+  static constexpr bool A_MINUS3 = false;
+  FEC_DEV static void B(u32 b[8]) {
+    b[0] = 7u;
+#pragma unroll
+    for (int i = 1; i < 8; i++) b[i] = 0u;
+  }
+  FEC_DEV static void N(u32 n[8]) {  // group order
+    n[0] = 0xD0364141u; n[1] = 0xBFD25E8Cu; n[2] = 0xAF48A03Bu; n[3] = 0xBAAEDCE6u;
+    n[4] = 0xFFFFFFFEu; n[5] = 0xFFFFFFFFu; n[6] = 0xFFFFFFFFu; n[7] = 0xFFFFFFFFu;
+  }
+  FEC_DEV static void G(u32 x[8], u32 y[8]) {
+    x[0] = 0x16F81798u; x[1] = 0x59F2815Bu; x[2] = 0x2DCE28D9u; x[3] = 0x029BFCDBu;
+    x[4] = 0xCE870B07u; x[5] = 0x55A06295u; x[6] = 0xF9DCBBACu; x[7] = 0x79BE667Eu;
+    y[0] = 0xFB10D4B8u; y[1] = 0x9C47D08Fu; y[2] = 0xA6855419u; y[3] = 0xFD17B448u;
+    y[4] = 0x0E1108A8u; y[5] = 0x5DA4FBFCu; y[6] = 0x26A3C465u; y[7] = 0x483ADA77u;
+  }
+};
+
+struct CurveP256 {
+  typedef FeP256 F;
+  static constexpr int CURVE_ID = 1;
+  static constexpr bool A_MINUS3 = true;
+  FEC_DEV static void B(u32 b[8]) {
+    b[0] = 0x27D2604Bu; b[1] = 0x3BCE3C3Eu; b[2] = 0xCC53B0F6u; b[3] = 0x651D06B0u;
+    b[4] = 0x769886BCu; b[5] = 0xB3EBBD55u; b[6] = 0xAA3A93E7u; b[7] = 0x5AC635D8u;
+  }
+  FEC_DEV static void N(u32 n[8]) {
+    n[0] = 0xFC632551u; n[1] = 0xF3B9CAC2u; n[2] = 0xA7179E84u; n[3] = 0xBCE6FAADu;
+    n[4] = 0xFFFFFFFFu; n[5] = 0xFFFFFFFFu; n[6] = 0x00000000u; n[7] = 0xFFFFFFFFu;
+  }
+  FEC_DEV static void G(u32 x[8], u32 y[8]) {
+    x[0] = 0xD898C296u; x[1] = 0xF4A13945u; x[2] = 0x2DEB33A0u; x[3] = 0x77037D81u;
+    x[4] = 0x63A440F2u; x[5] = 0xF8BCE6E5u; x[6] = 0xE12C4247u; x[7] = 0x6B17D1F2u;
+    y[0] = 0x37BF51F5u; y[1] = 0xCBB64068u; y[2] = 0x6B315ECEu; y[3] = 0x2BCE3357u;
+    y[4] = 0x7C0F9E16u; y[5] = 0x8EE7EB4Au; y[6] = 0xFE1A7F9Bu; y[7] = 0x4FE342E2u;
+  }
+};
+
+// -------------------------------------------------------------------------------------
+// Jacobian point (X:Y:Z), infinity <=> Z == 0
+// -------------------------------------------------------------------------------------
+struct Jac {
+  u32 X[8], Y[8], Z[8];
+};
+
+template <class C>
+FEC_DEV void jac_set_inf(Jac& q) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) { q.X[i] = 0; q.Y[i] = 0; q.Z[i] = 0; }
+  q.X[0] = 1; q.Y[0] = 1;
+}
+
+// Q <- 2Q.  a=0: dbl-2009-l (2M+5S).  a=-3: dbl-2001-b (3M+5S).  Z=0 stays Z=0.
+template <class C>
+FEC_DEV void jac_dbl(Jac& q) {
+  typedef typename C::F F;
+  if (!C::A_MINUS3) {
+    u32 A[8], B[8], Cc[8], D[8], t[8];
+    F::sqr(A, q.X);
+    F::sqr(B, q.Y);
+    F::sqr(Cc, B);
+    F::add(t, q.X, B);
+    F::sqr(t, t);
+    F::sub(t, t, A);
+    F::sub(t, t, Cc);
+    F::dbl(D, t);               // D = 2((X+B)^2 - A - C)
+    F::mul(q.Z, q.Y, q.Z);
+    F::dbl(q.Z, q.Z);           // Z3 = 2YZ
+    F::dbl(t, A);
+    F::add(A, t, A);            // E = 3A
+    F::sqr(t, A);               // F = E^2
+    F::sub(t, t, D);
+    F::sub(q.X, t, D);          // X3 = F - 2D
+    F::sub(t, D, q.X);
+    F::mul(t, A, t);            // E(D - X3)
+    F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);  // 8C
+    F::sub(q.Y, t, Cc);
+  } else {
+    u32 delta[8], gamma[8], beta[8], alpha[8], t[8];
+    F::sqr(delta, q.Z);
+    F::sqr(gamma, q.Y);
+    F::mul(beta, q.X, gamma);
+    F::sub(t, q.X, delta);
+    F::add(alpha, q.X, delta);
+    F::mul(alpha, t, alpha);
+    F::dbl(t, alpha);
+    F::add(alpha, t, alpha);    // alpha = 3(X-delta)(X+delta)
+    F::add(t, q.Y, q.Z);
+    F::sqr(t, t);
+    F::sub(t, t, gamma);
+    F::sub(q.Z, t, delta);      // Z3 = (Y+Z)^2 - gamma - delta
+    F::dbl(beta, beta); F::dbl(beta, beta);  // 4 beta
+    F::sqr(t, alpha);
+    F::sub(t, t, beta);
+    F::sub(q.X, t, beta);       // X3 = alpha^2 - 8 beta
+    F::sub(t, beta, q.X);
+    F::mul(t, alpha, t);
+    F::sqr(gamma, gamma);
+    F::dbl(gamma, gamma); F::dbl(gamma, gamma); F::dbl(gamma, gamma);  // 8 gamma^2
+    F::sub(q.Y, t, gamma);
+  }
+}
+
+// Q <- Q + (x2,y2) with (x2,y2) affine: madd-2007-bl (7M+4S), written without branches.
+//   t_inf : mask, the addend is the point at infinity (digit 0)  -> Q unchanged
+//   Q at infinity                                                -> (x2,y2,1)
+//   Q == +-(x2,y2) (H == 0): cannot happen for k < n on a prime-order curve with the digit
+//   sets used here; the flag is returned so the caller can take a
+//   warp-uniform slow path if it ever does.
+template <class C>
+FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
+  typedef typename C::F F;
+  u32 Z1Z1[8], U2[8], S2[8], H[8], HH[8], I[8], J[8], r[8], V[8], t[8];
+  Jac o;
+  u32 q_inf = F::is_zero(q.Z);
+  F::sqr(Z1Z1, q.Z);
+  F::mul(U2, x2, Z1Z1);
+  F::mul(S2, q.Z, Z1Z1);
+  F::mul(S2, y2, S2);
+  F::sub(H, U2, q.X);
+  F::sqr(HH, H);
+  F::dbl(I, HH); F::dbl(I, I);       // I = 4 HH
+  F::mul(J, H, I);
+  F::sub(r, S2, q.Y);
+  u32 h_zero = F::is_zero(H);
+  u32 r_zero = F::is_zero(r);
+  F::dbl(r, r);                      // r = 2(S2 - Y1)
+  F::mul(V, q.X, I);
+  F::sqr(o.X, r);
+  F::sub(o.X, o.X, J);
+  F::sub(o.X, o.X, V);
+  F::sub(o.X, o.X, V);               // X3 = r^2 - J - 2V
+  F::sub(t, V, o.X);
+  F::mul(t, r, t);
+  F::mul(J, q.Y, J);
+  F::dbl(J, J);
+  F::sub(o.Y, t, J);                 // Y3 = r(V - X3) - 2 Y1 J
+  F::add(t, q.Z, H);
+  F::sqr(t, t);
+  F::sub(t, t, Z1Z1);
+  F::sub(o.Z, t, HH);                // Z3 = (Z1+H)^2 - Z1Z1 - HH
+  u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  u32 keep = t_inf;                  // keep Q
+  u32 take_t = q_inf & ~t_inf;       // Q was infinity: result is the addend
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    q.X[i] = (keep & q.X[i]) | (~keep & ((take_t & x2[i]) | (~take_t & o.X[i])));
+    q.Y[i] = (keep & q.Y[i]) | (~keep & ((take_t & y2[i]) | (~take_t & o.Y[i])));
+    q.Z[i] = (keep & q.Z[i]) | (~keep & ((take_t & one[i]) | (~take_t & o.Z[i])));
+  }
+  // exceptional: both finite and same x.  bit0: exceptional, bit1: also same y (needs doubling)
+  u32 exc = h_zero & ~q_inf & ~t_inf;
+  return (exc & 1u) | (exc & r_zero & 2u);
+}
+
+// y^2 == x^3 + a x + b  (mask)
+template <class C>
+FEC_DEV u32 on_curve(const u32 x[8], const u32 y[8]) {
+  typedef typename C::F F;
+  u32 l[8], r[8], b[8], t[8];
+  F::sqr(l, y);
+  F::sqr(r, x);
+  F::mul(r, r, x);
+  if (C::A_MINUS3) {
+    F::dbl(t, x);
+    F::add(t, t, x);
+    F::sub(r, r, t);
+  }
+  C::B(b);
+  F::add(r, r, b);
+  F::sub(l, l, r);
+  return F::is_zero(l);
+}
+
+// -------------------------------------------------------------------------------------
+// Block-level simultaneous inversion (Montgomery's trick as a butterfly product tree):
+// every thread of the block contributes one z != 0 and receives z^-1.  Up-sweep: 5 warp-shuffle
+// levels + log2(warps) shared-memory levels, one multiplication each; ONE Fermat inversion per
+// block (warp 0); down-sweep multiplies the stored sibling products back in.
+// Cost per thread: 2*(5+log2 W) M  +  (1/W) of an inversion.   `sm` must hold 2*W*8 + 8 words.
+// All threads of the block must call it (it contains __syncthreads()).
+// -------------------------------------------------------------------------------------
+template <class F, int WARPS>
+FEC_DEV void block_batch_inv(u32 zinv[8], const u32 z[8], u32* sm) {
+  constexpr int LW = (WARPS == 1) ? 0 : (WARPS == 2) ? 1 : (WARPS == 4) ? 2 : (WARPS == 8) ? 3 : (WARPS == 16) ? 4 : -1;
+  static_assert(LW >= 0, "WARPS must be a power of two <= 16");
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  u32 sib[5 + (LW > 0 ? LW : 1)][8];
+  u32 p[8];
+  copy8(p, z);
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) sib[l][i] = __shfl_xor_sync(0xFFFFFFFFu, p[i], 1 << l);
+    F::mul(p, p, sib[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < LW; l++) {
+    u32* buf = sm + (l & 1) * WARPS * 8;
+    if (lane < 8) buf[warp * 8 + lane] = p[lane];
+    __syncthreads();
+    const unsigned partner = warp ^ (1u << l);
+#pragma unroll
+    for (int i = 0; i < 8; i++) sib[5 + l][i] = buf[partner * 8 + i];
+    F::mul(p, p, sib[5 + l]);
+    // (double-buffered: the next level writes the other half, the one after re-syncs first)
+  }
+  u32* slot = sm + 2 * WARPS * 8;
+  __syncthreads();
+  if (warp == 0) {  // warp-uniform
+    u32 inv[8];
+    F::inv(inv, p);
+    if (lane < 8) slot[lane] = inv[lane];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; i++) p[i] = slot[i];
+#pragma unroll
+  for (int l = 5 + LW - 1; l >= 0; l--) F::mul(p, p, sib[l]);
+  copy8(zinv, p);
+}
+
+// -------------------------------------------------------------------------------------
+// Ed25519: extended coordinates (X:Y:Z:T), Niels addends (y+x, y-x, 2dxy)
+// -------------------------------------------------------------------------------------
+struct EdExt {
+  u32 X[8], Y[8], Z[8], T[8];
+};
+FEC_DEV void ed_D2(u32 d2[8]) {  // 2d mod p, d = -121665/121666
+  d2[0] = 0x26B2F159u; d2[1] = 0xEBD69B94u; d2[2] = 0x8283B156u; d2[3] = 0x00E0149Au;
+  d2[4] = 0xEEF3D130u; d2[5] = 0x198E80F2u; d2[6] = 0x56DFFCE7u; d2[7] = 0x2406D9DCu;
+}
+FEC_DEV void ed_base(u32 x[8], u32 y[8]) {
+  x[0] = 0x8F25D51Au; x[1] = 0xC9562D60u; x[2] = 0x9525A7B2u; x[3] = 0x692CC760u;
+  x[4] = 0xFDD6DC5Cu; x[5] = 0xC0A4E231u; x[6] = 0xCD6E53FEu; x[7] = 0x216936D3u;
+  y[0] = 0x66666658u; y[1] = 0x66666666u; y[2] = 0x66666666u; y[3] = 0x66666666u;
+  y[4] = 0x66666666u; y[5] = 0x66666666u; y[6] = 0x66666666u; y[7] = 0x66666666u;
+}
+FEC_DEV void ed_set_identity(EdExt& q) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) { q.X[i] = 0; q.Y[i] = 0; q.Z[i] = 0; q.T[i] = 0; }
+  q.Y[0] = 1; q.Z[0] = 1;
+}
+// Q <- Q + N  (madd-2008-hwcd-3, 7M; complete: no exceptional cases, identity = (1,1,0))
+FEC_DEV void ed_madd(EdExt& q, const u32 ypx[8], const u32 ymx[8], const u32 t2d[8]) {
+  typedef Fe25519 F;
+  u32 A[8], B[8], Cc[8], D[8], E[8], Fv[8], G[8], H[8];
+  F::sub(A, q.Y, q.X);
+  F::mul(A, A, ymx);
+  F::add(B, q.Y, q.X);
+  F::mul(B, B, ypx);
+  F::mul(Cc, q.T, t2d);
+  F::dbl(D, q.Z);
+  F::sub(E, B, A);
+  F::sub(Fv, D, Cc);
+  F::add(G, D, Cc);
+  F::add(H, B, A);
+  F::mul(q.X, E, Fv);
+  F::mul(q.Y, G, H);
+  F::mul(q.T, E, H);
+  F::mul(q.Z, Fv, G);
+}
+// general extended addition with d2 (used only when building tables)
+FEC_DEV void ed_add(EdExt& q, const EdExt& r) {
+  typedef Fe25519 F;
+  u32 A[8], B[8], Cc[8], D[8], E[8], Fv[8], G[8], H[8], t[8], d2[8];
+  ed_D2(d2);
+  F::sub(A, q.Y, q.X);
+  F::sub(t, r.Y, r.X);
+  F::mul(A, A, t);
+  F::add(B, q.Y, q.X);
+  F::add(t, r.Y, r.X);
+  F::mul(B, B, t);
+  F::mul(Cc, q.T, r.T);
+  F::mul(Cc, Cc, d2);
+  F::mul(D, q.Z, r.Z);
+  F::dbl(D, D);
+  F::sub(E, B, A);
+  F::sub(Fv, D, Cc);
+  F::add(G, D, Cc);
+  F::add(H, B, A);
+  F::mul(q.X, E, Fv);
+  F::mul(q.Y, G, H);
+  F::mul(q.T, E, H);
+  F::mul(q.Z, Fv, G);
+}
+
+// -------------------------------------------------------------------------------------
+// X25519 ladder step (RFC 7748 section 5; one bit): 5M + 4S + one multiplication by a24
+// -------------------------------------------------------------------------------------
+FEC_DEV void x25519_step(u32 x2[8], u32 z2[8], u32 x3[8], u32 z3[8], const u32 x1[8]) {
+  typedef Fe25519 F;
+  u32 A[8], AA[8], B[8], BB[8], E[8], Cc[8], D[8], DA[8], CB[8];
+  F::add(A, x2, z2);
+  F::sqr(AA, A);
+  F::sub(B, x2, z2);
+  F::sqr(BB, B);
+  F::sub(E, AA, BB);
+  F::add(Cc, x3, z3);
+  F::sub(D, x3, z3);
+  F::mul(DA, D, A);
+  F::mul(CB, Cc, B);
+  F::add(x3, DA, CB);
+  F::sqr(x3, x3);
+  F::sub(z3, DA, CB);
+  F::sqr(z3, z3);
+  F::mul(z3, x1, z3);
+  F::mul(x2, AA, BB);
+  F::mul_small(z2, E, 121665u);
+  F::add(z2, AA, z2);
+  F::mul(z2, E, z2);
+}
+
+}  // namespace fec

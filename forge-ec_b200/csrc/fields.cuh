@@ -1,0 +1,482 @@
+// fields.cuh -- the three prime fields of the hot path on 8 x u32 register limbs.
+//
+//   FeK1    p = 2^256 - 2^32 - 977   (secp256k1; replaces forge-ec-curves/src/secp256k1.rs:353-539, 599-736)
+//   FeP256  p = 2^256 - 2^224 + 2^192 + 2^96 - 1  (replaces p256.rs:343-393, 416-534, 544-729, 772-776)
+//   Fe25519 p = 2^255 - 19           (replaces curve25519.rs:50-114, 186-314, 369-494 and
+//                                     ed25519.rs:214-289, 410-431, 458-625)
+//
+// Representation invariants
+//   FeK1 / Fe25519: "weak" form -- any value in [0, 2^256) stands for its residue; add/sub/mul
+//     fold the overflow with 2^256 = 2^32+977 (resp. 38) and never need a comparison with p.
+//     canon() produces the unique representative in [0,p) for output / equality.
+//   FeP256: always canonical in [0,p) (2^256 mod p is a 225-bit number, so weak form buys nothing).
+// All functions are branch-free (masks only): control flow never depends on data.
+//
+// IMAD.WIDE count per op (the canonical IMUL32 figures of SURVEY.md section 8d):
+//   FeK1 mul 74 / sqr 46, FeP256 mul 64 / sqr 36, Fe25519 mul 73 / sqr 45.
+#pragma once
+#include "u256.cuh"
+
+namespace fec {
+
+// =====================================================================================
+// secp256k1 base field
+// =====================================================================================
+struct FeK1 {
+  static constexpr int PRIME_ID = 0;
+  static constexpr u32 C977 = 977u;
+  FEC_DEV static void P(u32 p[8]) {
+    p[0] = 0xFFFFFC2Fu; p[1] = 0xFFFFFFFEu;
+#pragma unroll
+    for (int i = 2; i < 8; i++) p[i] = 0xFFFFFFFFu;
+  }
+
+  // 512 -> 256 bits:  lo + hi * (2^32 + 977), twice, plus a 1-bit wrap fix.
+  FEC_DEV static void reduce512(u32 o[8], const u32 r[16]) {
+    const u32* h = r + 8;
+    u32 acc[8];
+    copy8(acc, r);
+    u32 ca = mad_row<4, 0>(acc, h, C977);  // += {h0,h2,h4,h6}*977 at limb pairs (0,1)..(6,7)
+    u32 od[8];                             // {h1,h3,h5,h7}*977 at weight 2^32
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      od[2 * k] = mul_lo(h[2 * k + 1], C977);
+      od[2 * k + 1] = mul_hi(h[2 * k + 1], C977);
+    }
+    u32 s[8];
+    u32 s8 = add8(s, od, h);  // (od + hi) at weight 2^32  (the "<< 32" half of the fold)
+    acc[1] = add_cc(acc[1], s[0]);
+#pragma unroll
+    for (int i = 2; i < 8; i++) acc[i] = addc_cc(acc[i], s[i - 1]);
+    u32 v_lo = addc_cc(s[7], ca);  // overflow above 2^256:  v = v_lo + v_hi*2^32  (< 2^32 + 979)
+    u32 v_hi = addc(s8, 0u);
+    // second fold: acc += v*977 + (v << 32)   (three limbs)
+    u64 m = (u64)v_lo * C977 + ((u64)(v_hi * C977) << 32);
+    u32 w0 = (u32)m;
+    u64 t = (m >> 32) + v_lo;
+    u32 w1 = (u32)t;
+    u32 w2 = (u32)(t >> 32) + v_hi;
+    acc[0] = add_cc(acc[0], w0);
+    acc[1] = addc_cc(acc[1], w1);
+    acc[2] = addc_cc(acc[2], w2);
+#pragma unroll
+    for (int i = 3; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    // wrap fix: if that carried, the wrapped value is < 2^67, so adding 2^32+977 touches 3 limbs
+    o[0] = add_cc(acc[0], (0u - c2) & C977);
+    o[1] = addc_cc(acc[1], c2);
+    o[2] = addc(acc[2], 0u);
+#pragma unroll
+    for (int i = 3; i < 8; i++) o[i] = acc[i];
+  }
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 r[16];
+    mul_wide(r, a, b);
+    reduce512(o, r);
+  }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+    u32 r[16];
+    sqr_wide(r, a);
+    reduce512(o, r);
+  }
+  FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 s[8];
+    u32 c = add8(s, a, b);
+    // + c*(2^32+977); may wrap once more only if the sum was within 2^33 of 2^256
+    s[0] = add_cc(s[0], (0u - c) & C977);
+    s[1] = addc_cc(s[1], c);
+#pragma unroll
+    for (int i = 2; i < 8; i++) s[i] = addc_cc(s[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = add_cc(s[0], (0u - c2) & C977);
+    o[1] = addc(s[1], c2);
+#pragma unroll
+    for (int i = 2; i < 8; i++) o[i] = s[i];
+  }
+  FEC_DEV static void sub(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 d[8];
+    u32 bw = sub8(d, a, b);
+    // - bw*(2^32+977)  (== + p mod 2^256); may borrow once more only if d < 2^33
+    d[0] = sub_cc(d[0], (0u - bw) & C977);
+    d[1] = subc_cc(d[1], bw);
+#pragma unroll
+    for (int i = 2; i < 8; i++) d[i] = subc_cc(d[i], 0u);
+    u32 bw2 = subc(0u, 0u) & 1u;
+    o[0] = sub_cc(d[0], (0u - bw2) & C977);
+    o[1] = subc(d[1], bw2);
+#pragma unroll
+    for (int i = 2; i < 8; i++) o[i] = d[i];
+  }
+  FEC_DEV static void neg(u32 o[8], const u32 a[8]) {
+    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sub(o, z, a);
+  }
+  // o = a * c for a small constant c (< 2^16): one 9-limb product + fold
+  FEC_DEV static void mul_small(u32 o[8], const u32 a[8], u32 c) {
+    u32 t[8];
+    u64 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 m = (u64)a[i] * c + carry;
+      t[i] = (u32)m;
+      carry = m >> 32;
+    }
+    // fold carry (< 2^16): carry*(2^32+977)
+    u32 v = (u32)carry;
+    u64 m = (u64)v * C977;
+    u32 w0 = (u32)m;
+    u32 w1 = (u32)(m >> 32) + v;  // < 2^17, no overflow
+    t[0] = add_cc(t[0], w0);
+    t[1] = addc_cc(t[1], w1);
+#pragma unroll
+    for (int i = 2; i < 8; i++) t[i] = addc_cc(t[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = add_cc(t[0], (0u - c2) & C977);
+    o[1] = addc(t[1], c2);
+#pragma unroll
+    for (int i = 2; i < 8; i++) o[i] = t[i];
+  }
+  FEC_DEV static void dbl(u32 o[8], const u32 a[8]) { add(o, a, a); }
+  // unique representative in [0,p)
+  FEC_DEV static void canon(u32 o[8], const u32 a[8]) {
+    u32 t[8];
+    t[0] = add_cc(a[0], C977);
+    t[1] = addc_cc(a[1], 1u);
+#pragma unroll
+    for (int i = 2; i < 8; i++) t[i] = addc_cc(a[i], 0u);
+    u32 c = addc(0u, 0u);  // a + (2^256 - p) overflowed  <=>  a >= p
+    select8(o, 0u - c, t, a);
+  }
+  FEC_DEV static u32 is_zero(const u32 a[8]) {  // mask; accepts both representatives 0 and p
+    u32 t[8];
+    canon(t, a);
+    return is_zero8(t);
+  }
+  FEC_DEV static u32 in_range(const u32 a[8]) {  // mask: a < p (input validation)
+    u32 p[8];
+    P(p);
+    return ~geq8(a, p);
+  }
+  FEC_DEV static void sqr_n(u32 x[8], int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) sqr(x, x);
+  }
+  // a^(p-2): 255 S + 15 M (addition chain on the run structure of p-2 = 1^223 0 1^22 0000 1 0 11 0 1)
+  FEC_DEV static void inv(u32 o[8], const u32 a[8]) {
+    u32 x2[8], x3[8], x22[8], x44[8], t[8], u[8];
+    sqr(t, a); mul(x2, t, a);
+    sqr(t, x2); mul(x3, t, a);
+    copy8(t, x3); sqr_n(t, 3); mul(t, t, x3);        // x6
+    sqr_n(t, 3); mul(t, t, x3);                      // x9
+    sqr_n(t, 2); mul(t, t, x2);                      // x11
+    copy8(u, t); sqr_n(t, 11); mul(x22, t, u);       // x22
+    copy8(t, x22); sqr_n(t, 22); mul(x44, t, x22);   // x44
+    copy8(t, x44); sqr_n(t, 44); mul(t, t, x44);     // x88
+    copy8(u, t); sqr_n(t, 88); mul(t, t, u);         // x176
+    sqr_n(t, 44); mul(t, t, x44);                    // x220
+    sqr_n(t, 3); mul(t, t, x3);                      // x223
+    sqr_n(t, 23); mul(t, t, x22);
+    sqr_n(t, 5); mul(t, t, a);
+    sqr_n(t, 3); mul(t, t, x2);
+    sqr_n(t, 2); mul(o, t, a);
+  }
+  // a^((p+1)/4) (candidate square root; p = 3 mod 4).  (p+1)/4 = 1^223 0 1^22 0000 11 00
+  FEC_DEV static void sqrt_cand(u32 o[8], const u32 a[8]) {
+    u32 x2[8], x3[8], x22[8], x44[8], t[8], u[8];
+    sqr(t, a); mul(x2, t, a);
+    sqr(t, x2); mul(x3, t, a);
+    copy8(t, x3); sqr_n(t, 3); mul(t, t, x3);
+    sqr_n(t, 3); mul(t, t, x3);
+    sqr_n(t, 2); mul(t, t, x2);
+    copy8(u, t); sqr_n(t, 11); mul(x22, t, u);
+    copy8(t, x22); sqr_n(t, 22); mul(x44, t, x22);
+    copy8(t, x44); sqr_n(t, 44); mul(t, t, x44);
+    copy8(u, t); sqr_n(t, 88); mul(t, t, u);
+    sqr_n(t, 44); mul(t, t, x44);
+    sqr_n(t, 3); mul(t, t, x3);
+    sqr_n(t, 23); mul(t, t, x22);
+    sqr_n(t, 6); mul(t, t, x2);
+    sqr_n(t, 2);
+    copy8(o, t);
+  }
+};
+
+// =====================================================================================
+// Curve25519 / Ed25519 base field
+// =====================================================================================
+struct Fe25519 {
+  static constexpr int PRIME_ID = 2;
+  FEC_DEV static void P(u32 p[8]) {
+    p[0] = 0xFFFFFFEDu;
+#pragma unroll
+    for (int i = 1; i < 7; i++) p[i] = 0xFFFFFFFFu;
+    p[7] = 0x7FFFFFFFu;
+  }
+  FEC_DEV static void reduce512(u32 o[8], const u32 r[16]) {
+    const u32* h = r + 8;
+    u32 acc[8];
+    copy8(acc, r);
+    u32 ca = mad_row<4, 0>(acc, h, 38u);
+    u32 od[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      od[2 * k] = mul_lo(h[2 * k + 1], 38u);
+      od[2 * k + 1] = mul_hi(h[2 * k + 1], 38u);
+    }
+    acc[1] = add_cc(acc[1], od[0]);
+#pragma unroll
+    for (int i = 2; i < 8; i++) acc[i] = addc_cc(acc[i], od[i - 1]);
+    u32 v = addc(od[7], ca);  // < 40
+    acc[0] = add_cc(acc[0], v * 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = acc[0] + ((0u - c2) & 38u);  // wrapped value < 1520: no further carry
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = acc[i];
+  }
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 r[16];
+    mul_wide(r, a, b);
+    reduce512(o, r);
+  }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+    u32 r[16];
+    sqr_wide(r, a);
+    reduce512(o, r);
+  }
+  FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 s[8];
+    u32 c = add8(s, a, b);
+    s[0] = add_cc(s[0], (0u - c) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) s[i] = addc_cc(s[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = s[0] + ((0u - c2) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = s[i];
+  }
+  FEC_DEV static void sub(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 d[8];
+    u32 bw = sub8(d, a, b);
+    d[0] = sub_cc(d[0], (0u - bw) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) d[i] = subc_cc(d[i], 0u);
+    u32 bw2 = subc(0u, 0u) & 1u;
+    o[0] = d[0] - ((0u - bw2) & 38u);  // d >= 2^256 - 38 here: no further borrow
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = d[i];
+  }
+  FEC_DEV static void neg(u32 o[8], const u32 a[8]) {
+    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sub(o, z, a);
+  }
+  FEC_DEV static void dbl(u32 o[8], const u32 a[8]) { add(o, a, a); }
+  FEC_DEV static void mul_small(u32 o[8], const u32 a[8], u32 c) {  // c < 2^26
+    u32 t[8];
+    u64 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 m = (u64)a[i] * c + carry;
+      t[i] = (u32)m;
+      carry = m >> 32;
+    }
+    t[0] = add_cc(t[0], (u32)carry * 38u);  // carry < 2^26 -> < 2^32
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = addc_cc(t[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = t[0] + ((0u - c2) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = t[i];
+  }
+  FEC_DEV static void canon(u32 o[8], const u32 a[8]) {
+    // fold bit 255 (x19), then one conditional subtract of p
+    u32 t[8];
+    u32 top = a[7] >> 31;
+    t[0] = add_cc(a[0], top * 19u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[i] = addc_cc(a[i], 0u);
+    t[7] = addc(a[7] & 0x7FFFFFFFu, 0u);  // t in [0, 2^255 + 19)
+    u32 u[8];
+    u[0] = add_cc(t[0], 19u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) u[i] = addc_cc(t[i], 0u);
+    u[7] = addc(t[7], 0u);
+    u32 ge = 0u - (u[7] >> 31);  // t + 19 >= 2^255  <=>  t >= p
+    u[7] &= 0x7FFFFFFFu;
+    select8(o, ge, u, t);
+  }
+  FEC_DEV static u32 is_zero(const u32 a[8]) {
+    u32 t[8];
+    canon(t, a);
+    return is_zero8(t);
+  }
+  FEC_DEV static void sqr_n(u32 x[8], int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) sqr(x, x);
+  }
+  // z^(p-2) = z^(2^255-21): 254 S + 11 M
+  FEC_DEV static void inv(u32 o[8], const u32 z[8]) {
+    u32 z2[8], z9[8], z11[8], z5[8], z10[8], z50[8], t[8], u[8];
+    sqr(z2, z);
+    copy8(t, z2); sqr_n(t, 2);
+    mul(z9, z, t);
+    mul(z11, z2, z9);
+    sqr(t, z11);
+    mul(z5, z9, t);  // 2^5 - 1
+    copy8(t, z5); sqr_n(t, 5); mul(z10, t, z5);
+    copy8(t, z10); sqr_n(t, 10); mul(t, t, z10);      // z20
+    copy8(u, t); sqr_n(t, 20); mul(t, t, u);          // z40
+    sqr_n(t, 10); mul(z50, t, z10);                   // z50
+    copy8(t, z50); sqr_n(t, 50); mul(t, t, z50);      // z100
+    copy8(u, t); sqr_n(t, 100); mul(t, t, u);         // z200
+    sqr_n(t, 50); mul(t, t, z50);                     // z250
+    sqr_n(t, 5); mul(o, t, z11);
+  }
+};
+
+// =====================================================================================
+// NIST P-256 base field (canonical form)
+// =====================================================================================
+struct FeP256 {
+  static constexpr int PRIME_ID = 1;
+  FEC_DEV static void P(u32 p[8]) {
+    p[0] = 0xFFFFFFFFu; p[1] = 0xFFFFFFFFu; p[2] = 0xFFFFFFFFu; p[3] = 0u;
+    p[4] = 0u; p[5] = 0u; p[6] = 1u; p[7] = 0xFFFFFFFFu;
+  }
+  // l += t * (2^224 - 2^192 - 2^96 + 1)  (t small, signed); returns the new signed overflow
+  FEC_DEV static int fold_top(u32 l[8], int t) {
+    long long c = 0, tt = t;
+    c += (long long)l[0] + tt; l[0] = (u32)c; c >>= 32;
+    c += (long long)l[1];      l[1] = (u32)c; c >>= 32;
+    c += (long long)l[2];      l[2] = (u32)c; c >>= 32;
+    c += (long long)l[3] - tt; l[3] = (u32)c; c >>= 32;
+    c += (long long)l[4];      l[4] = (u32)c; c >>= 32;
+    c += (long long)l[5];      l[5] = (u32)c; c >>= 32;
+    c += (long long)l[6] - tt; l[6] = (u32)c; c >>= 32;
+    c += (long long)l[7] + tt; l[7] = (u32)c; c >>= 32;
+    return (int)c;
+  }
+  // FIPS 186-4 D.2.3 fast reduction, column-wise: T + 2S1 + 2S2 + S3 + S4 - D1 - D2 - D3 - D4
+  FEC_DEV static void reduce512(u32 o[8], const u32 c[16]) {
+    u32 l[8];
+    long long acc;
+    u64 pos, neg;
+#define FEC_U(x) ((u64)(x))
+    pos = FEC_U(c[0]) + c[8] + c[9];                      neg = FEC_U(c[11]) + c[12] + c[13] + c[14];
+    acc = (long long)(pos - neg);                         l[0] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[1]) + c[9] + c[10];                     neg = FEC_U(c[12]) + c[13] + c[14] + c[15];
+    acc += (long long)(pos - neg);                        l[1] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[2]) + c[10] + c[11];                    neg = FEC_U(c[13]) + c[14] + c[15];
+    acc += (long long)(pos - neg);                        l[2] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[3]) + 2 * (FEC_U(c[11]) + c[12]) + c[13];   neg = FEC_U(c[15]) + c[8] + c[9];
+    acc += (long long)(pos - neg);                        l[3] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[4]) + 2 * (FEC_U(c[12]) + c[13]) + c[14];   neg = FEC_U(c[9]) + c[10];
+    acc += (long long)(pos - neg);                        l[4] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[5]) + 2 * (FEC_U(c[13]) + c[14]) + c[15];   neg = FEC_U(c[10]) + c[11];
+    acc += (long long)(pos - neg);                        l[5] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[6]) + 3 * FEC_U(c[14]) + 2 * FEC_U(c[15]) + c[13];  neg = FEC_U(c[8]) + c[9];
+    acc += (long long)(pos - neg);                        l[6] = (u32)acc; acc >>= 32;
+    pos = FEC_U(c[7]) + 3 * FEC_U(c[15]) + c[8];          neg = FEC_U(c[10]) + c[11] + c[12] + c[13];
+    acc += (long long)(pos - neg);                        l[7] = (u32)acc; acc >>= 32;
+#undef FEC_U
+    int t = (int)acc;        // in [-4, 5]
+    t = fold_top(l, t);      // now in {-1,0,1}
+    t = fold_top(l, t);      // now 0, l in [0, 2^256)
+    (void)t;
+    u32 p[8], d[8];
+    P(p);
+    u32 bw = sub8(d, l, p);
+    select8(o, bw - 1u, d, l);  // bw==0 -> l >= p -> take d
+  }
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 r[16];
+    mul_wide(r, a, b);
+    reduce512(o, r);
+  }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+    u32 r[16];
+    sqr_wide(r, a);
+    reduce512(o, r);
+  }
+  FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 s[8], d[8], p[8];
+    P(p);
+    u32 c = add8(s, a, b);
+    u32 bw = sub8(d, s, p);
+    u32 take = (0u - c) | (bw - 1u);  // carried out, or s >= p
+    select8(o, take, d, s);
+  }
+  FEC_DEV static void sub(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 d[8];
+    u32 bw = sub8(d, a, b);
+    u32 m = 0u - bw;
+    // + (p & m): p = {~0,~0,~0,0,0,0,1,~0}
+    o[0] = add_cc(d[0], m);
+    o[1] = addc_cc(d[1], m);
+    o[2] = addc_cc(d[2], m);
+    o[3] = addc_cc(d[3], 0u);
+    o[4] = addc_cc(d[4], 0u);
+    o[5] = addc_cc(d[5], 0u);
+    o[6] = addc_cc(d[6], m & 1u);
+    o[7] = addc(d[7], m);
+  }
+  FEC_DEV static void neg(u32 o[8], const u32 a[8]) {
+    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sub(o, z, a);
+  }
+  FEC_DEV static void dbl(u32 o[8], const u32 a[8]) { add(o, a, a); }
+  FEC_DEV static void mul_small(u32 o[8], const u32 a[8], u32 c) {  // c in {2,3,4,8}: by additions
+    u32 t[8];
+    copy8(t, a);
+    u32 acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (u32 bit = 0; bit < 5; bit++) {
+      if ((c >> bit) & 1u) add(acc, acc, t);  // c is uniform: not data-dependent
+      add(t, t, t);
+    }
+    copy8(o, acc);
+  }
+  FEC_DEV static void canon(u32 o[8], const u32 a[8]) { copy8(o, a); }
+  FEC_DEV static u32 is_zero(const u32 a[8]) { return is_zero8(a); }
+  FEC_DEV static u32 in_range(const u32 a[8]) {
+    u32 p[8];
+    P(p);
+    return ~geq8(a, p);
+  }
+  FEC_DEV static void sqr_n(u32 x[8], int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) sqr(x, x);
+  }
+  // a^(p-2), p-2 = 1^32 0^31 1 0^96 1^94 0 1 : 255 S + 12 M
+  FEC_DEV static void inv(u32 o[8], const u32 a[8]) {
+    u32 x2[8], x3[8], x30[8], x32[8], t[8], u[8];
+    sqr(t, a); mul(x2, t, a);
+    sqr(t, x2); mul(x3, t, a);
+    copy8(t, x3); sqr_n(t, 3); mul(t, t, x3);      // x6
+    copy8(u, t); sqr_n(t, 6); mul(t, t, u);        // x12
+    sqr_n(t, 3); mul(t, t, x3);                    // x15
+    copy8(u, t); sqr_n(t, 15); mul(x30, t, u);     // x30
+    copy8(t, x30); sqr_n(t, 2); mul(x32, t, x2);   // x32
+    copy8(t, x32); sqr_n(t, 32); mul(t, t, a);
+    sqr_n(t, 128); mul(t, t, x32);
+    sqr_n(t, 32); mul(t, t, x32);
+    sqr_n(t, 30); mul(t, t, x30);
+    sqr_n(t, 2); mul(o, t, a);
+  }
+  // a^((p+1)/4), (p+1)/4 = 2^254 - 2^222 + 2^190 + 2^94 = 1^32 0^31 1 0^31 1 0^94
+  FEC_DEV static void sqrt_cand(u32 o[8], const u32 a[8]) {
+    u32 x2[8], x4[8], x8[8], x16[8], t[8];
+    sqr(t, a); mul(x2, t, a);
+    copy8(t, x2); sqr_n(t, 2); mul(x4, t, x2);
+    copy8(t, x4); sqr_n(t, 4); mul(x8, t, x4);
+    copy8(t, x8); sqr_n(t, 8); mul(x16, t, x8);
+    copy8(t, x16); sqr_n(t, 16); mul(t, t, x16);   // x32
+    sqr_n(t, 32); mul(t, t, a);
+    sqr_n(t, 96); mul(t, t, a);
+    sqr_n(t, 94);
+    copy8(o, t);
+  }
+};
+
+}  // namespace fec

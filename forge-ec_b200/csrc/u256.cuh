@@ -1,0 +1,219 @@
+// u256.cuh -- 256-bit integer building blocks on 8 x u32 limbs held in registers (sm_100a).
+//
+// Every 32x32->64 multiply is written as a `mad.lo.cc.u32` / `madc.hi.cc.u32` pair on the
+// same operands whose results land in an even-aligned register pair; ptxas fuses each pair
+// into ONE `IMAD.WIDE.U32(.X)` (checked with cuobjdump -sass, see profiles/).  A full 8x8
+// schoolbook product is therefore 64 IMAD.WIDE plus ~22 carry fix-ups on the ALU pipe, a
+// square is 36.  Column parities are kept in two accumulators (`ev`: limb positions i+j
+// even, `od`: odd) so that every product is pair-aligned, and are merged once at the end.
+//
+// Replaces (as a building block) the 4 x u64 -> u128 schoolbook loops of the reference:
+// forge-ec-curves/src/secp256k1.rs:449-466, p256.rs:501-533, curve25519.rs:230-313,
+// ed25519.rs:522-545.
+#pragma once
+#include <cstdint>
+
+namespace fec {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define FEC_DEV __device__ __forceinline__
+
+// ---- carry-flag primitives (one PTX instruction each; `volatile` keeps their order, the
+// compiler itself never emits .cc instructions so the flag cannot be clobbered in between)
+FEC_DEV u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 addc_cc(u32 a, u32 b) { u32 r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 mul_lo(u32 a, u32 b) { u32 r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 mul_hi(u32 a, u32 b) { u32 r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+FEC_DEV u32 mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FEC_DEV u32 madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FEC_DEV u32 madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FEC_DEV u32 madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// acc[0..2*NP) += {a0,a1,..}[k] * b laid out as NP (lo,hi) pairs, one carry chain.
+// `fresh` = how many of the top words of the span have never been written (their old value is
+// taken as 0); when fresh==0 the chain's carry-out is returned (else 0 -- it cannot carry).
+template <int NP, int FRESH>
+FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b) {
+  static_assert(FRESH >= 0 && FRESH <= 2, "fresh words");
+#pragma unroll
+  for (int k = 0; k < NP; k++) {
+    const u32 ak = a[2 * k];
+    const bool lo_fresh = (2 * k >= 2 * NP - FRESH);
+    const bool hi_fresh = (2 * k + 1 >= 2 * NP - FRESH);
+    const u32 lo_in = lo_fresh ? 0u : acc[2 * k];
+    const u32 hi_in = hi_fresh ? 0u : acc[2 * k + 1];
+    acc[2 * k] = (k == 0) ? mad_lo_cc(ak, b, lo_in) : madc_lo_cc(ak, b, lo_in);
+    if (k == NP - 1 && FRESH > 0)
+      acc[2 * k + 1] = madc_hi(ak, b, hi_in);
+    else
+      acc[2 * k + 1] = madc_hi_cc(ak, b, hi_in);
+  }
+  if (FRESH == 0) return addc(0u, 0u);
+  return 0u;
+}
+
+// r[0..16) = a[0..8) * b[0..8)
+FEC_DEV void mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) {
+  u32 ev[16];  // ev[k]: weight 2^(32k)
+  u32 od[15];  // od[k]: weight 2^(32(k+1))
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    ev[j] = mul_lo(a[j], b[0]);
+    ev[j + 1] = mul_hi(a[j], b[0]);
+    od[j] = mul_lo(a[j + 1], b[0]);
+    od[j + 1] = mul_hi(a[j + 1], b[0]);
+  }
+  // odd rows: a_odd*b[i] -> even positions, a_even*b[i] -> odd positions (full -> carry word)
+  // even rows: a_even*b[i] -> even positions (full -> carry word), a_odd*b[i] -> odd positions
+  mad_row<4, 2>(ev + 2, a + 1, b[1]);  od[8]  = mad_row<4, 0>(od + 0, a, b[1]);
+  ev[10] = mad_row<4, 0>(ev + 2, a, b[2]);  mad_row<4, 1>(od + 2, a + 1, b[2]);
+  mad_row<4, 1>(ev + 4, a + 1, b[3]);  od[10] = mad_row<4, 0>(od + 2, a, b[3]);
+  ev[12] = mad_row<4, 0>(ev + 4, a, b[4]);  mad_row<4, 1>(od + 4, a + 1, b[4]);
+  mad_row<4, 1>(ev + 6, a + 1, b[5]);  od[12] = mad_row<4, 0>(od + 4, a, b[5]);
+  ev[14] = mad_row<4, 0>(ev + 6, a, b[6]);  mad_row<4, 1>(od + 6, a + 1, b[6]);
+  mad_row<4, 1>(ev + 8, a + 1, b[7]);  od[14] = mad_row<4, 0>(od + 6, a, b[7]);
+  // merge: r = ev + (od << 32).  ev[15] was written by row 7 (fresh), od[14] by row 7's carry.
+  r[0] = ev[0];
+  r[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) r[k] = addc_cc(ev[k], od[k - 1]);
+  r[15] = addc(ev[15], od[14]);
+}
+
+// r[0..16) = a[0..8)^2 : 28 off-diagonal products (doubled by a 1-bit funnel shift) + 8 diagonals.
+FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
+  // off-diagonal sum S = sum_{i<j} a[i]a[j] 2^(32(i+j)); positions 1..14 (+carry word 15 stays 0)
+  u32 ev[16];  // even positions 2..14 used: ev[k] weight 2^(32k)
+  u32 od[15];  // odd positions: od[k] weight 2^(32(k+1)), positions 1..13 -> od[0..13]
+  // row 0: a0*a1 (1,2) a0*a3 (3,4) a0*a5 (5,6) a0*a7 (7,8) -> od[0..7]; a0*a2 (2,3) a0*a4 (4,5) a0*a6 (6,7) -> ev[2..7]
+  od[0] = mul_lo(a[0], a[1]); od[1] = mul_hi(a[0], a[1]);
+  od[2] = mul_lo(a[0], a[3]); od[3] = mul_hi(a[0], a[3]);
+  od[4] = mul_lo(a[0], a[5]); od[5] = mul_hi(a[0], a[5]);
+  od[6] = mul_lo(a[0], a[7]); od[7] = mul_hi(a[0], a[7]);
+  ev[2] = mul_lo(a[0], a[2]); ev[3] = mul_hi(a[0], a[2]);
+  ev[4] = mul_lo(a[0], a[4]); ev[5] = mul_hi(a[0], a[4]);
+  ev[6] = mul_lo(a[0], a[6]); ev[7] = mul_hi(a[0], a[6]);
+  // row 1: a1*a2 (3,4) a1*a4 (5,6) a1*a6 (7,8) -> od[2..7] full -> carry od[8];
+  //        a1*a3 (4,5) a1*a5 (6,7) a1*a7 (8,9) -> ev[4..9], ev[8],ev[9] fresh
+  od[8] = mad_row<3, 0>(od + 2, a + 2, a[1]);
+  mad_row<3, 2>(ev + 4, a + 3, a[1]);
+  // row 2: a2*a3 (5,6) a2*a5 (7,8) a2*a7 (9,10) -> od[4..9], od[9] fresh;
+  //        a2*a4 (6,7) a2*a6 (8,9) -> ev[6..9] full -> carry ev[10]
+  mad_row<3, 1>(od + 4, a + 3, a[2]);
+  ev[10] = mad_row<2, 0>(ev + 6, a + 4, a[2]);
+  // row 3: a3*a4 (7,8) a3*a6 (9,10) -> od[6..9] full -> carry od[10];
+  //        a3*a5 (8,9) a3*a7 (10,11) -> ev[8..11], ev[11] fresh
+  od[10] = mad_row<2, 0>(od + 6, a + 4, a[3]);
+  mad_row<2, 1>(ev + 8, a + 5, a[3]);
+  // row 4: a4*a5 (9,10) a4*a7 (11,12) -> od[8..11], od[11] fresh;  a4*a6 (10,11) -> ev[10..11] full -> carry ev[12]
+  mad_row<2, 1>(od + 8, a + 5, a[4]);
+  ev[12] = mad_row<1, 0>(ev + 10, a + 6, a[4]);
+  // row 5: a5*a6 (11,12) -> od[10..11] full -> carry od[12];  a5*a7 (12,13) -> ev[12..13], ev[13] fresh
+  od[12] = mad_row<1, 0>(od + 10, a + 6, a[5]);
+  mad_row<1, 1>(ev + 12, a + 7, a[5]);
+  // row 6: a6*a7 (13,14) -> od[12..13], od[13] fresh
+  mad_row<1, 1>(od + 12, a + 7, a[6]);
+  // merge off-diagonals: s[1..14] (s[0]=0, s[15] = 0); s fits in 15 words (sum < 2^480)
+  u32 s[16];
+  s[1] = od[0];
+  s[2] = add_cc(ev[2], od[1]);
+#pragma unroll
+  for (int k = 3; k < 14; k++) s[k] = addc_cc(ev[k], od[k - 1]);
+  s[14] = addc(0u, od[13]);
+  // double: t = 2*s (funnel shifts), then add diagonals a[i]^2 at (2i, 2i+1) in one chain
+  u32 t[16];
+  t[0] = 0;
+  t[1] = s[1] << 1;
+#pragma unroll
+  for (int k = 2; k < 15; k++) t[k] = __funnelshift_l(s[k - 1], s[k], 1);
+  t[15] = s[14] >> 31;
+  r[0] = mad_lo_cc(a[0], a[0], t[0]);
+  r[1] = madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    r[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
+    if (i < 7)
+      r[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+    else
+      r[2 * i + 1] = madc_hi(a[i], a[i], t[2 * i + 1]);
+  }
+}
+
+// ---- 8-limb helpers -------------------------------------------------------------------
+// r = a + b, returns carry
+FEC_DEV u32 add8(u32 r[8], const u32 a[8], const u32 b[8]) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = addc_cc(a[i], b[i]);
+  return addc(0u, 0u);
+}
+// r = a - b, returns borrow (0/1)
+FEC_DEV u32 sub8(u32 r[8], const u32 a[8], const u32 b[8]) {
+  r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = subc_cc(a[i], b[i]);
+  return subc(0u, 0u) & 1u;
+}
+FEC_DEV void copy8(u32 r[8], const u32 a[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = a[i];
+}
+// r = m ? a : b   (m is an all-ones / all-zero mask)
+FEC_DEV void select8(u32 r[8], u32 m, const u32 a[8], const u32 b[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = (a[i] & m) | (b[i] & ~m);
+}
+FEC_DEV u32 is_zero8(const u32 a[8]) {  // all-ones mask if a == 0
+  u32 o = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+  return (o == 0) ? 0xFFFFFFFFu : 0u;
+}
+FEC_DEV u32 eq8(const u32 a[8], const u32 b[8]) {
+  u32 o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a[i] ^ b[i];
+  return (o == 0) ? 0xFFFFFFFFu : 0u;
+}
+// a >= b (unsigned 256-bit) as mask
+FEC_DEV u32 geq8(const u32 a[8], const u32 b[8]) {
+  u32 t[8];
+  u32 bw = sub8(t, a, b);
+  return bw ? 0u : 0xFFFFFFFFu;
+}
+
+// 32-byte big-endian <-> limbs (limb 0 = least significant)
+FEC_DEV void load_be32(u32 r[8], const uint8_t* p) {  // p need not be aligned
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* q = p + 28 - 4 * i;
+    r[i] = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+  }
+}
+FEC_DEV void store_be32(uint8_t* p, const u32 a[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = p + 28 - 4 * i;
+    q[0] = (uint8_t)(a[i] >> 24); q[1] = (uint8_t)(a[i] >> 16); q[2] = (uint8_t)(a[i] >> 8); q[3] = (uint8_t)a[i];
+  }
+}
+FEC_DEV void load_le32(u32 r[8], const uint8_t* p) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* q = p + 4 * i;
+    r[i] = ((u32)q[3] << 24) | ((u32)q[2] << 16) | ((u32)q[1] << 8) | (u32)q[0];
+  }
+}
+FEC_DEV void store_le32(uint8_t* p, const u32 a[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = p + 4 * i;
+    q[0] = (uint8_t)a[i]; q[1] = (uint8_t)(a[i] >> 8); q[2] = (uint8_t)(a[i] >> 16); q[3] = (uint8_t)(a[i] >> 24);
+  }
+}
+
+}  // namespace fec

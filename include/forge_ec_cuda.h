@@ -1,0 +1,129 @@
+/* forge_ec_cuda.h -- C ABI of the B200 batched scalar-multiplication engine.
+ *
+ * This is the drop-in boundary for forge-ec's one data-parallel hot path.  The reference has no
+ * FFI of its own (every crate is #![forbid(unsafe_code)]); the seam it offers is the `Curve`
+ * trait, one call per scalar.  Each entry point below is the batched form of a reference call
+ * chain (file:line relative to the forge-ec repository):
+ *
+ *   fec_batch_mul            n x { Scalar::from_bytes            secp256k1.rs:2271-2297 / p256.rs:1041-1055
+ *                                  Curve::generator | from_affine secp256k1.rs:2608-2625, 1365-1373 / p256.rs:2092-2110
+ *                                  Curve::multiply               secp256k1.rs:2635-2692 / p256.rs:2120-2156
+ *                                  Curve::to_affine              secp256k1.rs:1342-1363 / p256.rs:1835-1857
+ *                                  PointAffine::to_bytes[_with_format] / CompressedPoint::from_affine /
+ *                                  UncompressedPoint::from_affine   secp256k1.rs:875-894, 1010-1067;
+ *                                                                   forge-ec-encoding/src/point.rs:39-67, 186-211 }
+ *                            with points_fmt = SEC1 compressed additionally
+ *                                  CompressedPoint::to_affine / Curve::validate_point
+ *                                                                   point.rs:70-144; forge-ec-core/src/lib.rs:905-923
+ *   fec_batch_x25519         n x   x25519(scalar, u)             curve25519.rs:1624-1716  (RFC 7748)
+ *   fec_batch_ed25519_pubkey n x   Ed25519Signature::derive_public_key   forge-ec-signature/src/eddsa.rs:450-509 (RFC 8032 5.1.5)
+ *   fec_field_bench          n x   FieldElement::mul / square    secp256k1.rs:442-507, 634-713; p256.rs:498-534, 772-776;
+ *                                                                curve25519.rs:227-314, 490-494
+ *
+ * Conventions
+ *   - Every buffer is caller-owned, tightly packed, lane-major (lane i at offset i*record_size).
+ *   - Host entry points take HOST pointers (pageable or pinned), shard the lanes in contiguous
+ *     ranges over the context's devices, copy in, compute, copy out, and return when the result
+ *     is in `out`.  `*_dev` entry points take DEVICE pointers valid on the context's device
+ *     `dev_index` (16-byte aligned), enqueue on `stream` (a cudaStream_t, NULL = legacy default
+ *     stream) and return without synchronising.
+ *   - Return value: 0 on success, else a fec_err (whole-call failure).  Per-lane outcomes that
+ *     depend on the data go to `status` (may be NULL): the device never branches on them.
+ *   - A lane whose status is not FEC_LANE_OK has an all-zero output record, which is also the
+ *     reference's encoding of the identity (point.rs:41-47).
+ *   - There is no CPU fallback: without a usable CUDA device fec_ctx_create fails.
+ *   - A context serialises its calls on an internal mutex; several contexts may coexist.
+ */
+#ifndef FORGE_EC_CUDA_H
+#define FORGE_EC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fec_ctx fec_ctx;
+
+typedef enum { FEC_SECP256K1 = 0, FEC_P256 = 1 } fec_curve;
+typedef enum { FEC_PRIME_SECP256K1 = 0, FEC_PRIME_P256 = 1, FEC_PRIME_25519 = 2 } fec_prime;
+typedef enum {
+  FEC_OUT_SEC1_COMPRESSED = 0,   /* 33 B: 02|03 || X          (PointFormat::Compressed)   */
+  FEC_OUT_SEC1_UNCOMPRESSED = 1, /* 65 B: 04 || X || Y        (PointFormat::Uncompressed) */
+  FEC_OUT_AFFINE_XY_BE = 2       /* 64 B: X || Y, big-endian  (FieldElement::to_bytes x2) */
+} fec_out;
+typedef enum { FEC_PT_AFFINE_XY_BE = 0 /* 64 B */, FEC_PT_SEC1_COMPRESSED = 1 /* 33 B */ } fec_points_fmt;
+typedef enum {
+  FEC_SEM_STD = 0,        /* SEC2 / FIPS 186-4 / RFC 7748 / RFC 8032 results (what the reference specifies) */
+  FEC_SEM_FORGE_QUIRK = 1 /* replay of the reference's literal limb code; not implemented: FEC_ERR_UNSUPPORTED */
+} fec_sem;
+typedef enum { FEC_FIELD_MUL = 0, FEC_FIELD_SQR = 1, FEC_FIELD_MULSQR = 2 } fec_field_op;
+
+typedef enum {
+  FEC_OK = 0,
+  FEC_ERR_INVALID_ARG = 1, /* NULL / bad enum / misaligned device pointer  -> Error::InvalidEncoding */
+  FEC_ERR_CUDA = 2,        /* a CUDA runtime call failed                  -> Error::GenericError    */
+  FEC_ERR_NO_DEVICE = 3,   /* no usable CUDA device                       -> Error::UnsupportedOperation */
+  FEC_ERR_UNSUPPORTED = 4, /* semantics / format not available            -> Error::UnsupportedOperation */
+  FEC_ERR_OOM = 5          /* host or device allocation failed            -> Error::GenericError    */
+} fec_err;
+
+/* per-lane status bytes */
+enum {
+  FEC_LANE_OK = 0,
+  FEC_LANE_SCALAR_RANGE = 1,  /* scalar >= group order      -> Error::InvalidScalar   */
+  FEC_LANE_POINT_INVALID = 2, /* not on curve / bad encoding -> Error::PointNotOnCurve / InvalidEncoding */
+  FEC_LANE_INFINITY = 3       /* result is the identity (k = 0)                          */
+};
+
+/* device_ids == NULL or n_devices <= 0: use the current CUDA device only. */
+int fec_ctx_create(const int* device_ids, int n_devices, fec_ctx** out);
+void fec_ctx_destroy(fec_ctx* ctx);
+int fec_ctx_device_count(const fec_ctx* ctx);
+/* number of kernels this context has launched since creation (for bench.py's gpu_launches) */
+uint64_t fec_ctx_launch_count(const fec_ctx* ctx);
+const char* fec_strerror(int err);
+/* last CUDA error string seen by this context (thread-unsafe diagnostic) */
+const char* fec_ctx_last_cuda_error(const fec_ctx* ctx);
+
+/* k_i*G when points == NULL, else k_i*P_i.
+ * scalars: n x 32 B big-endian (Scalar::from_bytes layout); points: n x 64 B (X||Y big-endian) or
+ * n x 33 B SEC1 compressed; out: n x {33,65,64} B; status: n x u8 or NULL. */
+int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
+                  fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status);
+int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
+                      const uint8_t* d_points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out,
+                      uint8_t* d_status, void* stream);
+
+/* RFC 7748 X25519: scalars n x 32 B (clamped inside), u n x 32 B little-endian (NULL = base point 9),
+ * out n x 32 B little-endian. */
+int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
+int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+                         uint8_t* d_out, void* stream);
+
+/* RFC 8032 5.1.5 public key.  input_is_seed != 0: 32-byte seeds (SHA-512 + clamp on device);
+ * input_is_seed == 0: 32-byte little-endian scalars used as they are.  out n x 32 B (y || sign x). */
+int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n,
+                             uint8_t* out);
+int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
+                                 uint8_t* d_out, void* stream);
+
+/* Field microbenchmark (config 2).  a, b, out: lanes x 32 B little-endian residues in [0,p).
+ * Per lane: x = a; repeat iters times { MUL: x = x*b;  SQR: x = x^2;  MULSQR: x = (x*b)^2 }; out = x.
+ * *seconds (may be NULL) receives the kernel time measured with CUDA events (host variant only). */
+int fec_field_bench(fec_ctx* ctx, fec_prime prime, fec_field_op op, size_t lanes, int iters, const uint8_t* a,
+                    const uint8_t* b, uint8_t* out, double* seconds);
+int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_op op, size_t lanes, int iters,
+                        const uint8_t* d_a, const uint8_t* d_b, uint8_t* d_out, void* stream);
+
+/* Roofline calibration: a register-resident loop of independent 32x32->64 multiply-adds.
+ * variant 0 = IMAD.WIDE.U32 (one instruction per IMUL32), 1 = mad.lo + mad.hi (two IMAD per IMUL32),
+ * 2 = carry-chained IMAD.WIDE.X as used by the field code.
+ * Returns multiply-add *instructions* per second over the whole device. */
+int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FORGE_EC_CUDA_H */
