@@ -200,6 +200,7 @@ FEC_DEV u32 on_curve(const u32 x[8], const u32 y[8]) {
 // Cost per thread: 2*(5+log2 W) M  +  (1/W) of an inversion.   `sm` must hold 2*W*8 + 8 words.
 // All threads of the block must call it (it contains __syncthreads()).
 // -------------------------------------------------------------------------------------
+#ifdef __CUDACC__
 template <class F, int WARPS>
 FEC_DEV void block_batch_inv(u32 zinv[8], const u32 z[8], u32* sm) {
   constexpr int LW = (WARPS == 1) ? 0 : (WARPS == 2) ? 1 : (WARPS == 4) ? 2 : (WARPS == 8) ? 3 : (WARPS == 16) ? 4 : -1;
@@ -239,6 +240,7 @@ FEC_DEV void block_batch_inv(u32 zinv[8], const u32 z[8], u32* sm) {
   for (int l = 5 + LW - 1; l >= 0; l--) F::mul(p, p, sib[l]);
   copy8(zinv, p);
 }
+#endif  // __CUDACC__
 
 // -------------------------------------------------------------------------------------
 // Ed25519: extended coordinates (X:Y:Z:T), Niels addends (y+x, y-x, 2dxy)

@@ -1,0 +1,466 @@
+// forge_ec_cuda.cu -- host side of the C ABI: context, device set-up, sharding over devices, the
+// host-buffer pipeline and the extern "C" entry points declared in include/forge_ec_cuda.h.
+// The kernels live in k_*.cu (see kernels.cuh).  There is no CPU code path in this library: every
+// entry point needs a CUDA device of compute capability 10.x.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+// ======================================================================================
+// host side: context, sharding, C ABI
+// ======================================================================================
+using namespace fec;
+
+namespace {
+
+constexpr size_t CHUNK_LANES = size_t(1) << 18;  // host-buffer pipeline granule (multiple of every tile size)
+constexpr int N_PIPE = 3;                        // in-flight chunks per device
+
+struct Device {
+  int id = -1;
+  int sms = 0;
+  u32* comb[2] = {nullptr, nullptr};  // secp256k1, P-256
+  u32* niels = nullptr;
+  cudaStream_t streams[N_PIPE] = {};
+  uint8_t* buf_in_a[N_PIPE] = {};   // scalars / seeds / field a
+  uint8_t* buf_in_b[N_PIPE] = {};   // points / u / field b
+  uint8_t* buf_out[N_PIPE] = {};
+  uint8_t* buf_st[N_PIPE] = {};
+  bool pipe_ready = false;
+};
+
+}  // namespace
+
+struct fec_ctx {
+  std::vector<Device> devs;
+  std::mutex mu;
+  std::atomic<uint64_t> launches{0};
+  char last_err[256] = {0};
+};
+
+namespace {
+
+thread_local int tl_err_line = 0;
+#define FEC_CUDA(ctx, call)                                                                     \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      snprintf((ctx)->last_err, sizeof((ctx)->last_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e_));                                                         \
+      tl_err_line = __LINE__;                                                                   \
+      return e_ == cudaErrorMemoryAllocation ? FEC_ERR_OOM : FEC_ERR_CUDA;                      \
+    }                                                                                           \
+  } while (0)
+
+int device_init(fec_ctx* ctx, Device& d) {
+  FEC_CUDA(ctx, cudaSetDevice(d.id));
+  cudaDeviceProp prop;
+  FEC_CUDA(ctx, cudaGetDeviceProperties(&prop, d.id));
+  if (prop.major < 10) {
+    snprintf(ctx->last_err, sizeof(ctx->last_err), "device %d is sm_%d%d; this library is built for sm_100a only", d.id,
+             prop.major, prop.minor);
+    return FEC_ERR_NO_DEVICE;
+  }
+  d.sms = prop.multiProcessorCount;
+  FEC_CUDA(ctx, wmul_var_setup());
+  FEC_CUDA(ctx, wmul_fixed_setup());
+  FEC_CUDA(ctx, ed25519_setup());
+  for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaStreamCreateWithFlags(&d.streams[s], cudaStreamNonBlocking));
+  FEC_CUDA(ctx, cudaMalloc(&d.comb[0], COMB_WORDS * 4));
+  FEC_CUDA(ctx, cudaMalloc(&d.comb[1], COMB_WORDS * 4));
+  FEC_CUDA(ctx, cudaMalloc(&d.niels, NIELS_WORDS * 4));
+  FEC_CUDA(ctx, build_comb_launch(FEC_SECP256K1, d.streams[0], d.comb[0]));
+  FEC_CUDA(ctx, build_comb_launch(FEC_P256, d.streams[0], d.comb[1]));
+  FEC_CUDA(ctx, build_niels_launch(d.streams[0], d.niels));
+  ctx->launches += 3;
+  FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[0]));
+  return FEC_OK;
+}
+
+int device_pipe_init(fec_ctx* ctx, Device& d) {
+  if (d.pipe_ready) return FEC_OK;
+  FEC_CUDA(ctx, cudaSetDevice(d.id));
+  for (int s = 0; s < N_PIPE; s++) {
+    FEC_CUDA(ctx, cudaMalloc(&d.buf_in_a[s], CHUNK_LANES * 32));
+    FEC_CUDA(ctx, cudaMalloc(&d.buf_in_b[s], CHUNK_LANES * 64));
+    FEC_CUDA(ctx, cudaMalloc(&d.buf_out[s], CHUNK_LANES * 65 + 64));
+    FEC_CUDA(ctx, cudaMalloc(&d.buf_st[s], CHUNK_LANES));
+  }
+  d.pipe_ready = true;
+  return FEC_OK;
+}
+
+void device_free(Device& d) {
+  if (d.id < 0) return;
+  cudaSetDevice(d.id);
+  for (int s = 0; s < N_PIPE; s++) {
+    if (d.streams[s]) cudaStreamSynchronize(d.streams[s]);
+    cudaFree(d.buf_in_a[s]); cudaFree(d.buf_in_b[s]); cudaFree(d.buf_out[s]); cudaFree(d.buf_st[s]);
+    if (d.streams[s]) cudaStreamDestroy(d.streams[s]);
+  }
+  cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- launches on device pointers ------------------------------------------------------
+int launch_mul(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
+               uint8_t* dout, uint8_t* dst, cudaStream_t st) {
+  if (n == 0) return FEC_OK;
+  ctx->launches++;
+  if (dp == nullptr)
+    FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
+  else
+    FEC_CUDA(ctx, wmul_var_launch(curve, d.sms, st, ds, dp, pfmt, n, ofmt, dout, dst));
+  return FEC_OK;
+}
+int launch_x25519(fec_ctx* ctx, Device& d, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
+  if (n == 0) return FEC_OK;
+  ctx->launches++;
+  FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
+  return FEC_OK;
+}
+int launch_ed(fec_ctx* ctx, Device& d, const uint8_t* din, int is_seed, size_t n, uint8_t* dout, cudaStream_t st) {
+  if (n == 0) return FEC_OK;
+  ctx->launches++;
+  FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed, d.niels, n, dout));
+  return FEC_OK;
+}
+int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int iters, const uint8_t* a, const uint8_t* b,
+                 uint8_t* o, cudaStream_t st) {
+  if (lanes == 0) return FEC_OK;
+  ctx->launches++;
+  FEC_CUDA(ctx, field_bench_launch(d.sms, st, prime, op, a, b, o, lanes, iters));
+  return FEC_OK;
+}
+
+// ---- host-buffer pipeline: H2D -> kernel -> D2H in CHUNK_LANES granules over N_PIPE streams ----
+struct HostJob {
+  int kind;  // 0 mul, 1 x25519, 2 ed25519
+  int curve, pfmt, ofmt, is_seed;
+  const uint8_t* in_a; size_t rec_a;
+  const uint8_t* in_b; size_t rec_b;
+  uint8_t* out; size_t rec_out;
+  uint8_t* status;
+};
+
+int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t count) {
+  if (count == 0) return FEC_OK;
+  int rc = device_pipe_init(ctx, d);
+  if (rc) return rc;
+  FEC_CUDA(ctx, cudaSetDevice(d.id));
+  int slot = 0;
+  for (size_t off = 0; off < count; off += CHUNK_LANES, slot = (slot + 1) % N_PIPE) {
+    const size_t m = (count - off) < CHUNK_LANES ? (count - off) : CHUNK_LANES;
+    const size_t g0 = first + off;
+    cudaStream_t st = d.streams[slot];
+    FEC_CUDA(ctx, cudaStreamSynchronize(st));  // slot's previous chunk fully drained
+    FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_a[slot], job.in_a + g0 * job.rec_a, m * job.rec_a, cudaMemcpyHostToDevice, st));
+    const uint8_t* db = nullptr;
+    if (job.in_b != nullptr) {
+      FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_b[slot], job.in_b + g0 * job.rec_b, m * job.rec_b, cudaMemcpyHostToDevice, st));
+      db = d.buf_in_b[slot];
+    }
+    if (job.kind == 0)
+      rc = launch_mul(ctx, d, job.curve, d.buf_in_a[slot], db, job.pfmt, m, job.ofmt, d.buf_out[slot],
+                      job.status ? d.buf_st[slot] : nullptr, st);
+    else if (job.kind == 1)
+      rc = launch_x25519(ctx, d, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
+    else
+      rc = launch_ed(ctx, d, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
+    if (rc) return rc;
+    FEC_CUDA(ctx, cudaMemcpyAsync(job.out + g0 * job.rec_out, d.buf_out[slot], m * job.rec_out, cudaMemcpyDeviceToHost, st));
+    if (job.status) FEC_CUDA(ctx, cudaMemcpyAsync(job.status + g0, d.buf_st[slot], m, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[s]));
+  return FEC_OK;
+}
+
+// contiguous lane ranges over the context's devices, one host thread per device
+int run_host_job(fec_ctx* ctx, const HostJob& job, size_t n) {
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t G = ctx->devs.size();
+  if (G == 1) return run_shard(ctx, ctx->devs[0], job, 0, n);
+  // shard boundaries on CHUNK-independent multiples of 1024 lanes so every record offset stays 16-byte aligned
+  std::vector<size_t> cut(G + 1, 0);
+  for (size_t i = 1; i < G; i++) cut[i] = ((n * i / G) + 1023) / 1024 * 1024 < n ? ((n * i / G) + 1023) / 1024 * 1024 : n;
+  cut[G] = n;
+  std::vector<int> rcs(G, FEC_OK);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < G; i++)
+    th.emplace_back([&, i]() { rcs[i] = run_shard(ctx, ctx->devs[i], job, cut[i], cut[i + 1] - cut[i]); });
+  for (auto& t : th) t.join();
+  for (int rc : rcs) if (rc) return rc;
+  return FEC_OK;
+}
+
+Device* dev_at(fec_ctx* ctx, int dev_index) {
+  if (ctx == nullptr || dev_index < 0 || (size_t)dev_index >= ctx->devs.size()) return nullptr;
+  return &ctx->devs[(size_t)dev_index];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fec_strerror(int err) {
+  switch (err) {
+    case FEC_OK: return "ok";
+    case FEC_ERR_INVALID_ARG: return "invalid argument";
+    case FEC_ERR_CUDA: return "CUDA runtime error";
+    case FEC_ERR_NO_DEVICE: return "no usable CUDA device (sm_100a required; there is no CPU fallback)";
+    case FEC_ERR_UNSUPPORTED: return "unsupported semantics or format";
+    case FEC_ERR_OOM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+int fec_ctx_create(const int* device_ids, int n_devices, fec_ctx** out) {
+  if (out == nullptr) return FEC_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FEC_ERR_NO_DEVICE;
+  fec_ctx* ctx = new (std::nothrow) fec_ctx();
+  if (ctx == nullptr) return FEC_ERR_OOM;
+  int cur = 0;
+  if (device_ids == nullptr || n_devices <= 0) {
+    if (cudaGetDevice(&cur) != cudaSuccess) { delete ctx; return FEC_ERR_NO_DEVICE; }
+    ctx->devs.resize(1);
+    ctx->devs[0].id = cur;
+  } else {
+    ctx->devs.resize((size_t)n_devices);
+    for (int i = 0; i < n_devices; i++) {
+      if (device_ids[i] < 0 || device_ids[i] >= count) { ctx->devs.clear(); delete ctx; return FEC_ERR_INVALID_ARG; }
+      ctx->devs[(size_t)i].id = device_ids[i];
+    }
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& d : ctx->devs) {
+    int rc = device_init(ctx, d);
+    if (rc) {
+      fprintf(stderr, "forge_ec_cuda: context creation failed: %s (%s)\n", fec_strerror(rc), ctx->last_err);
+      for (auto& dd : ctx->devs) device_free(dd);
+      delete ctx;
+      cudaSetDevice(prev);
+      return rc;
+    }
+  }
+  cudaSetDevice(prev);
+  *out = ctx;
+  return FEC_OK;
+}
+
+void fec_ctx_destroy(fec_ctx* ctx) {
+  if (ctx == nullptr) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  for (auto& d : ctx->devs) device_free(d);
+  cudaSetDevice(prev);
+  delete ctx;
+}
+
+int fec_ctx_device_count(const fec_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+uint64_t fec_ctx_launch_count(const fec_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+const char* fec_ctx_last_cuda_error(const fec_ctx* ctx) { return ctx ? ctx->last_err : ""; }
+
+int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
+                  fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status) {
+  if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  if (sem != FEC_SEM_STD) return FEC_ERR_UNSUPPORTED;
+  HostJob job{0, (int)curve, (int)points_fmt, (int)out_fmt, 0, scalars, 32, points,
+              (size_t)(points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64), out, (size_t)out_size(out_fmt), status};
+  return run_host_job(ctx, job, n);
+}
+
+int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
+                      const uint8_t* d_points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out,
+                      uint8_t* d_status, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  if (sem != FEC_SEM_STD) return FEC_ERR_UNSUPPORTED;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  int rc = launch_mul(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status,
+                      (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
+  if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
+  HostJob job{1, 0, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};
+  return run_host_job(ctx, job, n);
+}
+int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+                         uint8_t* d_out, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_scalars) || !aligned16(d_u) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  int rc = launch_x25519(ctx, *d, d_scalars, d_u, n, d_out, (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out) {
+  if (ctx == nullptr || (n > 0 && (seeds_or_scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
+  HostJob job{2, 0, 0, 0, input_is_seed, seeds_or_scalars, 32, nullptr, 0, out, 32, nullptr};
+  return run_host_job(ctx, job, n);
+}
+int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
+                                 uint8_t* d_out, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_in == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_in) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  int rc = launch_ed(ctx, *d, d_in, input_is_seed, n, d_out, (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_op op, size_t lanes, int iters,
+                        const uint8_t* d_a, const uint8_t* d_b, uint8_t* d_out, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (lanes > 0 && (d_a == nullptr || d_b == nullptr || d_out == nullptr)) || iters < 0)
+    return FEC_ERR_INVALID_ARG;
+  if ((int)prime < 0 || (int)prime > 2 || (int)op < 0 || (int)op > 2) return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_a) || !aligned16(d_b) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  int rc = launch_field(ctx, *d, (int)prime, (int)op, lanes, iters, d_a, d_b, d_out, (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int fec_field_bench(fec_ctx* ctx, fec_prime prime, fec_field_op op, size_t lanes, int iters, const uint8_t* a,
+                    const uint8_t* b, uint8_t* out, double* seconds) {
+  if (ctx == nullptr || (lanes > 0 && (a == nullptr || b == nullptr || out == nullptr)) || iters < 0) return FEC_ERR_INVALID_ARG;
+  if ((int)prime < 0 || (int)prime > 2 || (int)op < 0 || (int)op > 2) return FEC_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  Device& d = ctx->devs[0];
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d.id));
+  uint8_t *da = nullptr, *db = nullptr, *dout = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = FEC_OK;
+  auto cleanup = [&]() {
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaSetDevice(prev);
+  };
+#define FEC_TRY(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      snprintf(ctx->last_err, sizeof(ctx->last_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      cleanup();                                                                                        \
+      return e_ == cudaErrorMemoryAllocation ? FEC_ERR_OOM : FEC_ERR_CUDA;                              \
+    }                                                                                                   \
+  } while (0)
+  if (lanes > 0) {
+    FEC_TRY(cudaMalloc(&da, lanes * 32));
+    FEC_TRY(cudaMalloc(&db, lanes * 32));
+    FEC_TRY(cudaMalloc(&dout, lanes * 32));
+    FEC_TRY(cudaEventCreate(&e0));
+    FEC_TRY(cudaEventCreate(&e1));
+    cudaStream_t st = d.streams[0];
+    FEC_TRY(cudaMemcpyAsync(da, a, lanes * 32, cudaMemcpyHostToDevice, st));
+    FEC_TRY(cudaMemcpyAsync(db, b, lanes * 32, cudaMemcpyHostToDevice, st));
+    FEC_TRY(cudaEventRecord(e0, st));
+    rc = launch_field(ctx, d, (int)prime, (int)op, lanes, iters, da, db, dout, st);
+    if (rc) { cleanup(); return rc; }
+    FEC_TRY(cudaEventRecord(e1, st));
+    FEC_TRY(cudaMemcpyAsync(out, dout, lanes * 32, cudaMemcpyDeviceToHost, st));
+    FEC_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    FEC_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (seconds) *seconds = (double)ms * 1e-3;
+  } else if (seconds) {
+    *seconds = 0.0;
+  }
+  cleanup();
+  return rc;
+}
+
+int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || instr_per_sec == nullptr || variant < 0 || variant > 2) return FEC_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  const int blocks = d->sms * 8, trips = 4096;
+  u32* sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(sink);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaSetDevice(prev);
+  };
+  FEC_TRY(cudaMalloc(&sink, (size_t)blocks * PEAK_THREADS * 4));
+  FEC_TRY(cudaEventCreate(&e0));
+  FEC_TRY(cudaEventCreate(&e1));
+  cudaStream_t st = d->streams[0];
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {  // first repetition is the warm-up
+    FEC_TRY(cudaEventRecord(e0, st));
+    ctx->launches++;
+    FEC_TRY(imad_peak_launch(variant, blocks, st, sink, 0x1234567u + rep, trips));
+    FEC_TRY(cudaEventRecord(e1, st));
+    FEC_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    FEC_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    // multiply-add instructions issued: variant 1 issues two per chain step
+    const double per_step = (variant == 1) ? 2.0 : 1.0;
+    const double instr = (double)blocks * PEAK_THREADS * (double)trips * PEAK_INNER * PEAK_CHAINS * per_step;
+    const double rate = instr / ((double)ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  *instr_per_sec = best;
+  cleanup();
+  return FEC_OK;
+}
+
+int fec_synth_dev(fec_ctx* ctx, int dev_index, int mode, uint32_t stream_id, uint32_t sub, uint64_t first_lane, int edge,
+                  size_t n, uint8_t* d_out, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && d_out == nullptr) || mode < 0 || mode > 2 || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  if (n == 0) return FEC_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  const unsigned long long seed = 0x666F7267652D6563ULL;  // "forge-ec"
+  ctx->launches++;
+  cudaError_t e = synth_launch(d->sms, (cudaStream_t)stream, d_out, n, (u32)seed, (u32)(seed >> 32), stream_id, sub,
+                               (unsigned long long)first_lane, mode, edge);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    snprintf(ctx->last_err, sizeof(ctx->last_err), "k_synth: %s", cudaGetErrorString(e));
+    return FEC_ERR_CUDA;
+  }
+  return FEC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,17 @@
+#include "k_wmul_var.cuh"
+namespace fec {
+cudaError_t wmul_var_setup_k1() { return wmul_var_setup_t<CurveK1>(); }
+cudaError_t wmul_var_launch_k1(int sms, cudaStream_t st, const uint8_t* s, const uint8_t* p, int pf, size_t n, int of, uint8_t* o,
+                               uint8_t* status) {
+  return wmul_var_launch_t<CurveK1>(sms, st, s, p, pf, n, of, o, status);
+}
+cudaError_t wmul_var_setup() {
+  cudaError_t e = wmul_var_setup_k1();
+  return e != cudaSuccess ? e : wmul_var_setup_p256();
+}
+cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* s, const uint8_t* p, int pf, size_t n, int of,
+                            uint8_t* o, uint8_t* status) {
+  return curve == FEC_SECP256K1 ? wmul_var_launch_k1(sms, st, s, p, pf, n, of, o, status)
+                                : wmul_var_launch_p256(sms, st, s, p, pf, n, of, o, status);
+}
+}  // namespace fec

@@ -1,0 +1,139 @@
+// kernels.cuh -- shared device helpers, tile geometry and the launcher interface between the
+// kernel translation units (k_*.cu, one per kernel family so they compile in parallel) and the
+// host side of the C ABI (forge_ec_cuda.cu).
+//
+// Kernel shape (all of them): persistent blocks (grid = SMs x resident blocks), each block walks
+// tiles of THREADS consecutive lanes; one lane = one thread, all field elements in registers.
+// Inputs are 16-byte-aligned 32/64-byte records read with 128-bit loads; 33/65-byte records are
+// staged through shared memory so that global traffic stays word-coalesced.  The only
+// cross-thread step is the block-level simultaneous inversion (curves.cuh).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/forge_ec_cuda.h"
+#include "lanes.cuh"
+
+namespace fec {
+
+// ======================================================================================
+// small device helpers
+// ======================================================================================
+__device__ __forceinline__ void load_rec32_le(u32 r[8], const uint8_t* p) {  // p 16-byte aligned
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+__device__ __forceinline__ void load_rec32_be(u32 r[8], const uint8_t* p) {
+  u32 t[8];
+  load_rec32_le(t, p);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = __byte_perm(t[7 - i], 0, 0x0123);
+}
+__device__ __forceinline__ void store_rec32_le(uint8_t* p, const u32 r[8]) {
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(r[4], r[5], r[6], r[7]);
+}
+// block-cooperative copy, word-coalesced; src/dst 4-byte aligned
+__device__ __forceinline__ void block_copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  const size_t nw = bytes >> 2;
+  const u32* s = reinterpret_cast<const u32*>(src);
+  u32* d = reinterpret_cast<u32*>(dst);
+  for (size_t i = threadIdx.x; i < nw; i += blockDim.x) d[i] = s[i];
+  for (size_t i = (nw << 2) + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+__host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : 64); }
+
+// per-lane table of 8 affine points in shared memory, word-interleaved across the block:
+// word w of entry j of thread t at [(j*16 + w) * THREADS + t]  (conflict-free for any digits)
+template <int THREADS>
+struct SmemTab {
+  u32* base;
+  __device__ __forceinline__ void store(int j, const u32 x[8], const u32 y[8]) {
+    u32* e = base + (size_t)j * 16 * THREADS + threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { e[w * THREADS] = x[w]; e[(8 + w) * THREADS] = y[w]; }
+  }
+  __device__ __forceinline__ void load(u32 j, u32 x[8], u32 y[8]) const {
+    const u32* e = base + (size_t)j * 16 * THREADS + threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { x[w] = e[w * THREADS]; y[w] = e[(8 + w) * THREADS]; }
+  }
+};
+template <class F, int WARPS>
+struct BlockInv {
+  u32* scratch;
+  __device__ __forceinline__ void operator()(u32 zi[8], const u32 z[8]) { block_batch_inv<F, WARPS>(zi, z, scratch); }
+};
+// fixed-base comb in shared memory: entry (i,j) at word (i*8+j)*STRIDE; STRIDE = 20 words keeps the
+// eight rows of one window on disjoint banks for 128-bit reads
+constexpr int COMB_STRIDE = 20;
+constexpr int COMB_WORDS = 64 * 8 * COMB_STRIDE;
+struct SmemComb {
+  const u32* base;
+  __device__ __forceinline__ void operator()(int i, u32 idx, u32 x[8], u32 y[8]) const {
+    const uint4* e = reinterpret_cast<const uint4*>(base + (size_t)(i * 8 + idx) * COMB_STRIDE);
+    uint4 a = e[0], b = e[1], c = e[2], d = e[3];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    y[0] = c.x; y[1] = c.y; y[2] = c.z; y[3] = c.w; y[4] = d.x; y[5] = d.y; y[6] = d.z; y[7] = d.w;
+  }
+};
+constexpr int NIELS_STRIDE = 28;
+constexpr int NIELS_WORDS = 64 * 8 * NIELS_STRIDE;
+struct SmemNiels {
+  const u32* base;
+  __device__ __forceinline__ void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const {
+    const uint4* e = reinterpret_cast<const uint4*>(base + (size_t)(i * 8 + idx) * NIELS_STRIDE);
+    uint4 v0 = e[0], v1 = e[1], v2 = e[2], v3 = e[3], v4 = e[4], v5 = e[5];
+    a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+    b[0] = v2.x; b[1] = v2.y; b[2] = v2.z; b[3] = v2.w; b[4] = v3.x; b[5] = v3.y; b[6] = v3.z; b[7] = v3.w;
+    c[0] = v4.x; c[1] = v4.y; c[2] = v4.z; c[3] = v4.w; c[4] = v5.x; c[5] = v5.y; c[6] = v5.z; c[7] = v5.w;
+  }
+};
+
+
+// ---- tile geometry ----------------------------------------------------------------------
+constexpr int INV_SCRATCH_WORDS = 2 * 16 * 8 + 8;  // block_batch_inv scratch, enough for 16 warps
+constexpr int VAR_THREADS = 128;
+constexpr int VAR_BLOCKS_PER_SM = 3;
+constexpr int VAR_TAB_BYTES = 8 * 16 * VAR_THREADS * 4;  // 64 KiB per block
+constexpr int VAR_SMEM_BYTES = VAR_TAB_BYTES + INV_SCRATCH_WORDS * 4;
+constexpr int FIX_THREADS = 256;
+constexpr int FIX_BLOCKS_PER_SM = 2;
+constexpr int FIX_IO_BYTES = 65 * FIX_THREADS + 16;
+constexpr int FIX_SMEM_BYTES = COMB_WORDS * 4 + FIX_IO_BYTES + INV_SCRATCH_WORDS * 4;
+constexpr int X_THREADS = 256;
+constexpr int X_BLOCKS_PER_SM = 2;
+constexpr int ED_THREADS = 256;
+constexpr int ED_BLOCKS_PER_SM = 2;
+constexpr int ED_SMEM_BYTES = NIELS_WORDS * 4 + INV_SCRATCH_WORDS * 4;
+constexpr int FB_THREADS = 256;
+constexpr int PEAK_THREADS = 256;
+constexpr int PEAK_CHAINS = 8;
+constexpr int PEAK_INNER = 16;
+
+inline int persistent_grid(int sms, int blocks_per_sm, size_t tiles) {
+  size_t g = (size_t)sms * blocks_per_sm;
+  if (tiles < g) g = tiles;
+  return g < 1 ? 1 : (int)g;
+}
+
+// ---- launchers (defined in the k_*.cu files); each returns cudaGetLastError() ----------------
+cudaError_t wmul_var_setup();
+cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt,
+                            size_t n, int out_fmt, uint8_t* out, uint8_t* status);
+cudaError_t wmul_fixed_setup();
+cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n,
+                              int out_fmt, uint8_t* out, uint8_t* status);
+cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
+cudaError_t ed25519_setup();
+cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int input_is_seed, const u32* niels, size_t n,
+                           uint8_t* out);
+cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb);
+cudaError_t build_niels_launch(cudaStream_t st, u32* niels);
+cudaError_t field_bench_launch(int sms, cudaStream_t st, int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
+                               size_t lanes, int iters);
+cudaError_t imad_peak_launch(int variant, int blocks, cudaStream_t st, u32* sink, u32 seed, int trips);
+cudaError_t synth_launch(int sms, cudaStream_t st, uint8_t* out, size_t n, u32 seed_lo, u32 seed_hi, u32 stream_id, u32 sub,
+                         unsigned long long first_lane, int mode, int edge);
+
+}  // namespace fec

@@ -1,0 +1,464 @@
+// lanes.cuh -- what ONE lane (one thread) does on the hot path, independent of where its table
+// and its batch inversion live.  Everything here is branch-free with respect to secret data:
+// loops have fixed trip counts, selections are masks, table entries are fetched by index (the
+// address depends on the digit, the control flow does not).
+//
+//   scalar_prepare / next_digit   regular signed odd-digit recoding of k (all 64 digits non-zero)
+//   wmul_var_core                 variable-base k*P, short Weierstrass, 4-bit signed window
+//                                 (batched replacement of Curve::multiply,
+//                                  forge-ec-curves/src/secp256k1.rs:2635-2692, p256.rs:2120-2156)
+//   wmul_fixed_core               fixed-base k*G from a 64 x 8 comb table of odd multiples
+//   x25519_core                   RFC 7748 ladder (curve25519.rs:1624-1716)
+//   ed25519_expand_seed / ed_comb_core / ed_encode
+//                                 RFC 8032 5.1.5 key generation (forge-ec-signature/src/eddsa.rs:450-509,
+//                                 ed25519.rs:2062-2097, 1793-1811)
+//   sec1_encode                   PointAffine::to_bytes / CompressedPoint::from_affine
+//                                 (secp256k1.rs:875-894, forge-ec-encoding/src/point.rs:39-67, 186-211)
+//
+// Recoding.  For odd k' < 2^256 let K = 2^255 + (k'-1)/2 and u_i its i-th nibble.  Then
+// d_i = 2 u_i - 15 is odd, |d_i| <= 15 and sum d_i 16^i = 2K - (2^256 - 1) = k'.  The top digit
+// is positive.  An even scalar is replaced by n - k (odd, because n is odd) and the result is
+// negated at the end; k = 0 and k >= n are replaced by 1 and reported through the status byte.
+#pragma once
+#include "curves.cuh"
+#include "sha512_k.inc"
+
+namespace fec {
+
+enum { LANE_OK = 0, LANE_SCALAR_RANGE = 1, LANE_POINT_INVALID = 2, LANE_INFINITY = 3 };
+
+#ifdef __CUDA_ARCH__
+FEC_DEV bool warp_any(u32 m) { return __any_sync(0xFFFFFFFFu, m != 0u) != 0; }
+#else
+FEC_DEV bool warp_any(u32 m) { return m != 0u; }
+#endif
+
+FEC_DEV void set_small(u32 r[8], u32 v) {
+  r[0] = v;
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = 0u;
+}
+FEC_DEV void shl4_256(u32 K[8]) {
+#pragma unroll
+  for (int i = 7; i >= 1; i--) K[i] = funnel_l(K[i - 1], K[i], 4);
+  K[0] <<= 4;
+}
+// K = 2^255 | (k >> 1)
+FEC_DEV void recode_reg(u32 K[8], const u32 k[8]) {
+#pragma unroll
+  for (int i = 0; i < 7; i++) K[i] = funnel_l(k[i], k[i + 1], 31);
+  K[7] = (k[7] >> 1) | 0x80000000u;
+}
+// pops the most significant remaining digit: idx in 0..7 (|d| = 2 idx + 1), sgn = all-ones if d < 0
+FEC_DEV void next_digit(u32 K[8], u32& idx, u32& sgn) {
+  u32 u = K[7] >> 28;
+  shl4_256(K);
+  sgn = (u >> 3) - 1u;
+  idx = (u ^ sgn) & 7u;
+}
+
+// Weierstrass scalar: k (limbs, from big-endian bytes) -> recoding register, negate mask, status
+template <class C>
+FEC_DEV void scalar_prepare(u32 K[8], u32& negm, u32& st, const u32 k[8]) {
+  u32 n[8], one[8], kk[8], nk[8];
+  C::N(n);
+  set_small(one, 1u);
+  u32 bad = geq8(k, n);
+  u32 zero = is_zero8(k);
+  select8(kk, bad | zero, one, k);
+  sub8(nk, n, kk);
+  u32 even = (kk[0] & 1u) - 1u;
+  select8(kk, even, nk, kk);
+  negm = even;
+  recode_reg(K, kk);
+  st = (bad & LANE_SCALAR_RANGE) | (~bad & zero & LANE_INFINITY);
+}
+
+// Q <- Q + (x2,y2), (x2,y2) affine, as jac_madd but also returns zr = Z3/Z1 = 2H (table building)
+template <class C>
+FEC_DEV void jac_madd_zr(Jac& q, const u32 x2[8], const u32 y2[8], u32 zr[8]) {
+  typedef typename C::F F;
+  u32 Z1Z1[8], U2[8], S2[8], H[8], HH[8], I[8], J[8], r[8], V[8], t[8];
+  F::sqr(Z1Z1, q.Z);
+  F::mul(U2, x2, Z1Z1);
+  F::mul(S2, q.Z, Z1Z1);
+  F::mul(S2, y2, S2);
+  F::sub(H, U2, q.X);
+  F::sqr(HH, H);
+  F::dbl(I, HH); F::dbl(I, I);
+  F::mul(J, H, I);
+  F::sub(r, S2, q.Y);
+  F::dbl(r, r);
+  F::mul(V, q.X, I);
+  F::dbl(zr, H);
+  F::mul(q.Z, q.Z, zr);              // Z3 = 2 Z1 H
+  F::sqr(q.X, r);
+  F::sub(q.X, q.X, J);
+  F::sub(q.X, q.X, V);
+  F::sub(q.X, q.X, V);
+  F::sub(t, V, q.X);
+  F::mul(t, r, t);
+  F::mul(J, q.Y, J);
+  F::dbl(J, J);
+  F::sub(q.Y, t, J);
+}
+
+// mixed addition with the two exceptional cases repaired under a warp-uniform branch:
+// Q == T -> 2T, Q == -T -> infinity.  (They need k = +-d (mod n) for a partial scalar, which the
+// recoding only produces for a handful of scalars next to n; see DESIGN.md.)
+template <class C>
+FEC_DEV void jac_madd_safe(Jac& q, const u32 tx[8], const u32 ty[8]) {
+  u32 exc = jac_madd<C>(q, tx, ty, 0u);
+  if (warp_any(exc)) {
+    Jac d;
+    copy8(d.X, tx); copy8(d.Y, ty); set_small(d.Z, 1u);
+    jac_dbl<C>(d);
+    u32 isdbl = 0u - ((exc >> 1) & 1u);
+    u32 isinf = (0u - (exc & 1u)) & ~isdbl;
+    u32 one[8], zero[8];
+    set_small(one, 1u); set_small(zero, 0u);
+    select8(q.X, isdbl, d.X, q.X); select8(q.Y, isdbl, d.Y, q.Y); select8(q.Z, isdbl, d.Z, q.Z);
+    select8(q.X, isinf, one, q.X); select8(q.Y, isinf, one, q.Y); select8(q.Z, isinf, zero, q.Z);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// variable base.  Tab: per-lane table of 8 affine points with load(idx,x,y) / store(idx,x,y).
+// Inv: simultaneous inversion across the lanes that call it together: inv(zinv, z), z != 0.
+// Cost: table 1 dbl + 7 madd + 7 x (4M+1S) + shared inversion; loop 252 dbl + 63 madd.
+// -------------------------------------------------------------------------------------
+template <class C, class Tab, class Inv>
+FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], Tab& tab, Inv& inv) {
+  typedef typename C::F F;
+  {
+    // odd multiples P, 3P, .., 15P on the curve isomorphic by C = Z(2P), where 2P is affine
+    Jac D, A;
+    u32 C2[8], C3[8], zt[8], zi[8];
+    u32 zr[7][8];
+    copy8(D.X, px); copy8(D.Y, py); set_small(D.Z, 1u);
+    jac_dbl<C>(D);
+    F::sqr(C2, D.Z);
+    F::mul(C3, C2, D.Z);
+    F::mul(A.X, px, C2);
+    F::mul(A.Y, py, C3);
+    set_small(A.Z, 1u);
+    tab.store(0, px, py);
+#pragma unroll 1
+    for (int j = 1; j < 8; j++) {
+      jac_madd_zr<C>(A, D.X, D.Y, zr[j - 1]);
+      tab.store(j, A.X, A.Y);
+    }
+    F::mul(zt, A.Z, D.Z);  // true Z of 15P
+    inv(zi, zt);
+#pragma unroll 1
+    for (int j = 7; j >= 1; j--) {
+      u32 x[8], y[8], z2[8];
+      tab.load(j, x, y);
+      F::sqr(z2, zi);
+      F::mul(x, x, z2);
+      F::mul(z2, z2, zi);
+      F::mul(y, y, z2);
+      tab.store(j, x, y);
+      F::mul(zi, zi, zr[j - 1]);
+    }
+  }
+  u32 idx, sgn;
+  next_digit(K, idx, sgn);  // top digit: always positive
+  tab.load(idx, Q.X, Q.Y);
+  set_small(Q.Z, 1u);
+#pragma unroll 1
+  for (int i = 0; i < 63; i++) {
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) jac_dbl<C>(Q);
+    u32 tx[8], ty[8], ny[8];
+    next_digit(K, idx, sgn);
+    tab.load(idx, tx, ty);
+    F::neg(ny, ty);
+    select8(ty, sgn, ny, ty);
+    jac_madd_safe<C>(Q, tx, ty);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// fixed base.  comb(i, idx, x, y) returns (2 idx + 1) 16^i G, affine.  63 mixed additions.
+// -------------------------------------------------------------------------------------
+template <class C, class Comb>
+FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
+  typedef typename C::F F;
+  u32 idx, sgn;
+  next_digit(K, idx, sgn);
+  comb(63, idx, Q.X, Q.Y);
+  set_small(Q.Z, 1u);
+#pragma unroll 1
+  for (int i = 62; i >= 0; i--) {
+    u32 tx[8], ty[8], ny[8];
+    next_digit(K, idx, sgn);
+    comb(i, idx, tx, ty);
+    F::neg(ny, ty);
+    select8(ty, sgn, ny, ty);
+    jac_madd_safe<C>(Q, tx, ty);
+  }
+}
+
+// Jacobian -> affine with a supplied 1/Z, conditional negation, canonical limbs
+template <class C>
+FEC_DEV void jac_to_affine(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u32 negm) {
+  typedef typename C::F F;
+  u32 z2[8], t[8], ny[8];
+  F::sqr(z2, zi);
+  F::mul(t, Q.X, z2);
+  F::canon(x, t);
+  F::mul(z2, z2, zi);
+  F::mul(t, Q.Y, z2);
+  F::neg(ny, t);
+  select8(t, negm, ny, t);
+  F::canon(y, t);
+}
+
+// SEC1 / raw affine encodings.  fmt: 0 = 02|03 || X (33 B), 1 = 04 || X || Y (65 B), 2 = X || Y (64 B).
+// dead != 0 -> all-zero record (the reference's identity encoding, point.rs:41-47).
+FEC_DEV void sec1_encode(uint8_t* o, int fmt, const u32 x[8], const u32 y[8], u32 dead) {
+  u32 xx[8], yy[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { xx[i] = x[i] & ~dead; yy[i] = y[i] & ~dead; }
+  if (fmt == 0) {
+    o[0] = (uint8_t)((2u | (y[0] & 1u)) & ~dead);
+    store_be32(o + 1, xx);
+  } else if (fmt == 1) {
+    o[0] = (uint8_t)(4u & ~dead);
+    store_be32(o + 1, xx);
+    store_be32(o + 33, yy);
+  } else {
+    store_be32(o, xx);
+    store_be32(o + 32, yy);
+  }
+}
+
+// SEC1 compressed -> affine candidate (decode half of point.rs:70-144): returns the ok mask.
+template <class C>
+FEC_DEV u32 sec1_decompress(u32 x[8], u32 y[8], const uint8_t* rec) {
+  typedef typename C::F F;
+  u32 pre = rec[0];
+  load_be32(x, rec + 1);
+  u32 ok = ((pre == 2u) | (pre == 3u)) ? 0xFFFFFFFFu : 0u;
+  ok &= F::in_range(x);
+  u32 rhs[8], t[8], b[8], yc[8], ny[8];
+  F::sqr(rhs, x);
+  F::mul(rhs, rhs, x);
+  if (C::A_MINUS3) {
+    F::dbl(t, x);
+    F::add(t, t, x);
+    F::sub(rhs, rhs, t);
+  }
+  C::B(b);
+  F::add(rhs, rhs, b);
+  F::sqrt_cand(t, rhs);
+  F::canon(yc, t);
+  F::sqr(t, yc);
+  F::sub(t, t, rhs);
+  ok &= F::is_zero(t);
+  F::neg(t, yc);
+  F::canon(ny, t);
+  u32 flip = 0u - ((yc[0] ^ pre) & 1u);
+  select8(y, flip, ny, yc);
+  return ok;
+}
+
+// -------------------------------------------------------------------------------------
+// X25519: clamp, mask bit 255 of u, 255 ladder steps; returns (x2 : z2)
+// -------------------------------------------------------------------------------------
+FEC_DEV void cswap8(u32 a[8], u32 b[8], u32 m) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    u32 t = (a[i] ^ b[i]) & m;
+    a[i] ^= t;
+    b[i] ^= t;
+  }
+}
+FEC_DEV void x25519_core(u32 x2[8], u32 z2[8], const u32 k_le[8], const u32 u_le[8]) {
+  u32 k[8], x1[8], x3[8], z3[8];
+  copy8(k, k_le);
+  k[0] &= 0xFFFFFFF8u;
+  k[7] = (k[7] & 0x7FFFFFFFu) | 0x40000000u;
+  copy8(x1, u_le);
+  x1[7] &= 0x7FFFFFFFu;
+  set_small(x2, 1u); set_small(z2, 0u);
+  copy8(x3, x1); set_small(z3, 1u);
+  // bits 254..0, consumed from the top of a shifting register (bit 255 is clear after clamping)
+#pragma unroll
+  for (int i = 7; i >= 1; i--) k[i] = funnel_l(k[i - 1], k[i], 1);
+  k[0] <<= 1;
+  u32 swap = 0u;
+#pragma unroll 1
+  for (int t = 254; t >= 0; t--) {
+    u32 kt = 0u - (k[7] >> 31);
+#pragma unroll
+    for (int i = 7; i >= 1; i--) k[i] = funnel_l(k[i - 1], k[i], 1);
+    k[0] <<= 1;
+    swap ^= kt;
+    cswap8(x2, x3, swap);
+    cswap8(z2, z3, swap);
+    swap = kt;
+    x25519_step(x2, z2, x3, z3, x1);
+  }
+  cswap8(x2, x3, swap);
+  cswap8(z2, z3, swap);
+}
+
+// -------------------------------------------------------------------------------------
+// SHA-512 of a 32-byte message (one block) -- FIPS 180-4; only what Ed25519 key expansion needs
+// (the reference calls the `sha2` crate: eddsa.rs:464; KATs at forge-ec-hash/src/sha2.rs:13-41)
+// -------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__constant__ u64 FEC_SHA512_K_TABLE[80] = {FEC_SHA512_K};
+#else
+static const u64 FEC_SHA512_K_TABLE[80] = {FEC_SHA512_K};
+#endif
+FEC_DEV u64 rotr64(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
+// digest words h[0..8) (big-endian words as integers)
+FEC_DEV void sha512_32(u64 h[8], const uint8_t msg[32]) {
+  const u64 H0[8] = {FEC_SHA512_H0};
+  u64 w[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u64 v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v = (v << 8) | msg[8 * i + j];
+    w[i] = v;
+  }
+  w[4] = 0x8000000000000000ULL;
+#pragma unroll
+  for (int i = 5; i < 15; i++) w[i] = 0;
+  w[15] = 256;
+  u64 a = H0[0], b = H0[1], c = H0[2], d = H0[3], e = H0[4], f = H0[5], g = H0[6], hh = H0[7];
+#pragma unroll 1
+  for (int r = 0; r < 80; r += 16) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (r > 0) {
+        u64 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+        u64 s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+        u64 s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+        w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+      }
+      u64 S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
+      u64 ch = (e & f) ^ (~e & g);
+      u64 t1 = hh + S1 + ch + FEC_SHA512_K_TABLE[r + i] + w[i];
+      u64 S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
+      u64 mj = (a & b) ^ (a & c) ^ (b & c);
+      u64 t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+  }
+  h[0] = H0[0] + a; h[1] = H0[1] + b; h[2] = H0[2] + c; h[3] = H0[3] + d;
+  h[4] = H0[4] + e; h[5] = H0[5] + f; h[6] = H0[6] + g; h[7] = H0[7] + hh;
+}
+FEC_DEV u32 bswap32(u32 v) { return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24); }
+// seed -> little-endian limbs of the clamped secret scalar (first half of SHA-512(seed))
+FEC_DEV void ed25519_expand_seed(u32 s[8], const uint8_t seed[32]) {
+  u64 h[8];
+  sha512_32(h, seed);
+  // digest byte 8i+j = byte (7-j) of h[i]; little-endian limb l = bytes 4l..4l+3
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    s[2 * i] = bswap32((u32)(h[i] >> 32));
+    s[2 * i + 1] = bswap32((u32)h[i]);
+  }
+  s[0] &= 0xFFFFFFF8u;
+  s[7] = (s[7] & 0x7FFFFFFFu) | 0x40000000u;
+}
+FEC_DEV void ed_L(u32 l[8]) {  // group order 2^252 + 27742317777372353535851937790883648493
+  l[0] = 0x5CF5D3EDu; l[1] = 0x5812631Au; l[2] = 0xA2F79CD6u; l[3] = 0x14DEF9DEu;
+  l[4] = 0u; l[5] = 0u; l[6] = 0u; l[7] = 0x10000000u;
+}
+// any 256-bit s -> recoding register of an odd s' = s (mod L): s even -> s -+ L
+FEC_DEV void ed_scalar_prepare(u32 K[8], const u32 s[8]) {
+  u32 l[8], a[8], b[8], t[8];
+  ed_L(l);
+  add8(a, s, l);
+  sub8(b, s, l);
+  u32 hi = 0u - (s[7] >> 31);
+  select8(t, hi, b, a);
+  u32 even = (s[0] & 1u) - 1u;
+  select8(t, even, t, s);
+  recode_reg(K, t);
+}
+// Q = sum of 64 signed odd digits times the Niels comb: niels(i, idx, ypx, ymx, t2d) = (2 idx+1) 16^i B
+template <class Comb>
+FEC_DEV void ed_comb_core(EdExt& Q, u32 K[8], const Comb& niels) {
+  typedef Fe25519 F;
+  ed_set_identity(Q);
+#pragma unroll 1
+  for (int i = 63; i >= 0; i--) {
+    u32 idx, sgn, ypx[8], ymx[8], t2d[8], nt[8];
+    next_digit(K, idx, sgn);
+    niels(i, idx, ypx, ymx, t2d);
+    cswap8(ypx, ymx, sgn);
+    F::neg(nt, t2d);
+    select8(t2d, sgn, nt, t2d);
+    ed_madd(Q, ypx, ymx, t2d);
+  }
+}
+// RFC 8032 5.1.2 encoding with a supplied 1/Z: y little-endian, bit 255 = x & 1
+FEC_DEV void ed_encode(u32 out_le[8], const EdExt& Q, const u32 zi[8]) {
+  typedef Fe25519 F;
+  u32 x[8], y[8], t[8];
+  F::mul(t, Q.X, zi);
+  F::canon(x, t);
+  F::mul(t, Q.Y, zi);
+  F::canon(y, t);
+  copy8(out_le, y);
+  out_le[7] |= (x[0] & 1u) << 31;
+}
+
+// -------------------------------------------------------------------------------------
+// comb table entries (context set-up only; control flow depends on the public indices i, j)
+// -------------------------------------------------------------------------------------
+// (2j+1) 16^i G, Jacobian
+template <class C>
+FEC_DEV void comb_entry_jac(Jac& R, int i, int j) {
+  u32 gx[8], gy[8];
+  C::G(gx, gy);
+  copy8(R.X, gx); copy8(R.Y, gy); set_small(R.Z, 1u);
+  const int m = 2 * j + 1;
+  int top = 3;
+  while (top > 0 && !((m >> top) & 1)) top--;
+  for (int b = top - 1; b >= 0; b--) {
+    jac_dbl<C>(R);
+    if ((m >> b) & 1) jac_madd<C>(R, gx, gy, 0u);
+  }
+  for (int d = 0; d < 4 * i; d++) jac_dbl<C>(R);
+}
+// (2j+1) 16^i B as a Niels triple (y+x, y-x, 2dxy), canonical limbs
+FEC_DEV void ed_comb_entry(u32 ypx[8], u32 ymx[8], u32 t2d[8], int i, int j) {
+  typedef Fe25519 F;
+  EdExt Bp, R;
+  ed_base(Bp.X, Bp.Y);
+  set_small(Bp.Z, 1u);
+  F::mul(Bp.T, Bp.X, Bp.Y);
+  R = Bp;
+  const int m = 2 * j + 1;
+  int top = 3;
+  while (top > 0 && !((m >> top) & 1)) top--;
+  for (int b = top - 1; b >= 0; b--) {
+    EdExt c = R;
+    ed_add(R, c);
+    if ((m >> b) & 1) ed_add(R, Bp);
+  }
+  for (int d = 0; d < 4 * i; d++) {
+    EdExt c = R;
+    ed_add(R, c);
+  }
+  u32 zi[8], x[8], y[8], t[8], d2[8];
+  F::inv(zi, R.Z);
+  F::mul(x, R.X, zi);
+  F::mul(y, R.Y, zi);
+  F::add(t, y, x); F::canon(ypx, t);
+  F::sub(t, y, x); F::canon(ymx, t);
+  ed_D2(d2);
+  F::mul(t, x, y);
+  F::mul(t, t, d2);
+  F::canon(t2d, t);
+}
+
+}  // namespace fec

@@ -18,8 +18,13 @@ namespace fec {
 typedef uint32_t u32;
 typedef uint64_t u64;
 
+#if defined(__CUDACC__)
 #define FEC_DEV __device__ __forceinline__
+#else
+#define FEC_DEV inline
+#endif
 
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 // ---- carry-flag primitives (one PTX instruction each; `volatile` keeps their order, the
 // compiler itself never emits .cc instructions so the flag cannot be clobbered in between)
 FEC_DEV u32 add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -34,6 +39,27 @@ FEC_DEV u32 mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 
 FEC_DEV u32 madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 FEC_DEV u32 madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 FEC_DEV u32 madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+FEC_DEV u32 funnel_l(u32 lo, u32 hi, u32 s) { return __funnelshift_l(lo, hi, s); }
+#else
+// ---- TEST-ONLY host emulation of the PTX carry flag (tests/hostsim compiles these headers with
+// g++ so the limb arithmetic can be checked on a machine without a GPU).  It is never part of
+// the shipped library: forge_ec_cuda.cu is compiled by nvcc only and has no CPU code path.
+static thread_local u32 fec_cc_flag = 0;  // (FEC_DEV is plain `inline` on the host)
+FEC_DEV u32 fec_setcc(u64 t) { fec_cc_flag = (u32)(t >> 32) & 1u; return (u32)t; }
+FEC_DEV u32 add_cc(u32 a, u32 b) { return fec_setcc((u64)a + b); }
+FEC_DEV u32 addc_cc(u32 a, u32 b) { return fec_setcc((u64)a + b + fec_cc_flag); }
+FEC_DEV u32 addc(u32 a, u32 b) { return (u32)((u64)a + b + fec_cc_flag); }
+FEC_DEV u32 sub_cc(u32 a, u32 b) { return fec_setcc((u64)a - b); }  // borrow = bit 32 of the wrapped difference
+FEC_DEV u32 subc_cc(u32 a, u32 b) { return fec_setcc((u64)a - b - fec_cc_flag); }
+FEC_DEV u32 subc(u32 a, u32 b) { return (u32)((u64)a - b - fec_cc_flag); }
+FEC_DEV u32 mul_lo(u32 a, u32 b) { return (u32)((u64)a * b); }
+FEC_DEV u32 mul_hi(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+FEC_DEV u32 mad_lo_cc(u32 a, u32 b, u32 c) { return fec_setcc((u64)(u32)((u64)a * b) + c); }
+FEC_DEV u32 madc_lo_cc(u32 a, u32 b, u32 c) { return fec_setcc((u64)(u32)((u64)a * b) + c + fec_cc_flag); }
+FEC_DEV u32 madc_hi_cc(u32 a, u32 b, u32 c) { return fec_setcc((((u64)a * b) >> 32) + c + fec_cc_flag); }
+FEC_DEV u32 madc_hi(u32 a, u32 b, u32 c) { return (u32)((((u64)a * b) >> 32) + c + fec_cc_flag); }
+FEC_DEV u32 funnel_l(u32 lo, u32 hi, u32 s) { return s ? ((hi << s) | (lo >> (32 - s))) : hi; }
+#endif
 
 // acc[0..2*NP) += {a0,a1,..}[k] * b laid out as NP (lo,hi) pairs, one carry chain.
 // `fresh` = how many of the top words of the span have never been written (their old value is
@@ -131,7 +157,7 @@ FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
   t[0] = 0;
   t[1] = s[1] << 1;
 #pragma unroll
-  for (int k = 2; k < 15; k++) t[k] = __funnelshift_l(s[k - 1], s[k], 1);
+  for (int k = 2; k < 15; k++) t[k] = funnel_l(s[k - 1], s[k], 1);
   t[15] = s[14] >> 31;
   r[0] = mad_lo_cc(a[0], a[0], t[0]);
   r[1] = madc_hi_cc(a[0], a[0], t[1]);

@@ -1,0 +1,154 @@
+"""Mirror of the forge-ec-core trait surface for the batched path (value types are plain bytes).
+
+reference                                             here
+---------------------------------------------------   ------------------------------------------
+Scalar::from_bytes (secp256k1.rs:2271, p256.rs:1041)   Scalar.from_bytes(b) -> Scalar (32 B BE, < n)
+Curve::generator / multiply / to_affine (lib.rs:801-832) Secp256k1.generator(), .multiply(P, k), .to_affine
+PointAffine::to_bytes[_with_format] (lib.rs:606-632)   AffinePoint.to_bytes(), .to_bytes_with_format
+(new) BatchMul::batch_mul                              Secp256k1.batch_mul(points, scalars)
+x25519(scalar,u) (curve25519.rs:1624)                  x25519(scalar, u); batch_x25519(scalars, us)
+Ed25519Signature::derive_public_key (eddsa.rs:450)     Ed25519Signature.derive_public_key(seed)
+
+Every call goes to the GPU through the C ABI; single-point calls are batches of one.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import engine as _e
+
+_DEFAULT: Optional[_e.Engine] = None
+
+
+def default_engine() -> _e.Engine:
+    global _DEFAULT
+    if _DEFAULT is None:
+        _DEFAULT = _e.Engine()
+    return _DEFAULT
+
+
+@dataclass(frozen=True)
+class Scalar:
+    """32-byte big-endian scalar (the layout of Scalar::to_bytes / from_bytes)."""
+    be: bytes
+
+    @staticmethod
+    def from_bytes(b: bytes) -> "Scalar":
+        if len(b) != 32:
+            raise ValueError("InvalidEncoding: scalar must be 32 bytes")
+        return Scalar(bytes(b))
+
+    @staticmethod
+    def from_int(v: int) -> "Scalar":
+        return Scalar(v.to_bytes(32, "big"))
+
+    def to_bytes(self) -> bytes:
+        return self.be
+
+
+@dataclass(frozen=True)
+class AffinePoint:
+    """Affine point as X || Y big-endian (64 B); ``infinity`` mirrors the reference's flag."""
+    xy: bytes
+    infinity: bool = False
+
+    def x(self) -> bytes:
+        return self.xy[:32]
+
+    def y(self) -> bytes:
+        return self.xy[32:]
+
+    def is_identity(self) -> bool:
+        return self.infinity
+
+    def to_bytes(self) -> bytes:
+        """SEC1 compressed, identity -> 33 zero bytes (secp256k1.rs:875-894, point.rs:39-67)."""
+        return self.to_bytes_with_format("compressed")
+
+    def to_bytes_with_format(self, fmt: str) -> bytes:
+        if fmt == "compressed":
+            return bytes(33) if self.infinity else bytes([2 | (self.xy[63] & 1)]) + self.xy[:32]
+        if fmt == "uncompressed":
+            return bytes(65) if self.infinity else b"\x04" + self.xy
+        raise ValueError("UnsupportedOperation: format")
+
+
+class _WeierstrassCurve:
+    CURVE_ID = -1
+
+    @classmethod
+    def generator(cls) -> Optional[AffinePoint]:
+        return None  # marker: multiply(None, k) is the fixed-base path
+
+    @classmethod
+    def batch_mul(cls, points: Optional[Sequence[AffinePoint]], scalars: Sequence[Scalar], engine: Optional[_e.Engine] = None):
+        """BatchMul::batch_mul: k_i*G when points is None, else k_i*P_i.  Returns AffinePoints.
+        Raises ValueError (Error::InvalidScalar / PointNotOnCurve) if any lane is rejected."""
+        eng = engine or default_engine()
+        n = len(scalars)
+        s = np.frombuffer(b"".join(k.be for k in scalars), dtype=np.uint8)
+        p = None if points is None else np.frombuffer(b"".join(q.xy for q in points), dtype=np.uint8)
+        out, st = eng.batch_mul(cls.CURVE_ID, s, p, n=n, out_fmt=_e.OUT_AFFINE_XY_BE)
+        if np.any(st == _e.LANE_SCALAR_RANGE):
+            raise ValueError("InvalidScalar")
+        if np.any(st == _e.LANE_POINT_INVALID):
+            raise ValueError("PointNotOnCurve")
+        return [AffinePoint(out[i].tobytes(), bool(st[i] == _e.LANE_INFINITY)) for i in range(n)]
+
+    @classmethod
+    def multiply(cls, point: Optional[AffinePoint], scalar: Scalar, engine: Optional[_e.Engine] = None) -> AffinePoint:
+        """Curve::multiply followed by Curve::to_affine (secp256k1.rs:2635-2692 + 1342-1363)."""
+        return cls.batch_mul(None if point is None else [point], [scalar], engine)[0]
+
+    @staticmethod
+    def to_affine(p: AffinePoint) -> AffinePoint:
+        return p  # results already come back normalised (batch inversion on the device)
+
+
+class Secp256k1(_WeierstrassCurve):
+    CURVE_ID = _e.CURVE_SECP256K1
+
+
+class P256(_WeierstrassCurve):
+    CURVE_ID = _e.CURVE_P256
+
+
+def batch_x25519(scalars: Sequence[bytes], us: Optional[Sequence[bytes]] = None, engine: Optional[_e.Engine] = None):
+    eng = engine or default_engine()
+    n = len(scalars)
+    s = np.frombuffer(b"".join(scalars), dtype=np.uint8)
+    u = None if us is None else np.frombuffer(b"".join(us), dtype=np.uint8)
+    out = eng.batch_x25519(s, u, n=n)
+    return [out[i].tobytes() for i in range(n)]
+
+
+def x25519(scalar: bytes, u: bytes, engine: Optional[_e.Engine] = None) -> bytes:
+    """x25519(&scalar, &u) (curve25519.rs:1624-1716), RFC 7748 semantics."""
+    return batch_x25519([scalar], [u], engine)[0]
+
+
+class Curve25519:
+    @staticmethod
+    def generator() -> bytes:
+        return (9).to_bytes(32, "little")
+
+    @staticmethod
+    def multiply(u: bytes, scalar: bytes, engine: Optional[_e.Engine] = None) -> bytes:
+        return x25519(scalar, u, engine)
+
+
+class Ed25519Signature:
+    @staticmethod
+    def derive_public_key(seed: bytes, engine: Optional[_e.Engine] = None) -> bytes:
+        """RFC 8032 5.1.5 (what eddsa.rs:450-509 specifies)."""
+        eng = engine or default_engine()
+        return eng.batch_ed25519_pubkey(np.frombuffer(seed, dtype=np.uint8), True, n=1)[0].tobytes()
+
+    @staticmethod
+    def batch_derive_public_key(seeds: Sequence[bytes], engine: Optional[_e.Engine] = None):
+        eng = engine or default_engine()
+        out = eng.batch_ed25519_pubkey(np.frombuffer(b"".join(seeds), dtype=np.uint8), True, n=len(seeds))
+        return [out[i].tobytes() for i in range(len(seeds))]

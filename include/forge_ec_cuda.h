@@ -123,6 +123,14 @@ int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_
  * Returns multiply-add *instructions* per second over the whole device. */
 int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec);
 
+/* Synthetic benchmark inputs: Philox-4x32-10, key "forge-ec", counter = (lane, block, stream_id);
+ * lane i of the call is global lane first_lane + i and receives 32 bytes (blocks 2*sub, 2*sub+1).
+ * mode 0: raw bytes; mode 1 / 2: big-endian scalar below the secp256k1 / P-256 group order (what
+ * Scalar::random -> from_bytes_reduced yields, secp256k1.rs:2256-2263, forge-ec-core/src/lib.rs:326-332);
+ * edge != 0 overwrites global lanes 0..7 with {0,1,2,3,n-1,n-2,(n+1)/2,2^255 mod n}. */
+int fec_synth_dev(fec_ctx* ctx, int dev_index, int mode, uint32_t stream_id, uint32_t sub, uint64_t first_lane, int edge,
+                  size_t n, uint8_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

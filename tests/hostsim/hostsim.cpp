@@ -1,0 +1,143 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the device headers of forge-ec_b200/csrc with g++ (the PTX carry flag is emulated in
+// u256.cuh under #ifndef __CUDACC__) so that the per-lane limb arithmetic, recoding and encoders
+// can be compared with the oracle on a machine that has no GPU.  Nothing here is linked into
+// libforge_ec_cuda.so and nothing in the product calls it.
+#include <cstring>
+#include <vector>
+#include "../../forge-ec_b200/csrc/lanes.cuh"
+
+using namespace fec;
+
+namespace {
+struct HostTab {
+  u32 e[8][16];
+  void store(int j, const u32 x[8], const u32 y[8]) { copy8(e[j], x); copy8(e[j] + 8, y); }
+  void load(u32 j, u32 x[8], u32 y[8]) const { copy8(x, e[j]); copy8(y, e[j] + 8); }
+};
+template <class F> struct HostInv {
+  void operator()(u32 zi[8], const u32 z[8]) { F::inv(zi, z); }
+};
+template <class C> struct HostComb {
+  std::vector<u32> t;  // [64][8][16]
+  HostComb() : t(64 * 8 * 16) {
+    typedef typename C::F F;
+    for (int i = 0; i < 64; i++)
+      for (int j = 0; j < 8; j++) {
+        Jac R;
+        comb_entry_jac<C>(R, i, j);
+        u32 zi[8];
+        F::inv(zi, R.Z);
+        jac_to_affine<C>(&t[(i * 8 + j) * 16], &t[(i * 8 + j) * 16 + 8], R, zi, 0u);
+      }
+  }
+  void operator()(int i, u32 idx, u32 x[8], u32 y[8]) const {
+    copy8(x, &t[(i * 8 + idx) * 16]);
+    copy8(y, &t[(i * 8 + idx) * 16 + 8]);
+  }
+};
+struct HostNiels {
+  std::vector<u32> t;  // [64][8][24]
+  HostNiels() : t(64 * 8 * 24) {
+    for (int i = 0; i < 64; i++)
+      for (int j = 0; j < 8; j++) ed_comb_entry(&t[(i * 8 + j) * 24], &t[(i * 8 + j) * 24 + 8], &t[(i * 8 + j) * 24 + 16], i, j);
+  }
+  void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const {
+    const u32* e = &t[(i * 8 + idx) * 24];
+    copy8(a, e); copy8(b, e + 8); copy8(c, e + 16);
+  }
+};
+
+template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
+  u32 x[8], y[8], r[8], t[8];
+  load_le32(x, a); load_le32(y, b);
+  switch (op) {
+    case 0: F::mul(t, x, y); break;
+    case 1: F::sqr(t, x); break;
+    case 2: F::add(t, x, y); break;
+    case 3: F::sub(t, x, y); break;
+    case 4: F::neg(t, x); break;
+    case 5: F::inv(t, x); break;
+    default: F::dbl(t, x); break;
+  }
+  F::canon(r, t);
+  store_le32(o, r);
+}
+
+template <class C>
+int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {
+  typedef typename C::F F;
+  static HostComb<C> comb;
+  u32 k[8], K[8], negm, st, px[8], py[8];
+  load_be32(k, k_be);
+  scalar_prepare<C>(K, negm, st, k);
+  Jac Q;
+  if (fixed) {
+    wmul_fixed_core<C>(Q, K, comb);
+  } else {
+    u32 ok;
+    if (pfmt == 1) {
+      ok = sec1_decompress<C>(px, py, pt);
+    } else {
+      load_be32(px, pt); load_be32(py, pt + 32);
+      ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+    }
+    u32 gx[8], gy[8];
+    C::G(gx, gy);
+    select8(px, ok, px, gx); select8(py, ok, py, gy);
+    if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);
+    HostTab tab;
+    HostInv<F> inv;
+    wmul_var_core<C>(Q, K, px, py, tab, inv);
+  }
+  u32 z[8], zi[8], one[8], x[8], y[8];
+  set_small(one, 1u);
+  u32 zz = F::is_zero(Q.Z);
+  select8(z, zz, one, Q.Z);
+  F::inv(zi, z);
+  jac_to_affine<C>(x, y, Q, zi, negm);
+  if (zz && st == 0) st = LANE_INFINITY;
+  sec1_encode(out, ofmt, x, y, st ? 0xFFFFFFFFu : 0u);
+  return (int)st;
+}
+}  // namespace
+
+extern "C" {
+void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
+  if (prime == 0) field_op<FeK1>(op, a, b, o);
+  else if (prime == 1) field_op<FeP256>(op, a, b, o);
+  else field_op<Fe25519>(op, a, b, o);
+}
+int hs_wmul(int curve, const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {
+  return curve == 0 ? wmul<CurveK1>(k_be, pt, pfmt, fixed, ofmt, out) : wmul<CurveP256>(k_be, pt, pfmt, fixed, ofmt, out);
+}
+void hs_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out) {
+  u32 kk[8], uu[8], x2[8], z2[8], zi[8], t[8], r[8], one[8];
+  load_le32(kk, k); load_le32(uu, u);
+  x25519_core(x2, z2, kk, uu);
+  set_small(one, 1u);
+  u32 zz = Fe25519::is_zero(z2);
+  select8(t, zz, one, z2);
+  Fe25519::inv(zi, t);
+  Fe25519::mul(t, x2, zi);
+  Fe25519::canon(r, t);
+  for (int i = 0; i < 8; i++) r[i] &= ~zz;
+  store_le32(out, r);
+}
+void hs_ed25519_pubkey(const uint8_t* in, int is_seed, uint8_t* out) {
+  static HostNiels niels;
+  u32 s[8], K[8], zi[8], o[8];
+  if (is_seed) ed25519_expand_seed(s, in); else load_le32(s, in);
+  ed_scalar_prepare(K, s);
+  EdExt Q;
+  ed_comb_core(Q, K, niels);
+  Fe25519::inv(zi, Q.Z);
+  ed_encode(o, Q, zi);
+  store_le32(out, o);
+}
+void hs_sha512_32(const uint8_t* msg, uint8_t* digest) {
+  u64 h[8];
+  sha512_32(h, msg);
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) digest[8 * i + j] = (uint8_t)(h[i] >> (56 - 8 * j));
+}
+}

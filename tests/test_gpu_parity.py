@@ -1,0 +1,242 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on identical inputs.
+Bit-exact for every byte (integer work; no tolerance)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _be(v):
+    return v.to_bytes(32, "big")
+
+
+def _edge_scalars(c):
+    return [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, (1 << 255) % c.n, 0xDEADBEEF, c.n, c.n + 1, 2**256 - 1,
+            (30 << 252) - c.n, 15 << 252, c.n - 15, c.n - 30, 16, 17, (1 << 128) - 1]
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("out_fmt", [0, 1, 2])
+def test_fixed_base_matches_model(engine, pm, curve, out_fmt):
+    c = pm.CURVES[curve]
+    n = 300
+    sc = pm.random_scalars_be(curve, n, stream=1)
+    edge = _edge_scalars(c)
+    for i, v in enumerate(edge):
+        sc[8 + i] = np.frombuffer(_be(v), dtype=np.uint8)
+    out, st = engine.batch_mul(curve, sc, None, out_fmt=out_fmt)
+    exp, est = pm.batch_mul(curve, sc.tobytes(), None, n, out_fmt)
+    assert st.tobytes() == est
+    assert out.tobytes() == exp
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("points_fmt", [0, 1])
+def test_variable_base_matches_model(engine, pm, curve, points_fmt):
+    c = pm.CURVES[curve]
+    n = 200
+    sc = pm.random_scalars_be(curve, n, stream=3)
+    edge = _edge_scalars(c)
+    for i, v in enumerate(edge):
+        sc[8 + i] = np.frombuffer(_be(v), dtype=np.uint8)
+    r = pm.random_scalars_be(curve, n, stream=3, sub=1, edge=False)
+    pts_xy, _ = pm.batch_mul(curve, r.tobytes(), None, n, pm.OUT_AFFINE_XY_BE)
+    pts_xy = bytearray(pts_xy)
+    # lanes 40..59: P = G (small multiples meet the table); lane 60..: invalid points
+    g = _be(c.gx) + _be(c.gy)
+    for i in range(40, 60):
+        pts_xy[64 * i : 64 * i + 64] = g
+    bad = [_be(1) + _be(1), _be(c.p) + _be(c.gy), _be(c.gx) + _be(c.p + 1 if curve == 0 else c.p), bytes(64), b"\xff" * 64]
+    for j, b in enumerate(bad):
+        pts_xy[64 * (60 + j) : 64 * (61 + j)] = b
+    sc[64] = 0  # k = 0 on an invalid point: reported as an invalid point
+    pts_xy[64 * 64 : 64 * 65] = _be(2) + _be(2)
+    if points_fmt == 0:
+        pts = bytes(pts_xy)
+    else:
+        recs = []
+        for i in range(n):
+            x = int.from_bytes(pts_xy[64 * i : 64 * i + 32], "big")
+            y = int.from_bytes(pts_xy[64 * i + 32 : 64 * i + 64], "big")
+            recs.append(bytes([2 | (y & 1)]) + _be(x))
+        recs[60] = b"\x04" + recs[60][1:]          # bad prefix
+        recs[61] = b"\x02" + _be(c.p)              # x out of range
+        recs[62] = b"\x02" + _be(5 if curve == 0 else 1)  # no square root (checked below by the model)
+        recs[63] = bytes(33)
+        recs[64] = b"\x05" + recs[64][1:]
+        pts = b"".join(recs)
+    out, st = engine.batch_mul(curve, sc, np.frombuffer(pts, dtype=np.uint8), points_fmt=points_fmt)
+    exp, est = pm.batch_mul(curve, sc.tobytes(), pts, n, 0, points_fmt)
+    assert st.tobytes() == est
+    assert out.tobytes() == exp
+    assert est[60] == 2 and est[63] == 2 and est[64] == 2
+
+
+def test_golden_weierstrass(engine, fec, pm):
+    """SURVEY Appendix A.1 (independently produced with OpenSSL via `cryptography`)."""
+    k1 = {1: "0279be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798",
+          2: "02c6047f9441ed7d6d3045406e95c07cd85c778e4b8cef3ca7abac09b95c709ee5",
+          3: "02f9308a019258c31049344f85f89d5229b531c845836f99b08601f113bce036f9",
+          0xDEADBEEF: "0276d2fdf1302d1fa9556f4df94ec84cefba6d482e54f47c6c2a238c1baa560f0e"}
+    p256 = {1: "036b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296",
+            2: "037cf27b188d034f7e8a52380304b51ac3c08969e277f21b35a60b48fc47669978",
+            3: "025ecbe4d1a6330a44c8f7ef951d4bf165e6c6b721efada985fb41661bc6e7fd6c",
+            0xDEADBEEF: "02b487d183dc4806058eb31a29bedefd7bcca987b77a381a3684871d8449c18394"}
+    for curve, table in ((0, k1), (1, p256)):
+        ks = list(table)
+        sc = np.frombuffer(b"".join(_be(k) for k in ks), dtype=np.uint8)
+        out, st = engine.batch_mul(curve, sc, None)
+        assert [out[i].tobytes().hex() for i in range(len(ks))] == [table[k] for k in ks]
+        assert not st.any()
+    # ECDH x-coordinate: k = 0xdeadbeef, P = 0x1234567 G
+    P = fec.Secp256k1.multiply(None, fec.Scalar.from_int(0x1234567), engine)
+    S = fec.Secp256k1.multiply(P, fec.Scalar.from_int(0xDEADBEEF), engine)
+    assert S.x().hex() == "9f1817c02d82908ac12b2427a13b07c9a21fb8b797296eb8af47f4f91f1dac0f"
+    # identity
+    Z = fec.P256.multiply(None, fec.Scalar.from_int(0), engine)
+    assert Z.is_identity() and Z.to_bytes() == bytes(33)
+
+
+def test_x25519_matches_model_and_rfc7748(engine, fec, pm):
+    alice = bytes.fromhex("77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a")
+    bob_pub = bytes.fromhex("de9edb7d7b7dc1b4d35b61c2ece435373f8343c85b78674dadfc7e146f882b4f")
+    assert fec.x25519(alice, (9).to_bytes(32, "little"), engine).hex() == \
+        "8520f0098930a754748b7ddcb43ef75a0dbf3a0d26381af4eba4a98eaa9b4e6a"
+    assert fec.x25519(alice, bob_pub, engine).hex() == "4a5d9d5ba4ce2de1728e3bf480350f25e07e21c947d19e3376f09b3c1e161742"
+    n = 600
+    ks = pm.philox_bytes32(n, stream=4)
+    us = pm.philox_bytes32(n, stream=4, sub=1).copy()
+    special = [bytes(32), (1).to_bytes(32, "little"), (2**255 - 19).to_bytes(32, "little"), (2**255 - 1).to_bytes(32, "little"),
+               b"\xff" * 32, (2**255 - 20).to_bytes(32, "little"), (9).to_bytes(32, "little"),
+               # RFC 7748 section 5.2 second vector's u (bit 255 set: must be masked)
+               bytes.fromhex("e5210f12786811d3f4b7959d0538ae2c31dbe7106fc03c3efc4cd549c715a493")]
+    for i, s in enumerate(special):
+        us[i] = np.frombuffer(s, dtype=np.uint8)
+    out = engine.batch_x25519(ks, us)
+    for i in range(n):
+        assert out[i].tobytes() == pm.x25519(ks[i].tobytes(), us[i].tobytes()), i
+    base = engine.batch_x25519(ks[:50], None)
+    for i in range(50):
+        assert base[i].tobytes() == pm.x25519(ks[i].tobytes(), pm.X25519_BASE)
+    # RFC 7748 5.2 vector 1
+    k = bytes.fromhex("a546e36bf0527c9d3b16154b82465edd62144c0ac1fc5a18506a2244ba449ac4")
+    u = bytes.fromhex("e6db6867583030db3594c1a424b15f7c726624ec26b3353b10a903a6d0ab1c4c")
+    assert fec.x25519(k, u, engine).hex() == "c3da55379de9c6908e94ea4df28d084f32eccf03491c71f754b4075577a28552"
+
+
+def test_ed25519_pubkey_matches_model_and_rfc8032(engine, fec, pm):
+    seed = bytes.fromhex("9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60")
+    assert fec.Ed25519Signature.derive_public_key(seed, engine).hex() == \
+        "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a"
+    assert fec.Ed25519Signature.derive_public_key(bytes(range(32)), engine).hex() == \
+        "03a107bff3ce10be1d70dd18e74bc09967e4d6309ba50d5f1ddc8664125531b8"
+    assert fec.Ed25519Signature.derive_public_key(b"\x42" * 32, engine).hex() == \
+        "2152f8d19b791d24453242e15f2eab6cb7cffa7b6a5ed30097960e069881db12"
+    n = 300
+    seeds = pm.philox_bytes32(n, stream=5)
+    out = engine.batch_ed25519_pubkey(seeds, True)
+    for i in range(n):
+        assert out[i].tobytes() == pm.ed25519_pubkey(seeds[i].tobytes()), i
+    raw = pm.philox_bytes32(n, stream=5, sub=1).copy()
+    special = [0, 1, 2, pm.ED_L, pm.ED_L - 1, pm.ED_L + 1, 2**256 - 1, 2**255, 2**255 - 2, 8]
+    for i, v in enumerate(special):
+        raw[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+    out = engine.batch_ed25519_pubkey(raw, False)
+    for i in range(n):
+        assert out[i].tobytes() == pm.ed25519_pubkey(raw[i].tobytes(), False), i
+
+
+@pytest.mark.parametrize("prime", [0, 1, 2])
+@pytest.mark.parametrize("op", [0, 1, 2])
+def test_field_bench_matches_model(engine, pm, prime, op):
+    p = pm.PRIMES[prime]
+    n = 2048
+    a = pm.random_field_le(prime, n, stream=2).copy()
+    b = pm.random_field_le(prime, n, stream=2, sub=1).copy()
+    edge = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, (1 << 255) % p, (1 << 224) % p, (2**256 - 1) % p]
+    for i, v in enumerate(edge):
+        a[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+        b[(i * 3) % len(edge)] = np.frombuffer(edge[(i * 5) % len(edge)].to_bytes(32, "little"), dtype=np.uint8)
+    for iters in (1, 7):
+        out, sec = engine.field_bench(prime, op, a, b, iters)
+        assert sec > 0
+        for i in range(n):
+            ai = int.from_bytes(a[i].tobytes(), "little")
+            bi = int.from_bytes(b[i].tobytes(), "little")
+            assert int.from_bytes(out[i].tobytes(), "little") == pm.field_bench_model(prime, op, iters, ai, bi), (i, iters)
+
+
+def test_ragged_and_empty(engine, pm):
+    """n = 0, n = 1, n not a multiple of any tile size; outputs beyond n untouched."""
+    out, st = engine.batch_mul(0, np.empty(0, dtype=np.uint8), None, n=0)
+    assert out.shape == (0, 33) and st.shape == (0,)
+    assert engine.batch_x25519(np.empty(0, dtype=np.uint8), None, n=0).shape == (0, 32)
+    for n in (1, 31, 129, 257, 1000):
+        sc = pm.random_scalars_be(0, n, stream=6, edge=False)
+        out, st = engine.batch_mul(0, sc, None)
+        exp, est = pm.batch_mul(0, sc[: min(n, 40)].tobytes(), None, min(n, 40), 0)
+        assert out[: min(n, 40)].tobytes() == exp and not st.any()
+
+
+def test_synth_inputs_match_philox_model(engine, pm):
+    import torch
+
+    n = 5000
+    buf = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    for mode, stream_id, sub, first, edge in ((0, 3, 0, 0, False), (0, 4, 1, 12345, False), (1, 3, 0, 0, True), (2, 5, 0, 0, True),
+                                              (1, 3, 2, 4, True)):
+        engine.synth_dev(mode, stream_id, sub, first, n, buf, edge=edge, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy().reshape(n, 32)
+        if mode == 0:
+            exp = pm.philox_bytes32(n, stream_id, first, sub)
+        else:
+            exp = pm.random_scalars_be(mode - 1, n, stream_id, first, edge, sub)
+        assert np.array_equal(got, exp), (mode, stream_id, sub, first)
+
+
+def test_device_pointer_api_and_properties(engine, fec, pm):
+    """Full-size-style checks that need no oracle: ECDH commutes, (n-k)P = -(kP), k=0 -> identity."""
+    import torch
+
+    n = 1 << 14
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    b = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    engine.synth_dev(1, 3, 0, 0, n, a, edge=False, stream=st)
+    engine.synth_dev(1, 3, 1, 0, n, b, edge=False, stream=st)
+    A = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    B = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    engine.batch_mul_dev(0, a, None, n, A, out_fmt=2, stream=st)
+    engine.batch_mul_dev(0, b, None, n, B, out_fmt=2, stream=st)
+    s1 = torch.empty(n * 33, dtype=torch.uint8, device="cuda")
+    s2 = torch.empty(n * 33, dtype=torch.uint8, device="cuda")
+    st1 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    engine.batch_mul_dev(0, a, B, n, s1, st1, stream=st)
+    engine.batch_mul_dev(0, b, A, n, s2, None, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2)
+    assert int(st1.sum()) == 0
+    # first lanes against the model
+    exp, _ = pm.batch_mul(0, a[: 32 * 16].cpu().numpy().tobytes(), B[: 64 * 16].cpu().numpy().tobytes(), 16, 0)
+    assert s1[: 33 * 16].cpu().numpy().tobytes() == exp
+    # X25519: both sides derive the same secret
+    ka = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    kb = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    engine.synth_dev(0, 4, 0, 0, n, ka, stream=st)
+    engine.synth_dev(0, 4, 1, 0, n, kb, stream=st)
+    pa, pb, sa, sb = (torch.empty(n * 32, dtype=torch.uint8, device="cuda") for _ in range(4))
+    engine.batch_x25519_dev(ka, None, n, pa, stream=st)
+    engine.batch_x25519_dev(kb, None, n, pb, stream=st)
+    engine.batch_x25519_dev(ka, pb, n, sa, stream=st)
+    engine.batch_x25519_dev(kb, pa, n, sb, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(sa, sb)
+    assert engine.launch_count > 0
+
+
+def test_imad_peak_runs(engine):
+    rates = [engine.imad_peak(v) for v in (0, 1, 2)]
+    assert all(r > 1e11 for r in rates), rates
