@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched scalar-multiplication hot path on B200.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): secp256k1 variable-base
+k_i * P_i over 2^24 random (k, P) pairs per GPU with batch affine normalisation and SEC1 compressed
+output.  Inputs are synthetic (device Philox): k_i < n, P_i = r_i * G.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lanes L]
+
+One JSON line on stdout (rank 0).  `value` = lanes/s with inputs resident in HBM (CUDA events on
+the launching stream, max over ranks); `e2e` = the same metric through the host-buffer C-ABI call
+(fec_batch_mul) with pinned HOST buffers, H2D and D2H inside the timed region; `roofline` = the
+k*P kernel against the measured int32-multiply (IMAD.WIDE) issue rate, plus its HBM side;
+`cpu_baseline` = the CPU oracle port on the box's host cores over a bounded sample of the same
+workload (also used to check those lanes of the GPU output bit for bit).
+
+--impl reference times the reference's CPU implementation of the path (the oracle port: the
+reference is Rust and cannot be built in this image) with every host thread, rank 0 only.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scalar-mults/sec (secp256k1 k*P, 2^24 random (k,P) pairs, batch affine normalisation, SEC1 compressed out)"
+UNIT = "scalar-mults/s"
+CANON_IMUL32_PER_OP = 172_562   # SURVEY.md 8d, config 3 (fixed 4-bit window, Jacobian, Montgomery-trick inversion)
+IO_BYTES_PER_OP = 32 + 64 + 33  # scalar + affine point in, SEC1 compressed out
+SYNTH_STREAM = 3
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle (checker / baseline only)
+# ------------------------------------------------------------------------------------------
+def load_oracle():
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle_std.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(path)
+    lib.ostd_batch_mul.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.ostd_batch_mul.restype = None
+    return lib
+
+
+def load_oracle_ref():
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.oref_secp256k1_batch_mul.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]
+    lib.oref_secp256k1_batch_mul.restype = None
+    return lib
+
+
+def host_inputs(n, first_lane=0):
+    """the same Philox inputs as the device generator, restated on the CPU (oracle/pymodel.py)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pymodel as pm
+
+    k = pm.random_scalars_be(0, n, SYNTH_STREAM, first_lane, edge=True, sub=0)
+    r = pm.random_scalars_be(0, n, SYNTH_STREAM, first_lane, edge=False, sub=1)
+    return np.ascontiguousarray(k), np.ascontiguousarray(r)
+
+
+def cpu_points(lib, r, threads):
+    n = r.shape[0]
+    pts = np.empty((n, 64), dtype=np.uint8)
+    lib.ostd_batch_mul(0, r.ctypes.data, None, 0, n, 2, pts.ctypes.data, None, threads)
+    return pts
+
+
+def time_cpu(lib_std, lib_ref, k, pts, threads):
+    """returns (lanes/s, out, kind-description).  Prefers the literal restatement of the reference's
+    own algorithm (oracle_ref) for timing; outputs for the parity check always come from oracle_std."""
+    n = k.shape[0]
+    out = np.empty((n, 33), dtype=np.uint8)
+    t0 = time.perf_counter()
+    lib_std.ostd_batch_mul(0, k.ctypes.data, pts.ctypes.data, 0, n, 0, out.ctypes.data, None, threads)
+    t_std = time.perf_counter() - t0
+    t_ref = None
+    if lib_ref is not None:
+        o2 = np.empty((n, 33), dtype=np.uint8)
+        t0 = time.perf_counter()
+        lib_ref.oref_secp256k1_batch_mul(k.ctypes.data, pts.ctypes.data, n, o2.ctypes.data, threads)
+        t_ref = time.perf_counter() - t0
+    return n / t_std, (n / t_ref if t_ref else None), out
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.proc, self.lines = dev, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    """the reference arm: the path's CPU implementation on the host cores (oracle port), rank 0 only"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    lib_std, lib_ref = load_oracle(), load_oracle_ref()
+    # bounded sample per step: about 2 s of work per step
+    probe = 64 * threads
+    k, r = host_inputs(probe)
+    pts = cpu_points(lib_std, r, threads)
+    rate_std, rate_ref, _ = time_cpu(lib_std, lib_ref, k, pts, threads)
+    rate = rate_ref or rate_std
+    sample = max(threads, int(rate * 2.0) // threads * threads)
+    k, r = host_inputs(sample)
+    pts = cpu_points(lib_std, r, threads)
+    times = []
+    for i in range(args.warmup + args.steps):
+        out = np.empty((sample, 33), dtype=np.uint8)
+        t0 = time.perf_counter()
+        if lib_ref is not None:
+            lib_ref.oref_secp256k1_batch_mul(k.ctypes.data, pts.ctypes.data, sample, out.ctypes.data, threads)
+        else:
+            lib_std.ostd_batch_mul(0, k.ctypes.data, pts.ctypes.data, 0, sample, 0, out.ctypes.data, None, threads)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample * args.steps / total
+    kind = "port"
+    what = ("oracle/ref: literal C restatement of forge-ec's own limb code and 256-step ladder (secp256k1.rs:2635-2692)"
+            if lib_ref is not None else "oracle/std: C port with the reference's algorithm shape (double-and-add, per-point Fermat inversion)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (u64 on the CPU)", "data": "synthetic (Philox-4x32-10, seed 'forge-ec')",
+            "config": {"workload": "secp256k1 k*P, 2^24 (k,P) pairs [BASELINE.json configs[2]]; each step = a bounded sample of it",
+                       "lanes_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} lanes per step; {what}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=1 << 24, help="lanes per GPU (default 2^24 = the named configuration)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fec = importlib.import_module("forge-ec_b200")  # raises loudly if the CUDA library is missing
+    eng = fec.Engine()                               # current device; no CPU fallback exists
+    n = args.lanes
+    first_lane = rank * n                            # contiguous lane range of this rank (weak scaling)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    dev = torch.device("cuda", local)
+    d_k = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    d_r = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    d_p = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n * 33, dtype=torch.uint8, device=dev)
+    d_st = torch.empty(n, dtype=torch.uint8, device=dev)
+    # untimed set-up: k_i, r_i from the device Philox generator, P_i = r_i * G with the fixed-base kernel
+    eng.synth_dev(1, SYNTH_STREAM, 0, first_lane, n, d_k, edge=True, stream=sp)
+    eng.synth_dev(1, SYNTH_STREAM, 1, first_lane, n, d_r, edge=False, stream=sp)
+    eng.batch_mul_dev(fec.CURVE_SECP256K1, d_r, None, n, d_p, out_fmt=fec.OUT_AFFINE_XY_BE, stream=sp)
+    torch.cuda.synchronize()
+    # roofline denominator: measured multiply-pipe issue rates on this GPU (IMUL32/s)
+    peak_wide = eng.imad_peak(0)      # IMAD.WIDE.U32, one instruction per IMUL32
+    peak_lohi = eng.imad_peak(1) / 2  # IMAD + IMAD.HI, two instructions per IMUL32
+    peak_chain = eng.imad_peak(2)     # carry-chained IMAD.WIDE.U32.X
+    imad_peak = max(peak_wide, peak_lohi, peak_chain)
+
+    def step():
+        eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, d_p, n, d_out, d_st, stream=sp)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n * args.steps / (total_ms_max * 1e-3)
+    kernel_s = statistics.mean(kernel_ms) * 1e-3
+
+    # ---- end to end through the host-buffer C ABI: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_k = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+        h_p = torch.empty(n * 64, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(n * 33, dtype=torch.uint8).pin_memory()
+        h_st = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_k.copy_(d_k); h_p.copy_(d_p)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            eng.batch_mul_ptr(fec.CURVE_SECP256K1, h_k.data_ptr(), h_p.data_ptr(), n, h_out.data_ptr(), h_st.data_ptr())
+
+        e2e_steps = max(1, args.steps)
+        e2e_step()  # warm-up (allocates the pipeline buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(h_out, d_out.cpu())) and bool(torch.equal(h_st, d_st.cpu()))
+        e2e = {"value": world * n * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 96,
+               "d2h_bytes_per_step": n * 34, "steps": e2e_steps, "timer": "host wall clock around the synchronous fec_batch_mul call",
+               "matches_device_resident_run": same}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on the host cores, bounded sample of the same lanes; doubles as a parity check
+    cpu = None
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        lib_std, lib_ref = load_oracle(), load_oracle_ref()
+        probe = 32 * threads
+        k, r = host_inputs(probe)
+        pts = cpu_points(lib_std, r, threads)
+        rate_std, rate_ref, _ = time_cpu(lib_std, lib_ref, k, pts, threads)
+        slow = min(rate_std, rate_ref) if rate_ref else rate_std
+        sample = int(min(n, max(probe, int(slow * 8.0) // threads * threads)))
+        k, r = host_inputs(sample)
+        pts = cpu_points(lib_std, r, threads)
+        rate_std, rate_ref, out = time_cpu(lib_std, lib_ref, k, pts, threads)
+        gpu_head = d_out[: sample * 33].cpu().numpy().reshape(sample, 33)
+        gpu_pts = d_p[: sample * 64].cpu().numpy().reshape(sample, 64)
+        parity = bool(np.array_equal(gpu_head, out)) and bool(np.array_equal(gpu_pts, pts))
+        cpu = {"value": rate_ref if rate_ref else rate_std, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": (f"first {sample} lanes of the workload; " +
+                          ("oracle/ref = literal C restatement of forge-ec's limb code and 256-step ladder"
+                           if rate_ref else "oracle/std = C port shaped like the reference (double-and-add, per-point Fermat inversion)")),
+               "std_value": rate_std, "gpu_bit_exact_on_sample": parity}
+        if not parity:
+            print("PARITY FAILURE: GPU output differs from the CPU oracle on the sampled lanes", file=sys.stderr)
+
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = CANON_IMUL32_PER_OP * n / kernel_s
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (8 x 32-bit, IMAD.WIDE.U32 carry chains)", "data": "synthetic (device Philox-4x32-10, seed 'forge-ec')",
+        "config": {"workload": "secp256k1 variable-base k*P + batch affine normalisation + SEC1 compressed [BASELINE.json configs[2]]",
+                   "lanes_per_gpu": n, "sharding": "contiguous lane ranges, one rank per GPU, no collective on the data path",
+                   "l2": "inputs 1.5 GiB + outputs 0.55 GiB per step exceed the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "imad", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMUL32/s", "frac": achieved / imad_peak,
+                     "traffic": None, "kernel": "k_wmul_var<CurveK1>", "kernel_ms": kernel_s * 1e3,
+                     "algorithmic_imul32_per_op": CANON_IMUL32_PER_OP,
+                     "peak_source": "fec_imad_peak measured in this run (IMUL32/s): " +
+                                    f"IMAD.WIDE.U32 {peak_wide:.4g}, IMAD+IMAD.HI pairs {peak_lohi:.4g}, chained IMAD.WIDE.U32.X {peak_chain:.4g}",
+                     "hbm": {"bound": "hbm", "achieved": IO_BYTES_PER_OP * n / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": IO_BYTES_PER_OP * n / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                             "algorithmic_bytes_per_op": IO_BYTES_PER_OP}},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

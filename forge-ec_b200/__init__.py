@@ -36,6 +36,7 @@ from .engine import (  # noqa: F401
     EXPORTED_SYMBOLS,
     library_path,
     load_library,
+    shard_range,
 )
 from .traits import (  # noqa: F401
     AffinePoint,

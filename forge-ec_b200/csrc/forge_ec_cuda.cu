@@ -188,10 +188,13 @@ int run_host_job(fec_ctx* ctx, const HostJob& job, size_t n) {
   std::lock_guard<std::mutex> lock(ctx->mu);
   const size_t G = ctx->devs.size();
   if (G == 1) return run_shard(ctx, ctx->devs[0], job, 0, n);
-  // shard boundaries on CHUNK-independent multiples of 1024 lanes so every record offset stays 16-byte aligned
   std::vector<size_t> cut(G + 1, 0);
-  for (size_t i = 1; i < G; i++) cut[i] = ((n * i / G) + 1023) / 1024 * 1024 < n ? ((n * i / G) + 1023) / 1024 * 1024 : n;
-  cut[G] = n;
+  for (size_t i = 0; i < G; i++) {
+    size_t first = 0, count = 0;
+    fec_shard_range(n, (int)G, (int)i, &first, &count);
+    cut[i] = first;
+    cut[i + 1] = first + count;
+  }
   std::vector<int> rcs(G, FEC_OK);
   std::vector<std::thread> th;
   for (size_t i = 0; i < G; i++)
@@ -220,6 +223,21 @@ const char* fec_strerror(int err) {
     case FEC_ERR_OOM: return "out of memory";
     default: return "unknown error";
   }
+}
+
+// contiguous lane range of shard `index` of `n_shards`: boundaries rounded up to multiples of 1024 lanes so that
+// every record offset (32/33/64/65 B per lane) stays 16-byte aligned; pure arithmetic, no device needed
+void fec_shard_range(size_t n, int n_shards, int index, size_t* first, size_t* count) {
+  if (n_shards < 1) n_shards = 1;
+  auto cut = [&](int i) -> size_t {
+    if (i <= 0) return 0;
+    if (i >= n_shards) return n;
+    size_t c = (n / (size_t)n_shards * (size_t)i + n % (size_t)n_shards * (size_t)i / (size_t)n_shards + 1023) / 1024 * 1024;
+    return c < n ? c : n;
+  };
+  const size_t a = cut(index), b = cut(index + 1);
+  if (first) *first = a;
+  if (count) *count = b - a;
 }
 
 int fec_ctx_create(const int* device_ids, int n_devices, fec_ctx** out) {

@@ -49,17 +49,19 @@ k_imad_peak(u32* __restrict__ sink, u32 seed, int trips) {
 #pragma unroll
     for (int s = 0; s < PEAK_INNER; s++) {
       if (VARIANT == 0) {
+        // independent (lo,hi) pairs, no carry between pairs: ptxas fuses each into one IMAD.WIDE.U32.
+        // multiplicand = the neighbouring chain's high word, so nothing is loop-invariant
 #pragma unroll
         for (int c = 0; c < PEAK_CHAINS; c++) {
-          u64 acc = ((u64)hi[c] << 32) | lo[c];
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[c]), "r"(b));
-          lo[c] = (u32)acc; hi[c] = (u32)(acc >> 32);
+          const u32 m = hi[(c + 1) % PEAK_CHAINS];
+          lo[c] = mad_lo_cc(m, b, lo[c]);
+          hi[c] = madc_hi(m, b, hi[c]);
         }
       } else if (VARIANT == 1) {
 #pragma unroll
         for (int c = 0; c < PEAK_CHAINS; c++) {
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(a[c]), "r"(b));
-          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[c]) : "r"(a[c]), "r"(b));
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(hi[c]), "r"(b));
+          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[c]) : "r"(lo[c]), "r"(b));
         }
       } else {
         // one carry chain across the 8 pairs, as a row of the schoolbook product

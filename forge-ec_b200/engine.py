@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "fec_ctx_create", "fec_ctx_destroy", "fec_ctx_device_count", "fec_ctx_launch_count", "fec_strerror",
     "fec_ctx_last_cuda_error", "fec_batch_mul", "fec_batch_mul_dev", "fec_batch_x25519", "fec_batch_x25519_dev",
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
-    "fec_imad_peak", "fec_synth_dev",
+    "fec_imad_peak", "fec_synth_dev", "fec_shard_range",
 )
 
 
@@ -84,8 +84,18 @@ def load_library() -> ctypes.CDLL:
     lib.fec_imad_peak.restype = ip
     lib.fec_synth_dev.argtypes = [vp, ip, ip, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ip, sz, u8, vp]
     lib.fec_synth_dev.restype = ip
+    lib.fec_shard_range.argtypes = [sz, ip, ip, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+    lib.fec_shard_range.restype = None
     _LIB = lib
     return lib
+
+
+def shard_range(n: int, n_shards: int, index: int):
+    """(first, count) of the contiguous lane range that shard `index` of `n_shards` owns (no device needed)."""
+    lib = load_library()
+    first, count = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    lib.fec_shard_range(n, n_shards, index, ctypes.byref(first), ctypes.byref(count))
+    return first.value, count.value
 
 
 def _host_in(buf, n: int, rec: int, name: str) -> np.ndarray:

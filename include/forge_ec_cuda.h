@@ -87,6 +87,10 @@ const char* fec_strerror(int err);
 /* last CUDA error string seen by this context (thread-unsafe diagnostic) */
 const char* fec_ctx_last_cuda_error(const fec_ctx* ctx);
 
+/* Sharding rule used by the host entry points (and by bench.py across ranks): shard `index` of `n_shards` owns
+ * the contiguous lanes [first, first+count); cuts are multiples of 1024 lanes.  Needs no device. */
+void fec_shard_range(size_t n, int n_shards, int index, size_t* first, size_t* count);
+
 /* k_i*G when points == NULL, else k_i*P_i.
  * scalars: n x 32 B big-endian (Scalar::from_bytes layout); points: n x 64 B (X||Y big-endian) or
  * n x 33 B SEC1 compressed; out: n x {33,65,64} B; status: n x u8 or NULL. */

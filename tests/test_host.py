@@ -1,0 +1,178 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/forge_ec_cuda.h declares, fails
+loudly without a device, the device headers' limb arithmetic (compiled for the host by tests/hostsim) is
+bit-exact against the oracle, and the multi-rank sharding logic works under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(fec):
+    hdr = open(os.path.join(ROOT, "include", "forge_ec_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only
+    declared = sorted(set(re.findall(r"\b(fec_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 17
+    lib = fec.load_library()
+    for sym in declared:
+        assert hasattr(lib, sym), f"libforge_ec_cuda.so does not export {sym}"
+    assert sorted(fec.EXPORTED_SYMBOLS) == declared
+
+
+def test_strerror_and_argument_checks_need_no_device(fec):
+    lib = fec.load_library()
+    assert lib.fec_strerror(0) == b"ok"
+    assert b"no CPU fallback" in lib.fec_strerror(3)
+    assert lib.fec_ctx_create(None, 0, None) == 1             # FEC_ERR_INVALID_ARG
+    assert lib.fec_batch_mul(None, 0, 0, None, None, 0, 0, 0, None, None) == 1
+    assert lib.fec_ctx_device_count(None) == 0 and lib.fec_ctx_launch_count(None) == 0
+
+
+def test_no_cpu_fallback(fec):
+    """without a CUDA device the engine must refuse to exist (with one, it must come up)"""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        fec.Engine().close()
+    else:
+        with pytest.raises(fec.FecError) as e:
+            fec.Engine()
+        assert e.value.code == 3
+
+
+def test_shard_ranges(fec):
+    for n in (0, 1, 1023, 1024, 1025, 10_000, 1 << 24, (1 << 24) + 77):
+        for g in (1, 2, 3, 4, 8):
+            pos = 0
+            for i in range(g):
+                first, count = fec.shard_range(n, g, i)
+                assert first == pos and (first % 1024 == 0 or first == n)
+                pos += count
+            assert pos == n
+    assert fec.shard_range(1 << 24, 8, 3) == (3 << 21, 1 << 21)
+
+
+def test_trait_mirror_encoders(fec):
+    xy = bytes(range(1, 65))
+    p = fec.AffinePoint(xy)
+    assert p.to_bytes() == bytes([2 | (xy[63] & 1)]) + xy[:32] and p.to_bytes_with_format("uncompressed") == b"\x04" + xy
+    inf = fec.AffinePoint(bytes(64), True)
+    assert inf.to_bytes() == bytes(33) and inf.to_bytes_with_format("uncompressed") == bytes(65) and inf.is_identity()
+    with pytest.raises(ValueError):
+        fec.Scalar.from_bytes(b"\x00" * 31)
+    assert fec.Scalar.from_int(7).to_bytes() == (7).to_bytes(32, "big")
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libhostsim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
+def test_device_field_code_on_host_matches_model(hostsim, pm):
+    import random
+    rnd = random.Random(7)
+    for prime in (0, 1, 2):
+        p = pm.PRIMES[prime]
+        vals = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, (1 << 255) % p, (1 << 224) % p, (2**256 - 1) % p] + [rnd.randrange(p) for _ in range(60)]
+        for _ in range(600):
+            a, b = rnd.choice(vals), rnd.choice(vals)
+            exp = [a * b % p, a * a % p, (a + b) % p, (a - b) % p, (-a) % p]
+            for op in range(5):
+                o = ctypes.create_string_buffer(32)
+                hostsim.hs_field_op(prime, op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
+                assert int.from_bytes(o.raw, "little") == exp[op], (prime, op, hex(a), hex(b))
+        for a in vals[1:20]:
+            o = ctypes.create_string_buffer(32)
+            hostsim.hs_field_op(prime, 5, a.to_bytes(32, "little"), bytes(32), o)
+            assert int.from_bytes(o.raw, "little") == pow(a, -1, p)
+
+
+def test_device_lane_code_on_host_matches_model(hostsim, pm):
+    """recoding, table building, exceptional additions, encoders, ladder, SHA-512, Ed25519 comb"""
+    import random
+    rnd = random.Random(11)
+    be = lambda v: v.to_bytes(32, "big")
+    for curve in (0, 1):
+        c = pm.CURVES[curve]
+        ks = [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, c.n, 2**256 - 1, (30 << 252) - c.n, 15 << 252] + [rnd.randrange(c.n) for _ in range(6)]
+        for k in ks:
+            o = ctypes.create_string_buffer(33)
+            st = hostsim.hs_wmul(curve, be(k), None, 0, 1, 0, o)
+            assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), ("fixed", curve, hex(k))
+            P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
+            for pt, pfmt in ((be(P[0]) + be(P[1]), 0), (pm.sec1_encode(P, 0), 1), (be(c.gx) + be(c.gy), 0)):
+                st = hostsim.hs_wmul(curve, be(k), pt, pfmt, 0, 0, o)
+                assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), pt, 1, 0, pfmt), ("var", curve, hex(k), pfmt)
+        o = ctypes.create_string_buffer(33)
+        assert hostsim.hs_wmul(curve, be(0), be(2) + be(2), 0, 0, 0, o) == 2 and o.raw == bytes(33)
+    for i in range(8):
+        k = bytes(rnd.randrange(256) for _ in range(32))
+        u = bytes(rnd.randrange(256) for _ in range(32))
+        o = ctypes.create_string_buffer(32)
+        hostsim.hs_x25519(k, u, o)
+        assert o.raw == pm.x25519(k, u)
+        hostsim.hs_ed25519_pubkey(k, 1, o)
+        assert o.raw == pm.ed25519_pubkey(k)
+        hostsim.hs_ed25519_pubkey(k, 0, o)
+        assert o.raw == pm.ed25519_pubkey(k, False)
+
+
+def _gloo_worker(rank, world, port, n, tmp):
+    import importlib
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fec = importlib.import_module("forge-ec_b200")
+    import pymodel as pm
+
+    first, count = fec.shard_range(n, world, rank)
+    # every rank generates ONLY its own lanes (the Philox counter is the global lane index) ...
+    k = pm.random_scalars_be(0, count, stream=3, first_lane=first)
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_std.so"))
+    out = np.empty(count * 33, dtype=np.uint8)
+    lib.ostd_batch_mul(0, ctypes.c_void_p(k.ctypes.data), None, 0, ctypes.c_size_t(count), 0, ctypes.c_void_p(out.ctypes.data), None, 1)
+    # ... and the results are gathered on rank 0 (the path's only collective step, and an optional one)
+    pad = torch.zeros(((n + world - 1) // world + 1024) * 33, dtype=torch.uint8)
+    pad[: out.size] = torch.from_numpy(out)
+    bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0)
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # the max-over-ranks timing reduction of bench.py
+    if rank == 0:
+        parts = [bufs[r][: fec.shard_range(n, world, r)[1] * 33] for r in range(world)]
+        np.save(tmp, torch.cat(parts).numpy())
+        assert t.item() == float(world)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo(fec, pm, tmp_path):
+    import torch.multiprocessing as mp
+
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    n, world = 3000, 2
+    tmp = str(tmp_path / "gathered.npy")
+    mp.spawn(_gloo_worker, args=(world, 29591, n, tmp), nprocs=world, join=True)
+    got = np.load(tmp)
+    k = pm.random_scalars_be(0, n, stream=3)
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_std.so"))
+    exp = np.empty(n * 33, dtype=np.uint8)
+    lib.ostd_batch_mul(0, ctypes.c_void_p(k.ctypes.data), None, 0, ctypes.c_size_t(n), 0, ctypes.c_void_p(exp.ctypes.data), None, 4)
+    assert np.array_equal(got, exp)

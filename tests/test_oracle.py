@@ -1,0 +1,281 @@
+"""CPU tests: pin the oracles against every known-answer value the reference holds for the path and
+against fixtures produced with OpenSSL / libsodium (tests/golden/make_golden.py)."""
+import ctypes
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+vp, sz = ctypes.c_void_p, ctypes.c_size_t
+
+
+def _gold(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+@pytest.fixture(scope="session")
+def ostd():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_std.so"))
+
+    class O:
+        @staticmethod
+        def mul(curve, sc, pts=None, pfmt=0, ofmt=0, threads=4):
+            s = np.frombuffer(bytes(sc), dtype=np.uint8)
+            n = s.size // 32
+            p = None if pts is None else np.frombuffer(bytes(pts), dtype=np.uint8)
+            out = np.empty(n * {0: 33, 1: 65, 2: 64}[ofmt], dtype=np.uint8)
+            st = np.empty(n, dtype=np.uint8)
+            lib.ostd_batch_mul(curve, vp(s.ctypes.data), vp(p.ctypes.data) if p is not None else None, pfmt, sz(n), ofmt,
+                               vp(out.ctypes.data), vp(st.ctypes.data), threads)
+            return out.tobytes(), st.tobytes()
+
+        @staticmethod
+        def x25519(ks, us=None, threads=4):
+            k = np.frombuffer(bytes(ks), dtype=np.uint8)
+            n = k.size // 32
+            u = None if us is None else np.frombuffer(bytes(us), dtype=np.uint8)
+            out = np.empty(n * 32, dtype=np.uint8)
+            lib.ostd_batch_x25519(vp(k.ctypes.data), vp(u.ctypes.data) if u is not None else None, sz(n), vp(out.ctypes.data), threads)
+            return out.tobytes()
+
+        @staticmethod
+        def ed(data, is_seed=True, threads=4):
+            d = np.frombuffer(bytes(data), dtype=np.uint8)
+            n = d.size // 32
+            out = np.empty(n * 32, dtype=np.uint8)
+            lib.ostd_batch_ed25519_pubkey(vp(d.ctypes.data), int(is_seed), sz(n), vp(out.ctypes.data), threads)
+            return out.tobytes()
+
+        @staticmethod
+        def field(prime, op, iters, a, b, threads=2):
+            aa = np.frombuffer(bytes(a), dtype=np.uint8)
+            bb = np.frombuffer(bytes(b), dtype=np.uint8)
+            n = aa.size // 32
+            out = np.empty(n * 32, dtype=np.uint8)
+            lib.ostd_field_bench(prime, op, sz(n), iters, vp(aa.ctypes.data), vp(bb.ctypes.data), vp(out.ctypes.data), threads)
+            return out.tobytes()
+
+        @staticmethod
+        def sha512(m):
+            d = ctypes.create_string_buffer(64)
+            lib.ostd_sha512(m, sz(len(m)), d)
+            return d.raw
+
+    return O
+
+
+@pytest.fixture(scope="session")
+def oref():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
+
+
+CURVE_ID = {"secp256k1": 0, "p256": 1}
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "p256"])
+def test_weierstrass_against_openssl(ostd, pm, name):
+    g = _gold("weierstrass.json")[name]
+    cid = CURVE_ID[name]
+    sc = b"".join(bytes.fromhex(e["k"]) for e in g["fixed_base"])
+    n = len(g["fixed_base"])
+    for fmt, key in ((0, "compressed"), (1, "uncompressed")):
+        exp = b"".join(bytes.fromhex(e[key]) for e in g["fixed_base"])
+        out, st = ostd.mul(cid, sc, None, 0, fmt)
+        assert out == exp and st == bytes(n)
+        assert pm.batch_mul(cid, sc, None, n, fmt) == (exp, bytes(n))
+    # ECDH: x-coordinate of k * P for uncompressed and compressed inputs
+    e = g["ecdh_x"]
+    sc = b"".join(bytes.fromhex(v["k"]) for v in e)
+    xy = b"".join(bytes.fromhex(v["point_uncompressed"])[1:] for v in e)
+    comp = b"".join(bytes.fromhex(v["point_compressed"]) for v in e)
+    exp_x = [v["shared_x"] for v in e]
+    for pts, pfmt in ((xy, 0), (comp, 1)):
+        out, st = ostd.mul(cid, sc, pts, pfmt, 2)
+        assert [out[64 * i : 64 * i + 32].hex() for i in range(len(e))] == exp_x and st == bytes(len(e))
+        out2, _ = pm.batch_mul(cid, sc, pts, len(e), 2, pfmt)
+        assert out2 == out
+
+
+def test_survey_appendix_a1_vectors(ostd, pm):
+    """the values SURVEY.md Appendix A.1 lists (what the reference specifies / quotes)"""
+    be = lambda v: v.to_bytes(32, "big")
+    out, _ = ostd.mul(0, be(0xDEADBEEF), None)
+    assert out.hex() == "0276d2fdf1302d1fa9556f4df94ec84cefba6d482e54f47c6c2a238c1baa560f0e"
+    P, _ = ostd.mul(0, be(0x1234567), None, 0, 2)
+    S, _ = ostd.mul(0, be(0xDEADBEEF), P, 0, 2)
+    assert S[:32].hex() == "9f1817c02d82908ac12b2427a13b07c9a21fb8b797296eb8af47f4f91f1dac0f"
+    out, _ = ostd.mul(1, be(0xDEADBEEF), None)
+    assert out.hex() == "02b487d183dc4806058eb31a29bedefd7bcca987b77a381a3684871d8449c18394"
+    for c in (0, 1):  # identity: k = 0 and k = n*G (p256.rs:2498-2538 "n*G = infinity") -> all-zero record (point.rs:41-47)
+        out, st = ostd.mul(c, be(0), None)
+        assert out == bytes(33) and st == b"\x03"
+        out, st = ostd.mul(c, be(pm.CURVES[c].n), None)
+        assert out == bytes(33) and st == b"\x01"
+
+
+def test_group_laws_the_reference_tests_state(ostd, pm):
+    """p256.rs:2498-2556 / secp256k1.rs:2769-2786: 2G = G+G, 3G = G+2G, (n-1)G = -G, ECDH commutes"""
+    be = lambda v: v.to_bytes(32, "big")
+    for c in (0, 1):
+        cv = pm.CURVES[c]
+        g1, _ = ostd.mul(c, be(1), None, 0, 2)
+        assert g1 == be(cv.gx) + be(cv.gy)
+        g2, _ = ostd.mul(c, be(2), None, 0, 2)
+        g2b, _ = ostd.mul(c, be(2), g1, 0, 2)
+        assert g2 == g2b
+        g3, _ = ostd.mul(c, be(3), None, 0, 2)
+        six_a, _ = ostd.mul(c, be(2), g3, 0, 2)
+        six_b, _ = ostd.mul(c, be(3), g2, 0, 2)
+        assert six_a == six_b
+        gm, _ = ostd.mul(c, be(cv.n - 1), None, 0, 2)
+        assert gm[:32] == g1[:32] and int.from_bytes(gm[32:], "big") == cv.p - cv.gy
+        a, b = 0x1234567890ABCDEF, 0xFEDCBA0987654321
+        A, _ = ostd.mul(c, be(a), None, 0, 2)
+        B, _ = ostd.mul(c, be(b), None, 0, 2)
+        assert ostd.mul(c, be(a), B)[0] == ostd.mul(c, be(b), A)[0]
+
+
+def test_invalid_inputs(ostd, pm):
+    be = lambda v: v.to_bytes(32, "big")
+    for c in (0, 1):
+        cv = pm.CURVES[c]
+        bad_pts = [be(1) + be(1), be(cv.p) + be(cv.gy), bytes(64), b"\xff" * 64]
+        for p in bad_pts:
+            assert ostd.mul(c, be(5), p) == (bytes(33), b"\x02")
+            assert pm.batch_mul(c, be(5), p, 1) == (bytes(33), b"\x02")
+        for rec in (b"\x04" + be(cv.gx), b"\x02" + be(cv.p), bytes(33)):
+            assert ostd.mul(c, be(5), rec, 1) == (bytes(33), b"\x02")
+        for k in (cv.n, cv.n + 1, 2**256 - 1):
+            assert ostd.mul(c, be(k), None) == (bytes(33), b"\x01")
+
+
+def test_x25519_against_libsodium_and_rfc7748(ostd, pm):
+    g = _gold("x25519.json")
+    ks = b"".join(bytes.fromhex(e["k"]) for e in g)
+    us = b"".join(bytes.fromhex(e["u"]) for e in g)
+    exp = b"".join(bytes.fromhex(e["out"]) for e in g)
+    assert ostd.x25519(ks, us) == exp
+    for e in g:
+        assert pm.x25519(bytes.fromhex(e["k"]), bytes.fromhex(e["u"])).hex() == e["out"]
+    # base-point form (u = NULL)
+    base = [e for e in g if e["u"] == (9).to_bytes(32, "little").hex()]
+    assert len(base) >= 2
+    assert ostd.x25519(b"".join(bytes.fromhex(e["k"]) for e in base), None) == b"".join(bytes.fromhex(e["out"]) for e in base)
+    # low-order / non-canonical u (RFC 7748: mask bit 255, accept u >= p)
+    for u in (bytes(32), (1).to_bytes(32, "little"), (2**255 - 19).to_bytes(32, "little"), (2**255 - 1).to_bytes(32, "little"), b"\xff" * 32):
+        k = hashlib.sha256(u).digest()
+        assert ostd.x25519(k, u) == pm.x25519(k, u)
+
+
+def test_ed25519_against_openssl_libsodium_and_rfc8032(ostd, pm):
+    g = _gold("ed25519.json")
+    seeds = b"".join(bytes.fromhex(e["seed"]) for e in g["seeds"])
+    exp = b"".join(bytes.fromhex(e["pubkey"]) for e in g["seeds"])
+    assert ostd.ed(seeds, True) == exp
+    for e in g["seeds"][:8]:
+        assert pm.ed25519_pubkey(bytes.fromhex(e["seed"])).hex() == e["pubkey"]
+    raw = b"".join(bytes.fromhex(e["scalar"]) for e in g["raw_scalars"])
+    expr = b"".join(bytes.fromhex(e["pubkey"]) for e in g["raw_scalars"])
+    assert ostd.ed(raw, False) == expr
+    for e in g["raw_scalars"][:4]:
+        assert pm.ed25519_pubkey(bytes.fromhex(e["scalar"]), False).hex() == e["pubkey"]
+    # scalar 0 and L -> identity = (0, 1)
+    one = (1).to_bytes(32, "little")
+    assert ostd.ed(bytes(32), False) == one and ostd.ed(pm.ED_L.to_bytes(32, "little"), False) == one
+
+
+def test_sha512_kats(ostd):
+    """forge-ec-hash/src/sha2.rs:13-41 pins the sha2 crate with the FIPS 180-4 "abc" vectors"""
+    assert ostd.sha512(b"abc").hex() == ("ddaf35a193617abacc417349ae20413112e6fa4e89a97ea20a9eeee64b55d39a"
+                                         "2192992a274fc1a836ba3c23a3feebbd454d4423643ce80e2a9ac94fa54ca49f")
+    for m in (b"", bytes(111), bytes(112), bytes(range(200))):
+        assert ostd.sha512(m) == hashlib.sha512(m).digest()
+
+
+def test_field_small_operand_kats(ostd, pm):
+    """the small-operand checks of the reference's field tests (p256.rs:2357-2393: 5+7, 7-5, 5*7, 5^2, 5^3;
+    curve25519.rs:2012-2033: 1*2, a*a^-1) expressed through the field microbenchmark model"""
+    le = lambda v: v.to_bytes(32, "little")
+    for prime in (0, 1, 2):
+        assert int.from_bytes(ostd.field(prime, 0, 1, le(5), le(7)), "little") == 35
+        assert int.from_bytes(ostd.field(prime, 1, 1, le(5), le(0)), "little") == 25
+        assert int.from_bytes(ostd.field(prime, 0, 2, le(5), le(5)), "little") == 125
+        p = pm.PRIMES[prime]
+        a = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % p
+        assert int.from_bytes(ostd.field(prime, 0, 1, le(a), le(pow(a, -1, p))), "little") == 1
+        assert int.from_bytes(ostd.field(prime, 0, 1, le(p - 1), le(p - 1)), "little") == 1
+
+
+def test_c_oracle_matches_python_model_on_philox_inputs(ostd, pm):
+    n = 96
+    for c in (0, 1):
+        k = pm.random_scalars_be(c, n, stream=3)
+        r = pm.random_scalars_be(c, n, stream=3, sub=1, edge=False)
+        pts, _ = ostd.mul(c, r.tobytes(), None, 0, 2)
+        assert (pts, bytes(n)) == pm.batch_mul(c, r.tobytes(), None, n, 2)
+        assert ostd.mul(c, k.tobytes(), pts) == pm.batch_mul(c, k.tobytes(), pts, n, 0)
+    ks, us = pm.philox_bytes32(n, 4), pm.philox_bytes32(n, 4, sub=1)
+    out = ostd.x25519(ks.tobytes(), us.tobytes())
+    assert all(out[32 * i : 32 * i + 32] == pm.x25519(ks[i].tobytes(), us[i].tobytes()) for i in range(n))
+    out = ostd.ed(ks.tobytes(), True)
+    assert all(out[32 * i : 32 * i + 32] == pm.ed25519_pubkey(ks[i].tobytes()) for i in range(n))
+    for prime in (0, 1, 2):
+        a, b = pm.random_field_le(prime, 64, 2), pm.random_field_le(prime, 64, 2, sub=1)
+        for op in (0, 1, 2):
+            out = ostd.field(prime, op, 3, a.tobytes(), b.tobytes())
+            for i in range(64):
+                ai, bi = int.from_bytes(a[i].tobytes(), "little"), int.from_bytes(b[i].tobytes(), "little")
+                assert int.from_bytes(out[32 * i : 32 * i + 32], "little") == pm.field_bench_model(prime, op, 3, ai, bi)
+
+
+def test_philox_known_answer(pm):
+    """Random123 kat_vectors: philox4x32-10, counter = key = 0  and  all-ones"""
+    def one(ctr, key):
+        c = np.array([ctr[0] | (ctr[1] << 32)], dtype=np.uint64)
+        return [int(v) for v in pm.philox4x32(c, ctr[3], ctr[2], seed=key[0] | (key[1] << 32))[0]]
+    assert one((0, 0, 0, 0), (0, 0)) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert one((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF)) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+# ---- the literal restatement of forge-ec's own code (oracle/ref) -------------------------------------
+def test_oracle_ref_pinned_to_reference_kats(oref):
+    lit = _gold("forge_ec_literal.json")
+
+    def fop(op, a, b=(0, 0, 0, 0)):
+        A, B, O = (ctypes.c_uint64 * 4)(*a), (ctypes.c_uint64 * 4)(*b), (ctypes.c_uint64 * 4)()
+        oref.oref_secp256k1_field_op(op, A, B, O)
+        return list(O)
+
+    k = lit["secp256k1_field_kats"]
+    assert fop(0, (1, 0, 0, 0), (2, 0, 0, 0))[0] == k["mul_1_2_limb0"]     # secp256k1.rs:2750-2751
+    assert fop(1, (2, 0, 0, 0))[0] == k["square_2_limb0"]                  # secp256k1.rs:2759-2760
+    assert fop(2, (1, 0, 0, 0), (2, 0, 0, 0))[0] == k["add_1_2_limb0"]     # :2741-2743
+    assert fop(3, (3, 0, 0, 0), (1, 0, 0, 0))[0] == k["sub_3_1_limb0"]     # :2746-2747
+    O = (ctypes.c_uint64 * 4)()
+    oref.oref_secp256k1_generator_x_raw(O)
+    assert "%064x" % sum(v << (64 * i) for i, v in enumerate(O)) == lit["secp256k1_generator_x_raw"]
+    for ks, exp in lit["secp256k1_kG_compressed"].items():
+        sc = np.frombuffer(int(ks).to_bytes(32, "big"), dtype=np.uint8).copy()
+        out = np.zeros(33, dtype=np.uint8)
+        oref.oref_secp256k1_batch_mul(vp(sc.ctypes.data), None, sz(1), vp(out.ctypes.data), 1)
+        assert out.tobytes().hex() == exp
+
+
+def test_divergence_report_reference_vs_specified(oref, ostd, pm):
+    """forge-ec's literal secp256k1 path does not produce SEC2 results.  The fraction of
+    lanes on which it agrees with the specified behaviour is reported (expected: none)."""
+    n = 64
+    k = pm.random_scalars_be(0, n, stream=1, edge=False)
+    lit = np.zeros(n * 33, dtype=np.uint8)
+    oref.oref_secp256k1_batch_mul(vp(k.ctypes.data), None, sz(n), vp(lit.ctypes.data), 4)
+    std, _ = ostd.mul(0, k.tobytes(), None)
+    agree = sum(lit.tobytes()[33 * i : 33 * i + 33] == std[33 * i : 33 * i + 33] for i in range(n))
+    print(f"forge-ec literal secp256k1 k*G agrees with SEC2 on {agree}/{n} lanes")
+    assert agree == 0
