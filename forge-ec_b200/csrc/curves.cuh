@@ -240,6 +240,25 @@ FEC_DEV void block_batch_inv(u32 zinv[8], const u32 z[8], u32* sm) {
   for (int l = 5 + LW - 1; l >= 0; l--) F::mul(p, p, sib[l]);
   copy8(zinv, p);
 }
+// Warp-level simultaneous inversion: the 32 lanes of a warp each contribute one z != 0 and receive z^-1.
+// 5 shuffle levels up, one Fermat inversion (computed redundantly by all lanes: no divergence, no barrier),
+// 5 multiplications down.  Cost per lane: 10 M + one inversion per warp.  No shared memory, no __syncthreads.
+template <class F>
+FEC_DEV void warp_batch_inv(u32 zinv[8], const u32 z[8]) {
+  u32 sib[5][8];
+  u32 p[8];
+  copy8(p, z);
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) sib[l][i] = __shfl_xor_sync(0xFFFFFFFFu, p[i], 1 << l);
+    F::mul(p, p, sib[l]);
+  }
+  F::inv(p, p);
+#pragma unroll
+  for (int l = 4; l >= 0; l--) F::mul(p, p, sib[l]);
+  copy8(zinv, p);
+}
 #endif  // __CUDACC__
 
 // -------------------------------------------------------------------------------------

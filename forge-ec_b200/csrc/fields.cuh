@@ -19,6 +19,14 @@
 
 namespace fec {
 
+// Field multiplication / squaring entry points.  With FEC_NOINLINE_FIELD defined (device code of the scalar
+// multiplication kernels) they are calls to ONE out-of-line subroutine per field and kernel image, operands and
+// result in registers: the hot loops shrink from ~70 KB to ~15 KB of SASS and stay resident in the instruction
+// cache (measured: instruction-fetch stalls were the top stall reason with everything inlined).  Otherwise
+// (microbenchmark, host simulation) they are inlined.
+template <class F> FEC_DEV void field_mul(u32 o[8], const u32 a[8], const u32 b[8]);
+template <class F> FEC_DEV void field_sqr(u32 o[8], const u32 a[8]);
+
 // =====================================================================================
 // secp256k1 base field
 // =====================================================================================
@@ -69,16 +77,19 @@ struct FeK1 {
 #pragma unroll
     for (int i = 3; i < 8; i++) o[i] = acc[i];
   }
-  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+  FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 r[16];
     mul_wide(r, a, b);
     reduce512(o, r);
   }
-  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+  FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
     u32 r[16];
     sqr_wide(r, a);
     reduce512(o, r);
   }
+  // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<FeK1>(o, a, b); }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { field_sqr<FeK1>(o, a); }
   FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 s[8];
     u32 c = add8(s, a, b);
@@ -235,16 +246,19 @@ struct Fe25519 {
 #pragma unroll
     for (int i = 1; i < 8; i++) o[i] = acc[i];
   }
-  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+  FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 r[16];
     mul_wide(r, a, b);
     reduce512(o, r);
   }
-  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+  FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
     u32 r[16];
     sqr_wide(r, a);
     reduce512(o, r);
   }
+  // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<Fe25519>(o, a, b); }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { field_sqr<Fe25519>(o, a); }
   FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 s[8];
     u32 c = add8(s, a, b);
@@ -389,16 +403,19 @@ struct FeP256 {
     u32 bw = sub8(d, l, p);
     select8(o, bw - 1u, d, l);  // bw==0 -> l >= p -> take d
   }
-  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+  FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 r[16];
     mul_wide(r, a, b);
     reduce512(o, r);
   }
-  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) {
+  FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
     u32 r[16];
     sqr_wide(r, a);
     reduce512(o, r);
   }
+  // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<FeP256>(o, a, b); }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { field_sqr<FeP256>(o, a); }
   FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 s[8], d[8], p[8];
     P(p);
@@ -478,5 +495,26 @@ struct FeP256 {
     copy8(o, t);
   }
 };
+
+#if defined(__CUDACC__) && defined(FEC_NOINLINE_FIELD)
+struct fe8 { u32 v[8]; };
+template <class F> __device__ __noinline__ fe8 fe_mul_ni(fe8 a, fe8 b) { fe8 r; F::mul_inl(r.v, a.v, b.v); return r; }
+template <class F> __device__ __noinline__ fe8 fe_sqr_ni(fe8 a) { fe8 r; F::sqr_inl(r.v, a.v); return r; }
+template <class F> FEC_DEV void field_mul(u32 o[8], const u32 a[8], const u32 b[8]) {
+  fe8 x, y;
+  copy8(x.v, a); copy8(y.v, b);
+  const fe8 r = fe_mul_ni<F>(x, y);
+  copy8(o, r.v);
+}
+template <class F> FEC_DEV void field_sqr(u32 o[8], const u32 a[8]) {
+  fe8 x;
+  copy8(x.v, a);
+  const fe8 r = fe_sqr_ni<F>(x);
+  copy8(o, r.v);
+}
+#else
+template <class F> FEC_DEV void field_mul(u32 o[8], const u32 a[8], const u32 b[8]) { F::mul_inl(o, a, b); }
+template <class F> FEC_DEV void field_sqr(u32 o[8], const u32 a[8]) { F::sqr_inl(o, a); }
+#endif
 
 }  // namespace fec

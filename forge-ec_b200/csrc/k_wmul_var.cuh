@@ -1,12 +1,25 @@
 // k_wmul_var.cuh -- variable-base kernel template; instantiated per curve in k_wmul_var_{k1,p256}.cu
+//
+// Every WARP is independent (no __syncthreads anywhere): it walks tiles of 32 consecutive lanes, keeps its
+// Jacobian results of up to DEFER tiles in thread-local memory together with the running product of their Z
+// (Montgomery's trick along the tile axis), and only then performs ONE warp-level inversion (shuffle butterfly +
+// one Fermat inversion) for all 32 x DEFER results, normalises, encodes and writes them.  The inversion cost per
+// result is 3 M + (10 M + I) / DEFER and no warp ever waits for another one.
+//   secp256k1: GLV split + table on the isomorphic curve where it is affine (no inversion for the table)
+//   P-256    : 64 windows; the a = -3 doubling does not survive the isomorphism, so its table is normalised with
+//              a warp-level inversion per tile.
 #pragma once
 #include "kernels.cuh"
 
 namespace fec {
 
-// ======================================================================================
-// kernel: variable-base k*P  (config 3)
-// ======================================================================================
+constexpr int VAR_DEFER = 8;        // tiles per warp-level inversion
+constexpr int VAR_SLOT_WORDS = 36;  // X, Y, Z, prefix (8 words each) + meta + padding (16-byte multiples)
+
+template <class F>
+struct WarpInv {
+  __device__ __forceinline__ void operator()(u32 zi[8], const u32 z[8]) { warp_batch_inv<F>(zi, z); }
+};
 
 template <class C>
 __global__ void __launch_bounds__(VAR_THREADS, VAR_BLOCKS_PER_SM)
@@ -14,58 +27,110 @@ k_wmul_var(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
            uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
   typedef typename C::F F;
   extern __shared__ __align__(16) u32 smem[];
-  uint8_t* io = reinterpret_cast<uint8_t*>(smem);  // aliases the table outside its lifetime
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   SmemTab<VAR_THREADS> tab{smem};
-  BlockInv<F, VAR_THREADS / 32> inv{smem + VAR_TAB_BYTES / 4};
+  uint8_t* io = reinterpret_cast<uint8_t*>(smem) + VAR_TAB_BYTES + warp * VAR_IO_BYTES_PER_WARP;  // this warp's staging area
   const int osz = out_size(out_fmt);
-  const size_t ntiles = (n + VAR_THREADS - 1) / VAR_THREADS;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const size_t first = tile * VAR_THREADS;
-    const size_t lane = first + threadIdx.x;
-    const int cnt = (int)((n - first) < (size_t)VAR_THREADS ? (n - first) : (size_t)VAR_THREADS);
-    const bool live = threadIdx.x < cnt;
-    u32 k[8], px[8], py[8], K[8], negm, st, ok;
-    set_small(k, 1u);
-    C::G(px, py);
-    ok = 0xFFFFFFFFu;
-    if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
-      __syncthreads();
-      block_copy(io, points + first * 33, (size_t)cnt * 33);
-      __syncthreads();
-      if (live) ok = sec1_decompress<C>(px, py, io + threadIdx.x * 33);
-      __syncthreads();
-    } else if (live) {
-      load_rec32_be(px, points + lane * 64);
-      load_rec32_be(py, points + lane * 64 + 32);
-      ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+  const size_t ntiles = (n + 31) / 32;
+  const size_t gwarp = (size_t)blockIdx.x * (VAR_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (VAR_THREADS / 32);
+  u32 slots[VAR_DEFER][VAR_SLOT_WORDS];  // thread-local (coalesced by construction), indexed dynamically
+  u32 acc[8];
+  int cnt = 0;
+  size_t first_tile_of_batch = 0;
+  set_small(acc, 1u);
+
+  for (size_t tile = gwarp;; tile += nwarps) {
+    const bool have = tile < ntiles;                      // warp-uniform
+    if (have) {
+      const size_t first = tile * 32;
+      const size_t lane = first + lane_in_warp;
+      const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+      const bool live = (int)lane_in_warp < cnt_lanes;
+      u32 k[8], px[8], py[8], st, ok = 0xFFFFFFFFu;
+      set_small(k, 1u);
+      C::G(px, py);
+      if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
+        __syncwarp();
+        warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
+        __syncwarp();
+        if (live) ok = sec1_decompress<C>(px, py, io + lane_in_warp * 33);
+        __syncwarp();
+      } else if (live) {
+        load_rec32_be(px, points + lane * 64);
+        load_rec32_be(py, points + lane * 64 + 32);
+        ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+      }
+      if (live) load_rec32_be(k, scalars + lane * 32);
+      {
+        u32 gx[8], gy[8];
+        C::G(gx, gy);
+        select8(px, ok, px, gx);
+        select8(py, ok, py, gy);
+      }
+      Jac Q;
+      u32 negm = 0u;
+      if (C::CURVE_ID == 0) {
+        // secp256k1: GLV needs no odd scalar; only the range / zero substitution of scalar_prepare
+        u32 nn[8], one[8], zs[8];
+        C::N(nn);
+        set_small(one, 1u);
+        const u32 bad = geq8(k, nn), zero = is_zero8(k);
+        select8(k, bad | zero, one, k);
+        st = (bad & LANE_SCALAR_RANGE) | (~bad & zero & LANE_INFINITY);
+        wmul_var_glv_core(Q, zs, k, px, py, tab);
+        F::mul(Q.Z, Q.Z, zs);
+      } else {
+        u32 K[8];
+        WarpInv<F> inv;
+        scalar_prepare<C>(K, negm, st, k);
+        wmul_var_core<C>(Q, K, px, py, tab, inv);
+      }
+      if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);  // range > invalid point > k = 0
+      const u32 zz = F::is_zero(Q.Z);
+      st |= (st == 0u ? zz & LANE_INFINITY : 0u);
+      if (status != nullptr && live) status[lane] = (uint8_t)st;
+      // defer: store (X, +-Y, Z', prefix) with Z' = 1 for dead lanes, extend the running product
+      u32 ny[8], one[8], z[8];
+      F::neg(ny, Q.Y);
+      select8(Q.Y, negm, ny, Q.Y);
+      set_small(one, 1u);
+      select8(z, (st != 0u) ? 0xFFFFFFFFu : 0u, one, Q.Z);
+      if (cnt == 0) first_tile_of_batch = tile;
+      u32* s = slots[cnt];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { s[i] = Q.X[i]; s[8 + i] = Q.Y[i]; s[16 + i] = z[i]; s[24 + i] = acc[i]; }
+      s[32] = st;
+      if (cnt == 0) copy8(acc, z); else F::mul(acc, acc, z);
+      cnt++;
     }
-    if (live) load_rec32_be(k, scalars + lane * 32);
-    {
-      u32 gx[8], gy[8];
-      C::G(gx, gy);
-      select8(px, ok, px, gx);
-      select8(py, ok, py, gy);
+    if (cnt == VAR_DEFER || (!have && cnt > 0)) {
+      // one inversion for the whole batch of this warp, then unwind
+      u32 inv[8];
+      warp_batch_inv<F>(inv, acc);
+#pragma unroll 1
+      for (int t = cnt - 1; t >= 0; t--) {
+        const u32* s = slots[t];
+        Jac Q;
+        u32 z[8], pre[8], zi[8], x[8], y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { Q.X[i] = s[i]; Q.Y[i] = s[8 + i]; z[i] = s[16 + i]; pre[i] = s[24 + i]; }
+        const u32 st = s[32];
+        if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
+        jac_to_affine<C>(x, y, Q, zi, 0u);
+        const size_t tile_t = first_tile_of_batch + (size_t)t * nwarps;
+        const size_t first = tile_t * 32;
+        const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+        __syncwarp();
+        if ((int)lane_in_warp < cnt_lanes) sec1_encode(io + lane_in_warp * osz, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
+        __syncwarp();
+        warp_copy(out + first * osz, io, (size_t)cnt_lanes * osz);
+      }
+      cnt = 0;
+      set_small(acc, 1u);
     }
-    scalar_prepare<C>(K, negm, st, k);
-    if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);  // range > invalid point > k = 0
-    Jac Q;
-    wmul_var_core<C>(Q, K, px, py, tab, inv);
-    u32 z[8], zi[8], one[8], x[8], y[8];
-    set_small(one, 1u);
-    const u32 zz = F::is_zero(Q.Z);
-    select8(z, zz, one, Q.Z);
-    inv(zi, z);
-    jac_to_affine<C>(x, y, Q, zi, negm);
-    st |= (st == 0u ? zz & LANE_INFINITY : 0u);
-    __syncthreads();  // table is dead: reuse it as the output staging area
-    if (live) sec1_encode(io + threadIdx.x * osz, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
-    __syncthreads();
-    block_copy(out + first * osz, io, (size_t)cnt * osz);
-    if (status != nullptr && live) status[lane] = (uint8_t)st;
-    __syncthreads();
+    if (!have) break;
   }
 }
-
 
 template <class C>
 cudaError_t wmul_var_setup_t() {

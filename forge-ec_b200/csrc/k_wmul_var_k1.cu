@@ -1,3 +1,4 @@
+#define FEC_NOINLINE_FIELD 1
 #include "k_wmul_var.cuh"
 namespace fec {
 cudaError_t wmul_var_setup_k1() { return wmul_var_setup_t<CurveK1>(); }

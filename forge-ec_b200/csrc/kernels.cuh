@@ -41,6 +41,16 @@ __device__ __forceinline__ void block_copy(uint8_t* dst, const uint8_t* src, siz
   for (size_t i = (nw << 2) + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
 }
 
+// warp-cooperative copy, word-coalesced; src/dst 4-byte aligned; callers bracket it with __syncwarp()
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  const unsigned l = threadIdx.x & 31u;
+  const size_t nw = bytes >> 2;
+  const u32* s = reinterpret_cast<const u32*>(src);
+  u32* d = reinterpret_cast<u32*>(dst);
+  for (size_t i = l; i < nw; i += 32) d[i] = s[i];
+  for (size_t i = (nw << 2) + l; i < bytes; i += 32) dst[i] = src[i];
+}
+
 __host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : 64); }
 
 // per-lane table of 8 affine points in shared memory, word-interleaved across the block:
@@ -96,7 +106,8 @@ constexpr int INV_SCRATCH_WORDS = 2 * 16 * 8 + 8;  // block_batch_inv scratch, e
 constexpr int VAR_THREADS = 128;
 constexpr int VAR_BLOCKS_PER_SM = 3;
 constexpr int VAR_TAB_BYTES = 8 * 16 * VAR_THREADS * 4;  // 64 KiB per block
-constexpr int VAR_SMEM_BYTES = VAR_TAB_BYTES + INV_SCRATCH_WORDS * 4;
+constexpr int VAR_IO_BYTES_PER_WARP = 65 * 32;           // per-warp staging of 33/65-byte records
+constexpr int VAR_SMEM_BYTES = VAR_TAB_BYTES + (VAR_THREADS / 32) * VAR_IO_BYTES_PER_WARP;
 constexpr int FIX_THREADS = 256;
 constexpr int FIX_BLOCKS_PER_SM = 2;
 constexpr int FIX_IO_BYTES = 65 * FIX_THREADS + 16;

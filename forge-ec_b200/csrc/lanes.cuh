@@ -200,6 +200,187 @@ FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
   }
 }
 
+// -------------------------------------------------------------------------------------
+// secp256k1 only: GLV endomorphism phi(x,y) = (beta x, y) = lambda (x,y).
+// k = k1 + k2 lambda (mod n) with |k1|, |k2| < 2^128 (lattice basis and rounding constants g1, g2 as
+// in libsecp256k1's scalar_split_lambda; re-derived and bound-checked in tests/test_oracle.py):
+//   c1 = round(k b2 / n) = (k g1 + 2^383) >> 384,  c2 = round(-k b1 / n) = (k g2 + 2^383) >> 384
+//   k1 = k - c1 a1 - c2 a2,  k2 = -c1 b1 - c2 b2      (exact integers; computed mod 2^256, two's complement)
+// Halves the doublings of the variable-base loop: 124 doublings + 66 mixed additions instead of 252 + 63.
+// -------------------------------------------------------------------------------------
+template <int NA, int NB>
+FEC_DEV void mul_limbs(u32* r, const u32* a, const u32* b) {  // r[NA+NB] = a[NA] * b[NB]
+#pragma unroll
+  for (int i = 0; i < NA + NB; i++) r[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < NA; i++) {
+    u64 carry = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
+      r[i + j] = (u32)t;
+      carry = t >> 32;
+    }
+    r[i + NB] = (u32)carry;
+  }
+}
+FEC_DEV void k1_beta(u32 b[8]) {
+  b[0] = 0x719501EEu; b[1] = 0xC1396C28u; b[2] = 0x12F58995u; b[3] = 0x9CF04975u;
+  b[4] = 0xAC3434E9u; b[5] = 0x6E64479Eu; b[6] = 0x657C0710u; b[7] = 0x7AE96A2Bu;
+}
+// magnitudes s1, s2 (128 bits, 4 limbs) and sign masks of k1, k2
+FEC_DEV void glv_split(u32 s1[4], u32& neg1, u32 s2[4], u32& neg2, const u32 k[8]) {
+  const u32 G1[8] = {0x45DBB031u, 0xE893209Au, 0x71E8CA7Fu, 0x3DAA8A14u, 0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};
+  const u32 G2[8] = {0x8AC47F71u, 0x1571B4AEu, 0x9DF506C6u, 0x221208ACu, 0x0ABFE4C4u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};
+  const u32 A1[4] = {0x9284EB15u, 0xE86C90E4u, 0xA7D46BCDu, 0x3086D221u};           // a1 = b2
+  const u32 B1N[4] = {0x0ABFE4C3u, 0x6F547FA9u, 0x010E8828u, 0xE4437ED6u};          // -b1
+  const u32 A2[5] = {0x9D44CFD8u, 0x57C1108Du, 0xA8E2F3F6u, 0x14CA50F7u, 0x00000001u};
+  u32 prod[16], c1[4], c2[4];
+  mul_limbs<8, 8>(prod, k, G1);
+  {
+    u64 t = (u64)prod[11] + 0x80000000u;
+    u64 c = t >> 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { t = (u64)prod[12 + i] + c; c1[i] = (u32)t; c = t >> 32; }
+  }
+  mul_limbs<8, 8>(prod, k, G2);
+  {
+    u64 t = (u64)prod[11] + 0x80000000u;
+    u64 c = t >> 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { t = (u64)prod[12 + i] + c; c2[i] = (u32)t; c = t >> 32; }
+  }
+  u32 t1[8], t2[8], u2[9], k1[8], k2[8], z[8], nk[8];
+  mul_limbs<4, 4>(t1, c1, B1N);  // -c1 b1
+  mul_limbs<4, 4>(t2, c2, A1);   //  c2 b2
+  sub8(k2, t1, t2);
+  mul_limbs<4, 4>(t1, c1, A1);   //  c1 a1
+  mul_limbs<4, 5>(u2, c2, A2);   //  c2 a2 (low 256 bits are enough)
+  sub8(k1, k, t1);
+  sub8(k1, k1, u2);
+  set_small(z, 0u);
+  neg1 = 0u - (k1[7] >> 31);
+  sub8(nk, z, k1);
+  select8(k1, neg1, nk, k1);
+  neg2 = 0u - (k2[7] >> 31);
+  sub8(nk, z, k2);
+  select8(k2, neg2, nk, k2);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { s1[i] = k1[i]; s2[i] = k2[i]; }
+}
+// 128-bit odd s -> K = 2^127 | (s >> 1); digits as in next_digit, 32 of them
+FEC_DEV void recode_reg4(u32 K[4], const u32 s[4]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) K[i] = funnel_l(s[i], s[i + 1], 31);
+  K[3] = (s[3] >> 1) | 0x80000000u;
+}
+FEC_DEV void next_digit4(u32 K[4], u32& idx, u32& sgn) {
+  u32 u = K[3] >> 28;
+#pragma unroll
+  for (int i = 3; i >= 1; i--) K[i] = funnel_l(K[i - 1], K[i], 4);
+  K[0] <<= 4;
+  sgn = (u >> 3) - 1u;
+  idx = (u ^ sgn) & 7u;
+}
+// mixed addition with a skip mask, exceptional cases repaired under a warp-uniform branch
+template <class C>
+FEC_DEV void jac_madd_safe_skip(Jac& q, const u32 tx[8], const u32 ty[8], u32 skip) {
+  u32 exc = jac_madd<C>(q, tx, ty, skip);
+  if (warp_any(exc)) {
+    Jac d;
+    copy8(d.X, tx); copy8(d.Y, ty); set_small(d.Z, 1u);
+    jac_dbl<C>(d);
+    u32 isdbl = 0u - ((exc >> 1) & 1u);
+    u32 isinf = (0u - (exc & 1u)) & ~isdbl;
+    u32 one[8], zero[8];
+    set_small(one, 1u); set_small(zero, 0u);
+    select8(q.X, isdbl, d.X, q.X); select8(q.Y, isdbl, d.Y, q.Y); select8(q.Z, isdbl, d.Z, q.Z);
+    select8(q.X, isinf, one, q.X); select8(q.Y, isinf, one, q.Y); select8(q.Z, isinf, zero, q.Z);
+  }
+}
+// k in [1, n-1], (px,py) on the curve.  Result: Jacobian (Q.X, Q.Y, Q.Z * zs) -- the loop runs on the curve
+// isomorphic by zs = Z(2P) * Z(15P'), where all eight table entries are affine ("effective affine"; a = 0 only),
+// so building the table needs no inversion at all.
+template <class Tab>
+FEC_DEV void wmul_var_glv_core(Jac& Q, u32 zs[8], const u32 k[8], const u32 px[8], const u32 py[8], Tab& tab) {
+  typedef CurveK1 C;
+  typedef FeK1 F;
+  {
+    Jac D, A;
+    u32 C2[8], C3[8], s[8];
+    u32 zr[7][8];
+    copy8(D.X, px); copy8(D.Y, py); set_small(D.Z, 1u);
+    jac_dbl<C>(D);
+    F::sqr(C2, D.Z);
+    F::mul(C3, C2, D.Z);
+    F::mul(A.X, px, C2);
+    F::mul(A.Y, py, C3);
+    set_small(A.Z, 1u);
+    tab.store(0, A.X, A.Y);
+#pragma unroll 1
+    for (int j = 1; j < 8; j++) {
+      jac_madd_zr<C>(A, D.X, D.Y, zr[j - 1]);
+      tab.store(j, A.X, A.Y);
+    }
+    F::mul(zs, A.Z, D.Z);
+    copy8(s, zr[6]);
+#pragma unroll 1
+    for (int j = 6; j >= 0; j--) {
+      u32 x[8], y[8], s2[8];
+      tab.load(j, x, y);
+      F::sqr(s2, s);
+      F::mul(x, x, s2);
+      F::mul(s2, s2, s);
+      F::mul(y, y, s2);
+      tab.store(j, x, y);
+      if (j > 0) F::mul(s, s, zr[j - 1]);
+    }
+  }
+  u32 s1[4], s2[4], neg1, neg2, K1r[4], K2r[4], beta[8];
+  glv_split(s1, neg1, s2, neg2, k);
+  const u32 corr1 = (s1[0] & 1u) - 1u, corr2 = (s2[0] & 1u) - 1u;  // even -> use s+1, subtract the base afterwards
+  s1[0] |= 1u;
+  s2[0] |= 1u;
+  recode_reg4(K1r, s1);
+  recode_reg4(K2r, s2);
+  k1_beta(beta);
+  u32 idx, sgn, tx[8], ty[8], ny[8];
+  next_digit4(K1r, idx, sgn);
+  tab.load(idx, Q.X, Q.Y);
+  F::neg(ny, Q.Y);
+  select8(Q.Y, sgn ^ neg1, ny, Q.Y);
+  set_small(Q.Z, 1u);
+  next_digit4(K2r, idx, sgn);
+  tab.load(idx, tx, ty);
+  F::mul(tx, tx, beta);
+  F::neg(ny, ty);
+  select8(ty, sgn ^ neg2, ny, ty);
+  jac_madd_safe_skip<C>(Q, tx, ty, 0u);
+#pragma unroll 1
+  for (int i = 1; i < 32; i++) {
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) jac_dbl<C>(Q);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      if (h == 0) next_digit4(K1r, idx, sgn); else next_digit4(K2r, idx, sgn);
+      tab.load(idx, tx, ty);
+      if (h == 1) F::mul(tx, tx, beta);
+      F::neg(ny, ty);
+      select8(ty, sgn ^ (h == 0 ? neg1 : neg2), ny, ty);
+      jac_madd_safe_skip<C>(Q, tx, ty, 0u);
+    }
+  }
+  // parity corrections: subtract sign(k1) P and/or sign(k2) lambda P where s was bumped to s + 1
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    tab.load(0, tx, ty);
+    if (h == 1) F::mul(tx, tx, beta);
+    F::neg(ny, ty);
+    select8(ty, ~(h == 0 ? neg1 : neg2), ny, ty);
+    jac_madd_safe_skip<C>(Q, tx, ty, ~(h == 0 ? corr1 : corr2));
+  }
+}
+
 // Jacobian -> affine with a supplied 1/Z, conditional negation, canonical limbs
 template <class C>
 FEC_DEV void jac_to_affine(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u32 negm) {

@@ -88,7 +88,18 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
     if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);
     HostTab tab;
     HostInv<F> inv;
-    wmul_var_core<C>(Q, K, px, py, tab, inv);
+    if (C::CURVE_ID == 0) {  // secp256k1: GLV + effective-affine table, exactly as k_wmul_var does
+      u32 nn[8], one1[8], zs[8];
+      C::N(nn);
+      set_small(one1, 1u);
+      const u32 bad = geq8(k, nn), zero = is_zero8(k);
+      select8(k, bad | zero, one1, k);
+      negm = 0u;
+      wmul_var_glv_core(Q, zs, k, px, py, tab);
+      F::mul(Q.Z, Q.Z, zs);
+    } else {
+      wmul_var_core<C>(Q, K, px, py, tab, inv);
+    }
   }
   u32 z[8], zi[8], one[8], x[8], y[8];
   set_small(one, 1u);
