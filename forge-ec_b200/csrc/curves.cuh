@@ -17,6 +17,7 @@ namespace fec {
 
 struct CurveK1 {
   typedef FeK1 F;
+  typedef CurveK1 Cold;  // the instantiation used on rarely executed paths
   static constexpr int CURVE_ID = 0;
   static constexpr bool A_MINUS3 = false;
   FEC_DEV static void B(u32 b[8]) {
@@ -38,6 +39,7 @@ struct CurveK1 {
 
 struct CurveP256 {
   typedef FeP256 F;
+  typedef CurveP256 Cold;
   static constexpr int CURVE_ID = 1;
   static constexpr bool A_MINUS3 = true;
   FEC_DEV static void B(u32 b[8]) {
@@ -56,6 +58,18 @@ struct CurveP256 {
   }
 };
 
+// Same curves with field multiplication / squaring expanded in line (hot loops whose body is small enough to
+// stay in the instruction cache); everything else is inherited.
+struct FeK1Inl : FeK1 {
+  FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { mul_inl(o, a, b); }
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { sqr_inl(o, a); }
+};
+struct FeK1InlSqr : FeK1 {
+  FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { sqr_inl(o, a); }
+};
+struct CurveK1Inl : CurveK1 { typedef FeK1Inl F; };
+struct CurveK1InlSqr : CurveK1 { typedef FeK1InlSqr F; };
+
 // -------------------------------------------------------------------------------------
 // Jacobian point (X:Y:Z), infinity <=> Z == 0
 // -------------------------------------------------------------------------------------
@@ -63,6 +77,11 @@ struct Jac {
   u32 X[8], Y[8], Z[8];
 };
 
+FEC_DEV void set1(u32 r[8]) {
+  r[0] = 1u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = 0u;
+}
 template <class C>
 FEC_DEV void jac_set_inf(Jac& q) {
 #pragma unroll
@@ -70,12 +89,13 @@ FEC_DEV void jac_set_inf(Jac& q) {
   q.X[0] = 1; q.Y[0] = 1;
 }
 
-// Q <- 2Q.  a=0: dbl-2009-l (2M+5S).  a=-3: dbl-2001-b (3M+5S).  Z=0 stays Z=0.
+// Q <- 2Q, in place.  a=0: dbl-2009-l (2M+5S).  a=-3: dbl-2001-b (3M+5S).  Z=0 stays Z=0.
+// Written to keep few temporaries alive (Q + 4 field elements) and to use the single-pass small multiples.
 template <class C>
 FEC_DEV void jac_dbl(Jac& q) {
   typedef typename C::F F;
   if (!C::A_MINUS3) {
-    u32 A[8], B[8], Cc[8], D[8], t[8];
+    u32 A[8], B[8], Cc[8], t[8];
     F::sqr(A, q.X);
     F::sqr(B, q.Y);
     F::sqr(Cc, B);
@@ -83,17 +103,16 @@ FEC_DEV void jac_dbl(Jac& q) {
     F::sqr(t, t);
     F::sub(t, t, A);
     F::sub(t, t, Cc);
-    F::dbl(D, t);               // D = 2((X+B)^2 - A - C)
+    F::mul2(B, t);              // D = 2((X+B)^2 - A - C)        (B is free)
     F::mul(q.Z, q.Y, q.Z);
-    F::dbl(q.Z, q.Z);           // Z3 = 2YZ
-    F::dbl(t, A);
-    F::add(A, t, A);            // E = 3A
-    F::sqr(t, A);               // F = E^2
-    F::sub(t, t, D);
-    F::sub(q.X, t, D);          // X3 = F - 2D
-    F::sub(t, D, q.X);
+    F::mul2(q.Z, q.Z);          // Z3 = 2YZ
+    F::mul3(A, A);              // E = 3A
+    F::sqr(q.X, A);             // F = E^2
+    F::mul2(t, B);
+    F::sub(q.X, q.X, t);        // X3 = F - 2D
+    F::sub(t, B, q.X);
     F::mul(t, A, t);            // E(D - X3)
-    F::dbl(Cc, Cc); F::dbl(Cc, Cc); F::dbl(Cc, Cc);  // 8C
+    F::mul8(Cc, Cc);            // 8C
     F::sub(q.Y, t, Cc);
   } else {
     u32 delta[8], gamma[8], beta[8], alpha[8], t[8];
@@ -103,30 +122,79 @@ FEC_DEV void jac_dbl(Jac& q) {
     F::sub(t, q.X, delta);
     F::add(alpha, q.X, delta);
     F::mul(alpha, t, alpha);
-    F::dbl(t, alpha);
-    F::add(alpha, t, alpha);    // alpha = 3(X-delta)(X+delta)
+    F::mul3(alpha, alpha);      // alpha = 3(X-delta)(X+delta)
     F::add(t, q.Y, q.Z);
     F::sqr(t, t);
     F::sub(t, t, gamma);
     F::sub(q.Z, t, delta);      // Z3 = (Y+Z)^2 - gamma - delta
-    F::dbl(beta, beta); F::dbl(beta, beta);  // 4 beta
+    F::mul4(beta, beta);        // 4 beta
     F::sqr(t, alpha);
     F::sub(t, t, beta);
     F::sub(q.X, t, beta);       // X3 = alpha^2 - 8 beta
     F::sub(t, beta, q.X);
     F::mul(t, alpha, t);
     F::sqr(gamma, gamma);
-    F::dbl(gamma, gamma); F::dbl(gamma, gamma); F::dbl(gamma, gamma);  // 8 gamma^2
+    F::mul8(gamma, gamma);      // 8 gamma^2
     F::sub(q.Y, t, gamma);
   }
 }
 
-// Q <- Q + (x2,y2) with (x2,y2) affine: madd-2007-bl (7M+4S), written without branches.
-//   t_inf : mask, the addend is the point at infinity (digit 0)  -> Q unchanged
-//   Q at infinity                                                -> (x2,y2,1)
-//   Q == +-(x2,y2) (H == 0): cannot happen for k < n on a prime-order curve with the digit
-//   sets used here; the flag is returned so the caller can take a
-//   warp-uniform slow path if it ever does.
+// Q <- Q + (x2,y2) with (x2,y2) affine: madd-2007-bl (7M+4S), IN PLACE and without any selection.
+// Returns a flag word: bit 0 = the formula does not apply (Q at infinity, or Q == +-(x2,y2)),
+// bit 1 = Q was at infinity, bit 2 = same y as well (doubling).  When bit 0 is set Q holds garbage and the caller
+// repairs the lane (jac_madd_fix) -- under a warp-uniform branch, so no divergence depends on the data.
+template <class C>
+FEC_DEV u32 jac_madd_lean(Jac& q, const u32 x2[8], const u32 y2[8]) {
+  typedef typename C::F F;
+  u32 A[8], H[8], r[8], D[8];
+  const u32 q_inf = F::is_zero(q.Z);
+  F::sqr(A, q.Z);                    // Z1Z1
+  F::mul(H, x2, A);                  // U2
+  F::sub(H, H, q.X);                 // H = U2 - X1
+  F::mul(r, q.Z, A);
+  F::mul(r, y2, r);                  // S2
+  F::sub(r, r, q.Y);
+  const u32 h_zero = F::is_zero(H), r_zero = F::is_zero(r);
+  F::mul2(r, r);                     // r = 2(S2 - Y1)
+  F::add(D, q.Z, H);
+  F::sqr(D, D);
+  F::sub(D, D, A);
+  F::sqr(A, H);                      // HH
+  F::sub(q.Z, D, A);                 // Z3 = (Z1+H)^2 - Z1Z1 - HH
+  F::mul4(A, A);                     // I = 4 HH
+  F::mul(H, H, A);                   // J = H I
+  F::mul(A, q.X, A);                 // V = X1 I
+  F::sqr(q.X, r);
+  F::sub(q.X, q.X, H);
+  F::sub(q.X, q.X, A);
+  F::sub(q.X, q.X, A);               // X3 = r^2 - J - 2V
+  F::sub(A, A, q.X);
+  F::mul(A, r, A);                   // r (V - X3)
+  F::mul(H, q.Y, H);
+  F::mul2(H, H);                     // 2 Y1 J
+  F::sub(q.Y, A, H);
+  return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+}
+// repair of the lanes jac_madd_lean flagged: infinity + T = T, T + T = 2T, T + (-T) = infinity
+template <class C>
+FEC_DEV void jac_madd_fix(Jac& q, const u32 x2[8], const u32 y2[8], u32 flags) {
+  Jac d;
+  copy8(d.X, x2); copy8(d.Y, y2); set1(d.Z);
+  Jac t = d;
+  jac_dbl<C>(d);
+  const u32 bad = 0u - (flags & 1u), was_inf = 0u - ((flags >> 1) & 1u), isdbl = (0u - ((flags >> 2) & 1u)) & ~was_inf;
+  const u32 isinf = bad & ~was_inf & ~isdbl;
+  u32 one[8], zero[8];
+  set1(one);
+#pragma unroll
+  for (int i = 0; i < 8; i++) zero[i] = 0u;
+  select8(q.X, was_inf, t.X, q.X); select8(q.Y, was_inf, t.Y, q.Y); select8(q.Z, was_inf, t.Z, q.Z);
+  select8(q.X, isdbl, d.X, q.X); select8(q.Y, isdbl, d.Y, q.Y); select8(q.Z, isdbl, d.Z, q.Z);
+  select8(q.X, isinf, one, q.X); select8(q.Y, isinf, one, q.Y); select8(q.Z, isinf, zero, q.Z);
+}
+
+// Q <- Q + (x2,y2) with a skip mask, results selected by masks (used where the addend may be absent: corrections,
+// table construction).  Returns bit0: exceptional (same x, both finite), bit1: also same y (needs doubling).
 template <class C>
 FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   typedef typename C::F F;
@@ -139,12 +207,12 @@ FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   F::mul(S2, y2, S2);
   F::sub(H, U2, q.X);
   F::sqr(HH, H);
-  F::dbl(I, HH); F::dbl(I, I);       // I = 4 HH
+  F::mul4(I, HH);                    // I = 4 HH
   F::mul(J, H, I);
   F::sub(r, S2, q.Y);
   u32 h_zero = F::is_zero(H);
   u32 r_zero = F::is_zero(r);
-  F::dbl(r, r);                      // r = 2(S2 - Y1)
+  F::mul2(r, r);                     // r = 2(S2 - Y1)
   F::mul(V, q.X, I);
   F::sqr(o.X, r);
   F::sub(o.X, o.X, J);
@@ -153,13 +221,14 @@ FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   F::sub(t, V, o.X);
   F::mul(t, r, t);
   F::mul(J, q.Y, J);
-  F::dbl(J, J);
+  F::mul2(J, J);
   F::sub(o.Y, t, J);                 // Y3 = r(V - X3) - 2 Y1 J
   F::add(t, q.Z, H);
   F::sqr(t, t);
   F::sub(t, t, Z1Z1);
   F::sub(o.Z, t, HH);                // Z3 = (Z1+H)^2 - Z1Z1 - HH
-  u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  u32 one[8];
+  set1(one);
   u32 keep = t_inf;                  // keep Q
   u32 take_t = q_inf & ~t_inf;       // Q was infinity: result is the addend
 #pragma unroll

@@ -159,14 +159,53 @@ struct FeK1 {
     select8(o, 0u - c, t, a);
   }
   FEC_DEV static u32 is_zero(const u32 a[8]) {  // mask; accepts both representatives 0 and p
-    u32 t[8];
-    canon(t, a);
-    return is_zero8(t);
+    const u32 o = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+    const u32 n = (a[0] ^ 0xFFFFFC2Fu) | (a[1] ^ 0xFFFFFFFEu) | ~(a[2] & a[3] & a[4] & a[5] & a[6] & a[7]);
+    return ((o == 0u) | (n == 0u)) ? 0xFFFFFFFFu : 0u;
   }
   FEC_DEV static u32 in_range(const u32 a[8]) {  // mask: a < p (input validation)
     u32 p[8];
     P(p);
     return ~geq8(a, p);
+  }
+  // o = a * 2^S (S = 1, 2, 3): one funnel-shift pass, the S bits shifted out are folded with 2^32 + 977
+  template <int S>
+  FEC_DEV static void mul_pow2(u32 o[8], const u32 a[8]) {
+    const u32 v = a[7] >> (32 - S);
+    u32 t[8];
+#pragma unroll
+    for (int i = 7; i >= 1; i--) t[i] = funnel_l(a[i - 1], a[i], S);
+    t[0] = a[0] << S;
+    t[0] = add_cc(t[0], v * C977);
+    t[1] = addc_cc(t[1], v);
+#pragma unroll
+    for (int i = 2; i < 8; i++) t[i] = addc_cc(t[i], 0u);
+    const u32 c2 = addc(0u, 0u);
+    o[0] = add_cc(t[0], (0u - c2) & C977);
+    o[1] = addc_cc(t[1], c2);
+    o[2] = addc(t[2], 0u);
+#pragma unroll
+    for (int i = 3; i < 8; i++) o[i] = t[i];
+  }
+  FEC_DEV static void mul2(u32 o[8], const u32 a[8]) { mul_pow2<1>(o, a); }
+  FEC_DEV static void mul4(u32 o[8], const u32 a[8]) { mul_pow2<2>(o, a); }
+  FEC_DEV static void mul8(u32 o[8], const u32 a[8]) { mul_pow2<3>(o, a); }
+  FEC_DEV static void mul3(u32 o[8], const u32 a[8]) {  // 2a + a in one carry pass, overflow (0..2) folded once
+    u32 t[8];
+    t[0] = add_cc(a[0] << 1, a[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = addc_cc(funnel_l(a[i - 1], a[i], 1), a[i]);
+    const u32 v = addc(a[7] >> 31, 0u);
+    t[0] = add_cc(t[0], v * C977);
+    t[1] = addc_cc(t[1], v);
+#pragma unroll
+    for (int i = 2; i < 8; i++) t[i] = addc_cc(t[i], 0u);
+    const u32 c2 = addc(0u, 0u);
+    o[0] = add_cc(t[0], (0u - c2) & C977);
+    o[1] = addc_cc(t[1], c2);
+    o[2] = addc(t[2], 0u);
+#pragma unroll
+    for (int i = 3; i < 8; i++) o[i] = t[i];
   }
   FEC_DEV static void sqr_n(u32 x[8], int n) {
 #pragma unroll 1
@@ -320,11 +359,17 @@ struct Fe25519 {
     u[7] &= 0x7FFFFFFFu;
     select8(o, ge, u, t);
   }
-  FEC_DEV static u32 is_zero(const u32 a[8]) {
-    u32 t[8];
-    canon(t, a);
-    return is_zero8(t);
+  FEC_DEV static u32 is_zero(const u32 a[8]) {  // the three representatives below 2^256: 0, p, 2p
+    const u32 o = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+    const u32 mid = ~(a[1] & a[2] & a[3] & a[4] & a[5] & a[6]);
+    const u32 p1 = (a[0] ^ 0xFFFFFFEDu) | mid | (a[7] ^ 0x7FFFFFFFu);
+    const u32 p2 = (a[0] ^ 0xFFFFFFDAu) | mid | ~a[7];
+    return ((o == 0u) | (p1 == 0u) | (p2 == 0u)) ? 0xFFFFFFFFu : 0u;
   }
+  FEC_DEV static void mul2(u32 o[8], const u32 a[8]) { add(o, a, a); }
+  FEC_DEV static void mul3(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, a); }
+  FEC_DEV static void mul4(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, t); }
+  FEC_DEV static void mul8(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(t, t, t); add(o, t, t); }
   FEC_DEV static void sqr_n(u32 x[8], int n) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) sqr(x, x);
@@ -456,6 +501,10 @@ struct FeP256 {
   }
   FEC_DEV static void canon(u32 o[8], const u32 a[8]) { copy8(o, a); }
   FEC_DEV static u32 is_zero(const u32 a[8]) { return is_zero8(a); }
+  FEC_DEV static void mul2(u32 o[8], const u32 a[8]) { add(o, a, a); }
+  FEC_DEV static void mul3(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, a); }
+  FEC_DEV static void mul4(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, t); }
+  FEC_DEV static void mul8(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(t, t, t); add(o, t, t); }
   FEC_DEV static u32 in_range(const u32 a[8]) {
     u32 p[8];
     P(p);
@@ -507,10 +556,14 @@ template <class F> FEC_DEV void field_mul(u32 o[8], const u32 a[8], const u32 b[
   copy8(o, r.v);
 }
 template <class F> FEC_DEV void field_sqr(u32 o[8], const u32 a[8]) {
+#ifdef FEC_INLINE_SQR
+  F::sqr_inl(o, a);
+#else
   fe8 x;
   copy8(x.v, a);
   const fe8 r = fe_sqr_ni<F>(x);
   copy8(o, r.v);
+#endif
 }
 #else
 template <class F> FEC_DEV void field_mul(u32 o[8], const u32 a[8], const u32 b[8]) { F::mul_inl(o, a, b); }

@@ -16,6 +16,20 @@ namespace fec {
 constexpr int VAR_DEFER = 8;        // tiles per warp-level inversion
 constexpr int VAR_SLOT_WORDS = 36;  // X, Y, Z, prefix (8 words each) + meta + padding (16-byte multiples)
 
+// per-lane table of 8 affine points in thread-local memory (the hardware interleaves local memory across the lanes
+// of a warp, so every access is coalesced; it is cached in L1/L2 and private to the launch)
+struct LocalTab {
+  u32 e[8][16];
+  __device__ __forceinline__ void store(int j, const u32 x[8], const u32 y[8]) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) { e[j][w] = x[w]; e[j][8 + w] = y[w]; }
+  }
+  __device__ __forceinline__ void load(u32 j, u32 x[8], u32 y[8]) const {
+#pragma unroll
+    for (int w = 0; w < 8; w++) { x[w] = e[j][w]; y[w] = e[j][8 + w]; }
+  }
+};
+
 template <class F>
 struct WarpInv {
   __device__ __forceinline__ void operator()(u32 zi[8], const u32 z[8]) { warp_batch_inv<F>(zi, z); }
@@ -28,8 +42,8 @@ k_wmul_var(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
   typedef typename C::F F;
   extern __shared__ __align__(16) u32 smem[];
   const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  SmemTab<VAR_THREADS> tab{smem};
-  uint8_t* io = reinterpret_cast<uint8_t*>(smem) + VAR_TAB_BYTES + warp * VAR_IO_BYTES_PER_WARP;  // this warp's staging area
+  LocalTab tab;
+  uint8_t* io = reinterpret_cast<uint8_t*>(smem) + warp * VAR_IO_BYTES_PER_WARP;  // this warp's staging area
   const int osz = out_size(out_fmt);
   const size_t ntiles = (n + 31) / 32;
   const size_t gwarp = (size_t)blockIdx.x * (VAR_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (VAR_THREADS / 32);

@@ -104,10 +104,13 @@ struct SmemNiels {
 // ---- tile geometry ----------------------------------------------------------------------
 constexpr int INV_SCRATCH_WORDS = 2 * 16 * 8 + 8;  // block_batch_inv scratch, enough for 16 warps
 constexpr int VAR_THREADS = 128;
-constexpr int VAR_BLOCKS_PER_SM = 3;
+#ifndef FEC_VAR_BLOCKS_PER_SM
+#define FEC_VAR_BLOCKS_PER_SM 4
+#endif
+constexpr int VAR_BLOCKS_PER_SM = FEC_VAR_BLOCKS_PER_SM;
 constexpr int VAR_TAB_BYTES = 8 * 16 * VAR_THREADS * 4;  // 64 KiB per block
 constexpr int VAR_IO_BYTES_PER_WARP = 65 * 32;           // per-warp staging of 33/65-byte records
-constexpr int VAR_SMEM_BYTES = VAR_TAB_BYTES + (VAR_THREADS / 32) * VAR_IO_BYTES_PER_WARP;
+constexpr int VAR_SMEM_BYTES = (VAR_THREADS / 32) * VAR_IO_BYTES_PER_WARP;
 constexpr int FIX_THREADS = 256;
 constexpr int FIX_BLOCKS_PER_SM = 2;
 constexpr int FIX_IO_BYTES = 65 * FIX_THREADS + 16;

@@ -85,12 +85,12 @@ FEC_DEV void jac_madd_zr(Jac& q, const u32 x2[8], const u32 y2[8], u32 zr[8]) {
   F::mul(S2, y2, S2);
   F::sub(H, U2, q.X);
   F::sqr(HH, H);
-  F::dbl(I, HH); F::dbl(I, I);
+  F::mul4(I, HH);
   F::mul(J, H, I);
   F::sub(r, S2, q.Y);
-  F::dbl(r, r);
+  F::mul2(r, r);
   F::mul(V, q.X, I);
-  F::dbl(zr, H);
+  F::mul2(zr, H);
   F::mul(q.Z, q.Z, zr);              // Z3 = 2 Z1 H
   F::sqr(q.X, r);
   F::sub(q.X, q.X, J);
@@ -99,7 +99,7 @@ FEC_DEV void jac_madd_zr(Jac& q, const u32 x2[8], const u32 y2[8], u32 zr[8]) {
   F::sub(t, V, q.X);
   F::mul(t, r, t);
   F::mul(J, q.Y, J);
-  F::dbl(J, J);
+  F::mul2(J, J);
   F::sub(q.Y, t, J);
 }
 
@@ -108,18 +108,8 @@ FEC_DEV void jac_madd_zr(Jac& q, const u32 x2[8], const u32 y2[8], u32 zr[8]) {
 // recoding only produces for a handful of scalars next to n; see DESIGN.md.)
 template <class C>
 FEC_DEV void jac_madd_safe(Jac& q, const u32 tx[8], const u32 ty[8]) {
-  u32 exc = jac_madd<C>(q, tx, ty, 0u);
-  if (warp_any(exc)) {
-    Jac d;
-    copy8(d.X, tx); copy8(d.Y, ty); set_small(d.Z, 1u);
-    jac_dbl<C>(d);
-    u32 isdbl = 0u - ((exc >> 1) & 1u);
-    u32 isinf = (0u - (exc & 1u)) & ~isdbl;
-    u32 one[8], zero[8];
-    set_small(one, 1u); set_small(zero, 0u);
-    select8(q.X, isdbl, d.X, q.X); select8(q.Y, isdbl, d.Y, q.Y); select8(q.Z, isdbl, d.Z, q.Z);
-    select8(q.X, isinf, one, q.X); select8(q.Y, isinf, one, q.Y); select8(q.Z, isinf, zero, q.Z);
-  }
+  const u32 flags = jac_madd_lean<C>(q, tx, ty);
+  if (warp_any(flags)) jac_madd_fix<typename C::Cold>(q, tx, ty, flags);
 }
 
 // -------------------------------------------------------------------------------------
@@ -355,11 +345,18 @@ FEC_DEV void wmul_var_glv_core(Jac& Q, u32 zs[8], const u32 k[8], const u32 px[8
   F::mul(tx, tx, beta);
   F::neg(ny, ty);
   select8(ty, sgn ^ neg2, ny, ty);
-  jac_madd_safe_skip<C>(Q, tx, ty, 0u);
+  jac_madd_safe<C>(Q, tx, ty);
+#if defined(FEC_HOT_INLINE) && FEC_HOT_INLINE == 2
+  typedef CurveK1Inl CH;
+#elif defined(FEC_HOT_INLINE) && FEC_HOT_INLINE == 1
+  typedef CurveK1InlSqr CH;
+#else
+  typedef CurveK1 CH;
+#endif
 #pragma unroll 1
   for (int i = 1; i < 32; i++) {
 #pragma unroll 1
-    for (int d = 0; d < 4; d++) jac_dbl<C>(Q);
+    for (int d = 0; d < 4; d++) jac_dbl<CH>(Q);
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
       if (h == 0) next_digit4(K1r, idx, sgn); else next_digit4(K2r, idx, sgn);
@@ -367,7 +364,7 @@ FEC_DEV void wmul_var_glv_core(Jac& Q, u32 zs[8], const u32 k[8], const u32 px[8
       if (h == 1) F::mul(tx, tx, beta);
       F::neg(ny, ty);
       select8(ty, sgn ^ (h == 0 ? neg1 : neg2), ny, ty);
-      jac_madd_safe_skip<C>(Q, tx, ty, 0u);
+      jac_madd_safe<CH>(Q, tx, ty);
     }
   }
   // parity corrections: subtract sign(k1) P and/or sign(k2) lambda P where s was bumped to s + 1

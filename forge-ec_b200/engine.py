@@ -35,6 +35,9 @@ class FecError(RuntimeError):
 
 
 def library_path() -> str:
+    override = os.environ.get("FORGE_EC_CUDA_LIB")  # A/B experiments with differently tuned builds of the same library
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libforge_ec_cuda.so")
 
 

@@ -58,6 +58,11 @@ template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uin
     case 3: F::sub(t, x, y); break;
     case 4: F::neg(t, x); break;
     case 5: F::inv(t, x); break;
+    case 7: F::mul2(t, x); break;
+    case 8: F::mul3(t, x); break;
+    case 9: F::mul4(t, x); break;
+    case 10: F::mul8(t, x); break;
+    case 11: { u32 m = F::is_zero(x); set_small(t, m & 1u); } break;
     default: F::dbl(t, x); break;
   }
   F::canon(r, t);

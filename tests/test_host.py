@@ -97,6 +97,16 @@ def test_device_field_code_on_host_matches_model(hostsim, pm):
             o = ctypes.create_string_buffer(32)
             hostsim.hs_field_op(prime, 5, a.to_bytes(32, "little"), bytes(32), o)
             assert int.from_bytes(o.raw, "little") == pow(a, -1, p)
+        # single-pass small multiples and the zero test, also on non-canonical (weak) representatives
+        weak = vals + ([p, p + 1, 2**256 - 1, 2**256 - 2**32 - 978, 2**256 - 2**33] if prime != 1 else []) + ([2 * p] if prime == 2 else [])
+        for a in weak:
+            for op, m in ((7, 2), (8, 3), (9, 4), (10, 8)):
+                o = ctypes.create_string_buffer(32)
+                hostsim.hs_field_op(prime, op, a.to_bytes(32, "little"), bytes(32), o)
+                assert int.from_bytes(o.raw, "little") == a * m % p, (prime, op, hex(a))
+            o = ctypes.create_string_buffer(32)
+            hostsim.hs_field_op(prime, 11, a.to_bytes(32, "little"), bytes(32), o)
+            assert int.from_bytes(o.raw, "little") == (1 if a % p == 0 else 0), (prime, hex(a))
 
 
 def test_device_lane_code_on_host_matches_model(hostsim, pm):

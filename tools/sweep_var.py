@@ -19,12 +19,13 @@ def t(fn, reps=2):
     for _ in range(reps): fn()
     e1.record(s); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e-3
-for lg in (16, 17, 18, 19, 20, 22, 24):
+LGS = tuple(int(x) for x in os.environ.get("SWEEP_LG", "16,17,18,19,20,22,24").split(","))
+for lg in LGS:
     n = 1 << lg
     dt = t(lambda: eng.batch_mul_dev(0, k, P, n, out, stream=s.cuda_stream))
     print(f"n=2^{lg}: {n/dt/1e6:.2f} M/s  ({dt*1e3:.2f} ms)", flush=True)
 # chunked on one stream
-for lg in (18, 20):
+for lg in ((18, 20) if "SWEEP_LG" not in os.environ else ()):
     c = 1 << lg
     def chunked():
         for off in range(0, N, c):
