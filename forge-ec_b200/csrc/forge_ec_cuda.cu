@@ -114,11 +114,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 int launch_mul(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
                uint8_t* dout, uint8_t* dst, cudaStream_t st) {
   if (n == 0) return FEC_OK;
-  ctx->launches++;
-  if (dp == nullptr)
+  if (dp == nullptr) {
+    ctx->launches++;
     FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
-  else
-    FEC_CUDA(ctx, wmul_var_launch(curve, d.sms, st, ds, dp, pfmt, n, ofmt, dout, dst));
+  } else {
+    int launches = 0;
+    const cudaError_t e = wmul_var_launch(curve, d.sms, st, ds, dp, pfmt, n, ofmt, dout, dst, &launches);
+    ctx->launches += (uint64_t)launches;
+    FEC_CUDA(ctx, e);
+  }
   return FEC_OK;
 }
 int launch_x25519(fec_ctx* ctx, Device& d, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {

@@ -1,0 +1,179 @@
+// k_wmul_glv_k1.cu -- secp256k1 variable-base k*P (BASELINE.json configs[2], the headline workload) as three
+// kernels over a per-call scratch area in HBM (see glv3.cuh / vm.cuh for the why):
+//
+//   k_glv_prep    one lane per thread, registers: parse + validate (k, P), table of 8 odd multiples as
+//                 (x, beta x, y), GLV split           -> scratch: table 768 B, zs 32 B, digits 32 B, flags 4 B per lane
+//   k_glv_ladder  accumulator machine in shared memory, 9 slots of 32 B per lane, table entries fetched with
+//                 cp.async straight into the addend slots   -> scratch: Jacobian result 96 B per lane
+//   k_glv_finish  parity corrections, block-level simultaneous inversion, affine, SEC1 encoding, status
+//
+// Scratch traffic per lane: 932 B written + ~5 KB read (64 table entries of 64 B), i.e. ~0.4 TB/s at 7e7 lanes/s:
+// 6 % of HBM bandwidth, and the table of a chunk mostly stays in the 126 MB L2.
+#define FEC_NOINLINE_FIELD 1
+#include "glv3.cuh"
+#include "kernels.cuh"
+
+namespace fec {
+
+constexpr int GLV_PREP_THREADS = 128;
+constexpr int GLV_LAD_THREADS = 128;
+#ifndef FEC_GLV_LAD_BLOCKS
+#define FEC_GLV_LAD_BLOCKS 6
+#endif
+constexpr int GLV_LAD_SMEM = VS_COUNT * 32 * GLV_LAD_THREADS;
+constexpr int GLV_FIN_THREADS = 256;
+constexpr int GLV_FIN_SMEM = 65 * GLV_FIN_THREADS + 16 + INV_SCRATCH_WORDS * 4;
+
+struct GlvScratch {
+  u32* tab;    // [lane][192]
+  u32* zs;     // [lane][8]
+  u32* kk;     // [lane][8]
+  u32* flags;  // [lane]   bits 0-3 GLV flags, bits 8-15 status
+  u32* q;      // [lane][24]
+};
+constexpr size_t GLV_SCRATCH_BYTES_PER_LANE = (192 + 8 + 8 + 1 + 24) * 4;
+
+__global__ void __launch_bounds__(GLV_PREP_THREADS, 3)
+k_glv_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ points, int points_fmt, size_t n, GlvScratch sc) {
+  typedef CurveK1 C;
+  typedef FeK1 F;
+  __shared__ __align__(16) uint8_t io_all[(GLV_PREP_THREADS / 32) * 33 * 32 + 16];
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* io = io_all + warp * (33 * 32);
+  const size_t first = ((size_t)blockIdx.x * (GLV_PREP_THREADS / 32) + warp) * 32;
+  if (first >= n) return;  // warp-uniform
+  const size_t lane = first + lane_in_warp;
+  const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+  const bool live = (int)lane_in_warp < cnt_lanes;
+  u32 k[8], px[8], py[8], ok = 0xFFFFFFFFu;
+  set_small(k, 1u);
+  C::G(px, py);
+  if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
+    warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
+    __syncwarp();
+    if (live) ok = sec1_decompress<C>(px, py, io + lane_in_warp * 33);
+  } else if (live) {
+    load_rec32_be(px, points + lane * 64);
+    load_rec32_be(py, points + lane * 64 + 32);
+    ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+  }
+  if (live) load_rec32_be(k, scalars + lane * 32);
+  {
+    u32 gx[8], gy[8];
+    C::G(gx, gy);
+    select8(px, ok, px, gx);
+    select8(py, ok, py, gy);
+  }
+  u32 nn[8], one[8];
+  C::N(nn);
+  set_small(one, 1u);
+  const u32 bad = geq8(k, nn), zero = is_zero8(k);
+  select8(k, bad | zero, one, k);
+  u32 st = (bad & LANE_SCALAR_RANGE) | (~bad & zero & LANE_INFINITY);
+  if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);  // range > invalid point > k = 0
+  if (!live) return;
+  u32 zs[8], KK[8], flags;
+  glv_prepare(sc.tab + lane * GLV_TAB_WORDS, zs, KK, flags, k, px, py);
+  g_st8(sc.zs + lane * 8, zs);
+  g_st8(sc.kk + lane * 8, KK);
+  sc.flags[lane] = flags | (st << 8);
+}
+
+__global__ void __launch_bounds__(GLV_LAD_THREADS, FEC_GLV_LAD_BLOCKS)
+k_glv_ladder(size_t n, GlvScratch sc) {
+  extern __shared__ __align__(16) u32 smem[];
+  size_t lane = (size_t)blockIdx.x * GLV_LAD_THREADS + threadIdx.x;
+  const bool live = lane < n;
+  if (!live) lane = n - 1;  // recompute the last lane instead of branching around the whole loop
+  const saddr S = (saddr)__cvta_generic_to_shared(smem) + threadIdx.x * 16u;
+  u32 KK[8];
+  g_ld8(KK, sc.kk + lane * 8);
+  const u32 flags = sc.flags[lane];
+  glv_ladder<GLV_LAD_THREADS>(S, sc.tab + lane * GLV_TAB_WORDS, KK, flags);
+  if (live) {
+    typedef Vm<FeK1, GLV_LAD_THREADS> V;
+    u32 t[8];
+    V::ldv(t, V::slot(S, VS_X)); g_st8(sc.q + lane * 24, t);
+    V::ldv(t, V::slot(S, VS_Y)); g_st8(sc.q + lane * 24 + 8, t);
+    V::ldv(t, V::slot(S, VS_Z)); g_st8(sc.q + lane * 24 + 16, t);
+  }
+}
+
+__global__ void __launch_bounds__(GLV_FIN_THREADS, 2)
+k_glv_finish(size_t n, GlvScratch sc, int out_fmt, uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  typedef CurveK1 C;
+  typedef FeK1 F;
+  extern __shared__ __align__(16) u32 smem[];
+  uint8_t* io = reinterpret_cast<uint8_t*>(smem);
+  BlockInv<F, GLV_FIN_THREADS / 32> inv{smem + (65 * GLV_FIN_THREADS + 16) / 4};
+  const int osz = out_size(out_fmt);
+  const size_t first = (size_t)blockIdx.x * GLV_FIN_THREADS;
+  const int cnt = (int)((n - first) < (size_t)GLV_FIN_THREADS ? (n - first) : (size_t)GLV_FIN_THREADS);
+  const bool live = (int)threadIdx.x < cnt;
+  const size_t lane = live ? first + threadIdx.x : first;
+  Jac Q;
+  u32 zs[8];
+  g_ld8(Q.X, sc.q + lane * 24); g_ld8(Q.Y, sc.q + lane * 24 + 8); g_ld8(Q.Z, sc.q + lane * 24 + 16);
+  g_ld8(zs, sc.zs + lane * 8);
+  const u32 fl = sc.flags[lane];
+  u32 st = (fl >> 8) & 0xFFu;
+  glv_finish(Q, sc.tab + lane * GLV_TAB_WORDS, zs, fl);
+  const u32 zz = F::is_zero(Q.Z);
+  st |= (st == 0u ? zz & LANE_INFINITY : 0u);
+  u32 z[8], zi[8], one[8], x[8], y[8];
+  set_small(one, 1u);
+  select8(z, (st != 0u) ? 0xFFFFFFFFu : 0u, one, Q.Z);
+  inv(zi, z);
+  jac_to_affine<C>(x, y, Q, zi, 0u);
+  if (live) sec1_encode(io + threadIdx.x * osz, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
+  __syncthreads();
+  block_copy(out + first * osz, io, (size_t)cnt * osz);
+  if (status != nullptr && live) status[lane] = (uint8_t)st;
+}
+
+cudaError_t wmul_glv_setup_k1() {
+  cudaError_t e = cudaFuncSetAttribute(k_glv_ladder, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_LAD_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_glv_ladder, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  // keep the scratch memory of earlier calls in the stream-ordered pool instead of returning it at every synchronisation
+  int dev = 0;
+  cudaMemPool_t pool;
+  unsigned long long keep = ~0ull;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+  if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_glv_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_FIN_SMEM);
+}
+
+// n lanes in chunks of at most `chunk` lanes over one stream-ordered scratch allocation
+cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
+                               uint8_t* out, uint8_t* status, size_t chunk, int* launches) {
+  if (n == 0) return cudaSuccess;
+  const size_t cap = n < chunk ? n : chunk;
+  uint8_t* base = nullptr;
+  cudaError_t e = cudaMallocAsync(&base, cap * GLV_SCRATCH_BYTES_PER_LANE + 256, st);
+  if (e != cudaSuccess) return e;
+  GlvScratch sc;
+  sc.tab = reinterpret_cast<u32*>(base);
+  sc.q = sc.tab + cap * 192;
+  sc.zs = sc.q + cap * 24;
+  sc.kk = sc.zs + cap * 8;
+  sc.flags = sc.kk + cap * 8;
+  const int osz = out_size(out_fmt);
+  const int psz = points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64;
+  for (size_t off = 0; off < n; off += cap) {
+    const size_t m = (n - off) < cap ? (n - off) : cap;
+    k_glv_prep<<<(unsigned)((m + GLV_PREP_THREADS - 1) / GLV_PREP_THREADS), GLV_PREP_THREADS, 0, st>>>(
+        scalars + off * 32, points + off * psz, points_fmt, m, sc);
+    k_glv_ladder<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, GLV_LAD_SMEM, st>>>(m, sc);
+    k_glv_finish<<<(unsigned)((m + GLV_FIN_THREADS - 1) / GLV_FIN_THREADS), GLV_FIN_THREADS, GLV_FIN_SMEM, st>>>(
+        m, sc, out_fmt, out + off * osz, status ? status + off : nullptr);
+    if (launches) *launches += 3;
+  }
+  e = cudaGetLastError();
+  cudaError_t e2 = cudaFreeAsync(base, st);
+  return e != cudaSuccess ? e : e2;
+}
+
+}  // namespace fec

@@ -1,0 +1,204 @@
+// vm.cuh -- "accumulator machine" for long field-arithmetic programs (the doubling/addition loops).
+//
+// Why.  With whole points held in registers the scalar-multiplication loops need ~130-170 registers per thread
+// (12-16 warps per SM, or spills), and with the field multiplications expanded in line the loop no longer fits the
+// instruction cache (both measured).  Here a lane's field elements live in SHARED MEMORY
+// slots and ONE element, the accumulator, lives in registers:
+//
+//     acc = ld(slot)  |  st(slot, acc)  |  acc = acc * [slot]  |  acc = acc^2  |  acc = acc +- [slot]  | ...
+//
+// Every operation is one small out-of-line routine on the accumulator; operands arrive through the load/store
+// pipe (which the integer pipes do not share) as 128-bit shared-memory accesses, the whole loop is ~1.2k
+// instructions, and a thread needs 80 registers without spilling anything that is live in the loop, so 24 warps
+// per SM are resident.
+//
+// Slot layout (per block of T threads): slot s = two "halves" of 4 words per thread,
+//     byte address = base + ((2 s + h) T + thread) * 16        -> consecutive threads, consecutive 16-byte
+// cells: every 128-bit access of a warp is conflict-free.
+//
+// On the host (tests/hostsim, g++) a slot address is a plain pointer and T = 1.
+#pragma once
+#include "fields.cuh"
+
+namespace fec {
+
+struct fe { u32 v[8]; };
+
+#if defined(__CUDACC__)
+typedef u32 saddr;  // byte address in the shared window
+#define FEC_VMOP __device__ __noinline__
+FEC_DEV void lds128(u32 r[4], saddr p) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(p) : "memory");
+}
+FEC_DEV void sts128(saddr p, const u32 r[4]) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// 16 bytes global -> shared without passing through registers (completion: cp_async_wait)
+FEC_DEV void cp_async16(saddr dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+FEC_DEV void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+FEC_DEV saddr sa_add(saddr p, int bytes) { return p + (u32)bytes; }
+#else
+typedef u32* saddr;
+#define FEC_VMOP inline
+FEC_DEV void lds128(u32 r[4], saddr p) { for (int i = 0; i < 4; i++) r[i] = p[i]; }
+FEC_DEV void sts128(saddr p, const u32 r[4]) { for (int i = 0; i < 4; i++) p[i] = r[i]; }
+FEC_DEV void cp_async16(saddr dst, const void* src) { for (int i = 0; i < 4; i++) dst[i] = static_cast<const u32*>(src)[i]; }
+FEC_DEV void cp_async_wait() {}
+FEC_DEV saddr sa_add(saddr p, int bytes) { return p + bytes / 4; }
+#endif
+
+// F: field (FeK1, Fe25519, FeP256), T: threads per block (1 on the host)
+template <class F, int T>
+struct Vm {
+  static constexpr int HALF = T * 16;      // bytes between the two halves of a slot
+  static constexpr int SLOT = 2 * T * 16;  // bytes between slots
+  FEC_DEV static saddr slot(saddr base, int s) { return sa_add(base, s * SLOT); }
+  FEC_DEV static void ldv(u32 r[8], saddr p) { lds128(r, p); lds128(r + 4, sa_add(p, HALF)); }
+  FEC_DEV static fe ld(saddr p) { fe a; ldv(a.v, p); return a; }
+  FEC_DEV static void st(saddr p, const fe& a) { sts128(p, a.v); sts128(sa_add(p, HALF), a.v + 4); }
+};
+
+// ---- the out-of-line operations (one copy per kernel image) -----------------------------------------------
+template <class F, int T> FEC_VMOP fe vm_mul(fe a, saddr p) {  // a * [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::mul_inl(r.v, a.v, b);
+  return r;
+}
+template <class F> FEC_VMOP fe vm_sqr(fe a) {
+  fe r;
+  F::sqr_inl(r.v, a.v);
+  return r;
+}
+template <class F, int T> FEC_VMOP fe vm_add(fe a, saddr p) {  // a + [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::add(r.v, a.v, b);
+  return r;
+}
+template <class F, int T> FEC_VMOP fe vm_sub(fe a, saddr p) {  // a - [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::sub(r.v, a.v, b);
+  return r;
+}
+template <class F, int T> FEC_VMOP fe vm_rsub(fe a, saddr p) {  // [p] - a
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::sub(r.v, b, a.v);
+  return r;
+}
+template <class F, int K> FEC_VMOP fe vm_small(fe a) {  // a * K, K in {2,3,4,8}
+  fe r;
+  if (K == 2) F::mul2(r.v, a.v);
+  else if (K == 3) F::mul3(r.v, a.v);
+  else if (K == 4) F::mul4(r.v, a.v);
+  else F::mul8(r.v, a.v);
+  return r;
+}
+template <class F> FEC_VMOP fe vm_cneg(fe a, u32 m) {  // m ? -a : a
+  fe r;
+  u32 n[8];
+  F::neg(n, a.v);
+  select8(r.v, m, n, a.v);
+  return r;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Jacobian programs for a = 0 curves (secp256k1).  Slot map of a lane:
+//   0 X   1 Y   2 Z   3..6 temporaries   7 TX   8 TY  (the prefetched affine addend)
+// -------------------------------------------------------------------------------------------------------------
+enum { VS_X = 0, VS_Y = 1, VS_Z = 2, VS_A = 3, VS_B = 4, VS_C = 5, VS_D = 6, VS_TX = 7, VS_TY = 8, VS_COUNT = 9 };
+
+// Q <- 2Q  (dbl-2009-l, 2M + 5S), in place
+template <class F, int T>
+FEC_DEV void vm_jac_dbl_a0(saddr S) {
+  typedef Vm<F, T> V;
+  const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
+              Cs = V::slot(S, VS_C), D = V::slot(S, VS_D);
+  fe a = V::ld(Y);
+  a = vm_sqr<F>(a); V::st(B, a);                 // B = Y^2
+  a = vm_sqr<F>(a); V::st(Cs, a);                // C = B^2
+  a = V::ld(X);
+  a = vm_sqr<F>(a); V::st(A, a);                 // A = X^2
+  a = V::ld(X);
+  a = vm_add<F, T>(a, B);
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, A);
+  a = vm_sub<F, T>(a, Cs);
+  a = vm_small<F, 2>(a); V::st(D, a);            // D = 2((X+B)^2 - A - C)
+  a = V::ld(Y);
+  a = vm_mul<F, T>(a, Z);
+  a = vm_small<F, 2>(a); V::st(Z, a);            // Z3 = 2YZ
+  a = V::ld(A);
+  a = vm_small<F, 3>(a); V::st(A, a);            // E = 3A
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, D);
+  a = vm_sub<F, T>(a, D); V::st(X, a);           // X3 = E^2 - 2D
+  a = vm_rsub<F, T>(a, D);                       // D - X3
+  a = vm_mul<F, T>(a, A); V::st(B, a);           // E (D - X3)
+  a = V::ld(Cs);
+  a = vm_small<F, 8>(a);
+  a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
+}
+
+// Q <- Q + (TX, +-TY), madd-2007-bl (7M + 4S), in place, first half: up to r = 2(S2 - Y1).  After it the
+// addend slots are no longer needed (the caller may start the next prefetch into them).
+// Returns the flag word of jac_madd_lean: bit0 formula does not apply, bit1 Q was at infinity, bit2 doubling.
+template <class F, int T>
+FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
+  typedef Vm<F, T> V;
+  const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
+              R = V::slot(S, VS_C), TX = V::slot(S, VS_TX), TY = V::slot(S, VS_TY);
+  fe a = V::ld(Z);
+  const u32 q_inf = F::is_zero(a.v);
+  a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
+  a = vm_mul<F, T>(a, TX);
+  a = vm_sub<F, T>(a, X); V::st(H, a);           // H = U2 - X1
+  const u32 h_zero = F::is_zero(a.v);
+  a = V::ld(Z);
+  a = vm_mul<F, T>(a, A);
+  a = vm_mul<F, T>(a, TY);
+  a = vm_cneg<F>(a, neg_y);                      // S2 = +-y2 Z1^3
+  a = vm_sub<F, T>(a, Y);
+  const u32 r_zero = F::is_zero(a.v);
+  a = vm_small<F, 2>(a); V::st(R, a);            // r = 2(S2 - Y1)
+  return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+}
+template <class F, int T>
+FEC_DEV void vm_jac_madd_2(saddr S) {
+  typedef Vm<F, T> V;
+  const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
+              R = V::slot(S, VS_C), HH = V::slot(S, VS_D);
+  fe a = V::ld(H);
+  a = vm_sqr<F>(a); V::st(HH, a);                // HH
+  a = V::ld(Z);
+  a = vm_add<F, T>(a, H);
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, A);
+  a = vm_sub<F, T>(a, HH); V::st(Z, a);          // Z3 = (Z1+H)^2 - Z1Z1 - HH
+  a = V::ld(HH);
+  a = vm_small<F, 4>(a); V::st(HH, a);           // I = 4 HH
+  a = vm_mul<F, T>(a, H); V::st(H, a);           // J = H I
+  a = V::ld(X);
+  a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 I
+  a = V::ld(R);
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, H);
+  a = vm_sub<F, T>(a, A);
+  a = vm_sub<F, T>(a, A); V::st(X, a);           // X3 = r^2 - J - 2V
+  a = vm_rsub<F, T>(a, A);                       // V - X3
+  a = vm_mul<F, T>(a, R); V::st(R, a);           // r (V - X3)
+  a = V::ld(Y);
+  a = vm_mul<F, T>(a, H);
+  a = vm_small<F, 2>(a);                         // 2 Y1 J
+  a = vm_rsub<F, T>(a, R); V::st(Y, a);          // Y3
+}
+
+}  // namespace fec

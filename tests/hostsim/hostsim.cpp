@@ -6,10 +6,12 @@
 #include <cstring>
 #include <vector>
 #include "../../forge-ec_b200/csrc/lanes.cuh"
+#include "../../forge-ec_b200/csrc/glv3.cuh"
 
 using namespace fec;
 
 namespace {
+bool g_use_vm = true;  // secp256k1 variable base: three-stage accumulator-machine path (default) or the single-kernel path
 struct HostTab {
   u32 e[8][16];
   void store(int j, const u32 x[8], const u32 y[8]) { copy8(e[j], x); copy8(e[j] + 8, y); }
@@ -100,8 +102,18 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
       const u32 bad = geq8(k, nn), zero = is_zero8(k);
       select8(k, bad | zero, one1, k);
       negm = 0u;
-      wmul_var_glv_core(Q, zs, k, px, py, tab);
-      F::mul(Q.Z, Q.Z, zs);
+      if (g_use_vm) {
+        // the three stages of k_wmul_glv_k1.cu with T = 1: table in "global" memory, slots in "shared" memory
+        std::vector<u32> gtab(GLV_TAB_WORDS), slots(VS_COUNT * 8);
+        u32 KK[8], flags;
+        glv_prepare(gtab.data(), zs, KK, flags, k, px, py);
+        glv_ladder<1>(slots.data(), gtab.data(), KK, flags);
+        copy8(Q.X, &slots[VS_X * 8]); copy8(Q.Y, &slots[VS_Y * 8]); copy8(Q.Z, &slots[VS_Z * 8]);
+        glv_finish(Q, gtab.data(), zs, flags);
+      } else {
+        wmul_var_glv_core(Q, zs, k, px, py, tab);
+        F::mul(Q.Z, Q.Z, zs);
+      }
     } else {
       wmul_var_core<C>(Q, K, px, py, tab, inv);
     }
@@ -124,6 +136,7 @@ void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t*
   else if (prime == 1) field_op<FeP256>(op, a, b, o);
   else field_op<Fe25519>(op, a, b, o);
 }
+void hs_set_var_impl(int use_vm) { g_use_vm = use_vm != 0; }
 int hs_wmul(int curve, const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {
   return curve == 0 ? wmul<CurveK1>(k_be, pt, pfmt, fixed, ofmt, out) : wmul<CurveP256>(k_be, pt, pfmt, fixed, ofmt, out);
 }

@@ -53,7 +53,10 @@ def main(rep, dst):
             if len(r) < len(h):
                 continue
             m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
-            ex = int(r[ix["Instructions Executed"]] or 0)
+            try:
+                ex = int(r[ix["Instructions Executed"]] or 0)
+            except ValueError:  # repeated header row (one per function of the kernel image)
+                continue
             tot[m.group(2) if m else "?"] += ex
             n += ex
         lines.append(f"-- executed warp instructions by opcode (static SASS instructions: {len(src) - 2}; executed: {n})")
