@@ -33,6 +33,8 @@ from .engine import (  # noqa: F401
     PRIME_SECP256K1,
     PT_AFFINE_XY_BE,
     PT_SEC1_COMPRESSED,
+    SEM_FORGE_QUIRK,
+    SEM_STD,
     EXPORTED_SYMBOLS,
     library_path,
     load_library,

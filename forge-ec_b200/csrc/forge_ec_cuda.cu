@@ -111,10 +111,13 @@ void device_free(Device& d) {
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- launches on device pointers ------------------------------------------------------
-int launch_mul(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
+int launch_mul(fec_ctx* ctx, Device& d, int curve, int sem, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
                uint8_t* dout, uint8_t* dst, cudaStream_t st) {
   if (n == 0) return FEC_OK;
-  if (dp == nullptr) {
+  if (sem == FEC_SEM_FORGE_QUIRK) {  // validated by the entry points: secp256k1, affine X||Y points only
+    ctx->launches++;
+    FEC_CUDA(ctx, quirk_k1_launch(st, ds, dp, n, ofmt, dout, dst));
+  } else if (dp == nullptr) {
     ctx->launches++;
     FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
   } else {
@@ -148,7 +151,7 @@ int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int i
 // ---- host-buffer pipeline: H2D -> kernel -> D2H in CHUNK_LANES granules over N_PIPE streams ----
 struct HostJob {
   int kind;  // 0 mul, 1 x25519, 2 ed25519
-  int curve, pfmt, ofmt, is_seed;
+  int curve, sem, pfmt, ofmt, is_seed;
   const uint8_t* in_a; size_t rec_a;
   const uint8_t* in_b; size_t rec_b;
   uint8_t* out; size_t rec_out;
@@ -173,7 +176,7 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
       db = d.buf_in_b[slot];
     }
     if (job.kind == 0)
-      rc = launch_mul(ctx, d, job.curve, d.buf_in_a[slot], db, job.pfmt, m, job.ofmt, d.buf_out[slot],
+      rc = launch_mul(ctx, d, job.curve, job.sem, d.buf_in_a[slot], db, job.pfmt, m, job.ofmt, d.buf_out[slot],
                       job.status ? d.buf_st[slot] : nullptr, st);
     else if (job.kind == 1)
       rc = launch_x25519(ctx, d, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
@@ -206,6 +209,13 @@ int run_host_job(fec_ctx* ctx, const HostJob& job, size_t n) {
   for (auto& t : th) t.join();
   for (int rc : rcs) if (rc) return rc;
   return FEC_OK;
+}
+
+// FEC_SEM_FORGE_QUIRK replays the reference's literal limb code; restated for secp256k1 with affine X||Y input only
+// (the reference's own SEC1 decoder rejects its own encodings, test_summary.md:77-85, so there is nothing to replay)
+bool sem_supported(int sem, int curve, int points_fmt) {
+  if (sem == FEC_SEM_STD) return true;
+  return sem == FEC_SEM_FORGE_QUIRK && curve == FEC_SECP256K1 && points_fmt == FEC_PT_AFFINE_XY_BE;
 }
 
 Device* dev_at(fec_ctx* ctx, int dev_index) {
@@ -298,8 +308,8 @@ int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* sca
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
   if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
-  if (sem != FEC_SEM_STD) return FEC_ERR_UNSUPPORTED;
-  HostJob job{0, (int)curve, (int)points_fmt, (int)out_fmt, 0, scalars, 32, points,
+  if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
+  HostJob job{0, (int)curve, (int)sem, (int)points_fmt, (int)out_fmt, 0, scalars, 32, points,
               (size_t)(points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64), out, (size_t)out_size(out_fmt), status};
   return run_host_job(ctx, job, n);
 }
@@ -312,11 +322,11 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
   if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
-  if (sem != FEC_SEM_STD) return FEC_ERR_UNSUPPORTED;
+  if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
   int prev = 0;
   cudaGetDevice(&prev);
   FEC_CUDA(ctx, cudaSetDevice(d->id));
-  int rc = launch_mul(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status,
+  int rc = launch_mul(ctx, *d, (int)curve, (int)sem, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status,
                       (cudaStream_t)stream);
   cudaSetDevice(prev);
   return rc;
@@ -324,7 +334,7 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
 
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  HostJob job{1, 0, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};
+  HostJob job{1, 0, 0, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};
   return run_host_job(ctx, job, n);
 }
 int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
@@ -342,7 +352,7 @@ int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, 
 
 int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out) {
   if (ctx == nullptr || (n > 0 && (seeds_or_scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  HostJob job{2, 0, 0, 0, input_is_seed, seeds_or_scalars, 32, nullptr, 0, out, 32, nullptr};
+  HostJob job{2, 0, 0, 0, 0, input_is_seed, seeds_or_scalars, 32, nullptr, 0, out, 32, nullptr};
   return run_host_job(ctx, job, n);
 }
 int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,

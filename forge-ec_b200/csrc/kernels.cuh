@@ -140,6 +140,8 @@ constexpr size_t GLV_CHUNK_LANES = size_t(1) << 22;
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches);
+cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
+                            uint8_t* status);
 cudaError_t wmul_fixed_setup();
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n,
                               int out_fmt, uint8_t* out, uint8_t* status);

@@ -230,8 +230,8 @@ class Engine:
 
     # -- device-pointer entry points (torch tensors or raw addresses; asynchronous on `stream`) ----
     def batch_mul_dev(self, curve: int, d_scalars, d_points, n: int, d_out, d_status=None, *, out_fmt: int = 0,
-                      points_fmt: int = 0, stream: int = 0, dev_index: int = 0):
-        self._check(self._lib.fec_batch_mul_dev(self._ctx, dev_index, curve, SEM_STD, _ptr(d_scalars), _ptr(d_points), points_fmt,
+                      points_fmt: int = 0, stream: int = 0, dev_index: int = 0, sem: int = SEM_STD):
+        self._check(self._lib.fec_batch_mul_dev(self._ctx, dev_index, curve, sem, _ptr(d_scalars), _ptr(d_points), points_fmt,
                                                 n, out_fmt, _ptr(d_out), _ptr(d_status), stream))
 
     def batch_x25519_dev(self, d_scalars, d_us, n: int, d_out, *, stream: int = 0, dev_index: int = 0):

@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../forge-ec_b200/csrc/lanes.cuh"
 #include "../../forge-ec_b200/csrc/glv3.cuh"
+#include "../../forge-ec_b200/csrc/quirk_k1.cuh"
 
 using namespace fec;
 
@@ -136,6 +137,7 @@ void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t*
   else if (prime == 1) field_op<FeP256>(op, a, b, o);
   else field_op<Fe25519>(op, a, b, o);
 }
+int hs_quirk_k1(const uint8_t* k_be, const uint8_t* xy_be, int ofmt, uint8_t* out) { return quirk::q_lane(k_be, xy_be, ofmt, out); }
 void hs_set_var_impl(int use_vm) { g_use_vm = use_vm != 0; }
 int hs_wmul(int curve, const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {
   return curve == 0 ? wmul<CurveK1>(k_be, pt, pfmt, fixed, ofmt, out) : wmul<CurveP256>(k_be, pt, pfmt, fixed, ofmt, out);

@@ -240,3 +240,44 @@ def test_device_pointer_api_and_properties(engine, fec, pm):
 def test_imad_peak_runs(engine):
     rates = [engine.imad_peak(v) for v in (0, 1, 2)]
     assert all(r > 1e11 for r in rates), rates
+
+
+def test_forge_quirk_mode_replays_the_reference_literally(engine, fec, pm):
+    """FEC_SEM_FORGE_QUIRK: BASELINE.json configs[0] (secp256k1 k*G over 2^16 synthetic scalars) and a k*P batch,
+    byte for byte against oracle/ref (the literal restatement of forge-ec's own limb code) and the Appendix A.2
+    goldens; other curves / compressed input are refused."""
+    import ctypes
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(root, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(root, "tests", "golden", "forge_ec_literal.json")))
+    for ks, exp in lit["secp256k1_kG_compressed"].items():
+        out, st = engine.batch_mul(0, _be(int(ks)), None, sem=fec.SEM_FORGE_QUIRK)
+        assert out.tobytes().hex() == exp and st[0] == 0
+    n = 1 << 16
+    k = pm.random_scalars_be(0, n, stream=1)          # config 1 inputs, edge lanes included
+    out, st = engine.batch_mul(0, k, None, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(n * 33, dtype=np.uint8)
+    oref.oref_secp256k1_batch_mul(ctypes.c_void_p(k.ctypes.data), None, ctypes.c_size_t(n), ctypes.c_void_p(exp.ctypes.data),
+                                  os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
+    # the reference's N constant has its two top limbs swapped (secp256k1.rs:27-28): that is the bound its parser applies
+    n_ref = (0xFFFFFFFFFFFFFFFE << 192) | (0xFFFFFFFFFFFFFFFF << 128) | (pm.CURVES[0].n & ((1 << 128) - 1))
+    kv = [int.from_bytes(k[i].tobytes(), "big") for i in range(n)]
+    assert st.tolist() == [1 if v >= n_ref else 3 if v == 0 else 0 for v in kv]
+    m = 2048
+    r = pm.random_scalars_be(0, m, stream=3, sub=1, edge=False)
+    pts, _ = engine.batch_mul(0, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)          # true points r_i G
+    out, st = engine.batch_mul(0, k[:m], pts, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(m * 33, dtype=np.uint8)
+    pc = np.ascontiguousarray(pts)
+    oref.oref_secp256k1_batch_mul(ctypes.c_void_p(k.ctypes.data), ctypes.c_void_p(pc.ctypes.data), ctypes.c_size_t(m),
+                                  ctypes.c_void_p(exp.ctypes.data), os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
+    for args in ((1, k[:4], None), (0, k[:4], pts[:4, :33].copy())):
+        with pytest.raises(fec.FecError):
+            engine.batch_mul(args[0], args[1], args[2], sem=fec.SEM_FORGE_QUIRK,
+                             points_fmt=fec.PT_SEC1_COMPRESSED if args[2] is not None else fec.PT_AFFINE_XY_BE)

@@ -141,6 +141,39 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.ed25519_pubkey(k, False)
 
 
+def test_quirk_device_code_on_host_matches_literal_oracle(hostsim, pm):
+    """FEC_SEM_FORGE_QUIRK (csrc/quirk_k1.cuh, compiled for the host) against oracle/ref, the literal restatement
+    of forge-ec's own secp256k1 code, and against the transliteration goldens of SURVEY.md Appendix A.2."""
+    import json
+    import random
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(ROOT, "tests", "golden", "forge_ec_literal.json")))
+    o = ctypes.create_string_buffer(33)
+    for ks, exp in lit["secp256k1_kG_compressed"].items():
+        assert hostsim.hs_quirk_k1(int(ks).to_bytes(32, "big"), None, 0, o) == 0 and o.raw.hex() == exp
+    rnd = random.Random(5)
+    c = pm.CURVES[0]
+    # the reference's N constant has its two top limbs swapped (secp256k1.rs:27-28): that is the bound its parser applies
+    N_REF = (0xFFFFFFFFFFFFFFFE << 192) | (0xFFFFFFFFFFFFFFFF << 128) | (c.n & ((1 << 128) - 1))
+    ks = [0, 1, 2, c.n - 1, c.n, N_REF - 1, N_REF, 2**256 - 1] + [rnd.randrange(N_REF) for _ in range(6)]
+    for k in ks:
+        kb = k.to_bytes(32, "big")
+        P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
+        for xy in (None, P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big")):
+            exp = ctypes.create_string_buffer(33)
+            oref.oref_secp256k1_batch_mul(kb, xy, ctypes.c_size_t(1), exp, 1)
+            st = hostsim.hs_quirk_k1(kb, xy, 0, o)
+            assert o.raw == exp.raw, (hex(k), xy is None)
+            assert st == (1 if k >= N_REF else 3 if k == 0 else 0)
+    # the other two encodings carry the same x (and the y whose parity the compressed prefix reports)
+    kb = (0xDEADBEEF).to_bytes(32, "big")
+    o65, o64 = ctypes.create_string_buffer(65), ctypes.create_string_buffer(64)
+    hostsim.hs_quirk_k1(kb, None, 0, o); hostsim.hs_quirk_k1(kb, None, 1, o65); hostsim.hs_quirk_k1(kb, None, 2, o64)
+    assert o65.raw[0] == 4 and o65.raw[1:33] == o.raw[1:] == o64.raw[:32] and o65.raw[33:] == o64.raw[32:]
+    assert (o64.raw[63] & 1) == o.raw[0] - 2
+
+
 def _gloo_worker(rank, world, port, n, tmp):
     import importlib
     import sys
