@@ -38,6 +38,13 @@ UNIT = "scalar-mults/s"
 CANON_IMUL32_PER_OP = 172_562   # SURVEY.md 8d, config 3 (fixed 4-bit window, Jacobian, Montgomery-trick inversion)
 IO_BYTES_PER_OP = 32 + 64 + 33  # scalar + affine point in, SEC1 compressed out
 SYNTH_STREAM = 3
+# What the implemented algorithm (GLV split, 2 x 32 signed 4-bit digits, effective-affine table, shared inversion) really
+# executes, from ncu (profiles/r1d_*): IMAD.WIDE warp instructions x 32 / lanes.  Used for `pipe_utilisation` only.
+EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 4_429}
+# DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1d_*)
+LADDER_DRAM_BYTES_PER_LANE = 1_223  # 2^22-lane launch: 4.68 GB read + 0.45 GB written
+# canonical IMUL32 per operation of the secondary configurations
+CANON_OTHER = {"secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
 
 
 # ------------------------------------------------------------------------------------------
@@ -197,6 +204,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=1 << 24, help="lanes per GPU (default 2^24 = the named configuration)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development)")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary configurations (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -259,6 +267,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = evs[0].elapsed_time(evs[-1])
     kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    # per-kernel durations of the same step, live: one more (untimed) step with CUDA events between the three kernels
+    eng.stage_timing(True)
+    step()
+    torch.cuda.synchronize()
+    ms_prep, ms_lad, ms_fin, chunks = eng.stage_ms()
+    eng.stage_timing(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,6 +307,47 @@ def main():
         e2e = {"value": world * n * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 96,
                "d2h_bytes_per_step": n * 34, "steps": e2e_steps, "timer": "host wall clock around the synchronous fec_batch_mul call",
                "matches_device_resident_run": same}
+
+    # ---- the other configurations of BASELINE.json, device-resident, a few repetitions each (reported, not the headline)
+    others = None
+    if not args.no_others:
+        others = {}
+        m = min(n, 1 << 22)
+        d_o = torch.empty(m * 65, dtype=torch.uint8, device=dev)
+
+        def timed(fn, reps=3):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps * 1e-3
+
+        runs = {
+            "secp256k1_kG": lambda: eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, None, m, d_o, stream=sp),
+            "x25519": lambda: eng.batch_x25519_dev(d_k, d_r, m, d_o, stream=sp),
+            "ed25519_keygen": lambda: eng.batch_ed25519_pubkey_dev(d_k, True, m, d_o, stream=sp),
+        }
+        for name, fn in runs.items():
+            t = timed(fn)
+            others[name] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m,
+                            "imad_frac": CANON_OTHER[name] * m / t / imad_peak}
+        # P-256 needs scalars below its own order and points on its own curve
+        d_k2 = torch.empty(m * 32, dtype=torch.uint8, device=dev)
+        d_p2 = torch.empty(m * 64, dtype=torch.uint8, device=dev)
+        eng.synth_dev(2, 5, 0, first_lane, m, d_k2, edge=True, stream=sp)
+        t = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k2, None, m, d_p2, out_fmt=fec.OUT_AFFINE_XY_BE, stream=sp))
+        others["p256_kG"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "imad_frac": CANON_OTHER["p256_kG"] * m / t / imad_peak}
+        t = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, stream=sp))
+        others["p256_kP"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "imad_frac": CANON_OTHER["p256_kP"] * m / t / imad_peak}
+        if world > 1:
+            for v in others.values():  # max-over-ranks time -> min over ranks of the rate
+                tv = torch.tensor([v["value"], v["imad_frac"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(tv, op=dist.ReduceOp.MIN)
+                v["value"], v["imad_frac"] = float(tv[0]), float(tv[1])
+        del d_o, d_k2, d_p2
 
     if rank != 0:
         if world > 1:
@@ -331,6 +386,18 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = CANON_IMUL32_PER_OP * n / kernel_s
+    stage_total = ms_prep + ms_lad + ms_fin
+    lanes_per_launch = n / max(chunks, 1)
+    ladder_ms = ms_lad / max(chunks, 1)
+    stages = {
+        "kernels": ["k_glv_prep", "k_glv_ladder", "k_glv_finish"], "launches_per_step": 3 * chunks, "lanes_per_launch": lanes_per_launch,
+        "ms_per_step": [ms_prep, ms_lad, ms_fin], "share_of_step": [ms_prep / stage_total, ms_lad / stage_total, ms_fin / stage_total],
+        "executed_imul32_per_op": EXEC_IMUL32_PER_OP,
+        # IMAD.WIDE instructions the kernels really issue / measured IMAD.WIDE issue rate: how busy the multiply pipe is
+        "pipe_utilisation": {"ladder": EXEC_IMUL32_PER_OP["ladder"] * n / (ms_lad * 1e-3) / imad_peak,
+                             "step": sum(EXEC_IMUL32_PER_OP.values()) * n / kernel_s / imad_peak},
+        "source": "CUDA events between the kernels of one extra step (fec_ctx_stage_timing); instruction counts from ncu, profiles/",
+    }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -339,14 +406,19 @@ def main():
                    "lanes_per_gpu": n, "sharding": "contiguous lane ranges, one rank per GPU, no collective on the data path",
                    "l2": "inputs 1.5 GiB + outputs 0.55 GiB per step exceed the 126 MB L2; no flush needed"},
         "roofline": {"bound": "imad", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMUL32/s", "frac": achieved / imad_peak,
-                     "traffic": None, "kernel": "k_wmul_var<CurveK1>", "kernel_ms": kernel_s * 1e3,
-                     "algorithmic_imul32_per_op": CANON_IMUL32_PER_OP,
+                     "traffic": LADDER_DRAM_BYTES_PER_LANE * lanes_per_launch,
+                     "traffic_note": "k_glv_ladder, bytes per launch, from one ncu --set full capture (profiles/); its algorithmic "
+                                     "traffic is 64 table entries x 64 B + 36 B in + 96 B out = 4.2 KB per lane, most of it served by L2",
+                     "kernel": "k_glv_prep + k_glv_ladder + k_glv_finish (the canonical figure covers the whole operation; "
+                               "k_glv_ladder dominates, see stages)",
+                     "kernel_ms": kernel_s * 1e3, "dominant_kernel_ms_per_launch": ladder_ms,
+                     "algorithmic_imul32_per_op": CANON_IMUL32_PER_OP, "stages": stages,
                      "peak_source": "fec_imad_peak measured in this run (IMUL32/s): " +
                                     f"IMAD.WIDE.U32 {peak_wide:.4g}, IMAD+IMAD.HI pairs {peak_lohi:.4g}, chained IMAD.WIDE.U32.X {peak_chain:.4g}",
                      "hbm": {"bound": "hbm", "achieved": IO_BYTES_PER_OP * n / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": IO_BYTES_PER_OP * n / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_op": IO_BYTES_PER_OP}},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world, "other_configs": others, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

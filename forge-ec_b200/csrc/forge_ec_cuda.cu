@@ -39,6 +39,10 @@ struct Device {
 }  // namespace
 
 struct fec_ctx {
+  // per-stage timing of the secp256k1 k*P kernels (fec_ctx_stage_timing): events of the calls made while enabled
+  bool stage_timing = false;
+  std::vector<cudaEvent_t> stage_ev;
+  int stage_used = 0;
   std::vector<Device> devs;
   std::mutex mu;
   std::atomic<uint64_t> launches{0};
@@ -108,6 +112,7 @@ void device_free(Device& d) {
   cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels);
 }
 
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- launches on device pointers ------------------------------------------------------
@@ -122,7 +127,19 @@ int launch_mul(fec_ctx* ctx, Device& d, int curve, int sem, const uint8_t* ds, c
     FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
   } else {
     int launches = 0;
-    const cudaError_t e = wmul_var_launch(curve, d.sms, st, ds, dp, pfmt, n, ofmt, dout, dst, &launches);
+    StageEvents se{nullptr, 0, 0}, *sep = nullptr;
+    if (ctx->stage_timing && curve == FEC_SECP256K1) {
+      const int need = 4 * (int)((n + GLV_CHUNK_LANES - 1) / GLV_CHUNK_LANES);
+      while ((int)ctx->stage_ev.size() < ctx->stage_used + need) {
+        cudaEvent_t ev;
+        FEC_CUDA(ctx, cudaEventCreate(&ev));
+        ctx->stage_ev.push_back(ev);
+      }
+      se = StageEvents{ctx->stage_ev.data() + ctx->stage_used, need, 0};
+      sep = &se;
+    }
+    const cudaError_t e = wmul_var_launch(curve, d.sms, st, ds, dp, pfmt, n, ofmt, dout, dst, &launches, sep);
+    if (sep != nullptr) ctx->stage_used += se.used / 4 * 4;
     ctx->launches += (uint64_t)launches;
     FEC_CUDA(ctx, e);
   }
@@ -295,6 +312,7 @@ void fec_ctx_destroy(fec_ctx* ctx) {
   int prev = 0;
   cudaGetDevice(&prev);
   for (auto& d : ctx->devs) device_free(d);
+  for (cudaEvent_t ev : ctx->stage_ev) cudaEventDestroy(ev);
   cudaSetDevice(prev);
   delete ctx;
 }
@@ -330,6 +348,33 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
                       (cudaStream_t)stream);
   cudaSetDevice(prev);
   return rc;
+}
+
+// Development / measurement aid (bench.py): while enabled, the secp256k1 k*P path records CUDA events between its
+// three kernels for calls made through fec_batch_mul_dev.  fec_ctx_stage_ms waits for them and returns the summed
+// milliseconds of {prepare, ladder, finish} and the number of timed chunks, then forgets them.
+int fec_ctx_stage_timing(fec_ctx* ctx, int enable) {
+  if (ctx == nullptr) return FEC_ERR_INVALID_ARG;
+  ctx->stage_timing = enable != 0;
+  ctx->stage_used = 0;
+  return FEC_OK;
+}
+int fec_ctx_stage_ms(fec_ctx* ctx, double ms[3], int* chunks) {
+  if (ctx == nullptr || ms == nullptr) return FEC_ERR_INVALID_ARG;
+  ms[0] = ms[1] = ms[2] = 0.0;
+  int c = 0;
+  for (int i = 0; i + 3 < ctx->stage_used; i += 4) {
+    FEC_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[(size_t)i + 3]));
+    for (int s = 0; s < 3; s++) {
+      float t = 0.f;
+      FEC_CUDA(ctx, cudaEventElapsedTime(&t, ctx->stage_ev[(size_t)i + s], ctx->stage_ev[(size_t)i + s + 1]));
+      ms[s] += (double)t;
+    }
+    c++;
+  }
+  if (chunks) *chunks = c;
+  ctx->stage_used = 0;
+  return FEC_OK;
 }
 
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {

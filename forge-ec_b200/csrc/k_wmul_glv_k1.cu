@@ -148,7 +148,7 @@ cudaError_t wmul_glv_setup_k1() {
 
 // n lanes in chunks of at most `chunk` lanes over one stream-ordered scratch allocation
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
-                               uint8_t* out, uint8_t* status, size_t chunk, int* launches) {
+                               uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se) {
   if (n == 0) return cudaSuccess;
   const size_t cap = n < chunk ? n : chunk;
   uint8_t* base = nullptr;
@@ -162,13 +162,20 @@ cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const ui
   sc.flags = sc.kk + cap * 8;
   const int osz = out_size(out_fmt);
   const int psz = points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64;
+  auto mark = [&]() {
+    if (se != nullptr && se->used < se->cap) cudaEventRecord(se->ev[se->used++], st);
+  };
   for (size_t off = 0; off < n; off += cap) {
     const size_t m = (n - off) < cap ? (n - off) : cap;
+    mark();
     k_glv_prep<<<(unsigned)((m + GLV_PREP_THREADS - 1) / GLV_PREP_THREADS), GLV_PREP_THREADS, 0, st>>>(
         scalars + off * 32, points + off * psz, points_fmt, m, sc);
+    mark();
     k_glv_ladder<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, GLV_LAD_SMEM, st>>>(m, sc);
+    mark();
     k_glv_finish<<<(unsigned)((m + GLV_FIN_THREADS - 1) / GLV_FIN_THREADS), GLV_FIN_THREADS, GLV_FIN_SMEM, st>>>(
         m, sc, out_fmt, out + off * osz, status ? status + off : nullptr);
+    mark();
     if (launches) *launches += 3;
   }
   e = cudaGetLastError();

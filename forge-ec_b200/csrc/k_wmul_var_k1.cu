@@ -18,8 +18,8 @@ static bool var_mono() {
   return v;
 }
 cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* s, const uint8_t* p, int pf, size_t n, int of,
-                            uint8_t* o, uint8_t* status, int* launches) {
-  if (curve == FEC_SECP256K1 && !var_mono()) return wmul_glv_launch_k1(st, s, p, pf, n, of, o, status, GLV_CHUNK_LANES, launches);
+                            uint8_t* o, uint8_t* status, int* launches, StageEvents* se) {
+  if (curve == FEC_SECP256K1 && !var_mono()) return wmul_glv_launch_k1(st, s, p, pf, n, of, o, status, GLV_CHUNK_LANES, launches, se);
   if (launches) *launches += 1;
   return curve == FEC_SECP256K1 ? wmul_var_launch_k1(sms, st, s, p, pf, n, of, o, status)
                                 : wmul_var_launch_p256(sms, st, s, p, pf, n, of, o, status);

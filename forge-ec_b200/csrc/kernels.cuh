@@ -133,13 +133,18 @@ inline int persistent_grid(int sms, int blocks_per_sm, size_t tiles) {
 
 // ---- launchers (defined in the k_*.cu files); each returns cudaGetLastError() ----------------
 cudaError_t wmul_var_setup();
+// optional per-stage timing of the three-kernel k*P path: 4 events per chunk (start, after prepare, after ladder, after finish)
+struct StageEvents {
+  cudaEvent_t* ev;  // capacity `cap` events, `used` of them recorded
+  int cap, used;
+};
 cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt,
-                            size_t n, int out_fmt, uint8_t* out, uint8_t* status, int* launches);
+                            size_t n, int out_fmt, uint8_t* out, uint8_t* status, int* launches, StageEvents* se);
 // secp256k1 k*P as prepare / ladder / finish kernels over a stream-ordered scratch allocation (k_wmul_glv_k1.cu)
 constexpr size_t GLV_CHUNK_LANES = size_t(1) << 22;
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
-                               uint8_t* out, uint8_t* status, size_t chunk, int* launches);
+                               uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t wmul_fixed_setup();

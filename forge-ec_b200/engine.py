@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "fec_ctx_create", "fec_ctx_destroy", "fec_ctx_device_count", "fec_ctx_launch_count", "fec_strerror",
     "fec_ctx_last_cuda_error", "fec_batch_mul", "fec_batch_mul_dev", "fec_batch_x25519", "fec_batch_x25519_dev",
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
-    "fec_imad_peak", "fec_synth_dev", "fec_shard_range",
+    "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
 )
 
 
@@ -89,6 +89,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_synth_dev.restype = ip
     lib.fec_shard_range.argtypes = [sz, ip, ip, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     lib.fec_shard_range.restype = None
+    lib.fec_ctx_stage_timing.argtypes = [vp, ip]
+    lib.fec_ctx_stage_timing.restype = ip
+    lib.fec_ctx_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+    lib.fec_ctx_stage_ms.restype = ip
     _LIB = lib
     return lib
 
@@ -170,6 +174,17 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.fec_ctx_launch_count(self._ctx))
+
+    def stage_timing(self, enable: bool):
+        """record CUDA events between the three secp256k1 k*P kernels of the following batch_mul_dev calls"""
+        self._check(self._lib.fec_ctx_stage_timing(self._ctx, int(bool(enable))))
+
+    def stage_ms(self):
+        """(ms_prepare, ms_ladder, ms_finish, chunks) summed over the calls made since stage_timing(True)"""
+        ms = (ctypes.c_double * 3)()
+        chunks = ctypes.c_int(0)
+        self._check(self._lib.fec_ctx_stage_ms(self._ctx, ms, ctypes.byref(chunks)))
+        return ms[0], ms[1], ms[2], chunks.value
 
     # -- host-buffer entry points -----------------------------------------------------
     def batch_mul(self, curve: int, scalars, points=None, *, n: Optional[int] = None, out_fmt: int = OUT_SEC1_COMPRESSED,

@@ -131,6 +131,12 @@ int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_
  * Returns multiply-add *instructions* per second over the whole device. */
 int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec);
 
+/* Measurement aid: while enabled, fec_batch_mul_dev(FEC_SECP256K1, points != NULL) records CUDA events between its three
+ * kernels (prepare / ladder / finish).  fec_ctx_stage_ms waits for them, returns the summed milliseconds per stage and
+ * the number of timed chunks, and forgets them. */
+int fec_ctx_stage_timing(fec_ctx* ctx, int enable);
+int fec_ctx_stage_ms(fec_ctx* ctx, double ms[3], int* chunks);
+
 /* Synthetic benchmark inputs: Philox-4x32-10, key "forge-ec", counter = (lane, block, stream_id);
  * lane i of the call is global lane first_lane + i and receives 32 bytes (blocks 2*sub, 2*sub+1).
  * mode 0: raw bytes; mode 1 / 2: big-endian scalar below the secp256k1 / P-256 group order (what

@@ -281,3 +281,25 @@ def test_forge_quirk_mode_replays_the_reference_literally(engine, fec, pm):
         with pytest.raises(fec.FecError):
             engine.batch_mul(args[0], args[1], args[2], sem=fec.SEM_FORGE_QUIRK,
                              points_fmt=fec.PT_SEC1_COMPRESSED if args[2] is not None else fec.PT_AFFINE_XY_BE)
+
+
+def test_multi_device_context_shards_lanes(fec, pm):
+    """fec_ctx_create over every visible device: contiguous lane shards, one host thread and pipeline per device,
+    results identical to the single-device run (skipped on a one-GPU box)."""
+    import torch
+    g = torch.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 5000 + 1024 * g
+    k = pm.random_scalars_be(0, n, stream=3)
+    r = pm.random_scalars_be(0, n, stream=3, sub=1, edge=False)
+    with fec.Engine() as one, fec.Engine(devices=list(range(g))) as many:
+        assert many.device_count == g
+        pts, _ = one.batch_mul(0, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+        a, sa = one.batch_mul(0, k, pts)
+        b, sb = many.batch_mul(0, k, pts)
+        assert a.tobytes() == b.tobytes() and sa.tobytes() == sb.tobytes()
+        assert many.batch_x25519(k).tobytes() == one.batch_x25519(k).tobytes()
+        assert many.batch_ed25519_pubkey(k).tobytes() == one.batch_ed25519_pubkey(k).tobytes()
+        exp, est = pm.batch_mul(0, k[:64].tobytes(), pts[:64].tobytes(), 64, 0)
+        assert b[:64].tobytes() == exp and sb[:64].tobytes() == est
