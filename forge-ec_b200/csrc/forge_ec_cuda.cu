@@ -80,11 +80,14 @@ int device_init(fec_ctx* ctx, Device& d) {
   FEC_CUDA(ctx, cudaMalloc(&d.comb[0], COMB_WORDS * 4));
   FEC_CUDA(ctx, cudaMalloc(&d.comb[1], COMB_WORDS * 4));
   FEC_CUDA(ctx, cudaMalloc(&d.niels, NIELS_WORDS * 4));
-  FEC_CUDA(ctx, build_comb_launch(FEC_SECP256K1, d.streams[0], d.comb[0]));
-  FEC_CUDA(ctx, build_comb_launch(FEC_P256, d.streams[0], d.comb[1]));
-  FEC_CUDA(ctx, build_niels_launch(d.streams[0], d.niels));
-  ctx->launches += 3;
+  u32* bases = nullptr;  // window bases, only needed while the tables are built
+  FEC_CUDA(ctx, cudaMalloc(&bases, (size_t)COMB_WINDOWS * 32 * 4 * 3));
+  FEC_CUDA(ctx, build_comb_launch(FEC_SECP256K1, d.streams[0], d.comb[0], bases));
+  FEC_CUDA(ctx, build_comb_launch(FEC_P256, d.streams[0], d.comb[1], bases + COMB_WINDOWS * 32));
+  FEC_CUDA(ctx, build_niels_launch(d.streams[0], d.niels, bases + COMB_WINDOWS * 64));
+  ctx->launches += 6;
   FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[0]));
+  cudaFree(bases);
   return FEC_OK;
 }
 

@@ -11,11 +11,8 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* _
                  uint8_t* __restrict__ out) {
   typedef Fe25519 F;
   extern __shared__ __align__(16) u32 smem[];
-  u32* scratch = smem + NIELS_WORDS;
-  for (int i = threadIdx.x; i < NIELS_WORDS / 4; i += ED_THREADS)
-    reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(niels_g)[i];
-  __syncthreads();
-  SmemNiels niels{smem};
+  u32* scratch = smem;
+  GlobalNiels niels{niels_g};
   const size_t ntiles = (n + ED_THREADS - 1) / ED_THREADS;
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const size_t lane = tile * ED_THREADS + threadIdx.x;
@@ -45,14 +42,27 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* _
   }
 }
 
-__global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g) {
-  const int e = blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(32) k_build_niels_bases(u32* __restrict__ bases) {
+  if (threadIdx.x >= COMB_WINDOWS) return;
+  EdExt Bi;
+  ed_comb_base(Bi, (int)threadIdx.x);
+  u32* o = bases + threadIdx.x * 32;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { o[w] = Bi.X[w]; o[8 + w] = Bi.Y[w]; o[16 + w] = Bi.Z[w]; o[24 + w] = Bi.T[w]; }
+}
+__global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g, const u32* __restrict__ bases) {
+  const size_t e = (size_t)blockIdx.x * 128 + threadIdx.x;
+  const int i = (int)(e / COMB_ENTRIES), j = (int)(e % COMB_ENTRIES);
+  EdExt Bi;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    Bi.X[w] = bases[i * 32 + w]; Bi.Y[w] = bases[i * 32 + 8 + w]; Bi.Z[w] = bases[i * 32 + 16 + w]; Bi.T[w] = bases[i * 32 + 24 + w];
+  }
   u32 a[8], b[8], c[8];
-  ed_comb_entry(a, b, c, e >> 3, e & 7);
-  u32* o = niels_g + (size_t)e * NIELS_STRIDE;
+  ed_comb_entry(a, b, c, Bi, j);
+  u32* o = niels_g + e * 24;
 #pragma unroll
   for (int w = 0; w < 8; w++) { o[w] = a[w]; o[8 + w] = b[w]; o[16 + w] = c[w]; }
-  o[24] = o[25] = o[26] = o[27] = 0u;
 }
 
 
@@ -65,8 +75,9 @@ cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int inpu
   k_ed25519_pubkey<<<g, ED_THREADS, ED_SMEM_BYTES, st>>>(in, input_is_seed, niels, n, out);
   return cudaGetLastError();
 }
-cudaError_t build_niels_launch(cudaStream_t st, u32* niels) {
-  k_build_niels<<<4, 128, 0, st>>>(niels);
+cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases) {
+  k_build_niels_bases<<<1, 32, 0, st>>>(bases);
+  k_build_niels<<<(unsigned)((size_t)COMB_WINDOWS * COMB_ENTRIES / 128), 128, 0, st>>>(niels, bases);
   return cudaGetLastError();
 }
 

@@ -14,13 +14,9 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
              uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
   typedef typename C::F F;
   extern __shared__ __align__(16) u32 smem[];
-  u32* comb_s = smem;
-  uint8_t* io = reinterpret_cast<uint8_t*>(smem + COMB_WORDS);
-  BlockInv<F, FIX_THREADS / 32> inv{smem + COMB_WORDS + FIX_IO_BYTES / 4};
-  for (int i = threadIdx.x; i < COMB_WORDS / 4; i += FIX_THREADS)
-    reinterpret_cast<uint4*>(comb_s)[i] = reinterpret_cast<const uint4*>(comb_g)[i];
-  __syncthreads();
-  SmemComb comb{comb_s};
+  uint8_t* io = reinterpret_cast<uint8_t*>(smem);
+  BlockInv<F, FIX_THREADS / 32> inv{smem + FIX_IO_BYTES / 4};
+  GlobalComb comb{comb_g};
   const int osz = out_size(out_fmt);
   const size_t ntiles = (n + FIX_THREADS - 1) / FIX_THREADS;
   for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -49,21 +45,33 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
   }
 }
 
-// comb table construction (context set-up): one thread per entry, 512 entries
+// comb table construction (context set-up): the 16 window bases, then one thread per entry
 template <class C>
-__global__ void __launch_bounds__(128) k_build_comb(u32* __restrict__ comb_g) {
+__global__ void __launch_bounds__(32) k_build_comb_bases(u32* __restrict__ bases) {
+  if (threadIdx.x >= COMB_WINDOWS) return;
+  u32 bx[8], by[8];
+  comb_base<C>(bx, by, (int)threadIdx.x);
+  u32* o = bases + threadIdx.x * 16;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { o[w] = bx[w]; o[8 + w] = by[w]; }
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_build_comb(u32* __restrict__ comb_g, const u32* __restrict__ bases) {
   typedef typename C::F F;
   __shared__ u32 scratch[INV_SCRATCH_WORDS];
-  const int e = blockIdx.x * 128 + threadIdx.x;  // 0..511
+  const size_t e = (size_t)blockIdx.x * 128 + threadIdx.x;  // (window, entry); the grid covers the table exactly
+  const int i = (int)(e / COMB_ENTRIES), j = (int)(e % COMB_ENTRIES);
+  u32 bx[8], by[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) { bx[w] = bases[i * 16 + w]; by[w] = bases[i * 16 + 8 + w]; }
   Jac R;
-  comb_entry_jac<C>(R, e >> 3, e & 7);
+  comb_entry_jac<C>(R, bx, by, j);
   u32 zi[8], x[8], y[8];
   block_batch_inv<F, 4>(zi, R.Z, scratch);
   jac_to_affine<C>(x, y, R, zi, 0u);
-  u32* o = comb_g + (size_t)e * COMB_STRIDE;
+  u32* o = comb_g + e * 16;
 #pragma unroll
   for (int w = 0; w < 8; w++) { o[w] = x[w]; o[8 + w] = y[w]; }
-  o[16] = o[17] = o[18] = o[19] = 0u;
 }
 
 template <class C>
@@ -78,15 +86,16 @@ cudaError_t wmul_fixed_launch_t(int sms, cudaStream_t st, const uint8_t* scalars
   return cudaGetLastError();
 }
 template <class C>
-cudaError_t build_comb_launch_t(cudaStream_t st, u32* comb) {
-  k_build_comb<C><<<4, 128, 0, st>>>(comb);
+cudaError_t build_comb_launch_t(cudaStream_t st, u32* comb, u32* bases) {
+  k_build_comb_bases<C><<<1, 32, 0, st>>>(bases);
+  k_build_comb<C><<<(unsigned)((size_t)COMB_WINDOWS * COMB_ENTRIES / 128), 128, 0, st>>>(comb, bases);
   return cudaGetLastError();
 }
 cudaError_t wmul_fixed_setup_k1();
 cudaError_t wmul_fixed_setup_p256();
 cudaError_t wmul_fixed_launch_k1(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
 cudaError_t wmul_fixed_launch_p256(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
-cudaError_t build_comb_launch_k1(cudaStream_t, u32*);
-cudaError_t build_comb_launch_p256(cudaStream_t, u32*);
+cudaError_t build_comb_launch_k1(cudaStream_t, u32*, u32*);
+cudaError_t build_comb_launch_p256(cudaStream_t, u32*, u32*);
 
 }  // namespace fec

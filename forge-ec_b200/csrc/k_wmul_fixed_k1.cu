@@ -5,7 +5,7 @@ cudaError_t wmul_fixed_launch_k1(int sms, cudaStream_t st, const uint8_t* s, con
                                  uint8_t* status) {
   return wmul_fixed_launch_t<CurveK1>(sms, st, s, comb, n, of, o, status);
 }
-cudaError_t build_comb_launch_k1(cudaStream_t st, u32* comb) { return build_comb_launch_t<CurveK1>(st, comb); }
+cudaError_t build_comb_launch_k1(cudaStream_t st, u32* comb, u32* bases) { return build_comb_launch_t<CurveK1>(st, comb, bases); }
 cudaError_t wmul_fixed_setup() {
   cudaError_t e = wmul_fixed_setup_k1();
   return e != cudaSuccess ? e : wmul_fixed_setup_p256();
@@ -15,7 +15,7 @@ cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t
   return curve == FEC_SECP256K1 ? wmul_fixed_launch_k1(sms, st, s, comb, n, of, o, status)
                                 : wmul_fixed_launch_p256(sms, st, s, comb, n, of, o, status);
 }
-cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb) {
-  return curve == FEC_SECP256K1 ? build_comb_launch_k1(st, comb) : build_comb_launch_p256(st, comb);
+cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb, u32* bases) {
+  return curve == FEC_SECP256K1 ? build_comb_launch_k1(st, comb, bases) : build_comb_launch_p256(st, comb, bases);
 }
 }  // namespace fec

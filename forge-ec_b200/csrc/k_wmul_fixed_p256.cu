@@ -5,5 +5,5 @@ cudaError_t wmul_fixed_launch_p256(int sms, cudaStream_t st, const uint8_t* s, c
                                    uint8_t* status) {
   return wmul_fixed_launch_t<CurveP256>(sms, st, s, comb, n, of, o, status);
 }
-cudaError_t build_comb_launch_p256(cudaStream_t st, u32* comb) { return build_comb_launch_t<CurveP256>(st, comb); }
+cudaError_t build_comb_launch_p256(cudaStream_t st, u32* comb, u32* bases) { return build_comb_launch_t<CurveP256>(st, comb, bases); }
 }  // namespace fec

@@ -74,32 +74,29 @@ struct BlockInv {
   u32* scratch;
   __device__ __forceinline__ void operator()(u32 zi[8], const u32 z[8]) { block_batch_inv<F, WARPS>(zi, z, scratch); }
 };
-// fixed-base comb in shared memory: entry (i,j) at word (i*8+j)*STRIDE; STRIDE = 20 words keeps the
-// eight rows of one window on disjoint banks for 128-bit reads
-constexpr int COMB_STRIDE = 20;
-constexpr int COMB_WORDS = 64 * 8 * COMB_STRIDE;
-struct SmemComb {
+// fixed-base tables in global memory (L2-resident): entry (i,j) = (2j+1) 2^(16 i) G at word ((i * COMB_ENTRIES) + j) * 16
+// (affine X, Y; four 128-bit loads), Niels entries (y+x, y-x, 2dxy) at stride 24 words (six 128-bit loads)
+constexpr size_t COMB_WORDS = (size_t)COMB_WINDOWS * COMB_ENTRIES * 16;
+struct GlobalComb {
   const u32* base;
   __device__ __forceinline__ void operator()(int i, u32 idx, u32 x[8], u32 y[8]) const {
-    const uint4* e = reinterpret_cast<const uint4*>(base + (size_t)(i * 8 + idx) * COMB_STRIDE);
-    uint4 a = e[0], b = e[1], c = e[2], d = e[3];
+    const uint4* e = reinterpret_cast<const uint4*>(base + ((size_t)i * COMB_ENTRIES + idx) * 16);
+    const uint4 a = __ldg(e), b = __ldg(e + 1), c = __ldg(e + 2), d = __ldg(e + 3);
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
     y[0] = c.x; y[1] = c.y; y[2] = c.z; y[3] = c.w; y[4] = d.x; y[5] = d.y; y[6] = d.z; y[7] = d.w;
   }
 };
-constexpr int NIELS_STRIDE = 28;
-constexpr int NIELS_WORDS = 64 * 8 * NIELS_STRIDE;
-struct SmemNiels {
+constexpr size_t NIELS_WORDS = (size_t)COMB_WINDOWS * COMB_ENTRIES * 24;
+struct GlobalNiels {
   const u32* base;
   __device__ __forceinline__ void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const {
-    const uint4* e = reinterpret_cast<const uint4*>(base + (size_t)(i * 8 + idx) * NIELS_STRIDE);
-    uint4 v0 = e[0], v1 = e[1], v2 = e[2], v3 = e[3], v4 = e[4], v5 = e[5];
+    const uint4* e = reinterpret_cast<const uint4*>(base + ((size_t)i * COMB_ENTRIES + idx) * 24);
+    const uint4 v0 = __ldg(e), v1 = __ldg(e + 1), v2 = __ldg(e + 2), v3 = __ldg(e + 3), v4 = __ldg(e + 4), v5 = __ldg(e + 5);
     a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
     b[0] = v2.x; b[1] = v2.y; b[2] = v2.z; b[3] = v2.w; b[4] = v3.x; b[5] = v3.y; b[6] = v3.z; b[7] = v3.w;
     c[0] = v4.x; c[1] = v4.y; c[2] = v4.z; c[3] = v4.w; c[4] = v5.x; c[5] = v5.y; c[6] = v5.z; c[7] = v5.w;
   }
 };
-
 
 // ---- tile geometry ----------------------------------------------------------------------
 constexpr int INV_SCRATCH_WORDS = 2 * 16 * 8 + 8;  // block_batch_inv scratch, enough for 16 warps
@@ -114,12 +111,12 @@ constexpr int VAR_SMEM_BYTES = (VAR_THREADS / 32) * VAR_IO_BYTES_PER_WARP;
 constexpr int FIX_THREADS = 256;
 constexpr int FIX_BLOCKS_PER_SM = 2;
 constexpr int FIX_IO_BYTES = 65 * FIX_THREADS + 16;
-constexpr int FIX_SMEM_BYTES = COMB_WORDS * 4 + FIX_IO_BYTES + INV_SCRATCH_WORDS * 4;
+constexpr int FIX_SMEM_BYTES = FIX_IO_BYTES + INV_SCRATCH_WORDS * 4;
 constexpr int X_THREADS = 256;
 constexpr int X_BLOCKS_PER_SM = 2;
 constexpr int ED_THREADS = 256;
 constexpr int ED_BLOCKS_PER_SM = 2;
-constexpr int ED_SMEM_BYTES = NIELS_WORDS * 4 + INV_SCRATCH_WORDS * 4;
+constexpr int ED_SMEM_BYTES = INV_SCRATCH_WORDS * 4;
 constexpr int FB_THREADS = 256;
 constexpr int PEAK_THREADS = 256;
 constexpr int PEAK_CHAINS = 8;
@@ -154,8 +151,8 @@ cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, cons
 cudaError_t ed25519_setup();
 cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int input_is_seed, const u32* niels, size_t n,
                            uint8_t* out);
-cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb);
-cudaError_t build_niels_launch(cudaStream_t st, u32* niels);
+cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb, u32* bases /* COMB_WINDOWS x 16 words scratch */);
+cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases /* COMB_WINDOWS x 32 words scratch */);
 cudaError_t field_bench_launch(int sms, cudaStream_t st, int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
                                size_t lanes, int iters);
 cudaError_t imad_peak_launch(int variant, int blocks, cudaStream_t st, u32* sink, u32 seed, int trips);

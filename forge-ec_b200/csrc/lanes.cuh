@@ -7,7 +7,7 @@
 //   wmul_var_core                 variable-base k*P, short Weierstrass, 4-bit signed window
 //                                 (batched replacement of Curve::multiply,
 //                                  forge-ec-curves/src/secp256k1.rs:2635-2692, p256.rs:2120-2156)
-//   wmul_fixed_core               fixed-base k*G from a 64 x 8 comb table of odd multiples
+//   wmul_fixed_core               fixed-base k*G from a 16 x 32768 table of odd multiples (16-bit signed windows)
 //   x25519_core                   RFC 7748 ladder (curve25519.rs:1624-1716)
 //   ed25519_expand_seed / ed_comb_core / ed_encode
 //                                 RFC 8032 5.1.5 key generation (forge-ec-signature/src/eddsa.rs:450-509,
@@ -170,22 +170,44 @@ FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], T
 }
 
 // -------------------------------------------------------------------------------------
-// fixed base.  comb(i, idx, x, y) returns (2 idx + 1) 16^i G, affine.  63 mixed additions.
+// fixed base.  The same regular recoding with W-bit digits: d_i = 2 u_i - (2^W - 1), u_i the i-th W-bit chunk of
+// K = 2^255 + (k'-1)/2, so every digit is odd, |d_i| < 2^W, and the table holds the 2^(W-1) odd multiples of
+// 2^(W i) G per window.  With W = 16 that is 16 windows x 32768 affine points = 32 MiB per curve: it lives in HBM
+// and is served by the 126 MB L2, and a scalar multiplication is 15 mixed additions instead of the 63 of a 4-bit
+// comb.  comb(i, idx, x, y) returns (2 idx + 1) 2^(W i) G.
 // -------------------------------------------------------------------------------------
+constexpr int COMB_W = 16;
+constexpr int COMB_WINDOWS = 256 / COMB_W;
+constexpr int COMB_ENTRIES = 1 << (COMB_W - 1);
+template <int W>
+FEC_DEV void next_digit_w(u32 K[8], u32& idx, u32& sgn) {
+  const u32 u = K[7] >> (32 - W);
+#pragma unroll
+  for (int i = 7; i >= 1; i--) K[i] = (W == 32) ? K[i - 1] : funnel_l(K[i - 1], K[i], W & 31);
+  K[0] = (W == 32) ? 0u : (K[0] << (W & 31));
+  sgn = (u >> (W - 1)) - 1u;
+  idx = (u ^ sgn) & ((1u << (W - 1)) - 1u);
+}
 template <class C, class Comb>
 FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
   typedef typename C::F F;
-  u32 idx, sgn;
-  next_digit(K, idx, sgn);
-  comb(63, idx, Q.X, Q.Y);
+  u32 idx, sgn, nx[8], ny2[8];
+  next_digit_w<COMB_W>(K, idx, sgn);  // top digit: always positive
+  comb(COMB_WINDOWS - 1, idx, Q.X, Q.Y);
   set_small(Q.Z, 1u);
+  next_digit_w<COMB_W>(K, idx, sgn);
+  comb(COMB_WINDOWS - 2, idx, nx, ny2);
 #pragma unroll 1
-  for (int i = 62; i >= 0; i--) {
+  for (int i = COMB_WINDOWS - 2; i >= 0; i--) {
     u32 tx[8], ty[8], ny[8];
-    next_digit(K, idx, sgn);
-    comb(i, idx, tx, ty);
+    const u32 sg = sgn;
+    copy8(tx, nx); copy8(ty, ny2);
+    if (i > 0) {  // fetch the next addend while this addition runs
+      next_digit_w<COMB_W>(K, idx, sgn);
+      comb(i - 1, idx, nx, ny2);
+    }
     F::neg(ny, ty);
-    select8(ty, sgn, ny, ty);
+    select8(ty, sg, ny, ty);
     jac_madd_safe<C>(Q, tx, ty);
   }
 }
@@ -561,19 +583,26 @@ FEC_DEV void ed_scalar_prepare(u32 K[8], const u32 s[8]) {
   select8(t, even, t, s);
   recode_reg(K, t);
 }
-// Q = sum of 64 signed odd digits times the Niels comb: niels(i, idx, ypx, ymx, t2d) = (2 idx+1) 16^i B
+// Q = sum of COMB_WINDOWS signed odd digits times the Niels comb: niels(i, idx, ypx, ymx, t2d) = (2 idx+1) 2^(W i) B
 template <class Comb>
 FEC_DEV void ed_comb_core(EdExt& Q, u32 K[8], const Comb& niels) {
   typedef Fe25519 F;
   ed_set_identity(Q);
+  u32 idx, sgn, na[8], nb[8], nc[8];
+  next_digit_w<COMB_W>(K, idx, sgn);
+  niels(COMB_WINDOWS - 1, idx, na, nb, nc);
 #pragma unroll 1
-  for (int i = 63; i >= 0; i--) {
-    u32 idx, sgn, ypx[8], ymx[8], t2d[8], nt[8];
-    next_digit(K, idx, sgn);
-    niels(i, idx, ypx, ymx, t2d);
-    cswap8(ypx, ymx, sgn);
+  for (int i = COMB_WINDOWS - 1; i >= 0; i--) {
+    u32 ypx[8], ymx[8], t2d[8], nt[8];
+    const u32 sg = sgn;
+    copy8(ypx, na); copy8(ymx, nb); copy8(t2d, nc);
+    if (i > 0) {  // fetch the next addend while this addition runs
+      next_digit_w<COMB_W>(K, idx, sgn);
+      niels(i - 1, idx, na, nb, nc);
+    }
+    cswap8(ypx, ymx, sg);
     F::neg(nt, t2d);
-    select8(t2d, sgn, nt, t2d);
+    select8(t2d, sg, nt, t2d);
     ed_madd(Q, ypx, ymx, t2d);
   }
 }
@@ -592,40 +621,61 @@ FEC_DEV void ed_encode(u32 out_le[8], const EdExt& Q, const u32 zi[8]) {
 // -------------------------------------------------------------------------------------
 // comb table entries (context set-up only; control flow depends on the public indices i, j)
 // -------------------------------------------------------------------------------------
-// (2j+1) 16^i G, Jacobian
+// window base 2^(W i) G, affine (one Fermat inversion; 16 of them per curve)
 template <class C>
-FEC_DEV void comb_entry_jac(Jac& R, int i, int j) {
-  u32 gx[8], gy[8];
-  C::G(gx, gy);
-  copy8(R.X, gx); copy8(R.Y, gy); set_small(R.Z, 1u);
+FEC_DEV void comb_base(u32 bx[8], u32 by[8], int i) {
+  typedef typename C::F F;
+  Jac R;
+  C::G(R.X, R.Y);
+  set_small(R.Z, 1u);
+  for (int d = 0; d < COMB_W * i; d++) jac_dbl<C>(R);
+  u32 zi[8];
+  F::inv(zi, R.Z);
+  jac_to_affine<C>(bx, by, R, zi, 0u);
+}
+// (2j+1) (bx,by), Jacobian: MSB-first double-and-add over the COMB_W bits of 2j+1 (no exceptional case can occur:
+// the running multiple is >= 2 whenever the base is added)
+template <class C>
+FEC_DEV void comb_entry_jac(Jac& R, const u32 bx[8], const u32 by[8], int j) {
+  copy8(R.X, bx); copy8(R.Y, by); set_small(R.Z, 1u);
   const int m = 2 * j + 1;
-  int top = 3;
+  int top = COMB_W - 1;
   while (top > 0 && !((m >> top) & 1)) top--;
   for (int b = top - 1; b >= 0; b--) {
     jac_dbl<C>(R);
-    if ((m >> b) & 1) jac_madd<C>(R, gx, gy, 0u);
+    if ((m >> b) & 1) jac_madd<C>(R, bx, by, 0u);
   }
-  for (int d = 0; d < 4 * i; d++) jac_dbl<C>(R);
 }
-// (2j+1) 16^i B as a Niels triple (y+x, y-x, 2dxy), canonical limbs
-FEC_DEV void ed_comb_entry(u32 ypx[8], u32 ymx[8], u32 t2d[8], int i, int j) {
+// Ed25519 window base 2^(W i) B in extended coordinates with Z = 1
+FEC_DEV void ed_comb_base(EdExt& Bi, int i) {
   typedef Fe25519 F;
-  EdExt Bp, R;
-  ed_base(Bp.X, Bp.Y);
-  set_small(Bp.Z, 1u);
-  F::mul(Bp.T, Bp.X, Bp.Y);
-  R = Bp;
+  ed_base(Bi.X, Bi.Y);
+  set_small(Bi.Z, 1u);
+  F::mul(Bi.T, Bi.X, Bi.Y);
+  for (int d = 0; d < COMB_W * i; d++) {
+    EdExt c = Bi;
+    ed_add(Bi, c);
+  }
+  u32 zi[8], x[8], y[8];
+  F::inv(zi, Bi.Z);
+  F::mul(x, Bi.X, zi);
+  F::mul(y, Bi.Y, zi);
+  F::canon(Bi.X, x);
+  F::canon(Bi.Y, y);
+  set_small(Bi.Z, 1u);
+  F::mul(Bi.T, Bi.X, Bi.Y);
+}
+// (2j+1) Bi as a Niels triple (y+x, y-x, 2dxy), canonical limbs
+FEC_DEV void ed_comb_entry(u32 ypx[8], u32 ymx[8], u32 t2d[8], const EdExt& Bi, int j) {
+  typedef Fe25519 F;
+  EdExt R = Bi;
   const int m = 2 * j + 1;
-  int top = 3;
+  int top = COMB_W - 1;
   while (top > 0 && !((m >> top) & 1)) top--;
   for (int b = top - 1; b >= 0; b--) {
     EdExt c = R;
     ed_add(R, c);
-    if ((m >> b) & 1) ed_add(R, Bp);
-  }
-  for (int d = 0; d < 4 * i; d++) {
-    EdExt c = R;
-    ed_add(R, c);
+    if ((m >> b) & 1) ed_add(R, Bi);
   }
   u32 zi[8], x[8], y[8], t[8], d2[8];
   F::inv(zi, R.Z);

@@ -21,34 +21,28 @@ struct HostTab {
 template <class F> struct HostInv {
   void operator()(u32 zi[8], const u32 z[8]) { F::inv(zi, z); }
 };
+// the 16 x 32768 tables are far too large to build on the host for a test: entries are computed on demand with the
+// same routines the device table builders use (comb_base / comb_entry_jac, ed_comb_base / ed_comb_entry)
 template <class C> struct HostComb {
-  std::vector<u32> t;  // [64][8][16]
-  HostComb() : t(64 * 8 * 16) {
-    typedef typename C::F F;
-    for (int i = 0; i < 64; i++)
-      for (int j = 0; j < 8; j++) {
-        Jac R;
-        comb_entry_jac<C>(R, i, j);
-        u32 zi[8];
-        F::inv(zi, R.Z);
-        jac_to_affine<C>(&t[(i * 8 + j) * 16], &t[(i * 8 + j) * 16 + 8], R, zi, 0u);
-      }
+  u32 bases[COMB_WINDOWS][16];
+  HostComb() {
+    for (int i = 0; i < COMB_WINDOWS; i++) comb_base<C>(bases[i], bases[i] + 8, i);
   }
   void operator()(int i, u32 idx, u32 x[8], u32 y[8]) const {
-    copy8(x, &t[(i * 8 + idx) * 16]);
-    copy8(y, &t[(i * 8 + idx) * 16 + 8]);
+    typedef typename C::F F;
+    Jac R;
+    comb_entry_jac<C>(R, bases[i], bases[i] + 8, (int)idx);
+    u32 zi[8];
+    F::inv(zi, R.Z);
+    jac_to_affine<C>(x, y, R, zi, 0u);
   }
 };
 struct HostNiels {
-  std::vector<u32> t;  // [64][8][24]
-  HostNiels() : t(64 * 8 * 24) {
-    for (int i = 0; i < 64; i++)
-      for (int j = 0; j < 8; j++) ed_comb_entry(&t[(i * 8 + j) * 24], &t[(i * 8 + j) * 24 + 8], &t[(i * 8 + j) * 24 + 16], i, j);
+  EdExt bases[COMB_WINDOWS];
+  HostNiels() {
+    for (int i = 0; i < COMB_WINDOWS; i++) ed_comb_base(bases[i], i);
   }
-  void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const {
-    const u32* e = &t[(i * 8 + idx) * 24];
-    copy8(a, e); copy8(b, e + 8); copy8(c, e + 16);
-  }
+  void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const { ed_comb_entry(a, b, c, bases[i], (int)idx); }
 };
 
 template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
