@@ -6,39 +6,69 @@ namespace fec {
 // ======================================================================================
 // kernel: Ed25519 public keys  (config 5b)
 // ======================================================================================
+// Warp-independent tiles with a deferred warp-level inversion, as k_wmul_fixed (k_wmul_fixed.cuh).
+constexpr int ED_DEFER = 16;
 __global__ void __launch_bounds__(ED_THREADS, ED_BLOCKS_PER_SM)
 k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* __restrict__ niels_g, size_t n,
                  uint8_t* __restrict__ out) {
   typedef Fe25519 F;
-  extern __shared__ __align__(16) u32 smem[];
-  u32* scratch = smem;
   GlobalNiels niels{niels_g};
-  const size_t ntiles = (n + ED_THREADS - 1) / ED_THREADS;
-  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const size_t lane = tile * ED_THREADS + threadIdx.x;
-    const bool live = lane < n;
-    u32 s[8], K[8];
-    set_small(s, 1u);
-    if (live) {
-      if (input_is_seed) {
-        u32 w[8];
-        load_rec32_le(w, in + lane * 32);
-        uint8_t seed[32];
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const size_t ntiles = (n + 31) / 32;
+  const size_t gwarp = (size_t)blockIdx.x * (ED_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (ED_THREADS / 32);
+  u32 slots[ED_DEFER][32];  // X, Y, Z, prefix product
+  u32 acc[8];
+  int cnt = 0;
+  size_t first_tile_of_batch = 0;
+  set_small(acc, 1u);
+  for (size_t tile = gwarp;; tile += nwarps) {
+    const bool have = tile < ntiles;  // warp-uniform
+    if (have) {
+      const size_t lane = tile * 32 + lane_in_warp;
+      const bool live = lane < n;
+      u32 s[8], K[8];
+      set_small(s, 1u);
+      if (live) {
+        if (input_is_seed) {
+          u32 w[8];
+          load_rec32_le(w, in + lane * 32);
+          uint8_t seed[32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) seed[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-        ed25519_expand_seed(s, seed);
-      } else {
-        load_rec32_le(s, in + lane * 32);
+          for (int i = 0; i < 32; i++) seed[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+          ed25519_expand_seed(s, seed);
+        } else {
+          load_rec32_le(s, in + lane * 32);
+        }
       }
+      ed_scalar_prepare(K, s);
+      EdExt Q;
+      ed_comb_core(Q, K, niels);  // Z != 0 always (complete formulas)
+      if (cnt == 0) first_tile_of_batch = tile;
+      u32* sl = slots[cnt];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { sl[i] = Q.X[i]; sl[8 + i] = Q.Y[i]; sl[16 + i] = Q.Z[i]; sl[24 + i] = acc[i]; }
+      if (cnt == 0) copy8(acc, Q.Z); else F::mul(acc, acc, Q.Z);
+      cnt++;
     }
-    ed_scalar_prepare(K, s);
-    EdExt Q;
-    ed_comb_core(Q, K, niels);
-    u32 zi[8], o[8];
-    block_batch_inv<F, ED_THREADS / 32>(zi, Q.Z, scratch);  // Z != 0 always (complete formulas)
-    ed_encode(o, Q, zi);
-    if (live) store_rec32_le(out + lane * 32, o);
-    __syncthreads();
+    if (cnt == ED_DEFER || (!have && cnt > 0)) {
+      u32 inv[8];
+      warp_batch_inv<F>(inv, acc);
+#pragma unroll 1
+      for (int t = cnt - 1; t >= 0; t--) {
+        const u32* sl = slots[t];
+        EdExt Q;
+        u32 z[8], pre[8], zi[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { Q.X[i] = sl[i]; Q.Y[i] = sl[8 + i]; z[i] = sl[16 + i]; pre[i] = sl[24 + i]; }
+        if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
+        ed_encode(o, Q, zi);
+        const size_t lane = (first_tile_of_batch + (size_t)t * nwarps) * 32 + lane_in_warp;
+        if (lane < n) store_rec32_le(out + lane * 32, o);
+      }
+      cnt = 0;
+      set_small(acc, 1u);
+    }
+    if (!have) break;
   }
 }
 
@@ -66,13 +96,11 @@ __global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g, 
 }
 
 
-cudaError_t ed25519_setup() {
-  return cudaFuncSetAttribute(k_ed25519_pubkey, cudaFuncAttributeMaxDynamicSharedMemorySize, ED_SMEM_BYTES);
-}
+cudaError_t ed25519_setup() { return cudaSuccess; }
 cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int input_is_seed, const u32* niels, size_t n,
                            uint8_t* out) {
-  const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS - 1) / ED_THREADS);
-  k_ed25519_pubkey<<<g, ED_THREADS, ED_SMEM_BYTES, st>>>(in, input_is_seed, niels, n, out);
+  const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS * ED_DEFER - 1) / (ED_THREADS * ED_DEFER));
+  k_ed25519_pubkey<<<g, ED_THREADS, 0, st>>>(in, input_is_seed, niels, n, out);
   return cudaGetLastError();
 }
 cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases) {

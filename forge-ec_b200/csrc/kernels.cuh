@@ -108,15 +108,20 @@ constexpr int VAR_BLOCKS_PER_SM = FEC_VAR_BLOCKS_PER_SM;
 constexpr int VAR_TAB_BYTES = 8 * 16 * VAR_THREADS * 4;  // 64 KiB per block
 constexpr int VAR_IO_BYTES_PER_WARP = 65 * 32;           // per-warp staging of 33/65-byte records
 constexpr int VAR_SMEM_BYTES = (VAR_THREADS / 32) * VAR_IO_BYTES_PER_WARP;
-constexpr int FIX_THREADS = 256;
-constexpr int FIX_BLOCKS_PER_SM = 2;
-constexpr int FIX_IO_BYTES = 65 * FIX_THREADS + 16;
-constexpr int FIX_SMEM_BYTES = FIX_IO_BYTES + INV_SCRATCH_WORDS * 4;
+constexpr int FIX_THREADS = 128;
+#ifndef FEC_FIX_BLOCKS_PER_SM
+#define FEC_FIX_BLOCKS_PER_SM 3
+#endif
+constexpr int FIX_BLOCKS_PER_SM = FEC_FIX_BLOCKS_PER_SM;
+constexpr int FIX_IO_BYTES_PER_WARP = 65 * 32;  // per-warp staging of 33/65-byte records
+constexpr int FIX_SMEM_BYTES = (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP;
 constexpr int X_THREADS = 256;
 constexpr int X_BLOCKS_PER_SM = 2;
-constexpr int ED_THREADS = 256;
-constexpr int ED_BLOCKS_PER_SM = 2;
-constexpr int ED_SMEM_BYTES = INV_SCRATCH_WORDS * 4;
+constexpr int ED_THREADS = 128;
+#ifndef FEC_ED_BLOCKS_PER_SM
+#define FEC_ED_BLOCKS_PER_SM 3
+#endif
+constexpr int ED_BLOCKS_PER_SM = FEC_ED_BLOCKS_PER_SM;
 constexpr int FB_THREADS = 256;
 constexpr int PEAK_THREADS = 256;
 constexpr int PEAK_CHAINS = 8;
