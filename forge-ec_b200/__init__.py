@@ -24,7 +24,11 @@ from .engine import (  # noqa: F401
     LANE_OK,
     LANE_POINT_INVALID,
     LANE_SCALAR_RANGE,
+    KDF_HKDF_SHA256,
+    KDF_NONE,
+    KDF_XOR_INFO,
     OUT_AFFINE_XY_BE,
+    OUT_X_BE,
     OUT_SEC1_COMPRESSED,
     OUT_SEC1_UNCOMPRESSED,
     OUT_SIZE,

@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 
+#include "kdf.cuh"
 #include "kernels.cuh"
 
 // ======================================================================================
@@ -33,6 +34,7 @@ struct Device {
   uint8_t* buf_in_b[N_PIPE] = {};   // points / u / field b
   uint8_t* buf_out[N_PIPE] = {};
   uint8_t* buf_st[N_PIPE] = {};
+  uint8_t* buf_x[N_PIPE] = {};      // ECDH: the 32-byte shared secrets before key derivation
   bool pipe_ready = false;
 };
 
@@ -99,6 +101,7 @@ int device_pipe_init(fec_ctx* ctx, Device& d) {
     FEC_CUDA(ctx, cudaMalloc(&d.buf_in_b[s], CHUNK_LANES * 64));
     FEC_CUDA(ctx, cudaMalloc(&d.buf_out[s], CHUNK_LANES * 65 + 64));
     FEC_CUDA(ctx, cudaMalloc(&d.buf_st[s], CHUNK_LANES));
+    FEC_CUDA(ctx, cudaMalloc(&d.buf_x[s], CHUNK_LANES * 32));
   }
   d.pipe_ready = true;
   return FEC_OK;
@@ -109,7 +112,7 @@ void device_free(Device& d) {
   cudaSetDevice(d.id);
   for (int s = 0; s < N_PIPE; s++) {
     if (d.streams[s]) cudaStreamSynchronize(d.streams[s]);
-    cudaFree(d.buf_in_a[s]); cudaFree(d.buf_in_b[s]); cudaFree(d.buf_out[s]); cudaFree(d.buf_st[s]);
+    cudaFree(d.buf_in_a[s]); cudaFree(d.buf_in_b[s]); cudaFree(d.buf_out[s]); cudaFree(d.buf_st[s]); cudaFree(d.buf_x[s]);
     if (d.streams[s]) cudaStreamDestroy(d.streams[s]);
   }
   cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels);
@@ -148,6 +151,17 @@ int launch_mul(fec_ctx* ctx, Device& d, int curve, int sem, const uint8_t* ds, c
   }
   return FEC_OK;
 }
+// x(k*P) into `dx` (32 B per lane) with the lane status into `dst` (always needed: dead lanes give zero records), then the
+// key derivation into `dout`.  kdf == KDF_NONE: the shared secrets are the output.
+int launch_ecdh(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int kdf,
+                const uint8_t* info, int info_len, int out_len, uint8_t* dout, uint8_t* dst, uint8_t* dx, cudaStream_t st) {
+  if (n == 0) return FEC_OK;
+  int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, ds, dp, pfmt, n, 3, kdf == KDF_NONE ? dout : dx, dst, st);
+  if (rc || kdf == KDF_NONE) return rc;
+  ctx->launches++;
+  FEC_CUDA(ctx, kdf_launch(st, kdf, dx, dst, n, info, info_len, out_len, dout));
+  return FEC_OK;
+}
 int launch_x25519(fec_ctx* ctx, Device& d, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
@@ -170,12 +184,14 @@ int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int i
 
 // ---- host-buffer pipeline: H2D -> kernel -> D2H in CHUNK_LANES granules over N_PIPE streams ----
 struct HostJob {
-  int kind;  // 0 mul, 1 x25519, 2 ed25519
+  int kind;  // 0 mul, 1 x25519, 2 ed25519, 3 ecdh (mul + key derivation)
   int curve, sem, pfmt, ofmt, is_seed;
   const uint8_t* in_a; size_t rec_a;
   const uint8_t* in_b; size_t rec_b;
   uint8_t* out; size_t rec_out;
   uint8_t* status;
+  int kdf = 0, info_len = 0, out_len = 0;  // kind 3 only
+  const uint8_t* info = nullptr;
 };
 
 int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t count) {
@@ -198,6 +214,9 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
     if (job.kind == 0)
       rc = launch_mul(ctx, d, job.curve, job.sem, d.buf_in_a[slot], db, job.pfmt, m, job.ofmt, d.buf_out[slot],
                       job.status ? d.buf_st[slot] : nullptr, st);
+    else if (job.kind == 3)
+      rc = launch_ecdh(ctx, d, job.curve, d.buf_in_a[slot], db, job.pfmt, m, job.kdf, job.info, job.info_len, job.out_len,
+                       d.buf_out[slot], d.buf_st[slot], d.buf_x[slot], st);
     else if (job.kind == 1)
       rc = launch_x25519(ctx, d, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
     else
@@ -327,7 +346,7 @@ const char* fec_ctx_last_cuda_error(const fec_ctx* ctx) { return ctx ? ctx->last
 int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
                   fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status) {
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
   HostJob job{0, (int)curve, (int)sem, (int)points_fmt, (int)out_fmt, 0, scalars, 32, points,
@@ -340,7 +359,7 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
                       uint8_t* d_status, void* stream) {
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 2 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
@@ -378,6 +397,45 @@ int fec_ctx_stage_ms(fec_ctx* ctx, double ms[3], int* chunks) {
   if (chunks) *chunks = c;
   ctx->stage_used = 0;
   return FEC_OK;
+}
+
+static bool ecdh_args_ok(int curve, int pfmt, int kdf, const uint8_t* info, size_t info_len, size_t out_len) {
+  if (curve < 0 || curve > 1 || pfmt < 0 || pfmt > 1 || kdf < 0 || kdf > 2) return false;
+  if (kdf == KDF_NONE) return true;
+  return info_len <= (size_t)KDF_MAX_INFO && out_len >= 1 && out_len <= (size_t)KDF_MAX_OUT && (info != nullptr || info_len == 0);
+}
+int fec_batch_ecdh(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+                   fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len, uint8_t* out, uint8_t* status) {
+  if (ctx == nullptr || (n > 0 && (scalars == nullptr || points == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!ecdh_args_ok((int)curve, (int)points_fmt, (int)kdf, info, info_len, out_len)) return FEC_ERR_INVALID_ARG;
+  const size_t rec = kdf == FEC_KDF_NONE ? 32 : out_len;
+  HostJob job{3, (int)curve, FEC_SEM_STD, (int)points_fmt, 3, 0, scalars, 32, points,
+              (size_t)(points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64), out, rec, status};
+  job.kdf = (int)kdf; job.info = info; job.info_len = (int)info_len; job.out_len = (int)out_len;
+  return run_host_job(ctx, job, n);
+}
+int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+                       fec_points_fmt points_fmt, size_t n, fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len,
+                       uint8_t* d_out, uint8_t* d_status, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_points == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!ecdh_args_ok((int)curve, (int)points_fmt, (int)kdf, info, info_len, out_len)) return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  if (n == 0) return FEC_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* tmp = nullptr;  // shared secrets (kdf != NONE) and lane status when the caller wants none
+  const size_t xbytes = kdf == FEC_KDF_NONE ? 0 : n * 32, sbytes = d_status == nullptr ? (n + 15) / 16 * 16 : 0;
+  if (xbytes + sbytes > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp, xbytes + sbytes, st));
+  uint8_t* dx = tmp;
+  uint8_t* dst = d_status != nullptr ? d_status : tmp + xbytes;
+  int rc = launch_ecdh(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)kdf, info, (int)info_len, (int)out_len,
+                       d_out, dst, dx, st);
+  if (tmp != nullptr) cudaFreeAsync(tmp, st);
+  cudaSetDevice(prev);
+  return rc;
 }
 
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {

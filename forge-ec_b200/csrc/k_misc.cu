@@ -1,5 +1,6 @@
 // k_misc.cu -- field microbenchmark (config 2), multiply-pipe calibration, synthetic inputs
 #include "kernels.cuh"
+#include "kdf.cuh"
 
 namespace fec {
 
@@ -168,6 +169,34 @@ cudaError_t synth_launch(int sms, cudaStream_t st, uint8_t* out, size_t n, u32 s
                          unsigned long long first_lane, int mode, int edge) {
   const int g = persistent_grid(sms, 8, (n + 255) / 256);
   k_synth<<<g, 256, 0, st>>>(out, n, seed_lo, seed_hi, stream_id, sub, first_lane, mode, edge);
+  return cudaGetLastError();
+}
+
+// ======================================================================================
+// ECDH tail: key derivation from the 32-byte shared secrets (KeyExchange::derive_key)
+// ======================================================================================
+struct KdfInfo { uint8_t b[KDF_MAX_INFO]; };
+__global__ void __launch_bounds__(128)
+k_kdf(int kdf, const uint8_t* __restrict__ x_be, const uint8_t* __restrict__ status, size_t n, KdfInfo info, int info_len, int out_len,
+      uint8_t* __restrict__ out) {
+  const size_t lane = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (lane >= n) return;
+  u32 w[8], sec[8];
+  load_rec32_le(w, x_be + lane * 32);
+#pragma unroll
+  for (int i = 0; i < 8; i++) sec[i] = __byte_perm(w[i], 0, 0x0123);  // big-endian words of the byte string
+  uint8_t okm[KDF_MAX_OUT];
+  if (kdf == KDF_HKDF_SHA256) hkdf_sha256_x(okm, out_len, sec, info.b, info_len);
+  else kdf_xor_info(okm, out_len, sec, info.b, info_len);
+  const bool dead = status != nullptr && status[lane] != 0;
+  for (int i = 0; i < out_len; i++) out[lane * (size_t)out_len + i] = dead ? (uint8_t)0 : okm[i];
+}
+cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint8_t* status, size_t n, const uint8_t* info, int info_len,
+                       int out_len, uint8_t* out) {
+  if (n == 0) return cudaSuccess;
+  KdfInfo ib;
+  for (int i = 0; i < KDF_MAX_INFO; i++) ib.b[i] = i < info_len ? info[i] : (uint8_t)0;
+  k_kdf<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kdf, x_be, status, n, ib, info_len, out_len, out);
   return cudaGetLastError();
 }
 

@@ -51,7 +51,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, size
   for (size_t i = (nw << 2) + l; i < bytes; i += 32) dst[i] = src[i];
 }
 
-__host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : 64); }
+__host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : (fmt == 2 ? 64 : 32)); }
 
 // per-lane table of 8 affine points in shared memory, word-interleaved across the block:
 // word w of entry j of thread t at [(j*16 + w) * THREADS + t]  (conflict-free for any digits)
@@ -147,6 +147,9 @@ constexpr size_t GLV_CHUNK_LANES = size_t(1) << 22;
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);
+// ECDH tail: n x 32-byte big-endian x-coordinates -> n x out_len bytes (kdf.cuh); dead lanes (status != 0) give zero records
+cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint8_t* status, size_t n, const uint8_t* info, int info_len,
+                       int out_len, uint8_t* out);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t wmul_fixed_setup();

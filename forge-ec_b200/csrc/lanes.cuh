@@ -415,7 +415,8 @@ FEC_DEV void jac_to_affine(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u3
   F::canon(y, t);
 }
 
-// SEC1 / raw affine encodings.  fmt: 0 = 02|03 || X (33 B), 1 = 04 || X || Y (65 B), 2 = X || Y (64 B).
+// SEC1 / raw affine encodings.  fmt: 0 = 02|03 || X (33 B), 1 = 04 || X || Y (65 B), 2 = X || Y (64 B), 3 = X (32 B,
+// the ECDH shared secret of KeyExchange::derive_shared_secret, secp256k1.rs:1885-1905).
 // dead != 0 -> all-zero record (the reference's identity encoding, point.rs:41-47).
 FEC_DEV void sec1_encode(uint8_t* o, int fmt, const u32 x[8], const u32 y[8], u32 dead) {
   u32 xx[8], yy[8];
@@ -428,9 +429,11 @@ FEC_DEV void sec1_encode(uint8_t* o, int fmt, const u32 x[8], const u32 y[8], u3
     o[0] = (uint8_t)(4u & ~dead);
     store_be32(o + 1, xx);
     store_be32(o + 33, yy);
-  } else {
+  } else if (fmt == 2) {
     store_be32(o, xx);
     store_be32(o + 32, yy);
+  } else {
+    store_be32(o, xx);
   }
 }
 

@@ -10,8 +10,9 @@ import numpy as np
 
 CURVE_SECP256K1, CURVE_P256 = 0, 1
 PRIME_SECP256K1, PRIME_P256, PRIME_25519 = 0, 1, 2
-OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE = 0, 1, 2
-OUT_SIZE = {0: 33, 1: 65, 2: 64}
+OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE = 0, 1, 2, 3
+KDF_NONE, KDF_HKDF_SHA256, KDF_XOR_INFO = 0, 1, 2
+OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32}
 PT_AFFINE_XY_BE, PT_SEC1_COMPRESSED = 0, 1
 PT_SIZE = {0: 64, 1: 33}
 SEM_STD, SEM_FORGE_QUIRK = 0, 1
@@ -23,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "fec_ctx_last_cuda_error", "fec_batch_mul", "fec_batch_mul_dev", "fec_batch_x25519", "fec_batch_x25519_dev",
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
+    "fec_batch_ecdh", "fec_batch_ecdh_dev",
 )
 
 
@@ -89,6 +91,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_synth_dev.restype = ip
     lib.fec_shard_range.argtypes = [sz, ip, ip, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     lib.fec_shard_range.restype = None
+    lib.fec_batch_ecdh.argtypes = [vp, ip, u8, u8, ip, sz, ip, ctypes.c_char_p, sz, sz, u8, u8]
+    lib.fec_batch_ecdh.restype = ip
+    lib.fec_batch_ecdh_dev.argtypes = [vp, ip, ip, u8, u8, ip, sz, ip, ctypes.c_char_p, sz, sz, u8, u8, vp]
+    lib.fec_batch_ecdh_dev.restype = ip
     lib.fec_ctx_stage_timing.argtypes = [vp, ip]
     lib.fec_ctx_stage_timing.restype = ip
     lib.fec_ctx_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
@@ -208,6 +214,25 @@ class Engine:
         """Same call on raw HOST addresses (e.g. pinned torch tensors): nothing is allocated or copied here."""
         self._check(self._lib.fec_batch_mul(self._ctx, curve, SEM_STD, scalars_ptr, points_ptr, points_fmt, n, out_fmt, out_ptr,
                                             status_ptr))
+
+    def batch_ecdh(self, curve: int, scalars, points, *, n: Optional[int] = None, kdf: int = KDF_NONE, info: bytes = b"",
+                   out_len: int = 32, points_fmt: int = PT_AFFINE_XY_BE):
+        """x(k_i*P_i) followed by the reference's key derivation.  Returns (out[n, 32 | out_len] uint8, status[n])."""
+        if n is None:
+            n = (scalars.nbytes if isinstance(scalars, np.ndarray) else len(scalars)) // 32
+        s = _host_in(scalars, n, 32, "scalars")
+        p = _host_in(points, n, PT_SIZE[points_fmt], "points")
+        rec = 32 if kdf == KDF_NONE else out_len
+        out = np.empty((n, rec), dtype=np.uint8)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.fec_batch_ecdh(self._ctx, curve, _ptr(s), _ptr(p), points_fmt, n, kdf, bytes(info), len(info), out_len,
+                                             _ptr(out), _ptr(st)))
+        return out, st
+
+    def batch_ecdh_dev(self, curve: int, d_scalars, d_points, n: int, d_out, d_status=None, *, kdf: int = KDF_NONE,
+                       info: bytes = b"", out_len: int = 32, points_fmt: int = 0, stream: int = 0, dev_index: int = 0):
+        self._check(self._lib.fec_batch_ecdh_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, kdf,
+                                                 bytes(info), len(info), out_len, _ptr(d_out), _ptr(d_status), stream))
 
     def batch_x25519(self, scalars, us=None, *, n: Optional[int] = None) -> np.ndarray:
         if n is None:

@@ -8,6 +8,8 @@ PointAffine::to_bytes[_with_format] (lib.rs:606-632)   AffinePoint.to_bytes(), .
 (new) BatchMul::batch_mul                              Secp256k1.batch_mul(points, scalars)
 x25519(scalar,u) (curve25519.rs:1624)                  x25519(scalar, u); batch_x25519(scalars, us)
 Ed25519Signature::derive_public_key (eddsa.rs:450)     Ed25519Signature.derive_public_key(seed)
+KeyExchange::derive_shared_secret / derive_key          Secp256k1.derive_shared_secret(k, P), .derive_key(secret, info, n),
+  (secp256k1.rs:1846-1905, p256.rs:2281-2344)            .batch_ecdh(scalars, points, info, out_len)   (new, batched)
 
 Every call goes to the GPU through the C ABI; single-point calls are batches of one.
 """
@@ -107,6 +109,32 @@ class _WeierstrassCurve:
     def to_affine(p: AffinePoint) -> AffinePoint:
         return p  # results already come back normalised (batch inversion on the device)
 
+    # ---- KeyExchange (secp256k1.rs:1843-1906, p256.rs:2278-2345) ------------------------------------------
+    KDF = _e.KDF_HKDF_SHA256
+
+    @classmethod
+    def batch_ecdh(cls, scalars: Sequence[Scalar], points: Sequence[AffinePoint], info: Optional[bytes] = None, out_len: int = 32,
+                   engine: Optional[_e.Engine] = None):
+        """derive_shared_secret (info is None) or derive_key(derive_shared_secret(..), info, out_len) for every pair.
+        Raises ValueError where the reference returns Err (scalar out of range, invalid public key, identity)."""
+        eng = engine or default_engine()
+        n = len(scalars)
+        s = np.frombuffer(b"".join(k.be for k in scalars), dtype=np.uint8)
+        p = np.frombuffer(b"".join(q.xy for q in points), dtype=np.uint8)
+        out, st = eng.batch_ecdh(cls.CURVE_ID, s, p, n=n, kdf=_e.KDF_NONE if info is None else cls.KDF, info=info or b"",
+                                 out_len=out_len)
+        if np.any(st == _e.LANE_SCALAR_RANGE):
+            raise ValueError("InvalidScalar")
+        if np.any(st == _e.LANE_POINT_INVALID):
+            raise ValueError("InvalidPublicKey")
+        if np.any(st == _e.LANE_INFINITY):
+            raise ValueError("KeyExchangeError")
+        return [out[i].tobytes() for i in range(n)]
+
+    @classmethod
+    def derive_shared_secret(cls, private_key: Scalar, public_key: AffinePoint, engine: Optional[_e.Engine] = None) -> bytes:
+        return cls.batch_ecdh([private_key], [public_key], None, 32, engine)[0]
+
 
 class Secp256k1(_WeierstrassCurve):
     CURVE_ID = _e.CURVE_SECP256K1
@@ -114,6 +142,7 @@ class Secp256k1(_WeierstrassCurve):
 
 class P256(_WeierstrassCurve):
     CURVE_ID = _e.CURVE_P256
+    KDF = _e.KDF_XOR_INFO  # the reference's P-256 derive_key is a placeholder (p256.rs:2314-2344)
 
 
 def batch_x25519(scalars: Sequence[bytes], us: Optional[Sequence[bytes]] = None, engine: Optional[_e.Engine] = None):

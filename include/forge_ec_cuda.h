@@ -51,8 +51,14 @@ typedef enum { FEC_PRIME_SECP256K1 = 0, FEC_PRIME_P256 = 1, FEC_PRIME_25519 = 2 
 typedef enum {
   FEC_OUT_SEC1_COMPRESSED = 0,   /* 33 B: 02|03 || X          (PointFormat::Compressed)   */
   FEC_OUT_SEC1_UNCOMPRESSED = 1, /* 65 B: 04 || X || Y        (PointFormat::Uncompressed) */
-  FEC_OUT_AFFINE_XY_BE = 2       /* 64 B: X || Y, big-endian  (FieldElement::to_bytes x2) */
+  FEC_OUT_AFFINE_XY_BE = 2,      /* 64 B: X || Y, big-endian  (FieldElement::to_bytes x2) */
+  FEC_OUT_X_BE = 3               /* 32 B: X, big-endian       (the ECDH shared secret, secp256k1.rs:1885-1905) */
 } fec_out;
+typedef enum {
+  FEC_KDF_NONE = 0,        /* the 32-byte shared secret itself (KeyExchange::derive_shared_secret)                       */
+  FEC_KDF_HKDF_SHA256 = 1, /* Secp256k1::derive_key: RFC 5869 HKDF-SHA-256, salt = 32 zero bytes (secp256k1.rs:1846-1883) */
+  FEC_KDF_XOR_INFO = 2     /* P256::derive_key: the reference's placeholder, secret XOR info (p256.rs:2314-2344)         */
+} fec_kdf;
 typedef enum { FEC_PT_AFFINE_XY_BE = 0 /* 64 B */, FEC_PT_SEC1_COMPRESSED = 1 /* 33 B */ } fec_points_fmt;
 typedef enum {
   FEC_SEM_STD = 0,        /* SEC2 / FIPS 186-4 / RFC 7748 / RFC 8032 results (what the reference specifies) */
@@ -103,6 +109,16 @@ int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* sca
 int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
                       const uint8_t* d_points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out,
                       uint8_t* d_status, void* stream);
+
+/* Batched ECDH: shared_i = x(k_i * P_i), 32 bytes big-endian, then the reference's key derivation.
+ * kdf == FEC_KDF_NONE: out = n x 32 B shared secrets; otherwise out = n x out_len bytes (1 <= out_len <= 64, info_len <= 256;
+ * `info` is host memory in both variants).  A lane whose scalar is out of range, whose point is invalid or whose result is
+ * the identity gets an all-zero record and its status byte (the reference returns Err for it). */
+int fec_batch_ecdh(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+                   fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len, uint8_t* out, uint8_t* status);
+int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+                       fec_points_fmt points_fmt, size_t n, fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len,
+                       uint8_t* d_out, uint8_t* d_status, void* stream);
 
 /* RFC 7748 X25519: scalars n x 32 B (clamped inside), u n x 32 B little-endian (NULL = base point 9),
  * out n x 32 B little-endian. */

@@ -156,8 +156,8 @@ def w_is_on_curve(c: WeierstrassCurve, P) -> bool:
 # identity -> 0x00 followed by zero padding)
 # --------------------------------------------------------------------------------------
 
-OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE = 0, 1, 2
-OUT_SIZE = {0: 33, 1: 65, 2: 64}
+OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE = 0, 1, 2, 3
+OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32}
 
 
 def sec1_encode(P, fmt: int = OUT_SEC1_COMPRESSED) -> bytes:
@@ -168,6 +168,8 @@ def sec1_encode(P, fmt: int = OUT_SEC1_COMPRESSED) -> bytes:
         return bytes([2 | (y & 1)]) + x.to_bytes(32, "big")
     if fmt == OUT_SEC1_UNCOMPRESSED:
         return b"\x04" + x.to_bytes(32, "big") + y.to_bytes(32, "big")
+    if fmt == OUT_X_BE:
+        return x.to_bytes(32, "big")
     return x.to_bytes(32, "big") + y.to_bytes(32, "big")
 
 
@@ -223,6 +225,51 @@ def batch_mul(curve, scalars: bytes, points: bytes | None, n: int, fmt: int = 0,
             st[i] = ST_INFINITY
         out[osz * i : osz * (i + 1)] = sec1_encode(R, fmt)
     return bytes(out), bytes(st)
+
+
+# --------------------------------------------------------------------------------------
+# Batched ECDH: KeyExchange::derive_shared_secret + derive_key (secp256k1.rs:1846-1905, p256.rs:2281-2344)
+# --------------------------------------------------------------------------------------
+KDF_NONE, KDF_HKDF_SHA256, KDF_XOR_INFO = 0, 1, 2
+
+
+def hkdf_sha256_zero_salt(secret: bytes, info: bytes, out_len: int) -> bytes:
+    """Secp256k1::derive_key: RFC 5869 with a salt of 32 zero bytes, restated with hashlib/hmac."""
+    import hashlib
+    import hmac
+    prk = hmac.new(bytes(32), secret, hashlib.sha256).digest()
+    okm, t, counter = b"", b"", 1
+    while len(okm) < out_len:
+        t = hmac.new(prk, t + info + bytes([counter]), hashlib.sha256).digest()
+        okm += t
+        counter += 1
+    return okm[:out_len]
+
+
+def kdf_xor_info(secret: bytes, info: bytes, out_len: int) -> bytes:
+    """P256::derive_key: the reference's placeholder (p256.rs:2314-2344)."""
+    okm = bytearray(out_len)
+    for i, b in enumerate(secret):
+        if i < out_len:
+            okm[i] ^= b
+    for i, b in enumerate(info):
+        if i < out_len:
+            okm[i] ^= b
+    return bytes(okm)
+
+
+def batch_ecdh(curve, scalars: bytes, points: bytes, n: int, kdf: int = KDF_NONE, info: bytes = b"", out_len: int = 32,
+               points_fmt: int = 0):
+    """Model of fec_batch_ecdh: returns (out_bytes, status_bytes); rejected lanes give zero records."""
+    xs, st = batch_mul(curve, scalars, points, n, OUT_X_BE, points_fmt)
+    if kdf == KDF_NONE:
+        return xs, st
+    out = bytearray(n * out_len)
+    for i in range(n):
+        if st[i] == 0:
+            f = hkdf_sha256_zero_salt if kdf == KDF_HKDF_SHA256 else kdf_xor_info
+            out[out_len * i : out_len * (i + 1)] = f(xs[32 * i : 32 * i + 32], info, out_len)
+    return bytes(out), st
 
 
 # --------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include "../../forge-ec_b200/csrc/lanes.cuh"
 #include "../../forge-ec_b200/csrc/glv3.cuh"
 #include "../../forge-ec_b200/csrc/quirk_k1.cuh"
+#include "../../forge-ec_b200/csrc/kdf.cuh"
 
 using namespace fec;
 
@@ -132,6 +133,13 @@ void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t*
   else field_op<Fe25519>(op, a, b, o);
 }
 int hs_quirk_k1(const uint8_t* k_be, const uint8_t* xy_be, int ofmt, uint8_t* out) { return quirk::q_lane(k_be, xy_be, ofmt, out); }
+void hs_kdf(int kdf, const uint8_t* secret32, const uint8_t* info, int info_len, int out_len, uint8_t* okm) {
+  u32 sec[8];
+  for (int i = 0; i < 8; i++)
+    sec[i] = ((u32)secret32[4 * i] << 24) | ((u32)secret32[4 * i + 1] << 16) | ((u32)secret32[4 * i + 2] << 8) | secret32[4 * i + 3];
+  if (kdf == KDF_HKDF_SHA256) hkdf_sha256_x(okm, out_len, sec, info, info_len);
+  else kdf_xor_info(okm, out_len, sec, info, info_len);
+}
 void hs_set_var_impl(int use_vm) { g_use_vm = use_vm != 0; }
 int hs_wmul(int curve, const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {
   return curve == 0 ? wmul<CurveK1>(k_be, pt, pfmt, fixed, ofmt, out) : wmul<CurveP256>(k_be, pt, pfmt, fixed, ofmt, out);

@@ -303,3 +303,43 @@ def test_multi_device_context_shards_lanes(fec, pm):
         assert many.batch_ed25519_pubkey(k).tobytes() == one.batch_ed25519_pubkey(k).tobytes()
         exp, est = pm.batch_mul(0, k[:64].tobytes(), pts[:64].tobytes(), 64, 0)
         assert b[:64].tobytes() == exp and sb[:64].tobytes() == est
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_batched_ecdh_matches_model(engine, fec, pm, curve):
+    """x(k*P) + the reference's key derivations, against the model (hashlib HKDF); both parties of an
+    exchange derive the same key; rejected lanes give zero records and their status."""
+    c = pm.CURVES[curve]
+    n = 300
+    a = pm.random_scalars_be(curve, n, stream=6, edge=False)
+    b = pm.random_scalars_be(curve, n, stream=6, sub=1, edge=False)
+    A, _ = engine.batch_mul(curve, a, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    B, _ = engine.batch_mul(curve, b, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    s1, st1 = engine.batch_ecdh(curve, a, B)
+    s2, st2 = engine.batch_ecdh(curve, b, A)
+    assert s1.tobytes() == s2.tobytes() and not st1.any() and not st2.any()
+    exp, est = pm.batch_ecdh(curve, a[:40].tobytes(), B[:40].tobytes(), 40)
+    assert s1[:40].tobytes() == exp
+    xs, _ = engine.batch_mul(curve, a, B, out_fmt=fec.OUT_X_BE)          # the 32-byte output format on its own
+    assert xs.tobytes() == s1.tobytes()
+    for kdf, info, out_len in ((fec.KDF_HKDF_SHA256, b"forge-ec ecdh test", 32), (fec.KDF_HKDF_SHA256, b"", 64),
+                               (fec.KDF_HKDF_SHA256, bytes(range(200)), 48), (fec.KDF_XOR_INFO, b"info", 40)):
+        k1, _ = engine.batch_ecdh(curve, a, B, kdf=kdf, info=info, out_len=out_len)
+        k2, _ = engine.batch_ecdh(curve, b, A, kdf=kdf, info=info, out_len=out_len)
+        assert k1.tobytes() == k2.tobytes()
+        exp, _ = pm.batch_ecdh(curve, a[:40].tobytes(), B[:40].tobytes(), 40, kdf, info, out_len)
+        assert k1[:40].tobytes() == exp
+    # rejected lanes: scalar >= n, scalar 0, point off the curve; compressed public keys
+    bad_k = np.frombuffer(_be(c.n) + _be(0) + _be(5) + _be(7), dtype=np.uint8).reshape(4, 32)
+    pts = np.concatenate([B[:2], np.frombuffer(_be(2) + _be(2), dtype=np.uint8).reshape(1, 64), B[3:4]])
+    out, st = engine.batch_ecdh(curve, bad_k, pts, kdf=fec.KDF_HKDF_SHA256, info=b"x", out_len=32)
+    exp, est = pm.batch_ecdh(curve, bad_k.tobytes(), pts.tobytes(), 4, fec.KDF_HKDF_SHA256, b"x", 32)
+    assert out.tobytes() == exp and st.tobytes() == est and st.tolist() == [1, 3, 2, 0]
+    comp, _ = engine.batch_mul(curve, b, None)
+    k3, _ = engine.batch_ecdh(curve, a, comp, kdf=fec.KDF_HKDF_SHA256, info=b"c", out_len=32, points_fmt=fec.PT_SEC1_COMPRESSED)
+    k4, _ = engine.batch_ecdh(curve, a, B, kdf=fec.KDF_HKDF_SHA256, info=b"c", out_len=32)
+    assert k3.tobytes() == k4.tobytes()
+    # the trait mirror
+    cls = fec.Secp256k1 if curve == 0 else fec.P256
+    sec = cls.derive_shared_secret(fec.Scalar(a[0].tobytes()), fec.AffinePoint(B[0].tobytes()), engine)
+    assert sec == s1[0].tobytes()

@@ -141,6 +141,22 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.ed25519_pubkey(k, False)
 
 
+def test_device_kdf_code_on_host_matches_model(hostsim, pm):
+    """SHA-256 / HMAC / HKDF of csrc/kdf.cuh (compiled for the host) against hashlib/hmac, incl. RFC 5869 test case 3-like
+    shapes: empty info, info that crosses block boundaries, every output length up to 64."""
+    import random
+    rnd = random.Random(3)
+    for info_len in (0, 1, 22, 23, 31, 32, 54, 55, 56, 64, 100, 119, 120, 256):
+        secret = bytes(rnd.randrange(256) for _ in range(32))
+        info = bytes(rnd.randrange(256) for _ in range(info_len))
+        for out_len in (1, 16, 31, 32, 33, 48, 64):
+            o = ctypes.create_string_buffer(out_len)
+            hostsim.hs_kdf(1, secret, info, info_len, out_len, o)
+            assert o.raw == pm.hkdf_sha256_zero_salt(secret, info, out_len), (info_len, out_len)
+            hostsim.hs_kdf(2, secret, info, info_len, out_len, o)
+            assert o.raw == pm.kdf_xor_info(secret, info, out_len)
+
+
 def test_quirk_device_code_on_host_matches_literal_oracle(hostsim, pm):
     """FEC_SEM_FORGE_QUIRK (csrc/quirk_k1.cuh, compiled for the host) against oracle/ref, the literal restatement
     of forge-ec's own secp256k1 code, and against the transliteration goldens of SURVEY.md Appendix A.2."""
