@@ -21,8 +21,13 @@ constexpr int GLV_LAD_THREADS = 128;
 #define FEC_GLV_LAD_BLOCKS 6
 #endif
 constexpr int GLV_LAD_SMEM = VS_COUNT * 32 * GLV_LAD_THREADS;
-constexpr int GLV_FIN_THREADS = 256;
-constexpr int GLV_FIN_SMEM = 65 * GLV_FIN_THREADS + 16 + INV_SCRATCH_WORDS * 4;
+constexpr int GLV_FIN_THREADS = 128;
+#ifndef FEC_GLV_FIN_BLOCKS
+#define FEC_GLV_FIN_BLOCKS 5
+#endif
+constexpr int GLV_FIN_BLOCKS = FEC_GLV_FIN_BLOCKS;
+constexpr int GLV_FIN_DEFER = 16;
+constexpr int GLV_FIN_SMEM = (GLV_FIN_THREADS / 32) * 65 * 32;
 
 struct GlvScratch {
   u32* tab;    // [lane][192]
@@ -99,38 +104,79 @@ k_glv_ladder(size_t n, GlvScratch sc) {
   }
 }
 
-__global__ void __launch_bounds__(GLV_FIN_THREADS, 2)
+// Warp-independent: every warp walks tiles of 32 lanes, applies the corrections, keeps the Jacobian results of
+// GLV_FIN_DEFER tiles in thread-local memory with the running product of their Z and then inverts once per warp
+// (Montgomery's trick along the tile axis; no __syncthreads, no idle warps while one lane set is being inverted).
+__global__ void __launch_bounds__(GLV_FIN_THREADS, GLV_FIN_BLOCKS)
 k_glv_finish(size_t n, GlvScratch sc, int out_fmt, uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
   typedef CurveK1 C;
   typedef FeK1 F;
   extern __shared__ __align__(16) u32 smem[];
-  uint8_t* io = reinterpret_cast<uint8_t*>(smem);
-  BlockInv<F, GLV_FIN_THREADS / 32> inv{smem + (65 * GLV_FIN_THREADS + 16) / 4};
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* io = reinterpret_cast<uint8_t*>(smem) + warp * (65 * 32);
   const int osz = out_size(out_fmt);
-  const size_t first = (size_t)blockIdx.x * GLV_FIN_THREADS;
-  const int cnt = (int)((n - first) < (size_t)GLV_FIN_THREADS ? (n - first) : (size_t)GLV_FIN_THREADS);
-  const bool live = (int)threadIdx.x < cnt;
-  const size_t lane = live ? first + threadIdx.x : first;
-  Jac Q;
-  u32 zs[8];
-  g_ld8(Q.X, sc.q + lane * 24); g_ld8(Q.Y, sc.q + lane * 24 + 8); g_ld8(Q.Z, sc.q + lane * 24 + 16);
-  g_ld8(zs, sc.zs + lane * 8);
-  const u32 fl = sc.flags[lane];
-  u32 st = (fl >> 8) & 0xFFu;
-  glv_finish(Q, sc.tab + lane * GLV_TAB_WORDS, zs, fl);
-  const u32 zz = F::is_zero(Q.Z);
-  st |= (st == 0u ? zz & LANE_INFINITY : 0u);
-  u32 z[8], zi[8], one[8], x[8], y[8];
-  set_small(one, 1u);
-  select8(z, (st != 0u) ? 0xFFFFFFFFu : 0u, one, Q.Z);
-  inv(zi, z);
-  jac_to_affine<C>(x, y, Q, zi, 0u);
-  if (live) sec1_encode(io + threadIdx.x * osz, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
-  __syncthreads();
-  block_copy(out + first * osz, io, (size_t)cnt * osz);
-  if (status != nullptr && live) status[lane] = (uint8_t)st;
+  const size_t ntiles = (n + 31) / 32;
+  const size_t gwarp = (size_t)blockIdx.x * (GLV_FIN_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (GLV_FIN_THREADS / 32);
+  u32 slots[GLV_FIN_DEFER][36];  // X, Y, Z, prefix product, status
+  u32 acc[8];
+  int cnt = 0;
+  size_t first_tile_of_batch = 0;
+  set_small(acc, 1u);
+  for (size_t tile = gwarp;; tile += nwarps) {
+    const bool have = tile < ntiles;  // warp-uniform
+    if (have) {
+      size_t lane = tile * 32 + lane_in_warp;
+      const bool live = lane < n;
+      if (!live) lane = n - 1;
+      Jac Q;
+      u32 zs[8];
+      g_ld8(Q.X, sc.q + lane * 24); g_ld8(Q.Y, sc.q + lane * 24 + 8); g_ld8(Q.Z, sc.q + lane * 24 + 16);
+      g_ld8(zs, sc.zs + lane * 8);
+      const u32 fl = sc.flags[lane];
+      u32 st = (fl >> 8) & 0xFFu;
+      glv_finish(Q, sc.tab + lane * GLV_TAB_WORDS, zs, fl);
+      const u32 zz = F::is_zero(Q.Z);
+      st |= (st == 0u ? zz & LANE_INFINITY : 0u);
+      if (status != nullptr && live) status[lane] = (uint8_t)st;
+      u32 one[8], z[8];
+      set_small(one, 1u);
+      select8(z, (st != 0u) ? 0xFFFFFFFFu : 0u, one, Q.Z);
+      if (cnt == 0) first_tile_of_batch = tile;
+      u32* s = slots[cnt];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { s[i] = Q.X[i]; s[8 + i] = Q.Y[i]; s[16 + i] = z[i]; s[24 + i] = acc[i]; }
+      s[32] = st;
+      if (cnt == 0) copy8(acc, z); else F::mul(acc, acc, z);
+      cnt++;
+    }
+    if (cnt == GLV_FIN_DEFER || (!have && cnt > 0)) {
+      u32 inv[8];
+      warp_batch_inv<F>(inv, acc);
+#pragma unroll 1
+      for (int t = cnt - 1; t >= 0; t--) {
+        const u32* s = slots[t];
+        Jac Q;
+        u32 z[8], pre[8], zi[8], x[8], y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { Q.X[i] = s[i]; Q.Y[i] = s[8 + i]; z[i] = s[16 + i]; pre[i] = s[24 + i]; }
+        const u32 st = s[32];
+        if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
+        jac_to_affine<C>(x, y, Q, zi, 0u);
+        const size_t first = (first_tile_of_batch + (size_t)t * nwarps) * 32;
+        const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+        __syncwarp();
+        if ((int)lane_in_warp < cnt_lanes) sec1_encode(io + lane_in_warp * osz, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
+        __syncwarp();
+        warp_copy(out + first * osz, io, (size_t)cnt_lanes * osz);
+      }
+      cnt = 0;
+      set_small(acc, 1u);
+    }
+    if (!have) break;
+  }
 }
 
+static int g_sms = 0;
 cudaError_t wmul_glv_setup_k1() {
   cudaError_t e = cudaFuncSetAttribute(k_glv_ladder, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_LAD_SMEM);
   if (e != cudaSuccess) return e;
@@ -139,6 +185,7 @@ cudaError_t wmul_glv_setup_k1() {
   // keep the scratch memory of earlier calls in the stream-ordered pool instead of returning it at every synchronisation
   int dev = 0;
   cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
   unsigned long long keep = ~0ull;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
@@ -146,6 +193,13 @@ cudaError_t wmul_glv_setup_k1() {
   return cudaFuncSetAttribute(k_glv_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_FIN_SMEM);
 }
 
+// persistent grid of the finish kernel: enough warps to fill the device, each warp defers GLV_FIN_DEFER tiles
+static unsigned fin_grid(size_t m) {
+  const size_t want = (m + (size_t)GLV_FIN_THREADS * GLV_FIN_DEFER - 1) / ((size_t)GLV_FIN_THREADS * GLV_FIN_DEFER);
+  const size_t cap = (size_t)(g_sms > 0 ? g_sms : 148) * GLV_FIN_BLOCKS;
+  const size_t g = want < cap ? want : cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
 // n lanes in chunks of at most `chunk` lanes over one stream-ordered scratch allocation
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se) {
@@ -173,7 +227,7 @@ cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const ui
     mark();
     k_glv_ladder<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, GLV_LAD_SMEM, st>>>(m, sc);
     mark();
-    k_glv_finish<<<(unsigned)((m + GLV_FIN_THREADS - 1) / GLV_FIN_THREADS), GLV_FIN_THREADS, GLV_FIN_SMEM, st>>>(
+    k_glv_finish<<<fin_grid(m), GLV_FIN_THREADS, GLV_FIN_SMEM, st>>>(
         m, sc, out_fmt, out + off * osz, status ? status + off : nullptr);
     mark();
     if (launches) *launches += 3;
