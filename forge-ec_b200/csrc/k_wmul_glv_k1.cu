@@ -18,7 +18,7 @@ namespace fec {
 constexpr int GLV_PREP_THREADS = 128;
 constexpr int GLV_LAD_THREADS = 128;
 #ifndef FEC_GLV_LAD_BLOCKS
-#define FEC_GLV_LAD_BLOCKS 6
+#define FEC_GLV_LAD_BLOCKS 5
 #endif
 constexpr int GLV_LAD_SMEM = VS_COUNT * 32 * GLV_LAD_THREADS;
 constexpr int GLV_FIN_THREADS = 128;

@@ -32,3 +32,11 @@ for lg in ((18, 20) if "SWEEP_LG" not in os.environ else ()):
             eng.batch_mul_dev(0, k[off*32:], P[off*64:], c, out[off*33:], stream=s.cuda_stream)
     dt = t(chunked, 1)
     print(f"2^24 in chunks of 2^{lg} on one stream: {N/dt/1e6:.2f} M/s", flush=True)
+if os.environ.get("SWEEP_STAGES"):
+    n = 1 << 22
+    eng.stage_timing(True)
+    eng.batch_mul_dev(0, k, P, n, out, stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    a, b, c, ch = eng.stage_ms()
+    eng.stage_timing(False)
+    print(f"stages at 2^22: prepare {a:.2f} ms, ladder {b:.2f} ms ({n/b/1e3:.1f} M/s), finish {c:.2f} ms", flush=True)
