@@ -242,6 +242,60 @@ FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   return (exc & 1u) | (exc & r_zero & 2u);
 }
 
+// P <- P + Q, both Jacobian: add-2007-bl (11M + 5S), every special case resolved by masks except P == Q, for which the
+// returned mask is set and P is left unchanged (the caller doubles under a warp-uniform branch: jac_add_safe).
+// Replaces `impl Add for ProjectivePoint` (secp256k1.rs:1447-1497, p256.rs:1941-2006) in reductions of many points.
+template <class C>
+FEC_DEV u32 jac_add(Jac& p, const Jac& q) {
+  typedef typename C::F F;
+  u32 Z1Z1[8], Z2Z2[8], U1[8], U2[8], S1[8], S2[8], H[8], I[8], J[8], r[8], V[8], t[8];
+  Jac o;
+  const u32 p_inf = F::is_zero(p.Z), q_inf = F::is_zero(q.Z);
+  F::sqr(Z1Z1, p.Z);
+  F::sqr(Z2Z2, q.Z);
+  F::mul(U1, p.X, Z2Z2);
+  F::mul(U2, q.X, Z1Z1);
+  F::mul(S1, q.Z, Z2Z2);
+  F::mul(S1, p.Y, S1);
+  F::mul(S2, p.Z, Z1Z1);
+  F::mul(S2, q.Y, S2);
+  F::sub(H, U2, U1);
+  F::sub(r, S2, S1);
+  const u32 h_zero = F::is_zero(H), r_zero = F::is_zero(r);
+  F::mul2(r, r);
+  F::mul2(I, H);
+  F::sqr(I, I);
+  F::mul(J, H, I);
+  F::mul(V, U1, I);
+  F::sqr(o.X, r);
+  F::sub(o.X, o.X, J);
+  F::sub(o.X, o.X, V);
+  F::sub(o.X, o.X, V);
+  F::sub(t, V, o.X);
+  F::mul(t, r, t);
+  F::mul(J, S1, J);
+  F::mul2(J, J);
+  F::sub(o.Y, t, J);
+  F::add(t, p.Z, q.Z);
+  F::sqr(t, t);
+  F::sub(t, t, Z1Z1);
+  F::sub(t, t, Z2Z2);
+  F::mul(o.Z, t, H);
+  const u32 both = ~p_inf & ~q_inf;
+  const u32 same = both & h_zero & r_zero;     // P == Q: doubling needed, keep P
+  const u32 opp = both & h_zero & ~r_zero;     // P == -Q: infinity
+  const u32 keep = q_inf | same;               // result is P
+  const u32 take_q = p_inf & ~q_inf;           // result is Q
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const u32 x = (p.X[i] & keep) | (q.X[i] & take_q) | (o.X[i] & ~keep & ~take_q);
+    const u32 y = (p.Y[i] & keep) | (q.Y[i] & take_q) | (o.Y[i] & ~keep & ~take_q);
+    const u32 z = (p.Z[i] & keep) | (q.Z[i] & take_q) | (o.Z[i] & ~keep & ~take_q & ~opp);
+    p.X[i] = x; p.Y[i] = y; p.Z[i] = z;
+  }
+  return same;
+}
+
 // y^2 == x^3 + a x + b  (mask)
 template <class C>
 FEC_DEV u32 on_curve(const u32 x[8], const u32 y[8]) {

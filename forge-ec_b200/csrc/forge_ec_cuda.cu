@@ -438,6 +438,104 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
   return rc;
 }
 
+// sum_i k_i * P_i on one device: products through the batched k*P path (affine X || Y + lane status), then the reduction
+static int msm_on_device(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
+                         uint8_t* dout, uint8_t* dstatus, cudaStream_t st) {
+  const int blocks = msm_blocks(d.sms, n);
+  const size_t xy_bytes = n * 64, st_bytes = (n + 15) / 16 * 16, sc_bytes = ((size_t)blocks * 24 + 4) * 4;
+  uint8_t* tmp = nullptr;
+  FEC_CUDA(ctx, cudaMallocAsync(&tmp, xy_bytes + st_bytes + sc_bytes, st));
+  int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, ds, dp, pfmt, n, FEC_OUT_AFFINE_XY_BE, tmp, tmp + xy_bytes, st);
+  if (rc == FEC_OK) {
+    ctx->launches += 2;
+    cudaError_t e = msm_reduce_launch(curve, d.sms, st, tmp, tmp + xy_bytes, n, reinterpret_cast<u32*>(tmp + xy_bytes + st_bytes), ofmt,
+                                      dout, dstatus);
+    if (e != cudaSuccess) {
+      snprintf(ctx->last_err, sizeof(ctx->last_err), "msm_reduce: %s", cudaGetErrorString(e));
+      rc = FEC_ERR_CUDA;
+    }
+  }
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+                fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || n == 0 || d_scalars == nullptr || d_points == nullptr || d_out == nullptr) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_scalars) || !aligned16(d_points)) return FEC_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  int rc = msm_on_device(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status, (cudaStream_t)stream);
+  cudaSetDevice(prev);
+  return rc;
+}
+// host buffers: every device of the context sums its contiguous lane range, the per-device sums are added on device 0
+int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+            fec_out out_fmt, uint8_t* out, uint8_t* status) {
+  if (ctx == nullptr || n == 0 || scalars == nullptr || points == nullptr || out == nullptr) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t G = ctx->devs.size();
+  const size_t psz = points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64;
+  std::vector<uint8_t> part(G * 64, 0), pst(G, (uint8_t)FEC_LANE_INFINITY);
+  std::vector<int> rcs(G, FEC_OK);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  auto shard = [&](size_t i) -> int {
+    size_t first = 0, count = 0;
+    fec_shard_range(n, (int)G, (int)i, &first, &count);
+    if (count == 0) return FEC_OK;
+    Device& d = ctx->devs[i];
+    FEC_CUDA(ctx, cudaSetDevice(d.id));
+    cudaStream_t st = d.streams[0];
+    uint8_t* buf = nullptr;
+    const size_t sb = count * 32, pb = (count * psz + 15) / 16 * 16;
+    FEC_CUDA(ctx, cudaMallocAsync(&buf, sb + pb + 128, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(buf, scalars + first * 32, sb, cudaMemcpyHostToDevice, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(buf + sb, points + first * psz, count * psz, cudaMemcpyHostToDevice, st));
+    int rc = msm_on_device(ctx, d, (int)curve, buf, buf + sb, (int)points_fmt, count, FEC_OUT_AFFINE_XY_BE, buf + sb + pb, buf + sb + pb + 64, st);
+    if (rc == FEC_OK) {
+      FEC_CUDA(ctx, cudaMemcpyAsync(&part[i * 64], buf + sb + pb, 64, cudaMemcpyDeviceToHost, st));
+      FEC_CUDA(ctx, cudaMemcpyAsync(&pst[i], buf + sb + pb + 64, 1, cudaMemcpyDeviceToHost, st));
+    }
+    cudaFreeAsync(buf, st);
+    FEC_CUDA(ctx, cudaStreamSynchronize(st));
+    return rc;
+  };
+  if (G == 1) {
+    rcs[0] = shard(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < G; i++) th.emplace_back([&, i]() { rcs[i] = shard(i); });
+    for (auto& t : th) t.join();
+  }
+  for (int rc : rcs) if (rc) { cudaSetDevice(prev); return rc; }
+  // combine: the G partial sums are G more "products" for the same reduction (status 3 = identity contributes nothing)
+  Device& d0 = ctx->devs[0];
+  FEC_CUDA(ctx, cudaSetDevice(d0.id));
+  cudaStream_t st = d0.streams[0];
+  uint8_t* buf = nullptr;
+  const size_t sc_off = (G * 64 + G + 15) / 16 * 16;
+  FEC_CUDA(ctx, cudaMallocAsync(&buf, sc_off + (24 + 4) * 4 + 128, st));
+  FEC_CUDA(ctx, cudaMemcpyAsync(buf, part.data(), G * 64, cudaMemcpyHostToDevice, st));
+  FEC_CUDA(ctx, cudaMemcpyAsync(buf + G * 64, pst.data(), G, cudaMemcpyHostToDevice, st));
+  uint8_t* dres = buf + sc_off + (24 + 4) * 4;
+  ctx->launches += 2;
+  FEC_CUDA(ctx, msm_reduce_launch((int)curve, 1, st, buf, buf + G * 64, G, reinterpret_cast<u32*>(buf + sc_off), (int)out_fmt, dres, dres + 80));
+  uint8_t hst = 0;
+  FEC_CUDA(ctx, cudaMemcpyAsync(out, dres, (size_t)out_size(out_fmt), cudaMemcpyDeviceToHost, st));
+  FEC_CUDA(ctx, cudaMemcpyAsync(&hst, dres + 80, 1, cudaMemcpyDeviceToHost, st));
+  cudaFreeAsync(buf, st);
+  FEC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (status) *status = hst;
+  cudaSetDevice(prev);
+  return FEC_OK;
+}
+
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
   HostJob job{1, 0, 0, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};

@@ -150,6 +150,10 @@ cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const ui
 // ECDH tail: n x 32-byte big-endian x-coordinates -> n x out_len bytes (kdf.cuh); dead lanes (status != 0) give zero records
 cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint8_t* status, size_t n, const uint8_t* info, int info_len,
                        int out_len, uint8_t* out);
+// multi-scalar multiplication tail: sum of n affine products (X || Y, 64 B) with their lane status -> one encoded point
+int msm_blocks(int sms, size_t n);
+cudaError_t msm_reduce_launch(int curve, int sms, cudaStream_t st, const uint8_t* xy, const uint8_t* lane_status, size_t n, u32* scratch,
+                              int out_fmt, uint8_t* out, uint8_t* status);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t wmul_fixed_setup();

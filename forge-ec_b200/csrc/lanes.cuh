@@ -112,6 +112,17 @@ FEC_DEV void jac_madd_safe(Jac& q, const u32 tx[8], const u32 ty[8]) {
   if (warp_any(flags)) jac_madd_fix<typename C::Cold>(q, tx, ty, flags);
 }
 
+// P <- P + Q (Jacobian + Jacobian) including P == Q, which is repaired under a warp-uniform branch
+template <class C>
+FEC_DEV void jac_add_safe(Jac& p, const Jac& q) {
+  const u32 same = jac_add<C>(p, q);
+  if (warp_any(same)) {
+    Jac d = p;
+    jac_dbl<C>(d);
+    select8(p.X, same, d.X, p.X); select8(p.Y, same, d.Y, p.Y); select8(p.Z, same, d.Z, p.Z);
+  }
+}
+
 // -------------------------------------------------------------------------------------
 // variable base.  Tab: per-lane table of 8 affine points with load(idx,x,y) / store(idx,x,y).
 // Inv: simultaneous inversion across the lanes that call it together: inv(zinv, z), z != 0.

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "fec_ctx_last_cuda_error", "fec_batch_mul", "fec_batch_mul_dev", "fec_batch_x25519", "fec_batch_x25519_dev",
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
-    "fec_batch_ecdh", "fec_batch_ecdh_dev",
+    "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev",
 )
 
 
@@ -95,6 +95,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_batch_ecdh.restype = ip
     lib.fec_batch_ecdh_dev.argtypes = [vp, ip, ip, u8, u8, ip, sz, ip, ctypes.c_char_p, sz, sz, u8, u8, vp]
     lib.fec_batch_ecdh_dev.restype = ip
+    lib.fec_msm.argtypes = [vp, ip, u8, u8, ip, sz, ip, u8, u8]
+    lib.fec_msm.restype = ip
+    lib.fec_msm_dev.argtypes = [vp, ip, ip, u8, u8, ip, sz, ip, u8, u8, vp]
+    lib.fec_msm_dev.restype = ip
     lib.fec_ctx_stage_timing.argtypes = [vp, ip]
     lib.fec_ctx_stage_timing.restype = ip
     lib.fec_ctx_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
@@ -233,6 +237,23 @@ class Engine:
                        info: bytes = b"", out_len: int = 32, points_fmt: int = 0, stream: int = 0, dev_index: int = 0):
         self._check(self._lib.fec_batch_ecdh_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, kdf,
                                                  bytes(info), len(info), out_len, _ptr(d_out), _ptr(d_status), stream))
+
+    def msm(self, curve: int, scalars, points, *, n: Optional[int] = None, out_fmt: int = OUT_SEC1_COMPRESSED,
+            points_fmt: int = PT_AFFINE_XY_BE):
+        """sum_i k_i*P_i.  Returns (record bytes, status int): status 0 ok, 1/2 a lane was rejected, 3 identity."""
+        if n is None:
+            n = (scalars.nbytes if isinstance(scalars, np.ndarray) else len(scalars)) // 32
+        s = _host_in(scalars, n, 32, "scalars")
+        p = _host_in(points, n, PT_SIZE[points_fmt], "points")
+        out = np.empty(OUT_SIZE[out_fmt], dtype=np.uint8)
+        st = np.zeros(1, dtype=np.uint8)
+        self._check(self._lib.fec_msm(self._ctx, curve, _ptr(s), _ptr(p), points_fmt, n, out_fmt, _ptr(out), _ptr(st)))
+        return out.tobytes(), int(st[0])
+
+    def msm_dev(self, curve: int, d_scalars, d_points, n: int, d_out, d_status=None, *, out_fmt: int = 0, points_fmt: int = 0,
+                stream: int = 0, dev_index: int = 0):
+        self._check(self._lib.fec_msm_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, out_fmt,
+                                          _ptr(d_out), _ptr(d_status), stream))
 
     def batch_x25519(self, scalars, us=None, *, n: Optional[int] = None) -> np.ndarray:
         if n is None:

@@ -109,6 +109,22 @@ class _WeierstrassCurve:
     def to_affine(p: AffinePoint) -> AffinePoint:
         return p  # results already come back normalised (batch inversion on the device)
 
+    @classmethod
+    def multi_scalar_multiply(cls, points: Sequence[AffinePoint], scalars: Sequence[Scalar], engine: Optional[_e.Engine] = None) -> AffinePoint:
+        """Curve::multi_scalar_multiply (forge-ec-core/src/lib.rs:934-951): sum of scalars[i] * points[i]; the identity for
+        mismatched or empty inputs, as the reference."""
+        if len(points) != len(scalars) or not points:
+            return AffinePoint(bytes(64), True)
+        eng = engine or default_engine()
+        s = np.frombuffer(b"".join(k.be for k in scalars), dtype=np.uint8)
+        p = np.frombuffer(b"".join(q.xy for q in points), dtype=np.uint8)
+        rec, st = eng.msm(cls.CURVE_ID, s, p, n=len(scalars), out_fmt=_e.OUT_AFFINE_XY_BE)
+        if st == _e.LANE_SCALAR_RANGE:
+            raise ValueError("InvalidScalar")
+        if st == _e.LANE_POINT_INVALID:
+            raise ValueError("PointNotOnCurve")
+        return AffinePoint(rec, st == _e.LANE_INFINITY)
+
     # ---- KeyExchange (secp256k1.rs:1843-1906, p256.rs:2278-2345) ------------------------------------------
     KDF = _e.KDF_HKDF_SHA256
 

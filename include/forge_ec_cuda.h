@@ -120,6 +120,15 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
                        fec_points_fmt points_fmt, size_t n, fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len,
                        uint8_t* d_out, uint8_t* d_status, void* stream);
 
+/* Multi-scalar multiplication sum_i k_i * P_i (Curve::multi_scalar_multiply, forge-ec-core/src/lib.rs:934-951):
+ * the batched k*P kernels followed by a device-wide reduction.  out: ONE record of out_fmt; status: ONE byte -- 0 ok, 1 / 2 some
+ * lane had an out-of-range scalar / an invalid point (out is all-zero), 3 the sum is the identity.  n >= 1.  The host variant
+ * sums contiguous lane ranges on every device of the context and adds the per-device sums on the first one. */
+int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+            fec_out out_fmt, uint8_t* out, uint8_t* status);
+int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+                fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream);
+
 /* RFC 7748 X25519: scalars n x 32 B (clamped inside), u n x 32 B little-endian (NULL = base point 9),
  * out n x 32 B little-endian. */
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);

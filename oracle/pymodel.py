@@ -227,6 +227,39 @@ def batch_mul(curve, scalars: bytes, points: bytes | None, n: int, fmt: int = 0,
     return bytes(out), bytes(st)
 
 
+def w_add_affine(c: WeierstrassCurve, P, Q):
+    """affine addition with every special case (None = identity)"""
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    if P[0] == Q[0]:
+        if (P[1] + Q[1]) % c.p == 0:
+            return None
+        lam = (3 * P[0] * P[0] + c.a) * pow(2 * P[1], -1, c.p) % c.p
+    else:
+        lam = (Q[1] - P[1]) * pow(Q[0] - P[0], -1, c.p) % c.p
+    x = (lam * lam - P[0] - Q[0]) % c.p
+    return x, (lam * (P[0] - x) - P[1]) % c.p
+
+
+def msm(curve, scalars: bytes, points: bytes, n: int, fmt: int = 0, points_fmt: int = 0, products: bytes | None = None):
+    """Model of fec_msm: Curve::multi_scalar_multiply (lib.rs:934-951) adds multiply(points[i], scalars[i]) one by one.
+    `products` (n x 64 B affine + status computed elsewhere, e.g. by the C oracle) skips the slow Python multiplications."""
+    c = CURVES[curve]
+    if products is None:
+        xy, st = batch_mul(curve, scalars, points, n, OUT_AFFINE_XY_BE, points_fmt)
+    else:
+        xy, st = products
+    if any(s in (ST_SCALAR_RANGE, ST_POINT_INVALID) for s in st):
+        return bytes(OUT_SIZE[fmt]), (ST_SCALAR_RANGE if ST_SCALAR_RANGE in st else ST_POINT_INVALID)
+    acc = None
+    for i in range(n):
+        if st[i] == 0:
+            acc = w_add_affine(c, acc, (int.from_bytes(xy[64 * i : 64 * i + 32], "big"), int.from_bytes(xy[64 * i + 32 : 64 * i + 64], "big")))
+    return sec1_encode(acc, fmt), (ST_INFINITY if acc is None else 0)
+
+
 # --------------------------------------------------------------------------------------
 # Batched ECDH: KeyExchange::derive_shared_secret + derive_key (secp256k1.rs:1846-1905, p256.rs:2281-2344)
 # --------------------------------------------------------------------------------------

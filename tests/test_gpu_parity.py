@@ -343,3 +343,46 @@ def test_batched_ecdh_matches_model(engine, fec, pm, curve):
     cls = fec.Secp256k1 if curve == 0 else fec.P256
     sec = cls.derive_shared_secret(fec.Scalar(a[0].tobytes()), fec.AffinePoint(B[0].tobytes()), engine)
     assert sec == s1[0].tobytes()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_multi_scalar_multiply_matches_model(engine, fec, pm, curve):
+    """sum_i k_i*P_i = the batched products + a device-wide reduction, against the model that adds the
+    products one by one (lib.rs:934-951); cancellations, repeated points (the doubling case of the reduction), identity
+    lanes, rejected lanes, one to several thousand points."""
+    c = pm.CURVES[curve]
+    for n in (1, 2, 33, 257, 5000):
+        k = pm.random_scalars_be(curve, n, stream=7, edge=(n >= 33))
+        r = pm.random_scalars_be(curve, n, stream=7, sub=1, edge=False)
+        pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+        prods = engine.batch_mul(curve, k, pts, out_fmt=fec.OUT_AFFINE_XY_BE)     # checked against the oracle elsewhere
+        exp, est = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0, products=(prods[0].tobytes(), prods[1].tobytes()))
+        got, st = engine.msm(curve, k, pts)
+        assert (got, st) == (exp, est), (curve, n)
+    # a small case entirely in the model
+    n = 6
+    k = pm.random_scalars_be(curve, n, stream=8, edge=False)
+    r = pm.random_scalars_be(curve, n, stream=8, sub=1, edge=False)
+    pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    assert engine.msm(curve, k, pts, out_fmt=fec.OUT_SEC1_UNCOMPRESSED) == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 1)
+    # k P + (n - k) P = identity; P + P + P + P (every combine step is a doubling); identity lanes only
+    kk = int.from_bytes(k[0].tobytes(), "big")
+    two = np.frombuffer(_be(kk) + _be(c.n - kk), dtype=np.uint8)
+    rec, st = engine.msm(curve, two, np.concatenate([pts[0], pts[0]]))
+    assert rec == bytes(33) and st == 3
+    four = np.frombuffer(_be(1) * 64, dtype=np.uint8)
+    rec, st = engine.msm(curve, four, np.tile(pts[1], 64))
+    exp, _ = pm.batch_mul(curve, _be(64), pts[1].tobytes(), 1, 0)
+    assert rec == exp and st == 0
+    rec, st = engine.msm(curve, np.zeros(96, dtype=np.uint8), pts[:3])
+    assert rec == bytes(33) and st == 3
+    # rejected lanes
+    bad = np.frombuffer(_be(5) + _be(c.n), dtype=np.uint8)
+    assert engine.msm(curve, bad, pts[:2]) == (bytes(33), 1)
+    off = np.concatenate([pts[0], np.frombuffer(_be(2) + _be(2), dtype=np.uint8)])
+    assert engine.msm(curve, np.frombuffer(_be(5) + _be(6), dtype=np.uint8), off) == (bytes(33), 2)
+    # trait mirror
+    cls = fec.Secp256k1 if curve == 0 else fec.P256
+    P = cls.multi_scalar_multiply([fec.AffinePoint(pts[i].tobytes()) for i in range(n)], [fec.Scalar(k[i].tobytes()) for i in range(n)], engine)
+    assert P.to_bytes() == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0)[0]
+    assert cls.multi_scalar_multiply([], [], engine).is_identity()
