@@ -25,6 +25,10 @@ pub const FEC_PT_SEC1_COMPRESSED: c_int = 1;
 pub const FEC_OUT_SEC1_COMPRESSED: c_int = 0;
 pub const FEC_OUT_SEC1_UNCOMPRESSED: c_int = 1;
 pub const FEC_OUT_AFFINE_XY_BE: c_int = 2;
+pub const FEC_OUT_X_BE: c_int = 3;
+pub const FEC_KDF_NONE: c_int = 0;
+pub const FEC_KDF_HKDF_SHA256: c_int = 1;
+pub const FEC_KDF_XOR_INFO: c_int = 2;
 pub const FEC_LANE_OK: u8 = 0;
 pub const FEC_LANE_SCALAR_RANGE: u8 = 1;
 pub const FEC_LANE_POINT_INVALID: u8 = 2;
@@ -42,6 +46,14 @@ extern "C" {
     pub fn fec_batch_mul_dev(
         ctx: *mut fec_ctx, dev_index: c_int, curve: c_int, sem: c_int, d_scalars: *const u8, d_points: *const u8,
         points_fmt: c_int, n: usize, out_fmt: c_int, d_out: *mut u8, d_status: *mut u8, stream: *mut c_void,
+    ) -> c_int;
+    pub fn fec_batch_ecdh(
+        ctx: *mut fec_ctx, curve: c_int, scalars: *const u8, points: *const u8, points_fmt: c_int, n: usize, kdf: c_int,
+        info: *const u8, info_len: usize, out_len: usize, out: *mut u8, status: *mut u8,
+    ) -> c_int;
+    pub fn fec_msm(
+        ctx: *mut fec_ctx, curve: c_int, scalars: *const u8, points: *const u8, points_fmt: c_int, n: usize, out_fmt: c_int,
+        out: *mut u8, status: *mut u8,
     ) -> c_int;
     pub fn fec_batch_x25519(ctx: *mut fec_ctx, scalars: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn fec_batch_ed25519_pubkey(ctx: *mut fec_ctx, seeds_or_scalars: *const u8, input_is_seed: c_int, n: usize, out: *mut u8) -> c_int;
@@ -124,6 +136,32 @@ pub trait BatchMul: CudaCurve {
             }
         }
         Ok(res)
+    }
+
+    /// Batched `KeyExchange::derive_shared_secret` + `derive_key` (secp256k1.rs:1846-1905, p256.rs:2281-2344):
+    /// `info = None` returns the 32-byte x-coordinates, otherwise `out_len` bytes of the curve's key derivation.
+    fn batch_ecdh(engine: &Engine, scalars_be: &[u8], points_xy_be: &[u8], kdf: c_int, info: Option<&[u8]>, out_len: usize) -> Result<(Vec<u8>, Vec<u8>)> {
+        let n = scalars_be.len() / 32;
+        let rec = if info.is_none() { 32 } else { out_len };
+        let mut out = vec![0u8; rec * n];
+        let mut status = vec![0u8; n];
+        let (ip, il) = info.map_or((std::ptr::null(), 0), |v| (v.as_ptr(), v.len()));
+        let rc = unsafe {
+            fec_batch_ecdh(engine.ctx, Self::CURVE_ID, scalars_be.as_ptr(), points_xy_be.as_ptr(), FEC_PT_AFFINE_XY_BE, n,
+                           if info.is_none() { FEC_KDF_NONE } else { kdf }, ip, il, out_len, out.as_mut_ptr(), status.as_mut_ptr())
+        };
+        if rc != 0 { Err(map_err(rc)) } else { Ok((out, status)) }
+    }
+
+    /// `Curve::multi_scalar_multiply` (forge-ec-core/src/lib.rs:934-951) on the GPU: X || Y of the sum and its status.
+    fn multi_scalar_multiply_xy(engine: &Engine, scalars_be: &[u8], points_xy_be: &[u8]) -> Result<([u8; 64], u8)> {
+        let n = scalars_be.len() / 32;
+        let (mut out, mut st) = ([0u8; 64], 0u8);
+        let rc = unsafe {
+            fec_msm(engine.ctx, Self::CURVE_ID, scalars_be.as_ptr(), points_xy_be.as_ptr(), FEC_PT_AFFINE_XY_BE, n, FEC_OUT_AFFINE_XY_BE,
+                    out.as_mut_ptr(), &mut st)
+        };
+        if rc != 0 { Err(map_err(rc)) } else { Ok((out, st)) }
     }
 
     /// SEC1 compressed bytes straight from the GPU (what `CompressedPoint::from_affine` would produce).
