@@ -44,7 +44,7 @@ EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 4_429}
 # DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1d_*)
 LADDER_DRAM_BYTES_PER_LANE = 1_223  # 2^22-lane launch: 4.68 GB read + 0.45 GB written
 # canonical IMUL32 per operation of the secondary configurations
-CANON_OTHER = {"secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
+CANON_OTHER = {"x25519_base_point": 153_576, "secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
 
 
 # ------------------------------------------------------------------------------------------
@@ -328,12 +328,17 @@ def main():
         runs = {
             "secp256k1_kG": lambda: eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, None, m, d_o, stream=sp),
             "x25519": lambda: eng.batch_x25519_dev(d_k, d_r, m, d_o, stream=sp),
+            "x25519_base_point": lambda: eng.batch_x25519_dev(d_k, None, m, d_o, stream=sp),
             "ed25519_keygen": lambda: eng.batch_ed25519_pubkey_dev(d_k, True, m, d_o, stream=sp),
         }
         for name, fn in runs.items():
             t = timed(fn)
             others[name] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m,
                             "imad_frac": CANON_OTHER[name] * m / t / imad_peak}
+        # BASELINE.json configs[3]: one key exchange = X25519(a,9), X25519(b,9), X25519(a,B), X25519(b,A) = 2 base-point + 2 ladders
+        t_ex = 2.0 / others["x25519"]["value"] + 2.0 / others["x25519_base_point"]["value"]
+        others["x25519_key_exchange"] = {"value": 4.0 / t_ex, "unit": "scalar-mults/s (4 per exchange)", "lanes_per_gpu": m,
+                                         "imad_frac": 4.0 / t_ex * world ** 0 * CANON_OTHER["x25519"] / imad_peak / world}
         # P-256 needs scalars below its own order and points on its own curve
         d_k2 = torch.empty(m * 32, dtype=torch.uint8, device=dev)
         d_p2 = torch.empty(m * 64, dtype=torch.uint8, device=dev)

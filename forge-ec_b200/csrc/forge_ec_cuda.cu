@@ -165,13 +165,16 @@ int launch_ecdh(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uin
 int launch_x25519(fec_ctx* ctx, Device& d, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
-  FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
+  if (du == nullptr)  // base point u = 9: fixed-base path on the Edwards form of the curve (k_ed25519.cu, mode 2)
+    FEC_CUDA(ctx, ed25519_launch(d.sms, st, ds, 2, d.niels, n, dout));
+  else
+    FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
   return FEC_OK;
 }
 int launch_ed(fec_ctx* ctx, Device& d, const uint8_t* din, int is_seed, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
-  FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed, d.niels, n, dout));
+  FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
   return FEC_OK;
 }
 int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int iters, const uint8_t* a, const uint8_t* b,

@@ -9,8 +9,13 @@ namespace fec {
 // Warp-independent tiles with a deferred warp-level inversion, as k_wmul_fixed (k_wmul_fixed.cuh).
 constexpr int ED_DEFER = 16;
 __global__ void __launch_bounds__(ED_THREADS, ED_BLOCKS_PER_SM)
-k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* __restrict__ niels_g, size_t n,
+k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict__ niels_g, size_t n,
                  uint8_t* __restrict__ out) {
+  // mode 0: 32-byte little-endian scalars as they are -> RFC 8032 encoding of s*B;  mode 1: seeds (SHA-512 + clamp) -> same;
+  // mode 2: X25519 with the base point u = 9 (RFC 7748 6.1 key generation): clamp, s*B on the birationally equivalent
+  //         Edwards curve, u = (Z + Y) / (Z - Y) -- 16 table additions instead of a 255-step ladder.  Z - Y != 0 because a
+  //         clamped scalar is never a multiple of the group order.
+  const int input_is_seed = mode == 1;
   typedef Fe25519 F;
   GlobalNiels niels{niels_g};
   const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -38,11 +43,21 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* _
           ed25519_expand_seed(s, seed);
         } else {
           load_rec32_le(s, in + lane * 32);
+          if (mode == 2) {
+            s[0] &= 0xFFFFFFF8u;
+            s[7] = (s[7] & 0x7FFFFFFFu) | 0x40000000u;
+          }
         }
       }
       ed_scalar_prepare(K, s);
       EdExt Q;
       ed_comb_core(Q, K, niels);  // Z != 0 always (complete formulas)
+      if (mode == 2) {            // (Y, Z) <- (Z + Y, Z - Y): the unwinding multiplies Y by 1 / Z
+        u32 t[8];
+        F::add(t, Q.Z, Q.Y);
+        F::sub(Q.Z, Q.Z, Q.Y);
+        copy8(Q.Y, t);
+      }
       if (cnt == 0) first_tile_of_batch = tile;
       u32* sl = slots[cnt];
 #pragma unroll
@@ -61,7 +76,13 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int input_is_seed, const u32* _
 #pragma unroll
         for (int i = 0; i < 8; i++) { Q.X[i] = sl[i]; Q.Y[i] = sl[8 + i]; z[i] = sl[16 + i]; pre[i] = sl[24 + i]; }
         if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
-        ed_encode(o, Q, zi);
+        if (mode == 2) {
+          u32 t[8];
+          F::mul(t, Q.Y, zi);
+          F::canon(o, t);
+        } else {
+          ed_encode(o, Q, zi);
+        }
         const size_t lane = (first_tile_of_batch + (size_t)t * nwarps) * 32 + lane_in_warp;
         if (lane < n) store_rec32_le(out + lane * 32, o);
       }
@@ -97,10 +118,10 @@ __global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g, 
 
 
 cudaError_t ed25519_setup() { return cudaSuccess; }
-cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int input_is_seed, const u32* niels, size_t n,
+cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode, const u32* niels, size_t n,
                            uint8_t* out) {
   const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS * ED_DEFER - 1) / (ED_THREADS * ED_DEFER));
-  k_ed25519_pubkey<<<g, ED_THREADS, 0, st>>>(in, input_is_seed, niels, n, out);
+  k_ed25519_pubkey<<<g, ED_THREADS, 0, st>>>(in, mode, niels, n, out);
   return cudaGetLastError();
 }
 cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases) {

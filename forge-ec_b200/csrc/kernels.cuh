@@ -161,7 +161,7 @@ cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t
                               int out_fmt, uint8_t* out, uint8_t* status);
 cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
 cudaError_t ed25519_setup();
-cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int input_is_seed, const u32* niels, size_t n,
+cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode /* 0 scalars, 1 seeds, 2 X25519 base point */, const u32* niels, size_t n,
                            uint8_t* out);
 cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb, u32* bases /* COMB_WINDOWS x 16 words scratch */);
 cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases /* COMB_WINDOWS x 32 words scratch */);

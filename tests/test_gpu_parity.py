@@ -117,9 +117,17 @@ def test_x25519_matches_model_and_rfc7748(engine, fec, pm):
     out = engine.batch_x25519(ks, us)
     for i in range(n):
         assert out[i].tobytes() == pm.x25519(ks[i].tobytes(), us[i].tobytes()), i
-    base = engine.batch_x25519(ks[:50], None)
+    # u = NULL (the base point 9) takes the fixed-base route on the Edwards form of the curve: it must agree with the ladder
+    # run on an explicit u = 9, with the model, and on the extreme scalars (all zero / all one bits before clamping)
+    kb = ks.copy()
+    kb[0] = 0
+    kb[1] = 255
+    base = engine.batch_x25519(kb, None)
+    nine = np.tile(np.frombuffer(pm.X25519_BASE, dtype=np.uint8), (n, 1))
+    assert base.tobytes() == engine.batch_x25519(kb, nine).tobytes()
     for i in range(50):
-        assert base[i].tobytes() == pm.x25519(ks[i].tobytes(), pm.X25519_BASE)
+        assert base[i].tobytes() == pm.x25519(kb[i].tobytes(), pm.X25519_BASE)
+    assert fec.batch_x25519([alice], None, engine)[0].hex() == "8520f0098930a754748b7ddcb43ef75a0dbf3a0d26381af4eba4a98eaa9b4e6a"
     # RFC 7748 5.2 vector 1
     k = bytes.fromhex("a546e36bf0527c9d3b16154b82465edd62144c0ac1fc5a18506a2244ba449ac4")
     u = bytes.fromhex("e6db6867583030db3594c1a424b15f7c726624ec26b3353b10a903a6d0ab1c4c")
