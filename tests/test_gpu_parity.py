@@ -205,11 +205,13 @@ def test_synth_inputs_match_philox_model(engine, pm):
         assert np.array_equal(got, exp), (mode, stream_id, sub, first)
 
 
-def test_device_pointer_api_and_properties(engine, fec, pm):
-    """Full-size-style checks that need no oracle: ECDH commutes, (n-k)P = -(kP), k=0 -> identity."""
+@pytest.mark.parametrize("n", [1 << 14, (1 << 22) + 4099])
+def test_device_pointer_api_and_properties(engine, fec, pm, n):
+    """Size-independent properties at small and at full launch size (the larger case spans two scratch chunks of the
+    three-kernel k*P path and ends in a ragged tile): ECDH commutes on both curves, fixed-base and variable-base agree
+    on P = G, the first lanes match the model, X25519 exchanges agree and its base-point route equals the ladder."""
     import torch
 
-    n = 1 << 14
     st = torch.cuda.current_stream().cuda_stream
     a = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
     b = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
@@ -230,6 +232,25 @@ def test_device_pointer_api_and_properties(engine, fec, pm):
     # first lanes against the model
     exp, _ = pm.batch_mul(0, a[: 32 * 16].cpu().numpy().tobytes(), B[: 64 * 16].cpu().numpy().tobytes(), 16, 0)
     assert s1[: 33 * 16].cpu().numpy().tobytes() == exp
+    tail = n - 16   # and the last lanes (ragged tile, second chunk)
+    exp, _ = pm.batch_mul(0, a[32 * tail:].cpu().numpy().tobytes(), B[64 * tail:].cpu().numpy().tobytes(), 16, 0)
+    assert s1[33 * tail:].cpu().numpy().tobytes() == exp
+    # k*G through the fixed-base table == k*P with P = G through the variable-base kernels
+    G = torch.from_numpy(np.frombuffer((_be(pm.CURVES[0].gx) + _be(pm.CURVES[0].gy)) * 4096, dtype=np.uint8).copy()).cuda()
+    engine.batch_mul_dev(0, a, None, 4096, s1, stream=st)
+    engine.batch_mul_dev(0, a, G, 4096, s2, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(s1[: 33 * 4096], s2[: 33 * 4096])
+    # P-256: the same exchange
+    m = min(n, 1 << 20)
+    engine.synth_dev(2, 5, 0, 0, m, a, edge=False, stream=st)
+    engine.synth_dev(2, 5, 1, 0, m, b, edge=False, stream=st)
+    engine.batch_mul_dev(1, a, None, m, A, out_fmt=2, stream=st)
+    engine.batch_mul_dev(1, b, None, m, B, out_fmt=2, stream=st)
+    engine.batch_mul_dev(1, a, B, m, s1, st1, stream=st)
+    engine.batch_mul_dev(1, b, A, m, s2, None, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(s1[: 33 * m], s2[: 33 * m]) and int(st1[:m].sum()) == 0
     # X25519: both sides derive the same secret
     ka = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
     kb = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
@@ -242,6 +263,11 @@ def test_device_pointer_api_and_properties(engine, fec, pm):
     engine.batch_x25519_dev(kb, pa, n, sb, stream=st)
     torch.cuda.synchronize()
     assert torch.equal(sa, sb)
+    nine = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
+    nine[::32] = 9
+    engine.batch_x25519_dev(ka, nine, n, sb, stream=st)   # the ladder on an explicit u = 9 vs the fixed-base route
+    torch.cuda.synchronize()
+    assert torch.equal(pa, sb)
     assert engine.launch_count > 0
 
 
