@@ -141,6 +141,27 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.ed25519_pubkey(k, False)
 
 
+def test_karatsuba_variant_of_the_multiplier(pm):
+    """u256.cuh keeps a one-level Karatsuba 8x8 multiplier behind FEC_KARATSUBA (measured slower on B200: it trades 16
+    IMAD.WIDE for ~70 additions); it must stay correct, including equal and extreme halves."""
+    import random
+    so = os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim_karatsuba.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DFEC_KARATSUBA", "-x", "c++", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")], check=True)
+    hs = ctypes.CDLL(so)
+    rnd = random.Random(9)
+    for prime in (0, 1, 2):
+        p = pm.PRIMES[prime]
+        vals = [0, 1, p - 1, (1 << 128) - 1, 1 << 128, ((1 << 128) - 1) << 128, ((1 << 128) | 1) * 12345 % p, (2**256 - 1) % p]
+        vals += [rnd.randrange(p) for _ in range(40)]
+        for _ in range(3000):
+            a, b = rnd.choice(vals) % p, rnd.choice(vals) % p
+            o = ctypes.create_string_buffer(32)
+            hs.hs_field_op(prime, 0, a.to_bytes(32, "little"), b.to_bytes(32, "little"), o)
+            assert int.from_bytes(o.raw, "little") == a * b % p, (prime, hex(a), hex(b))
+
+
 def test_device_kdf_code_on_host_matches_model(hostsim, pm):
     """SHA-256 / HMAC / HKDF of csrc/kdf.cuh (compiled for the host) against hashlib/hmac, incl. RFC 5869 test case 3-like
     shapes: empty info, info that crosses block boundaries, every output length up to 64."""
