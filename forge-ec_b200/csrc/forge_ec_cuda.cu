@@ -444,6 +444,18 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
 // sum_i k_i * P_i on one device: products through the batched k*P path (affine X || Y + lane status), then the reduction
 static int msm_on_device(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
                          uint8_t* dout, uint8_t* dstatus, cudaStream_t st) {
+  static const bool no_pippenger = getenv("FORGE_EC_MSM_IMPL") != nullptr && getenv("FORGE_EC_MSM_IMPL")[0] == 'p';  // "products": A/B
+  if (n >= (curve == FEC_SECP256K1 ? MSM_PIPPENGER_MIN_K1 : MSM_PIPPENGER_MIN_P256) && n < (size_t(1) << 31) && !no_pippenger) {
+    uint8_t* scratch = nullptr;
+    FEC_CUDA(ctx, cudaMallocAsync(&scratch, msm_pippenger_scratch_bytes(n), st));
+    int skewed = 0;
+    const unsigned limit = (unsigned)(64 * (n >> 15) + 4096);
+    const cudaError_t e = msm_pippenger_launch(curve, st, ds, dp, pfmt, n, scratch, ofmt, dout, dstatus, limit, &skewed);
+    cudaFreeAsync(scratch, st);
+    FEC_CUDA(ctx, e);
+    ctx->launches += skewed ? 3 : 9;
+    if (!skewed) return FEC_OK;  // otherwise: pathologically repeated digits, use the products + reduction path below
+  }
   const int blocks = msm_blocks(d.sms, n);
   const size_t xy_bytes = n * 64, st_bytes = (n + 15) / 16 * 16, sc_bytes = ((size_t)blocks * 24 + 4) * 4;
   uint8_t* tmp = nullptr;

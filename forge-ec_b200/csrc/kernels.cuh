@@ -154,6 +154,12 @@ cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint
 int msm_blocks(int sms, size_t n);
 cudaError_t msm_reduce_launch(int curve, int sms, cudaStream_t st, const uint8_t* xy, const uint8_t* lane_status, size_t n, u32* scratch,
                               int out_fmt, uint8_t* out, uint8_t* status);
+// bucket method for n >= MSM_PIPPENGER_MIN_* points (k_msm_pippenger.cu); *skewed = 1 (and nothing else done) when some bucket holds
+// more than skew_limit points, in which case the caller uses the products + reduction path
+constexpr size_t MSM_PIPPENGER_MIN_K1 = size_t(1) << 17, MSM_PIPPENGER_MIN_P256 = size_t(1) << 16;  // measured crossovers
+size_t msm_pippenger_scratch_bytes(size_t n);
+cudaError_t msm_pippenger_launch(int curve, cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n,
+                                 uint8_t* scratch, int out_fmt, uint8_t* out, uint8_t* status, unsigned skew_limit, int* skewed);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t wmul_fixed_setup();

@@ -420,3 +420,36 @@ def test_multi_scalar_multiply_matches_model(engine, fec, pm, curve):
     P = cls.multi_scalar_multiply([fec.AffinePoint(pts[i].tobytes()) for i in range(n)], [fec.Scalar(k[i].tobytes()) for i in range(n)], engine)
     assert P.to_bytes() == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0)[0]
     assert cls.multi_scalar_multiply([], [], engine).is_identity()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_msm_bucket_method_matches_model(engine, fec, pm, curve):
+    """n >= 2^17 takes the bucket (Pippenger) path: against the model that adds the per-lane products (themselves
+    checked against the oracle elsewhere) one by one; SEC1 compressed input; a rejected lane; repeated scalars, which
+    overflow one bucket and must fall back to the products path with the same result."""
+    c = pm.CURVES[curve]
+    n = 140000
+    k = pm.random_scalars_be(curve, n, stream=9)                       # edge lanes: 0, 1, 2, 3, n-1, n-2, ...
+    r = pm.random_scalars_be(curve, n, stream=9, sub=1, edge=False)
+    pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    prods = engine.batch_mul(curve, k, pts, out_fmt=fec.OUT_AFFINE_XY_BE)
+    exp, est = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0, products=(prods[0].tobytes(), prods[1].tobytes()))
+    assert engine.msm(curve, k, pts) == (exp, est) and est == 0
+    comp, _ = engine.batch_mul(curve, r, None)
+    assert engine.msm(curve, k, comp, points_fmt=fec.PT_SEC1_COMPRESSED) == (exp, est)
+    exp65, _ = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 1, products=(prods[0].tobytes(), prods[1].tobytes()))
+    assert engine.msm(curve, k, pts, out_fmt=fec.OUT_SEC1_UNCOMPRESSED)[0] == exp65
+    # sum_i k_i P_i with every k_i negated is the negated point: same x, other y parity
+    kneg = np.frombuffer(b"".join(_be((c.n - int.from_bytes(k[i].tobytes(), "big")) % c.n) for i in range(n)), dtype=np.uint8)
+    rec, st = engine.msm(curve, kneg, pts)
+    assert st == 0 and rec[1:] == exp[1:] and rec[0] == exp[0] ^ 1
+    bad = k.copy()
+    bad[777] = np.frombuffer(_be(c.n + 5), dtype=np.uint8)
+    assert engine.msm(curve, bad, pts) == (bytes(33), 1)
+    offp = pts.copy()
+    offp[12345, 63] ^= 1
+    assert engine.msm(curve, k, offp) == (bytes(33), 2)
+    same = np.tile(np.frombuffer(_be(0x1234567 << 200 | 0xABCDEF), dtype=np.uint8), n)   # one bucket per window holds everything
+    exp1, _ = pm.msm(curve, same.tobytes(), pts.tobytes(), n, 0,
+                     products=tuple(x.tobytes() for x in engine.batch_mul(curve, same, pts, out_fmt=fec.OUT_AFFINE_XY_BE)))
+    assert engine.msm(curve, same, pts) == (exp1, 0)
