@@ -39,10 +39,10 @@ CANON_IMUL32_PER_OP = 172_562   # SURVEY.md 8d, config 3 (fixed 4-bit window, Ja
 IO_BYTES_PER_OP = 32 + 64 + 33  # scalar + affine point in, SEC1 compressed out
 SYNTH_STREAM = 3
 # What the implemented algorithm (GLV split, 2 x 32 signed 4-bit digits, effective-affine table, shared inversion) really
-# executes, from ncu (profiles/r1d_*): IMAD.WIDE warp instructions x 32 / lanes.  Used for `pipe_utilisation` only.
-EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 4_429}
-# DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1d_*)
-LADDER_DRAM_BYTES_PER_LANE = 1_223  # 2^22-lane launch: 4.68 GB read + 0.45 GB written
+# executes, from ncu (profiles/r1f_*): IMAD.WIDE warp instructions x 32 / lanes.  Used for `pipe_utilisation` only.
+EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 2_809}
+# DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1f_*)
+LADDER_DRAM_BYTES_PER_LANE = 975  # 2^22-lane launch: 3.67 GB read + 0.42 GB written
 # canonical IMUL32 per operation of the secondary configurations
 CANON_OTHER = {"x25519_base_point": 153_576, "secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
 
