@@ -115,8 +115,11 @@ constexpr int FIX_THREADS = 128;
 constexpr int FIX_BLOCKS_PER_SM = FEC_FIX_BLOCKS_PER_SM;
 constexpr int FIX_IO_BYTES_PER_WARP = 65 * 32;  // per-warp staging of 33/65-byte records
 constexpr int FIX_SMEM_BYTES = (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP;
-constexpr int X_THREADS = 256;
-constexpr int X_BLOCKS_PER_SM = 2;
+constexpr int X_THREADS = 128;
+#ifndef FEC_X_BLOCKS_PER_SM
+#define FEC_X_BLOCKS_PER_SM 4
+#endif
+constexpr int X_BLOCKS_PER_SM = FEC_X_BLOCKS_PER_SM;
 constexpr int ED_THREADS = 128;
 #ifndef FEC_ED_BLOCKS_PER_SM
 #define FEC_ED_BLOCKS_PER_SM 3

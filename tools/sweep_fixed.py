@@ -23,4 +23,5 @@ r.append(("p256_kG", n / t(lambda: eng.batch_mul_dev(1, k2, None, n, out, stream
 r.append(("ed_seed", n / t(lambda: eng.batch_ed25519_pubkey_dev(k, True, n, out, stream=s.cuda_stream))))
 r.append(("ed_scalar", n / t(lambda: eng.batch_ed25519_pubkey_dev(k, False, n, out, stream=s.cuda_stream))))
 r.append(("x25519_base", n / t(lambda: eng.batch_x25519_dev(k, None, n, out, stream=s.cuda_stream))))
+r.append(("x25519_var", n / t(lambda: eng.batch_x25519_dev(k, k2, n, out, stream=s.cuda_stream), 2)))
 print("  ".join(f"{a}={b/1e6:.1f}M/s" for a, b in r), flush=True)
