@@ -102,7 +102,7 @@ struct GlobalNiels {
 constexpr int INV_SCRATCH_WORDS = 2 * 16 * 8 + 8;  // block_batch_inv scratch, enough for 16 warps
 constexpr int VAR_THREADS = 128;
 #ifndef FEC_VAR_BLOCKS_PER_SM
-#define FEC_VAR_BLOCKS_PER_SM 4
+#define FEC_VAR_BLOCKS_PER_SM 5
 #endif
 constexpr int VAR_BLOCKS_PER_SM = FEC_VAR_BLOCKS_PER_SM;
 constexpr int VAR_TAB_BYTES = 8 * 16 * VAR_THREADS * 4;  // 64 KiB per block
