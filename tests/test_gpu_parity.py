@@ -449,6 +449,12 @@ def test_msm_bucket_method_matches_model(engine, fec, pm, curve):
     offp = pts.copy()
     offp[12345, 63] ^= 1
     assert engine.msm(curve, k, offp) == (bytes(33), 2)
+    # every lane the SAME point with random scalars: each bucket then adds P + P (doubling inside the mixed addition),
+    # 2P + P, and P + (-P) whenever both signs meet; the sum is (sum_i k_i mod n) P
+    onep = np.tile(pts[5], n)
+    ksum = sum(int.from_bytes(k[i].tobytes(), "big") for i in range(n)) % c.n
+    exp_one, _ = pm.batch_mul(curve, _be(ksum), pts[5].tobytes(), 1, 0)
+    assert engine.msm(curve, k, onep) == (exp_one, 0)
     same = np.tile(np.frombuffer(_be(0x1234567 << 200 | 0xABCDEF), dtype=np.uint8), n)   # one bucket per window holds everything
     exp1, _ = pm.msm(curve, same.tobytes(), pts.tobytes(), n, 0,
                      products=tuple(x.tobytes() for x in engine.batch_mul(curve, same, pts, out_fmt=fec.OUT_AFFINE_XY_BE)))
