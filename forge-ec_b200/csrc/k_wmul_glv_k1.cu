@@ -38,7 +38,10 @@ struct GlvScratch {
 };
 constexpr size_t GLV_SCRATCH_BYTES_PER_LANE = (192 + 8 + 8 + 1 + 24) * 4;
 
-__global__ void __launch_bounds__(GLV_PREP_THREADS, 3)
+#ifndef FEC_GLV_PREP_BLOCKS
+#define FEC_GLV_PREP_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(GLV_PREP_THREADS, FEC_GLV_PREP_BLOCKS)
 k_glv_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ points, int points_fmt, size_t n, GlvScratch sc) {
   typedef CurveK1 C;
   typedef FeK1 F;
