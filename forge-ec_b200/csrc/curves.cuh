@@ -43,18 +43,21 @@ struct CurveP256 {
   static constexpr int CURVE_ID = 1;
   static constexpr bool A_MINUS3 = true;
   FEC_DEV static void B(u32 b[8]) {
-    b[0] = 0x27D2604Bu; b[1] = 0x3BCE3C3Eu; b[2] = 0xCC53B0F6u; b[3] = 0x651D06B0u;
-    b[4] = 0x769886BCu; b[5] = 0xB3EBBD55u; b[6] = 0xAA3A93E7u; b[7] = 0x5AC635D8u;
+    // b * 2^256 mod p (FeP256 works in the Montgomery domain; b = 5AC635D8 AA3A93E7 B3EBBD55 769886BC 651D06B0 CC53B0F6 3BCE3C3E 27D2604B)
+    b[0] = 0x29C4BDDFu; b[1] = 0xD89CDF62u; b[2] = 0x78843090u; b[3] = 0xACF005CDu;
+    b[4] = 0xF7212ED6u; b[5] = 0xE5A220ABu; b[6] = 0x04874834u; b[7] = 0xDC30061Du;
   }
   FEC_DEV static void N(u32 n[8]) {
     n[0] = 0xFC632551u; n[1] = 0xF3B9CAC2u; n[2] = 0xA7179E84u; n[3] = 0xBCE6FAADu;
     n[4] = 0xFFFFFFFFu; n[5] = 0xFFFFFFFFu; n[6] = 0x00000000u; n[7] = 0xFFFFFFFFu;
   }
   FEC_DEV static void G(u32 x[8], u32 y[8]) {
-    x[0] = 0xD898C296u; x[1] = 0xF4A13945u; x[2] = 0x2DEB33A0u; x[3] = 0x77037D81u;
-    x[4] = 0x63A440F2u; x[5] = 0xF8BCE6E5u; x[6] = 0xE12C4247u; x[7] = 0x6B17D1F2u;
-    y[0] = 0x37BF51F5u; y[1] = 0xCBB64068u; y[2] = 0x6B315ECEu; y[3] = 0x2BCE3357u;
-    y[4] = 0x7C0F9E16u; y[5] = 0x8EE7EB4Au; y[6] = 0xFE1A7F9Bu; y[7] = 0x4FE342E2u;
+    // (Gx, Gy) * 2^256 mod p; Gx = 6B17D1F2 E12C4247 F8BCE6E5 63A440F2 77037D81 2DEB33A0 F4A13945 D898C296,
+    // Gy = 4FE342E2 FE1A7F9B 8EE7EB4A 7C0F9E16 2BCE3357 6B315ECE CBB64068 37BF51F5 (FIPS 186-4; p256.rs:2094-2106)
+    x[0] = 0x18A9143Cu; x[1] = 0x79E730D4u; x[2] = 0x5FEDB601u; x[3] = 0x75BA95FCu;
+    x[4] = 0x77622510u; x[5] = 0x79FB732Bu; x[6] = 0xA53755C6u; x[7] = 0x18905F76u;
+    y[0] = 0xCE95560Au; y[1] = 0xDDF25357u; y[2] = 0xBA19E45Cu; y[3] = 0x8B4AB8E4u;
+    y[4] = 0xDD21F325u; y[5] = 0xD2E88688u; y[6] = 0x25885D85u; y[7] = 0x8571FF18u;
   }
 };
 
@@ -71,17 +74,13 @@ struct CurveK1Inl : CurveK1 { typedef FeK1Inl F; };
 struct CurveK1InlSqr : CurveK1 { typedef FeK1InlSqr F; };
 
 // -------------------------------------------------------------------------------------
-// Jacobian point (X:Y:Z), infinity <=> Z == 0
+// Jacobian point (X:Y:Z), infinity <=> Z == 0.  Coordinates are field elements in the field's internal
+// representation (F::one() is the field's 1; G() and B() return constants in that representation).
 // -------------------------------------------------------------------------------------
 struct Jac {
   u32 X[8], Y[8], Z[8];
 };
 
-FEC_DEV void set1(u32 r[8]) {
-  r[0] = 1u;
-#pragma unroll
-  for (int i = 1; i < 8; i++) r[i] = 0u;
-}
 template <class C>
 FEC_DEV void jac_set_inf(Jac& q) {
 #pragma unroll
@@ -179,13 +178,13 @@ FEC_DEV u32 jac_madd_lean(Jac& q, const u32 x2[8], const u32 y2[8]) {
 template <class C>
 FEC_DEV void jac_madd_fix(Jac& q, const u32 x2[8], const u32 y2[8], u32 flags) {
   Jac d;
-  copy8(d.X, x2); copy8(d.Y, y2); set1(d.Z);
+  copy8(d.X, x2); copy8(d.Y, y2); C::F::one(d.Z);
   Jac t = d;
   jac_dbl<C>(d);
   const u32 bad = 0u - (flags & 1u), was_inf = 0u - ((flags >> 1) & 1u), isdbl = (0u - ((flags >> 2) & 1u)) & ~was_inf;
   const u32 isinf = bad & ~was_inf & ~isdbl;
   u32 one[8], zero[8];
-  set1(one);
+  C::F::one(one);
 #pragma unroll
   for (int i = 0; i < 8; i++) zero[i] = 0u;
   select8(q.X, was_inf, t.X, q.X); select8(q.Y, was_inf, t.Y, q.Y); select8(q.Z, was_inf, t.Z, q.Z);
@@ -228,7 +227,7 @@ FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   F::sub(t, t, Z1Z1);
   F::sub(o.Z, t, HH);                // Z3 = (Z1+H)^2 - Z1Z1 - HH
   u32 one[8];
-  set1(one);
+  F::one(one);
   u32 keep = t_inf;                  // keep Q
   u32 take_t = q_inf & ~t_inf;       // Q was infinity: result is the addend
 #pragma unroll

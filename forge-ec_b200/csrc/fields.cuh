@@ -9,7 +9,8 @@
 //   FeK1 / Fe25519: "weak" form -- any value in [0, 2^256) stands for its residue; add/sub/mul
 //     fold the overflow with 2^256 = 2^32+977 (resp. 38) and never need a comparison with p.
 //     canon() produces the unique representative in [0,p) for output / equality.
-//   FeP256: always canonical in [0,p) (2^256 mod p is a 225-bit number, so weak form buys nothing).
+//   FeP256: Montgomery domain (x held as x 2^256 mod p), always canonical in [0,p) (2^256 mod p is a 225-bit
+//     number, so weak form buys nothing).  from_plain / to_plain convert at the byte-record boundary.
 // All functions are branch-free (masks only): control flow never depends on data.
 //
 // IMAD.WIDE count per op (the canonical IMUL32 figures of SURVEY.md section 8d):
@@ -168,6 +169,10 @@ struct FeK1 {
     P(p);
     return ~geq8(a, p);
   }
+  // byte records <-> the internal representation (here the integer itself; FeP256 works in the Montgomery domain)
+  FEC_DEV static void one(u32 o[8]) { o[0] = 1u; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = 0u; }
+  FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) { copy8(o, a); }
+  FEC_DEV static void to_plain(u32 o[8], const u32 a[8]) { canon(o, a); }
   // o = a * 2^S (S = 1, 2, 3): one funnel-shift pass, the S bits shifted out are folded with 2^32 + 977
   template <int S>
   FEC_DEV static void mul_pow2(u32 o[8], const u32 a[8]) {
@@ -374,6 +379,10 @@ struct Fe25519 {
 #pragma unroll 1
     for (int i = 0; i < n; i++) sqr(x, x);
   }
+  // byte records <-> the internal representation (see FeK1)
+  FEC_DEV static void one(u32 o[8]) { o[0] = 1u; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = 0u; }
+  FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) { copy8(o, a); }
+  FEC_DEV static void to_plain(u32 o[8], const u32 a[8]) { canon(o, a); }
   // z^(p-2) = z^(2^255-21): 254 S + 11 M
   FEC_DEV static void inv(u32 o[8], const u32 z[8]) {
     u32 z2[8], z9[8], z11[8], z5[8], z10[8], z50[8], t[8], u[8];
@@ -395,7 +404,13 @@ struct Fe25519 {
 };
 
 // =====================================================================================
-// NIST P-256 base field (canonical form)
+// NIST P-256 base field, Montgomery domain: an element x is held as x * 2^256 mod p, canonical in [0,p)
+//
+// p = 2^256 - 2^224 + 2^192 + 2^96 - 1 is -1 modulo 2^96, so the Montgomery quotient digit of a 64-bit round is the
+// low 64 bits themselves and q * p is made of shifted copies of q: the reduction has NO multiplications and about half
+// the additions of the FIPS 186-4 Solinas sums on 32-bit words (which made P-256 ALU-bound).  Byte records enter with
+// from_plain (one multiplication by 2^512 mod p) and leave with to_plain (one reduction); everything between --
+// formulas, tables, inversion, square root, comparisons -- is domain-agnostic.
 // =====================================================================================
 struct FeP256 {
   static constexpr int PRIME_ID = 1;
@@ -403,50 +418,44 @@ struct FeP256 {
     p[0] = 0xFFFFFFFFu; p[1] = 0xFFFFFFFFu; p[2] = 0xFFFFFFFFu; p[3] = 0u;
     p[4] = 0u; p[5] = 0u; p[6] = 1u; p[7] = 0xFFFFFFFFu;
   }
-  // l += t * (2^224 - 2^192 - 2^96 + 1)  (t small, signed); returns the new signed overflow
-  FEC_DEV static int fold_top(u32 l[8], int t) {
-    long long c = 0, tt = t;
-    c += (long long)l[0] + tt; l[0] = (u32)c; c >>= 32;
-    c += (long long)l[1];      l[1] = (u32)c; c >>= 32;
-    c += (long long)l[2];      l[2] = (u32)c; c >>= 32;
-    c += (long long)l[3] - tt; l[3] = (u32)c; c >>= 32;
-    c += (long long)l[4];      l[4] = (u32)c; c >>= 32;
-    c += (long long)l[5];      l[5] = (u32)c; c >>= 32;
-    c += (long long)l[6] - tt; l[6] = (u32)c; c >>= 32;
-    c += (long long)l[7] + tt; l[7] = (u32)c; c >>= 32;
-    return (int)c;
+  FEC_DEV static void one(u32 o[8]) {  // 2^256 mod p
+    o[0] = 1u; o[1] = 0u; o[2] = 0u; o[3] = 0xFFFFFFFFu; o[4] = 0xFFFFFFFFu; o[5] = 0xFFFFFFFFu; o[6] = 0xFFFFFFFEu; o[7] = 0u;
   }
-  // FIPS 186-4 D.2.3 fast reduction, column-wise: T + 2S1 + 2S2 + S3 + S4 - D1 - D2 - D3 - D4
+  FEC_DEV static void RR(u32 o[8]) {  // 2^512 mod p
+    o[0] = 3u; o[1] = 0u; o[2] = 0xFFFFFFFFu; o[3] = 0xFFFFFFFBu; o[4] = 0xFFFFFFFEu; o[5] = 0xFFFFFFFFu; o[6] = 0xFFFFFFFDu; o[7] = 4u;
+  }
+  // o = c / 2^256 mod p for c < p * 2^256, canonical.  Four rounds on 64 bits: with q = the two lowest live words,
+  // c += q p = q (2^96 - 1) + (q (2^64 - 2^32 + 1)) 2^192 clears them; the carry out of a round's chain (at word
+  // o + 10) is folded into the next round's m (its word 2), so every chain is 7 words long.
   FEC_DEV static void reduce512(u32 o[8], const u32 c[16]) {
-    u32 l[8];
-    long long acc;
-    u64 pos, neg;
-#define FEC_U(x) ((u64)(x))
-    pos = FEC_U(c[0]) + c[8] + c[9];                      neg = FEC_U(c[11]) + c[12] + c[13] + c[14];
-    acc = (long long)(pos - neg);                         l[0] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[1]) + c[9] + c[10];                     neg = FEC_U(c[12]) + c[13] + c[14] + c[15];
-    acc += (long long)(pos - neg);                        l[1] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[2]) + c[10] + c[11];                    neg = FEC_U(c[13]) + c[14] + c[15];
-    acc += (long long)(pos - neg);                        l[2] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[3]) + 2 * (FEC_U(c[11]) + c[12]) + c[13];   neg = FEC_U(c[15]) + c[8] + c[9];
-    acc += (long long)(pos - neg);                        l[3] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[4]) + 2 * (FEC_U(c[12]) + c[13]) + c[14];   neg = FEC_U(c[9]) + c[10];
-    acc += (long long)(pos - neg);                        l[4] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[5]) + 2 * (FEC_U(c[13]) + c[14]) + c[15];   neg = FEC_U(c[10]) + c[11];
-    acc += (long long)(pos - neg);                        l[5] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[6]) + 3 * FEC_U(c[14]) + 2 * FEC_U(c[15]) + c[13];  neg = FEC_U(c[8]) + c[9];
-    acc += (long long)(pos - neg);                        l[6] = (u32)acc; acc >>= 32;
-    pos = FEC_U(c[7]) + 3 * FEC_U(c[15]) + c[8];          neg = FEC_U(c[10]) + c[11] + c[12] + c[13];
-    acc += (long long)(pos - neg);                        l[7] = (u32)acc; acc >>= 32;
-#undef FEC_U
-    int t = (int)acc;        // in [-4, 5]
-    t = fold_top(l, t);      // now in {-1,0,1}
-    t = fold_top(l, t);      // now 0, l in [0, 2^256)
-    (void)t;
+    u32 t[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = c[i];
+    u32 cy = 0u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int b = 2 * r;
+      const u32 q0 = t[b], q1 = t[b + 1];
+      // m = q + ((q + cy) << 64) - (q << 32)   (mod 2^128; the true value is below 2^128)
+      u32 s2, s3;
+      if (r == 0) { s2 = q0; s3 = q1; } else { s2 = add_cc(q0, cy); s3 = addc(q1, 0u); }
+      const u32 m1 = sub_cc(q1, q0);
+      const u32 m2 = subc_cc(s2, q1);
+      const u32 m3 = subc(s3, 0u);
+      t[b + 3] = add_cc(t[b + 3], q0);
+      t[b + 4] = addc_cc(t[b + 4], q1);
+      t[b + 5] = addc_cc(t[b + 5], 0u);
+      t[b + 6] = addc_cc(t[b + 6], q0);
+      t[b + 7] = addc_cc(t[b + 7], m1);
+      t[b + 8] = addc_cc(t[b + 8], m2);
+      t[b + 9] = addc_cc(t[b + 9], m3);
+      cy = addc(0u, 0u);
+    }
+    // (cy, t[8..16)) < 2p: one conditional subtraction
     u32 p[8], d[8];
     P(p);
-    u32 bw = sub8(d, l, p);
-    select8(o, bw - 1u, d, l);  // bw==0 -> l >= p -> take d
+    const u32 bw = sub8(d, t + 8, p);
+    select8(o, (0u - cy) | (bw - 1u), d, t + 8);
   }
   FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 r[16];
@@ -501,6 +510,17 @@ struct FeP256 {
   }
   FEC_DEV static void canon(u32 o[8], const u32 a[8]) { copy8(o, a); }
   FEC_DEV static u32 is_zero(const u32 a[8]) { return is_zero8(a); }
+  FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) {  // a < p as an integer -> a * 2^256 mod p
+    u32 rr[8];
+    RR(rr);
+    mul(o, a, rr);
+  }
+  FEC_DEV static void to_plain(u32 o[8], const u32 a[8]) {  // back to the integer in [0,p)
+    u32 t[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t[i] = a[i]; t[8 + i] = 0u; }
+    reduce512(o, t);
+  }
   FEC_DEV static void mul2(u32 o[8], const u32 a[8]) { add(o, a, a); }
   FEC_DEV static void mul3(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, a); }
   FEC_DEV static void mul4(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, t); }

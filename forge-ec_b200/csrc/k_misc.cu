@@ -14,6 +14,8 @@ k_field_bench(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint
     u32 x[8], y[8], r[8];
     load_rec32_le(x, a + lane * 32);
     load_rec32_le(y, b + lane * 32);
+    F::from_plain(x, x);  // P-256 computes in the Montgomery domain; the records are integers
+    F::from_plain(y, y);
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
       if (OP == FEC_FIELD_MUL) {
@@ -25,7 +27,7 @@ k_field_bench(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint
         F::sqr(x, x);
       }
     }
-    F::canon(r, x);
+    F::to_plain(r, x);
     store_rec32_le(out + lane * 32, r);
   }
 }

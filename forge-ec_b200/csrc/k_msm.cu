@@ -68,6 +68,8 @@ k_msm_partial(const uint8_t* __restrict__ xy, const uint8_t* __restrict__ st, si
     u32 x[8], y[8];
     load_rec32_be(x, xy + ld * 64);
     load_rec32_be(y, xy + ld * 64 + 32);
+    C::F::from_plain(x, x);  // the products are byte records (integers); no-op except for P-256
+    C::F::from_plain(y, y);
     const u32 s = live ? (u32)st[ld] : (u32)LANE_INFINITY;
     if (s == LANE_SCALAR_RANGE || s == LANE_POINT_INVALID) worst |= s;
     jac_madd_safe_skip<C>(acc, x, y, s != 0u ? 0xFFFFFFFFu : 0u);
@@ -109,10 +111,10 @@ k_msm_final(const u32* __restrict__ partials, int m, const u32* __restrict__ bad
     const u32 zz = F::is_zero(acc.Z);
     if (st == 0u && zz) st = LANE_INFINITY;
     u32 z[8], one[8], zi[8], x[8], y[8];
-    set_small(one, 1u);
+    F::one(one);
     select8(z, st != 0u ? 0xFFFFFFFFu : 0u, one, acc.Z);
     F::inv(zi, z);
-    jac_to_affine<C>(x, y, acc, zi, 0u);
+    jac_to_affine_plain<C>(x, y, acc, zi, 0u);
     uint8_t rec[65];
     sec1_encode(rec, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);
     const int osz = out_size(out_fmt);

@@ -61,7 +61,7 @@ k_pip_digits(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ po
   } else {
     load_rec32_be(px, points + ld * 64);
     load_rec32_be(py, points + ld * 64 + 32);
-    ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+    ok = affine_from_plain<C>(px, py);
   }
   u32 nn[8];
   C::N(nn);
@@ -244,10 +244,10 @@ __global__ void __launch_bounds__(32, 1) k_pip_final(PipScratch sc, int out_fmt,
   const u32 zz = F::is_zero(acc.Z);
   if (st == 0u && zz) st = LANE_INFINITY;
   u32 z[8], one[8], zi[8], x[8], y[8];
-  set_small(one, 1u);
+  F::one(one);
   select8(z, st != 0u ? 0xFFFFFFFFu : 0u, one, acc.Z);
   F::inv(zi, z);
-  jac_to_affine<C>(x, y, acc, zi, 0u);
+  jac_to_affine_plain<C>(x, y, acc, zi, 0u);
   if (threadIdx.x == 0) {
     uint8_t rec[65];
     sec1_encode(rec, out_fmt, x, y, st ? 0xFFFFFFFFu : 0u);

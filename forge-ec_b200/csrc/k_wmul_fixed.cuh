@@ -31,7 +31,7 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
-  set_small(acc, 1u);
+  F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
     if (have) {
@@ -49,7 +49,7 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
       u32 ny[8], one[8], z[8];
       F::neg(ny, Q.Y);
       select8(Q.Y, negm, ny, Q.Y);
-      set_small(one, 1u);
+      F::one(one);
       select8(z, (st != 0u) ? 0xFFFFFFFFu : 0u, one, Q.Z);
       if (cnt == 0) first_tile_of_batch = tile;
       u32* s = slots[cnt];
@@ -71,7 +71,7 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
         for (int i = 0; i < 8; i++) { Q.X[i] = s[i]; Q.Y[i] = s[8 + i]; z[i] = s[16 + i]; pre[i] = s[24 + i]; }
         const u32 st = s[32];
         if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
-        jac_to_affine<C>(x, y, Q, zi, 0u);
+        jac_to_affine_plain<C>(x, y, Q, zi, 0u);
         const size_t first = (first_tile_of_batch + (size_t)t * nwarps) * 32;
         const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
         __syncwarp();
@@ -80,7 +80,7 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
         warp_copy(out + first * osz, io, (size_t)cnt_lanes * osz);
       }
       cnt = 0;
-      set_small(acc, 1u);
+      F::one(acc);
     }
     if (!have) break;
   }

@@ -63,7 +63,7 @@ k_glv_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
   } else if (live) {
     load_rec32_be(px, points + lane * 64);
     load_rec32_be(py, points + lane * 64 + 32);
-    ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+    ok = affine_from_plain<C>(px, py);
   }
   if (live) load_rec32_be(k, scalars + lane * 32);
   {
@@ -164,7 +164,7 @@ k_glv_finish(size_t n, GlvScratch sc, int out_fmt, uint8_t* __restrict__ out, ui
         for (int i = 0; i < 8; i++) { Q.X[i] = s[i]; Q.Y[i] = s[8 + i]; z[i] = s[16 + i]; pre[i] = s[24 + i]; }
         const u32 st = s[32];
         if (t > 0) { F::mul(zi, inv, pre); F::mul(inv, inv, z); } else { copy8(zi, inv); }
-        jac_to_affine<C>(x, y, Q, zi, 0u);
+        jac_to_affine_plain<C>(x, y, Q, zi, 0u);
         const size_t first = (first_tile_of_batch + (size_t)t * nwarps) * 32;
         const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
         __syncwarp();

@@ -136,13 +136,13 @@ FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], T
     Jac D, A;
     u32 C2[8], C3[8], zt[8], zi[8];
     u32 zr[7][8];
-    copy8(D.X, px); copy8(D.Y, py); set_small(D.Z, 1u);
+    copy8(D.X, px); copy8(D.Y, py); F::one(D.Z);
     jac_dbl<C>(D);
     F::sqr(C2, D.Z);
     F::mul(C3, C2, D.Z);
     F::mul(A.X, px, C2);
     F::mul(A.Y, py, C3);
-    set_small(A.Z, 1u);
+    F::one(A.Z);
     tab.store(0, px, py);
 #pragma unroll 1
     for (int j = 1; j < 8; j++) {
@@ -166,7 +166,7 @@ FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], T
   u32 idx, sgn;
   next_digit(K, idx, sgn);  // top digit: always positive
   tab.load(idx, Q.X, Q.Y);
-  set_small(Q.Z, 1u);
+  F::one(Q.Z);
 #pragma unroll 1
   for (int i = 0; i < 63; i++) {
 #pragma unroll 1
@@ -205,7 +205,7 @@ FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
   u32 idx, sgn, nx[8], ny2[8];
   next_digit_w<COMB_W>(K, idx, sgn);  // top digit: always positive
   comb(COMB_WINDOWS - 1, idx, Q.X, Q.Y);
-  set_small(Q.Z, 1u);
+  F::one(Q.Z);
   next_digit_w<COMB_W>(K, idx, sgn);
   comb(COMB_WINDOWS - 2, idx, nx, ny2);
 #pragma unroll 1
@@ -311,12 +311,12 @@ FEC_DEV void jac_madd_safe_skip(Jac& q, const u32 tx[8], const u32 ty[8], u32 sk
   u32 exc = jac_madd<C>(q, tx, ty, skip);
   if (warp_any(exc)) {
     Jac d;
-    copy8(d.X, tx); copy8(d.Y, ty); set_small(d.Z, 1u);
+    copy8(d.X, tx); copy8(d.Y, ty); C::F::one(d.Z);
     jac_dbl<C>(d);
     u32 isdbl = 0u - ((exc >> 1) & 1u);
     u32 isinf = (0u - (exc & 1u)) & ~isdbl;
     u32 one[8], zero[8];
-    set_small(one, 1u); set_small(zero, 0u);
+    C::F::one(one); set_small(zero, 0u);
     select8(q.X, isdbl, d.X, q.X); select8(q.Y, isdbl, d.Y, q.Y); select8(q.Z, isdbl, d.Z, q.Z);
     select8(q.X, isinf, one, q.X); select8(q.Y, isinf, one, q.Y); select8(q.Z, isinf, zero, q.Z);
   }
@@ -411,7 +411,8 @@ FEC_DEV void wmul_var_glv_core(Jac& Q, u32 zs[8], const u32 k[8], const u32 px[8
   }
 }
 
-// Jacobian -> affine with a supplied 1/Z, conditional negation, canonical limbs
+// Jacobian -> affine with a supplied 1/Z, conditional negation, canonical limbs in the field's internal
+// representation (table entries, intermediate points); jac_to_affine_plain gives the integers that are encoded
 template <class C>
 FEC_DEV void jac_to_affine(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u32 negm) {
   typedef typename C::F F;
@@ -424,6 +425,29 @@ FEC_DEV void jac_to_affine(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u3
   F::neg(ny, t);
   select8(t, negm, ny, t);
   F::canon(y, t);
+}
+template <class C>
+FEC_DEV void jac_to_affine_plain(u32 x[8], u32 y[8], const Jac& Q, const u32 zi[8], u32 negm) {
+  typedef typename C::F F;
+  u32 z2[8], t[8], ny[8];
+  F::sqr(z2, zi);
+  F::mul(t, Q.X, z2);
+  F::to_plain(x, t);
+  F::mul(z2, z2, zi);
+  F::mul(t, Q.Y, z2);
+  F::neg(ny, t);
+  select8(t, negm, ny, t);
+  F::to_plain(y, t);
+}
+// affine point from its byte record (big-endian X || Y already loaded as integers): range and curve checks, then
+// the internal representation.  Returns the ok mask; x, y are only meaningful where it is set.
+template <class C>
+FEC_DEV u32 affine_from_plain(u32 x[8], u32 y[8]) {
+  typedef typename C::F F;
+  const u32 ok = F::in_range(x) & F::in_range(y);
+  F::from_plain(x, x);
+  F::from_plain(y, y);
+  return ok & on_curve<C>(x, y);
 }
 
 // SEC1 / raw affine encodings.  fmt: 0 = 02|03 || X (33 B), 1 = 04 || X || Y (65 B), 2 = X || Y (64 B), 3 = X (32 B,
@@ -456,7 +480,8 @@ FEC_DEV u32 sec1_decompress(u32 x[8], u32 y[8], const uint8_t* rec) {
   load_be32(x, rec + 1);
   u32 ok = ((pre == 2u) | (pre == 3u)) ? 0xFFFFFFFFu : 0u;
   ok &= F::in_range(x);
-  u32 rhs[8], t[8], b[8], yc[8], ny[8];
+  F::from_plain(x, x);
+  u32 rhs[8], t[8], b[8], yc[8], ny[8], yp[8];
   F::sqr(rhs, x);
   F::mul(rhs, rhs, x);
   if (C::A_MINUS3) {
@@ -473,7 +498,8 @@ FEC_DEV u32 sec1_decompress(u32 x[8], u32 y[8], const uint8_t* rec) {
   ok &= F::is_zero(t);
   F::neg(t, yc);
   F::canon(ny, t);
-  u32 flip = 0u - ((yc[0] ^ pre) & 1u);
+  F::to_plain(yp, yc);  // the parity that the prefix byte names is that of the integer y
+  u32 flip = 0u - ((yp[0] ^ pre) & 1u);
   select8(y, flip, ny, yc);
   return ok;
 }
@@ -641,7 +667,7 @@ FEC_DEV void comb_base(u32 bx[8], u32 by[8], int i) {
   typedef typename C::F F;
   Jac R;
   C::G(R.X, R.Y);
-  set_small(R.Z, 1u);
+  F::one(R.Z);
   for (int d = 0; d < COMB_W * i; d++) jac_dbl<C>(R);
   u32 zi[8];
   F::inv(zi, R.Z);
@@ -651,7 +677,7 @@ FEC_DEV void comb_base(u32 bx[8], u32 by[8], int i) {
 // the running multiple is >= 2 whenever the base is added)
 template <class C>
 FEC_DEV void comb_entry_jac(Jac& R, const u32 bx[8], const u32 by[8], int j) {
-  copy8(R.X, bx); copy8(R.Y, by); set_small(R.Z, 1u);
+  copy8(R.X, bx); copy8(R.Y, by); C::F::one(R.Z);
   const int m = 2 * j + 1;
   int top = COMB_W - 1;
   while (top > 0 && !((m >> top) & 1)) top--;

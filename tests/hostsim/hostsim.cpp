@@ -49,6 +49,7 @@ struct HostNiels {
 template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
   u32 x[8], y[8], r[8], t[8];
   load_le32(x, a); load_le32(y, b);
+  F::from_plain(x, x); F::from_plain(y, y);  // byte records are integers; FeP256 computes in the Montgomery domain
   switch (op) {
     case 0: F::mul(t, x, y); break;
     case 1: F::sqr(t, x); break;
@@ -60,10 +61,10 @@ template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uin
     case 8: F::mul3(t, x); break;
     case 9: F::mul4(t, x); break;
     case 10: F::mul8(t, x); break;
-    case 11: { u32 m = F::is_zero(x); set_small(t, m & 1u); } break;
+    case 11: { u32 m = F::is_zero(x); set_small(t, 0u); if (m & 1u) F::one(t); } break;
     default: F::dbl(t, x); break;
   }
-  F::canon(r, t);
+  F::to_plain(r, t);
   store_le32(o, r);
 }
 
@@ -83,7 +84,7 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
       ok = sec1_decompress<C>(px, py, pt);
     } else {
       load_be32(px, pt); load_be32(py, pt + 32);
-      ok = F::in_range(px) & F::in_range(py) & on_curve<C>(px, py);
+      ok = affine_from_plain<C>(px, py);
     }
     u32 gx[8], gy[8];
     C::G(gx, gy);
@@ -115,11 +116,11 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
     }
   }
   u32 z[8], zi[8], one[8], x[8], y[8];
-  set_small(one, 1u);
+  F::one(one);
   u32 zz = F::is_zero(Q.Z);
   select8(z, zz, one, Q.Z);
   F::inv(zi, z);
-  jac_to_affine<C>(x, y, Q, zi, negm);
+  jac_to_affine_plain<C>(x, y, Q, zi, negm);
   if (zz && st == 0) st = LANE_INFINITY;
   sec1_encode(out, ofmt, x, y, st ? 0xFFFFFFFFu : 0u);
   return (int)st;
