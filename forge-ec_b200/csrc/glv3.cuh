@@ -16,24 +16,6 @@ namespace fec {
 constexpr int GLV_TAB_WORDS = 8 * 24;  // per lane: 8 entries x (x, beta x, y)
 enum { GLV_NEG1 = 1u, GLV_NEG2 = 2u, GLV_CORR1 = 4u, GLV_CORR2 = 8u };
 
-// 8 words <-> 32-byte aligned global memory (two 128-bit accesses on the device)
-FEC_DEV void g_st8(u32* p, const u32 v[8]) {
-#ifdef __CUDACC__
-  reinterpret_cast<uint4*>(p)[0] = make_uint4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<uint4*>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
-#else
-  copy8(p, v);
-#endif
-}
-FEC_DEV void g_ld8(u32 v[8], const u32* p) {
-#ifdef __CUDACC__
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-#else
-  copy8(v, p);
-#endif
-}
-
 // tab: u32[192] of this lane (global memory on the device).  KK: recoding registers of |k1|, |k2| (4 words each).
 FEC_DEV void glv_prepare(u32* tab, u32 zs[8], u32 KK[8], u32& flags, const u32 k[8], const u32 px[8], const u32 py[8]) {
   typedef CurveK1 C;

@@ -150,6 +150,10 @@ constexpr size_t GLV_CHUNK_LANES = size_t(1) << 22;
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);
+// P-256 k*P, the same three-kernel shape without an endomorphism (k_wmul_vm_p256.cu)
+cudaError_t wmul_vm_setup_p256();
+cudaError_t wmul_vm_launch_p256(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
+                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);
 // ECDH tail: n x 32-byte big-endian x-coordinates -> n x out_len bytes (kdf.cuh); dead lanes (status != 0) give zero records
 cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint8_t* status, size_t n, const uint8_t* info, int info_len,
                        int out_len, uint8_t* out);

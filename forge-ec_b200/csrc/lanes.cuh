@@ -128,8 +128,9 @@ FEC_DEV void jac_add_safe(Jac& p, const Jac& q) {
 // Inv: simultaneous inversion across the lanes that call it together: inv(zinv, z), z != 0.
 // Cost: table 1 dbl + 7 madd + 7 x (4M+1S) + shared inversion; loop 252 dbl + 63 madd.
 // -------------------------------------------------------------------------------------
+// the table: affine odd multiples P, 3P, .., 15P (entry j = (2j+1) P), ONE shared inversion
 template <class C, class Tab, class Inv>
-FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], Tab& tab, Inv& inv) {
+FEC_DEV void wmul_var_table(Tab& tab, const u32 px[8], const u32 py[8], Inv& inv) {
   typedef typename C::F F;
   {
     // odd multiples P, 3P, .., 15P on the curve isomorphic by C = Z(2P), where 2P is affine
@@ -163,6 +164,11 @@ FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], T
       F::mul(zi, zi, zr[j - 1]);
     }
   }
+}
+template <class C, class Tab, class Inv>
+FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], Tab& tab, Inv& inv) {
+  typedef typename C::F F;
+  wmul_var_table<C>(tab, px, py, inv);
   u32 idx, sgn;
   next_digit(K, idx, sgn);  // top digit: always positive
   tab.load(idx, Q.X, Q.Y);

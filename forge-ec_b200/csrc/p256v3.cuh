@@ -1,0 +1,84 @@
+// p256v3.cuh -- P-256 variable-base k*P as three stages (the per-lane work of k_p3_prep, k_p3_ladder, k_p3_finish in
+// k_wmul_vm_p256.cu; host-compilable for tests/hostsim), the same split as glv3.cuh makes for secp256k1:
+//
+//   prepare : 8 affine odd multiples of P (built on the curve isomorphic by Z(2P), brought back with ONE inversion
+//             shared by the lanes that call it together), regular signed recoding of k.
+//   ladder  : 63 x (4 doublings a = -3 + 1 mixed addition) on the accumulator machine of vm.cuh (95 % of the work).
+//   finish  : conditional negation (even scalars were replaced by n - k).  Normalisation/encoding follow in the kernel.
+//
+// P-256 has no efficient endomorphism, so there is one 64-digit scalar and no isomorphic-curve loop (the a = -3
+// doubling does not survive the isomorphism).  Replaces P256::multiply (forge-ec-curves/src/p256.rs:2120-2156).
+#pragma once
+#include "lanes.cuh"
+#include "vm.cuh"
+
+namespace fec {
+
+constexpr int P3_TAB_WORDS = 8 * 16;  // per lane: 8 entries x (x, y)
+
+// the lane's table in global memory behind the Tab interface of wmul_var_table
+struct GlobalLaneTab {
+  u32* e;
+  FEC_DEV void store(int j, const u32 x[8], const u32 y[8]) { g_st8(e + 16 * j, x); g_st8(e + 16 * j + 8, y); }
+  FEC_DEV void load(u32 j, u32 x[8], u32 y[8]) const { g_ld8(x, e + 16 * j); g_ld8(y, e + 16 * j + 8); }
+};
+
+// rare repair of a lane whose mixed addition hit Q = infinity or Q = +-T (warp-uniform branch in the caller)
+template <class C, int T>
+FEC_DEV void vm_madd_fix(saddr S, const u32* e, u32 neg_y, u32 flags) {
+  typedef typename C::F F;
+  typedef Vm<F, T> V;
+  u32 tx[8], ty[8], ny[8];
+  g_ld8(tx, e);
+  g_ld8(ty, e + 8);
+  F::neg(ny, ty);
+  select8(ty, neg_y, ny, ty);
+  Jac q;
+  V::ldv(q.X, V::slot(S, VS_X)); V::ldv(q.Y, V::slot(S, VS_Y)); V::ldv(q.Z, V::slot(S, VS_Z));
+  jac_madd_fix<C>(q, tx, ty, flags);
+  fe t;
+  copy8(t.v, q.X); V::st(V::slot(S, VS_X), t);
+  copy8(t.v, q.Y); V::st(V::slot(S, VS_Y), t);
+  copy8(t.v, q.Z); V::st(V::slot(S, VS_Z), t);
+}
+
+// the loop: on return slots X, Y, Z hold k' P, k' the odd scalar behind the recoding register Kin
+template <int T>
+FEC_DEV void p3_ladder(saddr S, const u32* tab, const u32 Kin[8]) {
+  typedef CurveP256 C;
+  typedef FeP256 F;
+  typedef Vm<F, T> V;
+  u32 K[8];
+  copy8(K, Kin);
+  u32 idx, sgn;
+  next_digit(K, idx, sgn);  // top digit: always positive
+  vm_prefetch_xy<F, T>(S, tab + idx * 16);
+  cp_async_wait();
+  {
+    fe a = V::ld(V::slot(S, VS_TX));
+    V::st(V::slot(S, VS_X), a);
+    a = V::ld(V::slot(S, VS_TY));
+    V::st(V::slot(S, VS_Y), a);
+    F::one(a.v);
+    V::st(V::slot(S, VS_Z), a);
+  }
+  next_digit(K, idx, sgn);
+  vm_prefetch_xy<F, T>(S, tab + idx * 16);
+#pragma unroll 1
+  for (int i = 0; i < 63; i++) {
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) vm_jac_dbl_am3<F, T>(S);
+    const u32 cur = idx, neg_y = sgn;
+    cp_async_wait();
+    const u32 fl = vm_jac_madd_1<F, T>(S, neg_y);
+    // the addend slots are free again: start fetching the next addend (none after the last addition)
+    if (i < 62) {
+      next_digit(K, idx, sgn);
+      vm_prefetch_xy<F, T>(S, tab + idx * 16);
+    }
+    vm_jac_madd_2<F, T>(S);
+    if (warp_any(fl)) vm_madd_fix<C, T>(S, tab + cur * 16, neg_y, fl);
+  }
+}
+
+}  // namespace fec

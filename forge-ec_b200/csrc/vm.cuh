@@ -57,6 +57,24 @@ FEC_DEV void cp_async_wait() {}
 FEC_DEV saddr sa_add(saddr p, int bytes) { return p + bytes / 4; }
 #endif
 
+// 8 words <-> 32-byte aligned global memory (two 128-bit accesses on the device)
+FEC_DEV void g_st8(u32* p, const u32 v[8]) {
+#ifdef __CUDACC__
+  reinterpret_cast<uint4*>(p)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<uint4*>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+#else
+  copy8(p, v);
+#endif
+}
+FEC_DEV void g_ld8(u32 v[8], const u32* p) {
+#ifdef __CUDACC__
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#else
+  copy8(v, p);
+#endif
+}
+
 // F: field (FeK1, Fe25519, FeP256), T: threads per block (1 on the host)
 template <class F, int T>
 struct Vm {
@@ -154,6 +172,49 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = V::ld(Cs);
   a = vm_small<F, 8>(a);
   a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
+}
+
+// Q <- 2Q for a = -3 curves (P-256): dbl-2001-b (3M + 5S), in place
+template <class F, int T>
+FEC_DEV void vm_jac_dbl_am3(saddr S) {
+  typedef Vm<F, T> V;
+  const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
+              Cs = V::slot(S, VS_C), D = V::slot(S, VS_D);
+  fe a = V::ld(Z);
+  a = vm_sqr<F>(a); V::st(A, a);                 // delta = Z^2
+  a = vm_rsub<F, T>(a, X); V::st(D, a);          // X - delta
+  a = V::ld(X);
+  a = vm_add<F, T>(a, A);
+  a = vm_mul<F, T>(a, D);
+  a = vm_small<F, 3>(a); V::st(D, a);            // alpha = 3 (X - delta)(X + delta)
+  a = V::ld(Y);
+  a = vm_sqr<F>(a); V::st(B, a);                 // gamma = Y^2
+  a = vm_mul<F, T>(a, X);
+  a = vm_small<F, 4>(a); V::st(Cs, a);           // 4 beta = 4 X gamma
+  a = V::ld(Y);
+  a = vm_add<F, T>(a, Z);
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, B);
+  a = vm_sub<F, T>(a, A); V::st(Z, a);           // Z3 = (Y + Z)^2 - gamma - delta
+  a = V::ld(D);
+  a = vm_sqr<F>(a);
+  a = vm_sub<F, T>(a, Cs);
+  a = vm_sub<F, T>(a, Cs); V::st(X, a);          // X3 = alpha^2 - 8 beta
+  a = vm_rsub<F, T>(a, Cs);                      // 4 beta - X3
+  a = vm_mul<F, T>(a, D); V::st(A, a);           // alpha (4 beta - X3)
+  a = V::ld(B);
+  a = vm_sqr<F>(a);
+  a = vm_small<F, 8>(a);
+  a = vm_rsub<F, T>(a, A); V::st(Y, a);          // Y3 = alpha (4 beta - X3) - 8 gamma^2
+}
+
+// start the copy of an affine table entry (x at e, y at e + 8 words, global memory) into the addend slots
+template <class F, int T>
+FEC_DEV void vm_prefetch_xy(saddr S, const u32* e) {
+  typedef Vm<F, T> V;
+  const saddr TX = V::slot(S, VS_TX), TY = V::slot(S, VS_TY);
+  cp_async16(TX, e); cp_async16(sa_add(TX, V::HALF), e + 4);
+  cp_async16(TY, e + 8); cp_async16(sa_add(TY, V::HALF), e + 12);
 }
 
 // Q <- Q + (TX, +-TY), madd-2007-bl (7M + 4S), in place, first half: up to r = 2(S2 - Y1).  After it the

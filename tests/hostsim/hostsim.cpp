@@ -7,13 +7,14 @@
 #include <vector>
 #include "../../forge-ec_b200/csrc/lanes.cuh"
 #include "../../forge-ec_b200/csrc/glv3.cuh"
+#include "../../forge-ec_b200/csrc/p256v3.cuh"
 #include "../../forge-ec_b200/csrc/quirk_k1.cuh"
 #include "../../forge-ec_b200/csrc/kdf.cuh"
 
 using namespace fec;
 
 namespace {
-bool g_use_vm = true;  // secp256k1 variable base: three-stage accumulator-machine path (default) or the single-kernel path
+bool g_use_vm = true;  // variable base: three-stage accumulator-machine path (default) or the single-kernel path
 struct HostTab {
   u32 e[8][16];
   void store(int j, const u32 x[8], const u32 y[8]) { copy8(e[j], x); copy8(e[j] + 8, y); }
@@ -111,6 +112,13 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
         wmul_var_glv_core(Q, zs, k, px, py, tab);
         F::mul(Q.Z, Q.Z, zs);
       }
+    } else if (g_use_vm) {
+      // the stages of k_wmul_vm_p256.cu with T = 1 (the sign is applied by jac_to_affine_plain below, as k_p3_finish does)
+      std::vector<u32> gtab(P3_TAB_WORDS), slots(VS_COUNT * 8);
+      GlobalLaneTab gt{gtab.data()};
+      wmul_var_table<C>(gt, px, py, inv);
+      p3_ladder<1>(slots.data(), gtab.data(), K);
+      copy8(Q.X, &slots[VS_X * 8]); copy8(Q.Y, &slots[VS_Y * 8]); copy8(Q.Z, &slots[VS_Z * 8]);
     } else {
       wmul_var_core<C>(Q, K, px, py, tab, inv);
     }

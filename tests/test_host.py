@@ -123,7 +123,7 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
             assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), ("fixed", curve, hex(k))
             P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
             for pt, pfmt in ((be(P[0]) + be(P[1]), 0), (pm.sec1_encode(P, 0), 1), (be(c.gx) + be(c.gy), 0)):
-                for use_vm in ((1, 0) if curve == 0 else (1,)):  # secp256k1: three-stage VM path and single-kernel path
+                for use_vm in (1, 0):  # three-stage accumulator-machine path and single-kernel path
                     hostsim.hs_set_var_impl(use_vm)
                     st = hostsim.hs_wmul(curve, be(k), pt, pfmt, 0, 0, o)
                     assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), pt, 1, 0, pfmt), ("var", curve, hex(k), pfmt, use_vm)
