@@ -20,6 +20,11 @@ struct CurveK1 {
   typedef CurveK1 Cold;  // the instantiation used on rarely executed paths
   static constexpr int CURVE_ID = 0;
   static constexpr bool A_MINUS3 = false;
+  // which pipe bounds the field arithmetic decides the point formulas of the long loops (vm.cuh): false = multiply pipe
+  // (squarings are cheap, additions free), true = ALU pipe (a canonical-form addition costs a quarter of a squaring: trade
+  // additions for multiplications).  The register-resident mixed addition below keeps 7M + 4S for both curves: with the
+  // field routines called out of line the 8M + 3S form measured 5 % slower in the fixed-base kernel.
+  static constexpr bool ALU_BOUND = false;
   FEC_DEV static void B(u32 b[8]) {
     b[0] = 7u;
 #pragma unroll
@@ -42,6 +47,7 @@ struct CurveP256 {
   typedef CurveP256 Cold;
   static constexpr int CURVE_ID = 1;
   static constexpr bool A_MINUS3 = true;
+  static constexpr bool ALU_BOUND = true;
   FEC_DEV static void B(u32 b[8]) {
     // b * 2^256 mod p (FeP256 works in the Montgomery domain; b = 5AC635D8 AA3A93E7 B3EBBD55 769886BC 651D06B0 CC53B0F6 3BCE3C3E 27D2604B)
     b[0] = 0x29C4BDDFu; b[1] = 0xD89CDF62u; b[2] = 0x78843090u; b[3] = 0xACF005CDu;
@@ -88,12 +94,13 @@ FEC_DEV void jac_set_inf(Jac& q) {
   q.X[0] = 1; q.Y[0] = 1;
 }
 
-// Q <- 2Q, in place.  a=0: dbl-2009-l (2M+5S).  a=-3: dbl-2001-b (3M+5S).  Z=0 stays Z=0.
+// Q <- 2Q, in place.  a=0: dbl-2009-l (2M+5S).  a=-3: 4M+4S with 2Y carried through (Z3 = 2Y Z, 4 beta = X (2Y)^2,
+// 8 gamma^2 = (2Y)^4 / 2): 4 additions + 5 subtractions + a halving instead of the 9 + 7 of dbl-2001-b.  Z=0 stays Z=0.
 // Written to keep few temporaries alive (Q + 4 field elements) and to use the single-pass small multiples.
 template <class C>
 FEC_DEV void jac_dbl(Jac& q) {
   typedef typename C::F F;
-  if (!C::A_MINUS3) {
+  if constexpr (!C::A_MINUS3) {
     u32 A[8], B[8], Cc[8], t[8];
     F::sqr(A, q.X);
     F::sqr(B, q.Y);
@@ -114,27 +121,24 @@ FEC_DEV void jac_dbl(Jac& q) {
     F::mul8(Cc, Cc);            // 8C
     F::sub(q.Y, t, Cc);
   } else {
-    u32 delta[8], gamma[8], beta[8], alpha[8], t[8];
+    u32 delta[8], g4[8], beta[8], alpha[8], t[8];
     F::sqr(delta, q.Z);
-    F::sqr(gamma, q.Y);
-    F::mul(beta, q.X, gamma);
     F::sub(t, q.X, delta);
     F::add(alpha, q.X, delta);
     F::mul(alpha, t, alpha);
     F::mul3(alpha, alpha);      // alpha = 3(X-delta)(X+delta)
-    F::add(t, q.Y, q.Z);
-    F::sqr(t, t);
-    F::sub(t, t, gamma);
-    F::sub(q.Z, t, delta);      // Z3 = (Y+Z)^2 - gamma - delta
-    F::mul4(beta, beta);        // 4 beta
+    F::mul2(t, q.Y);            // 2Y
+    F::mul(q.Z, t, q.Z);        // Z3 = 2YZ
+    F::sqr(g4, t);              // 4 gamma
+    F::mul(beta, q.X, g4);      // 4 beta
     F::sqr(t, alpha);
     F::sub(t, t, beta);
     F::sub(q.X, t, beta);       // X3 = alpha^2 - 8 beta
     F::sub(t, beta, q.X);
     F::mul(t, alpha, t);
-    F::sqr(gamma, gamma);
-    F::mul8(gamma, gamma);      // 8 gamma^2
-    F::sub(q.Y, t, gamma);
+    F::sqr(g4, g4);
+    F::half(g4, g4);            // 8 gamma^2
+    F::sub(q.Y, t, g4);
   }
 }
 
@@ -206,11 +210,11 @@ FEC_DEV u32 jac_madd(Jac& q, const u32 x2[8], const u32 y2[8], u32 t_inf) {
   F::mul(S2, y2, S2);
   F::sub(H, U2, q.X);
   F::sqr(HH, H);
-  F::mul4(I, HH);                    // I = 4 HH
-  F::mul(J, H, I);
   F::sub(r, S2, q.Y);
   u32 h_zero = F::is_zero(H);
   u32 r_zero = F::is_zero(r);
+  F::mul4(I, HH);                    // I = 4 HH
+  F::mul(J, H, I);
   F::mul2(r, r);                     // r = 2(S2 - Y1)
   F::mul(V, q.X, I);
   F::sqr(o.X, r);

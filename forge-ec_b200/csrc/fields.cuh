@@ -530,6 +530,23 @@ struct FeP256 {
     P(p);
     return ~geq8(a, p);
   }
+  // a / 2: (a + (a odd ? p : 0)) >> 1; canonical in, canonical out
+  FEC_DEV static void half(u32 o[8], const u32 a[8]) {
+    const u32 m = 0u - (a[0] & 1u);
+    u32 t[8];
+    t[0] = add_cc(a[0], m);
+    t[1] = addc_cc(a[1], m);
+    t[2] = addc_cc(a[2], m);
+    t[3] = addc_cc(a[3], 0u);
+    t[4] = addc_cc(a[4], 0u);
+    t[5] = addc_cc(a[5], 0u);
+    t[6] = addc_cc(a[6], m & 1u);
+    t[7] = addc_cc(a[7], m);
+    const u32 c = addc(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 7; i++) o[i] = funnel_l(t[i], t[i + 1], 31);
+    o[7] = funnel_l(t[7], c, 31);
+  }
   FEC_DEV static void sqr_n(u32 x[8], int n) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) sqr(x, x);

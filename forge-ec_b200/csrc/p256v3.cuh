@@ -3,7 +3,8 @@
 //
 //   prepare : 8 affine odd multiples of P (built on the curve isomorphic by Z(2P), brought back with ONE inversion
 //             shared by the lanes that call it together), regular signed recoding of k.
-//   ladder  : 63 x (4 doublings a = -3 + 1 mixed addition) on the accumulator machine of vm.cuh (95 % of the work).
+//   ladder  : 63 x (4 doublings a = -3, 4M+4S + 1 mixed addition, 8M+3S) on the accumulator machine of vm.cuh (95 % of
+//             the work); the formulas are the ones with the fewest additions, because this field is ALU-bound.
 //   finish  : conditional negation (even scalars were replaced by n - k).  Normalisation/encoding follow in the kernel.
 //
 // P-256 has no efficient endomorphism, so there is one 64-digit scalar and no isomorphic-curve loop (the a = -3
@@ -70,13 +71,13 @@ FEC_DEV void p3_ladder(saddr S, const u32* tab, const u32 Kin[8]) {
     for (int d = 0; d < 4; d++) vm_jac_dbl_am3<F, T>(S);
     const u32 cur = idx, neg_y = sgn;
     cp_async_wait();
-    const u32 fl = vm_jac_madd_1<F, T>(S, neg_y);
+    const u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND>(S, neg_y);
     // the addend slots are free again: start fetching the next addend (none after the last addition)
     if (i < 62) {
       next_digit(K, idx, sgn);
       vm_prefetch_xy<F, T>(S, tab + idx * 16);
     }
-    vm_jac_madd_2<F, T>(S);
+    vm_jac_madd_2<F, T, C::ALU_BOUND>(S);
     if (warp_any(fl)) vm_madd_fix<C, T>(S, tab + cur * 16, neg_y, fl);
   }
 }

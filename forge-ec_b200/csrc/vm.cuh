@@ -128,6 +128,11 @@ template <class F, int K> FEC_VMLIN fe vm_small(fe a) {  // a * K, K in {2,3,4,8
   else F::mul8(r.v, a.v);
   return r;
 }
+template <class F> FEC_VMLIN fe vm_half(fe a) {  // a / 2 (fields that provide it)
+  fe r;
+  F::half(r.v, a.v);
+  return r;
+}
 template <class F> FEC_VMLIN fe vm_cneg(fe a, u32 m) {  // m ? -a : a
   fe r;
   u32 n[8];
@@ -174,7 +179,8 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
 }
 
-// Q <- 2Q for a = -3 curves (P-256): dbl-2001-b (3M + 5S), in place
+// Q <- 2Q for a = -3 curves (P-256), in place: 4M + 4S with 2Y carried through (see jac_dbl in curves.cuh) -- the
+// canonical-form additions of P-256 run on the ALU pipe, which bounds this field, so they are traded for a multiplication
 template <class F, int T>
 FEC_DEV void vm_jac_dbl_am3(saddr S) {
   typedef Vm<F, T> V;
@@ -188,14 +194,11 @@ FEC_DEV void vm_jac_dbl_am3(saddr S) {
   a = vm_mul<F, T>(a, D);
   a = vm_small<F, 3>(a); V::st(D, a);            // alpha = 3 (X - delta)(X + delta)
   a = V::ld(Y);
-  a = vm_sqr<F>(a); V::st(B, a);                 // gamma = Y^2
-  a = vm_mul<F, T>(a, X);
-  a = vm_small<F, 4>(a); V::st(Cs, a);           // 4 beta = 4 X gamma
-  a = V::ld(Y);
-  a = vm_add<F, T>(a, Z);
-  a = vm_sqr<F>(a);
-  a = vm_sub<F, T>(a, B);
-  a = vm_sub<F, T>(a, A); V::st(Z, a);           // Z3 = (Y + Z)^2 - gamma - delta
+  a = vm_small<F, 2>(a); V::st(B, a);            // 2Y
+  a = vm_mul<F, T>(a, Z); V::st(Z, a);           // Z3 = 2Y Z
+  a = V::ld(B);
+  a = vm_sqr<F>(a); V::st(B, a);                 // 4 gamma
+  a = vm_mul<F, T>(a, X); V::st(Cs, a);          // 4 beta
   a = V::ld(D);
   a = vm_sqr<F>(a);
   a = vm_sub<F, T>(a, Cs);
@@ -204,7 +207,7 @@ FEC_DEV void vm_jac_dbl_am3(saddr S) {
   a = vm_mul<F, T>(a, D); V::st(A, a);           // alpha (4 beta - X3)
   a = V::ld(B);
   a = vm_sqr<F>(a);
-  a = vm_small<F, 8>(a);
+  a = vm_half<F>(a);                             // 8 gamma^2
   a = vm_rsub<F, T>(a, A); V::st(Y, a);          // Y3 = alpha (4 beta - X3) - 8 gamma^2
 }
 
@@ -220,7 +223,8 @@ FEC_DEV void vm_prefetch_xy(saddr S, const u32* e) {
 // Q <- Q + (TX, +-TY), madd-2007-bl (7M + 4S), in place, first half: up to r = 2(S2 - Y1).  After it the
 // addend slots are no longer needed (the caller may start the next prefetch into them).
 // Returns the flag word of jac_madd_lean: bit0 formula does not apply, bit1 Q was at infinity, bit2 doubling.
-template <class F, int T>
+// SUBS_ONLY (fields bound by the ALU pipe): the 8M + 3S form of jac_madd_lean, r = S2 - Y1 undoubled.
+template <class F, int T, bool SUBS_ONLY = false>
 FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
@@ -237,14 +241,35 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   a = vm_cneg<F>(a, neg_y);                      // S2 = +-y2 Z1^3
   a = vm_sub<F, T>(a, Y);
   const u32 r_zero = F::is_zero(a.v);
-  a = vm_small<F, 2>(a); V::st(R, a);            // r = 2(S2 - Y1)
+  if (!SUBS_ONLY) a = vm_small<F, 2>(a);
+  V::st(R, a);                                   // r = 2(S2 - Y1), or S2 - Y1
   return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
 }
-template <class F, int T>
+template <class F, int T, bool SUBS_ONLY = false>
 FEC_DEV void vm_jac_madd_2(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
               R = V::slot(S, VS_C), HH = V::slot(S, VS_D);
+  if (SUBS_ONLY) {
+    fe a = V::ld(Z);
+    a = vm_mul<F, T>(a, H); V::st(Z, a);           // Z3 = Z1 H
+    a = V::ld(H);
+    a = vm_sqr<F>(a); V::st(HH, a);                // HH
+    a = vm_mul<F, T>(a, H); V::st(H, a);           // HHH
+    a = V::ld(X);
+    a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 HH
+    a = V::ld(R);
+    a = vm_sqr<F>(a);
+    a = vm_sub<F, T>(a, H);
+    a = vm_sub<F, T>(a, A);
+    a = vm_sub<F, T>(a, A); V::st(X, a);           // X3 = r^2 - HHH - 2V
+    a = vm_rsub<F, T>(a, A);                       // V - X3
+    a = vm_mul<F, T>(a, R); V::st(R, a);           // r (V - X3)
+    a = V::ld(Y);
+    a = vm_mul<F, T>(a, H);                        // Y1 HHH
+    a = vm_rsub<F, T>(a, R); V::st(Y, a);          // Y3
+    return;
+  }
   fe a = V::ld(H);
   a = vm_sqr<F>(a); V::st(HH, a);                // HH
   a = V::ld(Z);
