@@ -136,6 +136,10 @@ cudaError_t wmul_fixed_setup_k1();
 cudaError_t wmul_fixed_setup_p256();
 cudaError_t wmul_fixed_launch_k1(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
 cudaError_t wmul_fixed_launch_p256(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
+cudaError_t wmul_fixed_vm_setup_k1();
+cudaError_t wmul_fixed_vm_setup_p256();
+cudaError_t wmul_fixed_vm_launch_k1(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
+cudaError_t wmul_fixed_vm_launch_p256(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
 cudaError_t build_comb_launch_k1(cudaStream_t, u32*, u32*);
 cudaError_t build_comb_launch_p256(cudaStream_t, u32*, u32*);
 

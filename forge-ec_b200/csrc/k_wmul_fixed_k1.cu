@@ -8,10 +8,24 @@ cudaError_t wmul_fixed_launch_k1(int sms, cudaStream_t st, const uint8_t* s, con
 cudaError_t build_comb_launch_k1(cudaStream_t st, u32* comb, u32* bases) { return build_comb_launch_t<CurveK1>(st, comb, bases); }
 cudaError_t wmul_fixed_setup() {
   cudaError_t e = wmul_fixed_setup_k1();
+  if (e == cudaSuccess) e = wmul_fixed_vm_setup_k1();
+  if (e == cudaSuccess) e = wmul_fixed_vm_setup_p256();
   return e != cudaSuccess ? e : wmul_fixed_setup_p256();
+}
+// Which kernel serves a curve was measured (2^22 lanes): the accumulator-machine kernel wins where the field is bound by
+// the ALU pipe (P-256: 351 -> 441 M/s), the register-resident kernel with the field routines in line where it is bound
+// by the multiply pipe (secp256k1: 493 vs 483 M/s).  FORGE_EC_FIXED_IMPL=regs|vm forces one of them (A/B measurements).
+static int fixed_impl() {
+  static const int v = [] { const char* e = getenv("FORGE_EC_FIXED_IMPL"); return e == nullptr ? 0 : (e[0] == 'r' ? 1 : (e[0] == 'v' ? 2 : 0)); }();
+  return v;
 }
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* s, const u32* comb, size_t n, int of, uint8_t* o,
                               uint8_t* status) {
+  const int impl = fixed_impl();
+  const bool vm = impl == 2 || (impl == 0 && curve == FEC_P256);
+  if (vm)
+    return curve == FEC_SECP256K1 ? wmul_fixed_vm_launch_k1(sms, st, s, comb, n, of, o, status)
+                                  : wmul_fixed_vm_launch_p256(sms, st, s, comb, n, of, o, status);
   return curve == FEC_SECP256K1 ? wmul_fixed_launch_k1(sms, st, s, comb, n, of, o, status)
                                 : wmul_fixed_launch_p256(sms, st, s, comb, n, of, o, status);
 }

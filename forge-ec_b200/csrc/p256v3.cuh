@@ -10,8 +10,7 @@
 // P-256 has no efficient endomorphism, so there is one 64-digit scalar and no isomorphic-curve loop (the a = -3
 // doubling does not survive the isomorphism).  Replaces P256::multiply (forge-ec-curves/src/p256.rs:2120-2156).
 #pragma once
-#include "lanes.cuh"
-#include "vm.cuh"
+#include "vm_points.cuh"
 
 namespace fec {
 
@@ -23,25 +22,6 @@ struct GlobalLaneTab {
   FEC_DEV void store(int j, const u32 x[8], const u32 y[8]) { g_st8(e + 16 * j, x); g_st8(e + 16 * j + 8, y); }
   FEC_DEV void load(u32 j, u32 x[8], u32 y[8]) const { g_ld8(x, e + 16 * j); g_ld8(y, e + 16 * j + 8); }
 };
-
-// rare repair of a lane whose mixed addition hit Q = infinity or Q = +-T (warp-uniform branch in the caller)
-template <class C, int T>
-FEC_DEV void vm_madd_fix(saddr S, const u32* e, u32 neg_y, u32 flags) {
-  typedef typename C::F F;
-  typedef Vm<F, T> V;
-  u32 tx[8], ty[8], ny[8];
-  g_ld8(tx, e);
-  g_ld8(ty, e + 8);
-  F::neg(ny, ty);
-  select8(ty, neg_y, ny, ty);
-  Jac q;
-  V::ldv(q.X, V::slot(S, VS_X)); V::ldv(q.Y, V::slot(S, VS_Y)); V::ldv(q.Z, V::slot(S, VS_Z));
-  jac_madd_fix<C>(q, tx, ty, flags);
-  fe t;
-  copy8(t.v, q.X); V::st(V::slot(S, VS_X), t);
-  copy8(t.v, q.Y); V::st(V::slot(S, VS_Y), t);
-  copy8(t.v, q.Z); V::st(V::slot(S, VS_Z), t);
-}
 
 // the loop: on return slots X, Y, Z hold k' P, k' the odd scalar behind the recoding register Kin
 template <int T>

@@ -39,6 +39,18 @@ template <class C> struct HostComb {
     jac_to_affine<C>(x, y, R, zi, 0u);
   }
 };
+// the same entries behind the address interface of wmul_fixed_vm_core (a small ring of buffers: an address stays valid
+// while the next entry is being fetched)
+template <class C> struct HostCombEntry {
+  const HostComb<C>& comb;
+  mutable u32 ring[4][16];
+  mutable int next = 0;
+  const u32* operator()(int i, u32 idx) const {
+    u32* e = ring[next++ & 3];
+    comb(i, idx, e, e + 8);
+    return e;
+  }
+};
 struct HostNiels {
   EdExt bases[COMB_WINDOWS];
   HostNiels() {
@@ -77,7 +89,12 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
   load_be32(k, k_be);
   scalar_prepare<C>(K, negm, st, k);
   Jac Q;
-  if (fixed) {
+  if (fixed && g_use_vm) {
+    std::vector<u32> slots(VS_COUNT * 8);
+    HostCombEntry<C> entry{comb};
+    wmul_fixed_vm_core<C, 1>(slots.data(), K, entry);
+    copy8(Q.X, &slots[VS_X * 8]); copy8(Q.Y, &slots[VS_Y * 8]); copy8(Q.Z, &slots[VS_Z * 8]);
+  } else if (fixed) {
     wmul_fixed_core<C>(Q, K, comb);
   } else {
     u32 ok;

@@ -241,8 +241,8 @@ def test_device_pointer_api_and_properties(engine, fec, pm, n):
     engine.batch_mul_dev(0, a, G, 4096, s2, stream=st)
     torch.cuda.synchronize()
     assert torch.equal(s1[: 33 * 4096], s2[: 33 * 4096])
-    # P-256: the same exchange
-    m = min(n, 1 << 20)
+    # P-256: the same exchange, at the full size too (two scratch chunks and a ragged tile of its three-kernel path)
+    m = n
     engine.synth_dev(2, 5, 0, 0, m, a, edge=False, stream=st)
     engine.synth_dev(2, 5, 1, 0, m, b, edge=False, stream=st)
     engine.batch_mul_dev(1, a, None, m, A, out_fmt=2, stream=st)
@@ -251,6 +251,13 @@ def test_device_pointer_api_and_properties(engine, fec, pm, n):
     engine.batch_mul_dev(1, b, A, m, s2, None, stream=st)
     torch.cuda.synchronize()
     assert torch.equal(s1[: 33 * m], s2[: 33 * m]) and int(st1[:m].sum()) == 0
+    exp, _ = pm.batch_mul(1, a[32 * tail : 32 * n].cpu().numpy().tobytes(), B[64 * tail : 64 * n].cpu().numpy().tobytes(), 16, 0)
+    assert s1[33 * tail : 33 * n].cpu().numpy().tobytes() == exp
+    G = torch.from_numpy(np.frombuffer((_be(pm.CURVES[1].gx) + _be(pm.CURVES[1].gy)) * 4096, dtype=np.uint8).copy()).cuda()
+    engine.batch_mul_dev(1, a, None, 4096, s1, stream=st)
+    engine.batch_mul_dev(1, a, G, 4096, s2, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(s1[: 33 * 4096], s2[: 33 * 4096])
     # X25519: both sides derive the same secret
     ka = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
     kb = torch.empty(n * 32, dtype=torch.uint8, device="cuda")

@@ -119,8 +119,10 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         ks = [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, c.n, 2**256 - 1, (30 << 252) - c.n, 15 << 252] + [rnd.randrange(c.n) for _ in range(6)]
         for k in ks:
             o = ctypes.create_string_buffer(33)
-            st = hostsim.hs_wmul(curve, be(k), None, 0, 1, 0, o)
-            assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), ("fixed", curve, hex(k))
+            for use_vm in (1, 0):  # accumulator-machine kernel and register-resident kernel
+                hostsim.hs_set_var_impl(use_vm)
+                st = hostsim.hs_wmul(curve, be(k), None, 0, 1, 0, o)
+                assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), ("fixed", curve, hex(k), use_vm)
             P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
             for pt, pfmt in ((be(P[0]) + be(P[1]), 0), (pm.sec1_encode(P, 0), 1), (be(c.gx) + be(c.gy), 0)):
                 for use_vm in (1, 0):  # three-stage accumulator-machine path and single-kernel path
