@@ -26,7 +26,12 @@ struct fe { u32 v[8]; };
 
 #if defined(__CUDACC__)
 typedef u32 saddr;  // byte address in the shared window
+// FEC_VM_INLINE_MUL expands multiplication and squaring in line as well (short loop bodies: the fixed-base kernel)
+#ifdef FEC_VM_INLINE_MUL
+#define FEC_VMOP __device__ __forceinline__
+#else
 #define FEC_VMOP __device__ __noinline__
+#endif
 // the linear operations (~25 instructions each) are expanded in line: measured 3.5 % faster than calling them, and the
 // loop body (~2.2 k instructions with them) still fits the instruction cache; define FEC_VM_CALL_LINEAR to call them
 #ifdef FEC_VM_CALL_LINEAR
