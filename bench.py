@@ -209,9 +209,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # keep stdout to the one JSON line: NCCL prints a version banner there when NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the ONE JSON line: libraries (NCCL's version banner, for one) write to file descriptor 1 directly,
+    # so everything that is not the result goes to stderr and the result is written to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -431,7 +433,8 @@ def main():
                              "algorithmic_bytes_per_op": IO_BYTES_PER_OP}},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world, "other_configs": others, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

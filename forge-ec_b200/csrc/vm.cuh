@@ -158,6 +158,32 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
               Cs = V::slot(S, VS_C), D = V::slot(S, VS_D);
+#ifdef FEC_K1_DBL_3M4S
+  // A/B variant: D = 4 X B by a multiplication (3M + 4S, 8 linear operations instead of 11)
+  {
+    fe a = V::ld(Y);
+    a = vm_sqr<F>(a); V::st(B, a);                 // B = Y^2
+    a = vm_sqr<F>(a); V::st(Cs, a);                // C = B^2
+    a = V::ld(B);
+    a = vm_mul<F, T>(a, X);
+    a = vm_small<F, 4>(a); V::st(D, a);            // D = 4 X B
+    a = V::ld(X);
+    a = vm_sqr<F>(a);
+    a = vm_small<F, 3>(a); V::st(A, a);            // E = 3 X^2
+    a = vm_sqr<F>(a);
+    a = vm_sub<F, T>(a, D);
+    a = vm_sub<F, T>(a, D); V::st(X, a);           // X3 = E^2 - 2D
+    a = vm_rsub<F, T>(a, D);
+    a = vm_mul<F, T>(a, A); V::st(B, a);           // E (D - X3)
+    a = V::ld(Y);
+    a = vm_mul<F, T>(a, Z);
+    a = vm_small<F, 2>(a); V::st(Z, a);            // Z3 = 2YZ
+    a = V::ld(Cs);
+    a = vm_small<F, 8>(a);
+    a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
+    return;
+  }
+#endif
   fe a = V::ld(Y);
   a = vm_sqr<F>(a); V::st(B, a);                 // B = Y^2
   a = vm_sqr<F>(a); V::st(Cs, a);                // C = B^2
@@ -277,6 +303,13 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
   }
   fe a = V::ld(H);
   a = vm_sqr<F>(a); V::st(HH, a);                // HH
+#ifdef FEC_K1_MADD_Z_MUL
+  a = vm_small<F, 4>(a); V::st(HH, a);           // I = 4 HH       (A/B variant: Z3 = 2 Z1 H by a multiplication)
+  a = V::ld(Z);
+  a = vm_mul<F, T>(a, H);
+  a = vm_small<F, 2>(a); V::st(Z, a);
+  a = V::ld(HH);
+#else
   a = V::ld(Z);
   a = vm_add<F, T>(a, H);
   a = vm_sqr<F>(a);
@@ -284,6 +317,7 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
   a = vm_sub<F, T>(a, HH); V::st(Z, a);          // Z3 = (Z1+H)^2 - Z1Z1 - HH
   a = V::ld(HH);
   a = vm_small<F, 4>(a); V::st(HH, a);           // I = 4 HH
+#endif
   a = vm_mul<F, T>(a, H); V::st(H, a);           // J = H I
   a = V::ld(X);
   a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 I
