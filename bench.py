@@ -352,8 +352,24 @@ def main():
         others["p256_kG"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": CANON_OTHER["p256_kG"] * m / t / imad_peak}
         t = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, stream=sp))
         others["p256_kP"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": CANON_OTHER["p256_kP"] * m / t / imad_peak}
+        # SURVEY 8f rows next to the path: ECDH (k*P, x-coordinate, HKDF-SHA-256 on the device) and the multi-scalar
+        # multiplication sum k_i*P_i (bucket method); per GPU, no canonical IMUL32 figure exists for them
+        d_st2 = torch.empty(m, dtype=torch.uint8, device=dev)
+        t = timed(lambda: eng.batch_ecdh_dev(fec.CURVE_SECP256K1, d_k, d_p, m, d_o, d_st2, kdf=fec.KDF_HKDF_SHA256, info=b"bench", stream=sp))
+        others["secp256k1_ecdh_hkdf"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": None}
+        t = timed(lambda: eng.batch_ecdh_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, d_st2, kdf=fec.KDF_HKDF_SHA256, info=b"bench", stream=sp))
+        others["p256_ecdh_hkdf"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": None}
+        t = timed(lambda: eng.msm_dev(fec.CURVE_SECP256K1, d_k, d_p, m, d_o, stream=sp))
+        others["secp256k1_msm"] = {"value": world * m / t, "unit": "points/s (one sum per GPU)", "lanes_per_gpu": m, "canonical_imad_frac": None}
+        t = timed(lambda: eng.msm_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, stream=sp))
+        others["p256_msm"] = {"value": world * m / t, "unit": "points/s (one sum per GPU)", "lanes_per_gpu": m, "canonical_imad_frac": None}
         if world > 1:
             for v in others.values():  # max-over-ranks time -> min over ranks of the rate
+                if v["canonical_imad_frac"] is None:
+                    tv = torch.tensor([v["value"]], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tv, op=dist.ReduceOp.MIN)
+                    v["value"] = float(tv[0])
+                    continue
                 tv = torch.tensor([v["value"], v["canonical_imad_frac"]], dtype=torch.float64, device=dev)
                 dist.all_reduce(tv, op=dist.ReduceOp.MIN)
                 v["value"], v["canonical_imad_frac"] = float(tv[0]), float(tv[1])

@@ -177,28 +177,42 @@ cudaError_t synth_launch(int sms, cudaStream_t st, uint8_t* out, size_t n, u32 s
 // ======================================================================================
 // ECDH tail: key derivation from the 32-byte shared secrets (KeyExchange::derive_key)
 // ======================================================================================
-struct KdfInfo { uint8_t b[KDF_MAX_INFO]; };
+// One lane per thread, everything in registers (kdf.cuh); the lane-independent message blocks arrive as a kernel
+// parameter.  Output records of a multiple of 16 bytes are written with 128-bit stores.
 __global__ void __launch_bounds__(128)
-k_kdf(int kdf, const uint8_t* __restrict__ x_be, const uint8_t* __restrict__ status, size_t n, KdfInfo info, int info_len, int out_len,
+k_kdf(int kdf, const uint8_t* __restrict__ x_be, const uint8_t* __restrict__ status, size_t n, const __grid_constant__ KdfPlan plan,
       uint8_t* __restrict__ out) {
   const size_t lane = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (lane >= n) return;
-  u32 w[8], sec[8];
+  u32 w[8], sec[8], okm[16];
   load_rec32_le(w, x_be + lane * 32);
 #pragma unroll
   for (int i = 0; i < 8; i++) sec[i] = __byte_perm(w[i], 0, 0x0123);  // big-endian words of the byte string
-  uint8_t okm[KDF_MAX_OUT];
-  if (kdf == KDF_HKDF_SHA256) hkdf_sha256_x(okm, out_len, sec, info.b, info_len);
-  else kdf_xor_info(okm, out_len, sec, info.b, info_len);
-  const bool dead = status != nullptr && status[lane] != 0;
-  for (int i = 0; i < out_len; i++) out[lane * (size_t)out_len + i] = dead ? (uint8_t)0 : okm[i];
+#pragma unroll
+  for (int i = 8; i < 16; i++) okm[i] = 0u;
+  kdf_lane(okm, kdf, sec, plan);
+  const u32 dead = (status != nullptr && status[lane] != 0) ? 0u : 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < 16; i++) okm[i] = __byte_perm(okm[i], 0, 0x0123) & dead;  // memory order
+  const int out_len = plan.out_len;
+  uint8_t* o = out + lane * (size_t)out_len;
+  if ((out_len & 15) == 0 && (reinterpret_cast<size_t>(out) & 15) == 0) {
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (16 * q < out_len) o4[q] = make_uint4(okm[4 * q], okm[4 * q + 1], okm[4 * q + 2], okm[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 64; i++)
+      if (i < out_len) o[i] = (uint8_t)(okm[i >> 2] >> (8 * (i & 3)));
+  }
 }
 cudaError_t kdf_launch(cudaStream_t st, int kdf, const uint8_t* x_be, const uint8_t* status, size_t n, const uint8_t* info, int info_len,
                        int out_len, uint8_t* out) {
   if (n == 0) return cudaSuccess;
-  KdfInfo ib;
-  for (int i = 0; i < KDF_MAX_INFO; i++) ib.b[i] = i < info_len ? info[i] : (uint8_t)0;
-  k_kdf<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kdf, x_be, status, n, ib, info_len, out_len, out);
+  KdfPlan plan;
+  kdf_plan_build(plan, kdf, info, info_len, out_len);
+  k_kdf<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kdf, x_be, status, n, plan, out);
   return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ namespace fec {
 
 constexpr int P3_PREP_THREADS = 128;
 #ifndef FEC_P3_PREP_BLOCKS
-#define FEC_P3_PREP_BLOCKS 3
+#define FEC_P3_PREP_BLOCKS 4
 #endif
 constexpr int P3_LAD_THREADS = 128;
 #ifndef FEC_P3_LAD_BLOCKS

@@ -32,124 +32,140 @@ FEC_DEV void sha256_init(u32 h[8]) {
   h[0] = 0x6a09e667u; h[1] = 0xbb67ae85u; h[2] = 0x3c6ef372u; h[3] = 0xa54ff53au;
   h[4] = 0x510e527fu; h[5] = 0x9b05688cu; h[6] = 0x1f83d9abu; h[7] = 0x5be0cd19u;
 }
-// one FIPS 180-4 compression: w = the 16 big-endian words of the block (destroyed)
+// one FIPS 180-4 compression: w = the 16 big-endian words of the block (destroyed).  Fully unrolled: every index is a
+// compile-time constant, so the message schedule and the state live in registers and the round constants are immediates.
 FEC_DEV void sha256_compress(u32 h[8], u32 w[16]) {
   u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-#pragma unroll 1
-  for (int r = 0; r < 64; r += 16) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      if (r > 0) {
-        const u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-        const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-        const u32 s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-        w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
-      }
-      const u32 S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
-      const u32 ch = (e & f) ^ (~e & g);
-      const u32 t1 = hh + S1 + ch + sha256_k(r + i) + w[i];
-      const u32 S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
-      const u32 mj = (a & b) ^ (a & c) ^ (b & c);
-      const u32 t2 = S0 + mj;
-      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  for (int i = 0; i < 64; i++) {
+    if (i >= 16) {
+      const u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+      const u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+      const u32 s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
     }
+    const u32 S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+    const u32 ch = (e & f) ^ (~e & g);
+    const u32 t1 = hh + S1 + ch + sha256_k(i) + w[i & 15];
+    const u32 S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+    const u32 mj = (a & b) ^ (a & c) ^ (b & c);
+    const u32 t2 = S0 + mj;
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
   }
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
-// streaming SHA-256 over bytes (messages here are at most 64 + 32 + 256 + 1 bytes)
-struct Sha256 {
-  u32 h[8];
-  u32 w[16];
-  u32 fill;   // bytes in the current block
-  u32 total;  // bytes so far
+
+// ---- HKDF-SHA-256 with the all-zero salt (secp256k1.rs:1846-1883):
+//        PRK = HMAC(0^32, secret);  T(i) = HMAC(PRK, T(i-1) || info || i);  OKM = T(1) || T(2) ...
+// Everything that does not depend on the lane is prepared once per call on the host (KdfPlan, passed as a kernel
+// parameter): the padded message blocks `info || counter || 0x80 0.. || length` of T(1) and T(2) (out_len <= 64, so
+// there are at most two), with eight placeholder words for T(1) at the head of T(2)'s message.  The states after the
+// ipad / opad blocks of the zero key are constants.  A lane then runs 6 compressions for 32 bytes of output and a short
+// info (2 for PRK, 2 for the key pads of PRK, 1 + 1 for T(1)), all in registers.
+constexpr int KDF_MAX_BLOCKS = 5;  // 32 + 256 + 1 + 9 bytes padded to 64
+struct KdfPlan {
+  u32 msg1[KDF_MAX_BLOCKS * 16];  // T(1): info || 0x01, padded
+  u32 msg2[KDF_MAX_BLOCKS * 16];  // T(2): T(1) (words 0..7, filled in per lane) || info || 0x02, padded
+  int blocks1, blocks2;
+  int out_len;
 };
-FEC_DEV void sha256_begin(Sha256& s) {
-  sha256_init(s.h);
-#pragma unroll
-  for (int i = 0; i < 16; i++) s.w[i] = 0u;
-  s.fill = 0u;
-  s.total = 0u;
+// host side (also tests/hostsim): big-endian words of prefix_zeros || info || counter, SHA-256 padding for a message that
+// follows one 64-byte key-pad block
+inline int kdf_plan_message(u32* words, int prefix_bytes, const uint8_t* info, int info_len, int counter) {
+  const int len = prefix_bytes + info_len + 1;
+  const int blocks = (len + 9 + 63) / 64;
+  for (int i = 0; i < blocks * 16; i++) words[i] = 0u;
+  auto put = [&](int pos, u32 v) { words[pos >> 2] |= (v & 0xFFu) << (24 - 8 * (pos & 3)); };
+  for (int i = 0; i < info_len; i++) put(prefix_bytes + i, info[i]);
+  put(prefix_bytes + info_len, (u32)counter);
+  put(len, 0x80u);
+  words[blocks * 16 - 1] = (u32)(64 + len) * 8u;
+  return blocks;
 }
-FEC_DEV void sha256_byte(Sha256& s, u32 v) {
-  s.w[s.fill >> 2] |= (v & 0xFFu) << (24 - 8 * (s.fill & 3u));
-  s.fill++;
-  s.total++;
-  if (s.fill == 64u) {
-    sha256_compress(s.h, s.w);
-#pragma unroll
-    for (int i = 0; i < 16; i++) s.w[i] = 0u;
-    s.fill = 0u;
+inline void kdf_plan_build(KdfPlan& p, int kdf, const uint8_t* info, int info_len, int out_len) {
+  p.out_len = out_len;
+  if (kdf == KDF_HKDF_SHA256) {
+    p.blocks1 = kdf_plan_message(p.msg1, 0, info, info_len, 1);
+    p.blocks2 = kdf_plan_message(p.msg2, 32, info, info_len, 2);
+  } else {  // KDF_XOR_INFO: the first 64 info bytes as big-endian words, zero-padded
+    p.blocks1 = p.blocks2 = 0;
+    for (int i = 0; i < 16; i++) p.msg1[i] = 0u;
+    for (int i = 0; i < info_len && i < 64; i++) p.msg1[i >> 2] |= (u32)info[i] << (24 - 8 * (i & 3));
   }
 }
-FEC_DEV void sha256_words(Sha256& s, const u32* be_words, int nwords) {  // only on a word boundary
-  for (int i = 0; i < nwords; i++) {
-    s.w[s.fill >> 2] = be_words[i];
-    s.fill += 4u;
-    s.total += 4u;
-    if (s.fill == 64u) {
-      sha256_compress(s.h, s.w);
+// HMAC tail shared by every use: outer = compress(outer_state, inner_digest || 0x80 0.. || (64 + 32) * 8)
+FEC_DEV void hmac256_finish(u32 mac[8], const u32 outer_state[8], const u32 inner_digest[8]) {
+  u32 w[16];
 #pragma unroll
-      for (int j = 0; j < 16; j++) s.w[j] = 0u;
-      s.fill = 0u;
+  for (int i = 0; i < 8; i++) { w[i] = inner_digest[i]; mac[i] = outer_state[i]; }
+  w[8] = 0x80000000u;
+#pragma unroll
+  for (int i = 9; i < 15; i++) w[i] = 0u;
+  w[15] = 768u;
+  sha256_compress(mac, w);
+}
+// okm: out_len bytes as big-endian words okm_be[0 .. (out_len + 3) / 4)
+FEC_DEV void hkdf_sha256_plan(u32 okm_be[16], const u32 secret_be[8], const KdfPlan& plan) {
+  const u32 IPAD0[8] = {0xf454deadu, 0x9725214fu, 0x90daf2a0u, 0xdf1228eau, 0x64e5750fu, 0xa3924181u, 0x824a932bu, 0xf8e04e32u};
+  const u32 OPAD0[8] = {0xd385480fu, 0x7abb6477u, 0x37c9c538u, 0x5dd82467u, 0x8e043a72u, 0x753434b0u, 0xdeb82818u, 0x361d45a6u};
+  u32 w[16], st[8], prk[8], kin[8], kout[8];
+  // PRK = HMAC(0^32, secret)
+#pragma unroll
+  for (int i = 0; i < 8; i++) { w[i] = secret_be[i]; st[i] = IPAD0[i]; }
+  w[8] = 0x80000000u;
+#pragma unroll
+  for (int i = 9; i < 15; i++) w[i] = 0u;
+  w[15] = 768u;
+  sha256_compress(st, w);
+  hmac256_finish(prk, OPAD0, st);
+  // the two key-pad states of PRK
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = (i < 8 ? prk[i] : 0u) ^ 0x36363636u;
+  sha256_init(kin);
+  sha256_compress(kin, w);
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = (i < 8 ? prk[i] : 0u) ^ 0x5c5c5c5cu;
+  sha256_init(kout);
+  sha256_compress(kout, w);
+  // T(1)
+#pragma unroll
+  for (int i = 0; i < 8; i++) st[i] = kin[i];
+#pragma unroll 1
+  for (int b = 0; b < plan.blocks1; b++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = plan.msg1[16 * b + i];
+    sha256_compress(st, w);
+  }
+  hmac256_finish(okm_be, kout, st);
+  if (plan.out_len <= 32) return;  // uniform
+  // T(2)
+#pragma unroll
+  for (int i = 0; i < 8; i++) st[i] = kin[i];
+#pragma unroll 1
+  for (int b = 0; b < plan.blocks2; b++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = plan.msg2[16 * b + i];
+    if (b == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) w[i] = okm_be[i];
     }
+    sha256_compress(st, w);
   }
+  hmac256_finish(okm_be + 8, kout, st);
 }
-FEC_DEV void sha256_end(Sha256& s, u32 digest[8]) {
-  const u32 bits = s.total * 8u;
-  sha256_byte(s, 0x80u);
-  if (s.fill > 56u) {
-    sha256_compress(s.h, s.w);
+// p256.rs:2314-2344: okm = zeros; okm[i] ^= secret[i]; okm[i] ^= info[i]   (each for i < out_len).  info_be: the info
+// bytes as big-endian words, zero-padded to 64 bytes (only the first out_len <= 64 bytes of info take part)
+FEC_DEV void kdf_xor_plan(u32 okm_be[16], const u32 secret_be[8], const u32 info_be[16]) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) s.w[i] = 0u;
-  }
-  s.w[15] = bits;  // messages are far below 2^32 bits
-  sha256_compress(s.h, s.w);
-#pragma unroll
-  for (int i = 0; i < 8; i++) digest[i] = s.h[i];
+  for (int i = 0; i < 16; i++) okm_be[i] = (i < 8 ? secret_be[i] : 0u) ^ info_be[i];
 }
-// HMAC-SHA-256 with a 32-byte key (8 big-endian words): begin -> feed message -> end
-FEC_DEV void hmac256_begin(Sha256& s, const u32 key[8]) {
-  sha256_begin(s);
-  u32 pad[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) pad[i] = (i < 8 ? key[i] : 0u) ^ 0x36363636u;
-  sha256_words(s, pad, 16);
-}
-FEC_DEV void hmac256_end(Sha256& s, const u32 key[8], u32 mac[8]) {
-  u32 inner[8], pad[16];
-  sha256_end(s, inner);
-  sha256_begin(s);
-#pragma unroll
-  for (int i = 0; i < 16; i++) pad[i] = (i < 8 ? key[i] : 0u) ^ 0x5c5c5c5cu;
-  sha256_words(s, pad, 16);
-  sha256_words(s, inner, 8);
-  sha256_end(s, mac);
-}
-// secp256k1.rs:1846-1883: PRK = HMAC(0^32, secret); T(i) = HMAC(PRK, T(i-1) || info || i); OKM = T(1) || T(2) ...
-// secret: 8 big-endian words (the x-coordinate as FieldElement::to_bytes writes it); okm: out_len <= KDF_MAX_OUT bytes
-FEC_DEV void hkdf_sha256_x(uint8_t* okm, int out_len, const u32 secret_be[8], const uint8_t* info, int info_len) {
-  Sha256 s;
-  u32 zero[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prk[8], t[8];
-  hmac256_begin(s, zero);
-  sha256_words(s, secret_be, 8);
-  hmac256_end(s, zero, prk);
-  int done = 0;
-  for (u32 counter = 1; done < out_len; counter++) {
-    hmac256_begin(s, prk);
-    if (counter > 1) sha256_words(s, t, 8);
-    for (int i = 0; i < info_len; i++) sha256_byte(s, info[i]);
-    sha256_byte(s, counter);
-    hmac256_end(s, prk, t);
-    for (int i = 0; i < 32 && done < out_len; i++, done++) okm[done] = (uint8_t)(t[i >> 2] >> (24 - 8 * (i & 3)));
-  }
-}
-// p256.rs:2314-2344: okm = zeros; okm[i] ^= secret[i]; okm[i] ^= info[i]   (each for i < out_len)
-FEC_DEV void kdf_xor_info(uint8_t* okm, int out_len, const u32 secret_be[8], const uint8_t* info, int info_len) {
-  for (int i = 0; i < out_len; i++) {
-    u32 v = 0u;
-    if (i < 32) v ^= (secret_be[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
-    if (i < info_len) v ^= info[i];
-    okm[i] = (uint8_t)v;
+
+// one lane: the derived key as big-endian words (the first plan.out_len bytes are the output)
+FEC_DEV void kdf_lane(u32 okm_be[16], int kdf, const u32 secret_be[8], const KdfPlan& plan) {
+  if (kdf == KDF_HKDF_SHA256) {
+    hkdf_sha256_plan(okm_be, secret_be, plan);
+  } else {
+    kdf_xor_plan(okm_be, secret_be, plan.msg1);
   }
 }
 

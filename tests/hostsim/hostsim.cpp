@@ -163,8 +163,11 @@ void hs_kdf(int kdf, const uint8_t* secret32, const uint8_t* info, int info_len,
   u32 sec[8];
   for (int i = 0; i < 8; i++)
     sec[i] = ((u32)secret32[4 * i] << 24) | ((u32)secret32[4 * i + 1] << 16) | ((u32)secret32[4 * i + 2] << 8) | secret32[4 * i + 3];
-  if (kdf == KDF_HKDF_SHA256) hkdf_sha256_x(okm, out_len, sec, info, info_len);
-  else kdf_xor_info(okm, out_len, sec, info, info_len);
+  KdfPlan plan;  // the per-call part the host prepares (kdf_launch does the same), then one lane of k_kdf
+  kdf_plan_build(plan, kdf, info, info_len, out_len);
+  u32 o[16] = {0};
+  kdf_lane(o, kdf, sec, plan);
+  for (int i = 0; i < out_len; i++) okm[i] = (uint8_t)(o[i >> 2] >> (24 - 8 * (i & 3)));
 }
 void hs_set_var_impl(int use_vm) { g_use_vm = use_vm != 0; }
 int hs_wmul(int curve, const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, uint8_t* out) {

@@ -364,7 +364,8 @@ def test_batched_ecdh_matches_model(engine, fec, pm, curve):
     xs, _ = engine.batch_mul(curve, a, B, out_fmt=fec.OUT_X_BE)          # the 32-byte output format on its own
     assert xs.tobytes() == s1.tobytes()
     for kdf, info, out_len in ((fec.KDF_HKDF_SHA256, b"forge-ec ecdh test", 32), (fec.KDF_HKDF_SHA256, b"", 64),
-                               (fec.KDF_HKDF_SHA256, bytes(range(200)), 48), (fec.KDF_XOR_INFO, b"info", 40)):
+                               (fec.KDF_HKDF_SHA256, bytes(range(200)), 48), (fec.KDF_HKDF_SHA256, bytes(range(256)), 33),
+                               (fec.KDF_HKDF_SHA256, b"ab", 17), (fec.KDF_XOR_INFO, b"info", 40), (fec.KDF_XOR_INFO, bytes(range(70)), 64)):
         k1, _ = engine.batch_ecdh(curve, a, B, kdf=kdf, info=info, out_len=out_len)
         k2, _ = engine.batch_ecdh(curve, b, A, kdf=kdf, info=info, out_len=out_len)
         assert k1.tobytes() == k2.tobytes()
