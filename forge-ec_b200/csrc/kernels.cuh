@@ -9,6 +9,7 @@
 // cross-thread step is the block-level simultaneous inversion (curves.cuh).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "../../include/forge_ec_cuda.h"
 #include "lanes.cuh"
@@ -146,7 +147,17 @@ struct StageEvents {
 cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt,
                             size_t n, int out_fmt, uint8_t* out, uint8_t* status, int* launches, StageEvents* se);
 // secp256k1 k*P as prepare / ladder / finish kernels over a stream-ordered scratch allocation (k_wmul_glv_k1.cu)
-constexpr size_t GLV_CHUNK_LANES = size_t(1) << 22;
+// lanes per scratch allocation / kernel launch of the three-kernel paths (2^22 lanes = 3.9 GB of scratch for secp256k1);
+// FORGE_EC_SCRATCH_LG=18..24 overrides it (measurements)
+inline size_t glv_chunk_lanes() {
+  static const size_t v = [] {
+    const char* e = getenv("FORGE_EC_SCRATCH_LG");
+    const int lg = e != nullptr ? atoi(e) : 0;
+    return size_t(1) << ((lg >= 18 && lg <= 24) ? lg : 22);
+  }();
+  return v;
+}
+#define GLV_CHUNK_LANES (glv_chunk_lanes())
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);

@@ -278,6 +278,36 @@ def test_device_pointer_api_and_properties(engine, fec, pm, n):
     assert engine.launch_count > 0
 
 
+def test_host_buffer_pipeline_spans_chunks(engine, fec, pm):
+    """The host-buffer entry points move data in 2^19-lane chunks over three streams: a call of 2^20 + 4133 lanes (three
+    chunks, a ragged last one) must equal the device-pointer call on the same inputs, for k*G, k*P and Ed25519 keygen."""
+    import torch
+
+    n = (1 << 20) + 4133
+    st = torch.cuda.current_stream().cuda_stream
+    k = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    r = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    engine.synth_dev(1, 3, 0, 0, n, k, edge=True, stream=st)
+    engine.synth_dev(1, 3, 1, 0, n, r, edge=False, stream=st)
+    P = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    o_dev = torch.empty(n * 33, dtype=torch.uint8, device="cuda")
+    s_dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+    engine.batch_mul_dev(0, r, None, n, P, out_fmt=2, stream=st)
+    engine.batch_mul_dev(0, k, P, n, o_dev, s_dev, stream=st)
+    torch.cuda.synchronize()
+    hk, hr, hP = k.cpu().numpy(), r.cpu().numpy(), P.cpu().numpy()
+    out, stat = engine.batch_mul(0, hr, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    assert out.tobytes() == hP.tobytes() and not stat.any()
+    out, stat = engine.batch_mul(0, hk, hP)
+    assert out.tobytes() == o_dev.cpu().numpy().tobytes() and stat.tobytes() == s_dev.cpu().numpy().tobytes()
+    exp, est = pm.batch_mul(0, hk[-32 * 8:].tobytes(), hP[-64 * 8:].tobytes(), 8, 0)   # the ragged tail against the model
+    assert out[-8:].tobytes() == exp and stat[-8:].tobytes() == est
+    pk_dev = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    engine.batch_ed25519_pubkey_dev(k, True, n, pk_dev, stream=st)
+    torch.cuda.synchronize()
+    assert engine.batch_ed25519_pubkey(hk, True).tobytes() == pk_dev.cpu().numpy().tobytes()
+
+
 def test_imad_peak_runs(engine):
     rates = [engine.imad_peak(v) for v in (0, 1, 2)]
     assert all(r > 1e11 for r in rates), rates
