@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g, 
 cudaError_t ed25519_setup() { return cudaSuccess; }
 cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode, const u32* niels, size_t n,
                            uint8_t* out) {
-  const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS * ED_DEFER - 1) / (ED_THREADS * ED_DEFER));
+  const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS - 1) / ED_THREADS);
   k_ed25519_pubkey<<<g, ED_THREADS, 0, st>>>(in, mode, niels, n, out);
   return cudaGetLastError();
 }

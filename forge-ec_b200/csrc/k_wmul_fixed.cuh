@@ -122,7 +122,7 @@ cudaError_t wmul_fixed_setup_t() {
 template <class C>
 cudaError_t wmul_fixed_launch_t(int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n, int out_fmt,
                                 uint8_t* out, uint8_t* status) {
-  const int g = persistent_grid(sms, FIX_BLOCKS_PER_SM, (n + FIX_THREADS * FIX_DEFER - 1) / (FIX_THREADS * FIX_DEFER));
+  const int g = persistent_grid(sms, FIX_BLOCKS_PER_SM, (n + FIX_THREADS - 1) / FIX_THREADS);
   k_wmul_fixed<C><<<g, FIX_THREADS, FIX_SMEM_BYTES, st>>>(scalars, comb, n, out_fmt, out, status);
   return cudaGetLastError();
 }

@@ -107,7 +107,7 @@ cudaError_t wmul_fixed_vm_setup_t() {
 template <class C>
 cudaError_t wmul_fixed_vm_launch_t(int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n, int out_fmt,
                                    uint8_t* out, uint8_t* status) {
-  const int g = persistent_grid(sms, FIXVM_BLOCKS, (n + FIXVM_THREADS * FIXVM_DEFER - 1) / (FIXVM_THREADS * FIXVM_DEFER));
+  const int g = persistent_grid(sms, FIXVM_BLOCKS, (n + FIXVM_THREADS - 1) / FIXVM_THREADS);
   k_wmul_fixed_vm<C><<<g, FIXVM_THREADS, FIXVM_SMEM, st>>>(scalars, comb, n, out_fmt, out, status);
   return cudaGetLastError();
 }

@@ -196,9 +196,10 @@ cudaError_t wmul_glv_setup_k1() {
   return cudaFuncSetAttribute(k_glv_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_FIN_SMEM);
 }
 
-// persistent grid of the finish kernel: enough warps to fill the device, each warp defers GLV_FIN_DEFER tiles
+// persistent grid of the finish kernel: as many warps as tiles until the device is full (small batches finish in one
+// tile time), then each warp walks several tiles and defers up to GLV_FIN_DEFER of them per inversion
 static unsigned fin_grid(size_t m) {
-  const size_t want = (m + (size_t)GLV_FIN_THREADS * GLV_FIN_DEFER - 1) / ((size_t)GLV_FIN_THREADS * GLV_FIN_DEFER);
+  const size_t want = (m + (size_t)GLV_FIN_THREADS - 1) / (size_t)GLV_FIN_THREADS;  // one tile per warp until the device is full
   const size_t cap = (size_t)(g_sms > 0 ? g_sms : 148) * GLV_FIN_BLOCKS;
   const size_t g = want < cap ? want : cap;
   return (unsigned)(g < 1 ? 1 : g);

@@ -186,7 +186,7 @@ cudaError_t wmul_vm_setup_p256() {
 }
 
 static unsigned p3_fin_grid(size_t m) {
-  const size_t want = (m + (size_t)P3_FIN_THREADS * P3_FIN_DEFER - 1) / ((size_t)P3_FIN_THREADS * P3_FIN_DEFER);
+  const size_t want = (m + (size_t)P3_FIN_THREADS - 1) / (size_t)P3_FIN_THREADS;  // one tile per warp until the device is full
   const size_t cap = (size_t)(g_sms_p3 > 0 ? g_sms_p3 : 148) * P3_FIN_BLOCKS;
   const size_t g = want < cap ? want : cap;
   return (unsigned)(g < 1 ? 1 : g);

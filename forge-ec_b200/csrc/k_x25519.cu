@@ -72,7 +72,7 @@ k_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, si
 
 
 cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out) {
-  const int g = persistent_grid(sms, X_BLOCKS_PER_SM, (n + X_THREADS * X_DEFER - 1) / (X_THREADS * X_DEFER));
+  const int g = persistent_grid(sms, X_BLOCKS_PER_SM, (n + X_THREADS - 1) / X_THREADS);
   k_x25519<<<g, X_THREADS, 0, st>>>(scalars, us, n, out);
   return cudaGetLastError();
 }

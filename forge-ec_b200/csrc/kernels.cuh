@@ -131,6 +131,9 @@ constexpr int PEAK_THREADS = 256;
 constexpr int PEAK_CHAINS = 8;
 constexpr int PEAK_INNER = 16;
 
+// grid of a persistent kernel: one block per `tiles` unit of work until the device is full (sms x resident blocks).  The
+// deferred-inversion kernels pass the number of 128-lane tiles, so a small batch spreads over all SMs (one tile per warp,
+// one inversion each) and only a large one makes every warp walk several tiles and share an inversion among them.
 inline int persistent_grid(int sms, int blocks_per_sm, size_t tiles) {
   size_t g = (size_t)sms * blocks_per_sm;
   if (tiles < g) g = tiles;
