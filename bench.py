@@ -340,6 +340,11 @@ def main():
             t = timed(fn)
             others[name] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m,
                             "canonical_imad_frac": CANON_OTHER[name] * m / t / imad_peak}
+        # BASELINE.json configs[0] at its own size (2^16 scalars: a batch that does not fill the persistent grids)
+        m0 = min(m, 1 << 16)
+        t = timed(lambda: eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, None, m0, d_o, stream=sp), reps=10)
+        others["secp256k1_kG_2p16"] = {"value": world * m0 / t, "unit": "ops/s", "lanes_per_gpu": m0,
+                                       "canonical_imad_frac": CANON_OTHER["secp256k1_kG"] * m0 / t / imad_peak}
         # BASELINE.json configs[3]: one key exchange = X25519(a,9), X25519(b,9), X25519(a,B), X25519(b,A) = 2 base-point + 2 ladders
         t_ex = 2.0 / others["x25519"]["value"] + 2.0 / others["x25519_base_point"]["value"]
         others["x25519_key_exchange"] = {"value": 4.0 / t_ex, "unit": "scalar-mults/s (4 per exchange)", "lanes_per_gpu": m,
