@@ -134,6 +134,18 @@ def test_x25519_matches_model_and_rfc7748(engine, fec, pm):
     assert fec.x25519(k, u, engine).hex() == "c3da55379de9c6908e94ea4df28d084f32eccf03491c71f754b4075577a28552"
 
 
+def test_x25519_rfc7748_iterated_vector_on_gpu(engine):
+    """RFC 7748 section 5.2: k = u = 9, (k, u) <- (X25519(k, u), k); the RFC's values after 1 and 1000 iterations, each step
+    one single-lane call of the ladder kernel."""
+    k = u = (9).to_bytes(32, "little")
+    for i in range(1, 1001):
+        r = engine.batch_x25519(np.frombuffer(k, dtype=np.uint8), np.frombuffer(u, dtype=np.uint8), n=1)[0].tobytes()
+        k, u = r, k
+        if i == 1:
+            assert k.hex() == "422c8e7a6227d7bca1350b3e2bb7279f7897b87bb6854b783c60e80311ae3079"
+    assert k.hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
+
+
 def test_ed25519_pubkey_matches_model_and_rfc8032(engine, fec, pm):
     seed = bytes.fromhex("9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60")
     assert fec.Ed25519Signature.derive_public_key(seed, engine).hex() == \

@@ -174,6 +174,22 @@ def test_x25519_against_libsodium_and_rfc7748(ostd, pm):
         assert ostd.x25519(k, u) == pm.x25519(k, u)
 
 
+def test_x25519_rfc7748_iterated_vector(ostd, pm):
+    """RFC 7748 section 5.2, the iterated test: k = u = 9, then (k, u) <- (X25519(k, u), k).  The values after 1 and after
+    1000 iterations are the RFC's (re-derived with OpenSSL when the golden files were made); 1000 dependent calls leave no
+    room for an error that the random vectors happen to miss."""
+    k = u = (9).to_bytes(32, "little")
+    kp, up = k, u
+    for i in range(1, 1001):
+        k, u = ostd.x25519(k, u, threads=1), k
+        if i <= 50:  # the Python model is slower: the first 50 steps in lock step with the C oracle
+            kp, up = pm.x25519(kp, up), kp
+            assert kp == k
+        if i == 1:
+            assert k.hex() == "422c8e7a6227d7bca1350b3e2bb7279f7897b87bb6854b783c60e80311ae3079"
+    assert k.hex() == "684cf59ba83309552800ef566f2f4d3c1c3887c49360e3875f2eb94d99532c51"
+
+
 def test_ed25519_against_openssl_libsodium_and_rfc8032(ostd, pm):
     g = _gold("ed25519.json")
     seeds = b"".join(bytes.fromhex(e["seed"]) for e in g["seeds"])
