@@ -509,3 +509,14 @@ def test_msm_bucket_method_matches_model(engine, fec, pm, curve):
     exp1, _ = pm.msm(curve, same.tobytes(), pts.tobytes(), n, 0,
                      products=tuple(x.tobytes() for x in engine.batch_mul(curve, same, pts, out_fmt=fec.OUT_AFFINE_XY_BE)))
     assert engine.msm(curve, same, pts) == (exp1, 0)
+
+
+def test_cpp_host_side_on_gpu():
+    """tests/cpp/test_traits.cpp: the reference's own trait-level checks (generator, small multiples, n-1, out-of-range
+    scalar, off-curve point, ECDH commutes, multi_scalar_multiply, RFC 7748 6.1, RFC 8032 TEST 1) through the C++ host side
+    and the host-buffer C ABI."""
+    import subprocess
+    from test_host import _build_cpp_traits_test
+    r = subprocess.run([_build_cpp_traits_test()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout

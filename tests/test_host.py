@@ -260,3 +260,31 @@ def test_two_rank_sharding_gloo(fec, pm, tmp_path):
     exp = np.empty(n * 33, dtype=np.uint8)
     lib.ostd_batch_mul(0, ctypes.c_void_p(k.ctypes.data), None, 0, ctypes.c_size_t(n), 0, ctypes.c_void_p(exp.ctypes.data), None, 4)
     assert np.array_equal(got, exp)
+
+
+def _build_cpp_traits_test():
+    """compiles tests/cpp/test_traits.cpp (the C++ host side over the C ABI, include/forge_ec.hpp) against the built library"""
+    out_dir = os.path.join(ROOT, "tests", "cpp", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "test_traits")
+    lib_dir = os.path.join(ROOT, "forge-ec_b200", "lib")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "test_traits.cpp"), "-L", lib_dir, "-lforge_ec_cuda", "-Wl,-rpath," + lib_dir],
+                   check=True)
+    return exe
+
+
+def test_cpp_host_side_compiles_and_fails_loudly_without_a_device():
+    """The C++ mirror of the trait surface builds against include/*.h and links every symbol it uses; without a GPU its
+    Engine constructor must throw UnsupportedOperation (exit code 77 of the test program), never compute on the CPU."""
+    exe = _build_cpp_traits_test()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77 and "no usable" in r.stdout, (r.returncode, r.stdout, r.stderr)
