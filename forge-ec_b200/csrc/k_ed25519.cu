@@ -25,6 +25,8 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
+  __shared__ u32 inv_scratch[INV_SCRATCH_WORDS];
+  const bool small = small_batch_mode(ntiles, nwarps, ED_DEFER);  // kernel-uniform
   set_small(acc, 1u);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
@@ -65,9 +67,10 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict
       if (cnt == 0) copy8(acc, Q.Z); else F::mul(acc, acc, Q.Z);
       cnt++;
     }
-    if (cnt == ED_DEFER || (!have && cnt > 0)) {
+    if (small ? !have : (cnt == ED_DEFER || (!have && cnt > 0))) {
       u32 inv[8];
-      warp_batch_inv<F>(inv, acc);
+      if (small) block_batch_inv<F, ED_THREADS / 32>(inv, acc, inv_scratch);  // every warp of the block, exactly once
+      else warp_batch_inv<F>(inv, acc);
 #pragma unroll 1
       for (int t = cnt - 1; t >= 0; t--) {
         const u32* sl = slots[t];

@@ -31,6 +31,8 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
+  const bool small = small_batch_mode(ntiles, nwarps, FIX_DEFER);  // kernel-uniform
+  u32* inv_scratch = smem + (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP / 4;
   F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
@@ -59,9 +61,10 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
       if (cnt == 0) copy8(acc, z); else F::mul(acc, acc, z);
       cnt++;
     }
-    if (cnt == FIX_DEFER || (!have && cnt > 0)) {
+    if (small ? !have : (cnt == FIX_DEFER || (!have && cnt > 0))) {
       u32 inv[8];
-      warp_batch_inv<F>(inv, acc);
+      if (small) block_batch_inv<F, FIX_THREADS / 32>(inv, acc, inv_scratch);  // every warp of the block, exactly once
+      else warp_batch_inv<F>(inv, acc);
 #pragma unroll 1
       for (int t = cnt - 1; t >= 0; t--) {
         const u32* s = slots[t];

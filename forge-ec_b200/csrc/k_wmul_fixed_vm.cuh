@@ -14,7 +14,8 @@ constexpr int FIXVM_THREADS = 128;
 constexpr int FIXVM_BLOCKS = FEC_FIXVM_BLOCKS;
 constexpr int FIXVM_DEFER = 16;
 constexpr int FIXVM_SLOT_BYTES = VS_COUNT * 32 * FIXVM_THREADS;
-constexpr int FIXVM_SMEM = FIXVM_SLOT_BYTES + (FIXVM_THREADS / 32) * 65 * 32;
+constexpr int FIXVM_IO_BYTES = (FIXVM_THREADS / 32) * 65 * 32;
+constexpr int FIXVM_SMEM = FIXVM_SLOT_BYTES + FIXVM_IO_BYTES + INV_SCRATCH_WORDS * 4;  // slots, staging, block-level inversion scratch
 
 struct GlobalCombEntry {
   const u32* base;
@@ -39,6 +40,8 @@ k_wmul_fixed_vm(const uint8_t* __restrict__ scalars, const u32* __restrict__ com
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
+  const bool small = small_batch_mode(ntiles, nwarps, FIXVM_DEFER);  // kernel-uniform
+  u32* inv_scratch = smem + (FIXVM_SLOT_BYTES + FIXVM_IO_BYTES) / 4;
   F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
@@ -71,9 +74,10 @@ k_wmul_fixed_vm(const uint8_t* __restrict__ scalars, const u32* __restrict__ com
       if (cnt == 0) copy8(acc, z); else F::mul(acc, acc, z);
       cnt++;
     }
-    if (cnt == FIXVM_DEFER || (!have && cnt > 0)) {
+    if (small ? !have : (cnt == FIXVM_DEFER || (!have && cnt > 0))) {
       u32 inv[8];
-      warp_batch_inv<F>(inv, acc);
+      if (small) block_batch_inv<F, FIXVM_THREADS / 32>(inv, acc, inv_scratch);  // every warp of the block, exactly once
+      else warp_batch_inv<F>(inv, acc);
 #pragma unroll 1
       for (int t = cnt - 1; t >= 0; t--) {
         const u32* s = slots[t];

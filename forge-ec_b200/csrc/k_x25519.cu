@@ -19,6 +19,8 @@ k_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, si
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
+  __shared__ u32 inv_scratch[INV_SCRATCH_WORDS];
+  const bool small = small_batch_mode(ntiles, nwarps, X_DEFER);  // kernel-uniform
   set_small(acc, 1u);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
@@ -45,9 +47,10 @@ k_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, si
       if (cnt == 0) copy8(acc, z); else F::mul(acc, acc, z);
       cnt++;
     }
-    if (cnt == X_DEFER || (!have && cnt > 0)) {
+    if (small ? !have : (cnt == X_DEFER || (!have && cnt > 0))) {
       u32 inv[8];
-      warp_batch_inv<F>(inv, acc);
+      if (small) block_batch_inv<F, X_THREADS / 32>(inv, acc, inv_scratch);  // every warp of the block, exactly once
+      else warp_batch_inv<F>(inv, acc);
 #pragma unroll 1
       for (int t = cnt - 1; t >= 0; t--) {
         const u32* s = slots[t];

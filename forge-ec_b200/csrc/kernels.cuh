@@ -115,7 +115,7 @@ constexpr int FIX_THREADS = 128;
 #endif
 constexpr int FIX_BLOCKS_PER_SM = FEC_FIX_BLOCKS_PER_SM;
 constexpr int FIX_IO_BYTES_PER_WARP = 65 * 32;  // per-warp staging of 33/65-byte records
-constexpr int FIX_SMEM_BYTES = (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP;
+constexpr int FIX_SMEM_BYTES = (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP + INV_SCRATCH_WORDS * 4;  // + block-level inversion scratch
 constexpr int X_THREADS = 128;
 #ifndef FEC_X_BLOCKS_PER_SM
 #define FEC_X_BLOCKS_PER_SM 4
@@ -134,6 +134,15 @@ constexpr int PEAK_INNER = 16;
 // grid of a persistent kernel: one block per `tiles` unit of work until the device is full (sms x resident blocks).  The
 // deferred-inversion kernels pass the number of 128-lane tiles, so a small batch spreads over all SMs (one tile per warp,
 // one inversion each) and only a large one makes every warp walk several tiles and share an inversion among them.
+// Small-batch mode of the deferred-inversion kernels: when no warp of the grid gets more than `defer` / 2 tiles, every warp
+// inverts exactly once, after its last tile, and the warps of a block then share ONE inversion (block_batch_inv) instead
+// of running one each.  (With more tiles per warp the warps stay independent: a barrier per batch would make three warps
+// wait for the fourth's Fermat chain.)
+// Below two blocks per SM (148 SMs, 4 warps per block) the device is not full and a batch is latency-bound: the barrier
+// only adds latency there (measured: -3 % at 2^14 lanes), so those grids keep the warp-level inversion too.
+__host__ __device__ inline bool small_batch_mode(size_t ntiles, size_t nwarps, int defer) {
+  return 2 * ntiles <= nwarps * (size_t)defer && nwarps >= 2 * 148 * 4;  // up to defer / 2 tiles per warp (beyond: -1 %)
+}
 inline int persistent_grid(int sms, int blocks_per_sm, size_t tiles) {
   size_t g = (size_t)sms * blocks_per_sm;
   if (tiles < g) g = tiles;
