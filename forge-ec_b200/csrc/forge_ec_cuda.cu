@@ -134,9 +134,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 int launch_mul(fec_ctx* ctx, Device& d, int curve, int sem, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
                uint8_t* dout, uint8_t* dst, cudaStream_t st) {
   if (n == 0) return FEC_OK;
-  if (sem == FEC_SEM_FORGE_QUIRK) {  // validated by the entry points: secp256k1, affine X||Y points only
+  if (sem == FEC_SEM_FORGE_QUIRK) {  // validated by the entry points: affine X||Y points only
     ctx->launches++;
-    FEC_CUDA(ctx, quirk_k1_launch(st, ds, dp, n, ofmt, dout, dst));
+    FEC_CUDA(ctx, curve == FEC_SECP256K1 ? quirk_k1_launch(st, ds, dp, n, ofmt, dout, dst) : quirk_p256_launch(st, ds, dp, n, ofmt, dout, dst));
   } else if (dp == nullptr) {
     ctx->launches++;
     FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
@@ -262,11 +262,11 @@ int run_host_job(fec_ctx* ctx, const HostJob& job, size_t n) {
   return FEC_OK;
 }
 
-// FEC_SEM_FORGE_QUIRK replays the reference's literal limb code; restated for secp256k1 with affine X||Y input only
+// FEC_SEM_FORGE_QUIRK replays the reference's literal limb code; restated for both Weierstrass curves, affine X||Y input only
 // (the reference's own SEC1 decoder rejects its own encodings, test_summary.md:77-85, so there is nothing to replay)
 bool sem_supported(int sem, int curve, int points_fmt) {
   if (sem == FEC_SEM_STD) return true;
-  return sem == FEC_SEM_FORGE_QUIRK && curve == FEC_SECP256K1 && points_fmt == FEC_PT_AFFINE_XY_BE;
+  return sem == FEC_SEM_FORGE_QUIRK && (curve == FEC_SECP256K1 || curve == FEC_P256) && points_fmt == FEC_PT_AFFINE_XY_BE;
 }
 
 Device* dev_at(fec_ctx* ctx, int dev_index) {

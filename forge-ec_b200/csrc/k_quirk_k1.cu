@@ -1,7 +1,8 @@
-// k_quirk_k1.cu -- FEC_SEM_FORGE_QUIRK kernel: the reference's literal secp256k1 code path, one lane per thread
-// (see quirk_k1.cuh).  A parity artefact for BASELINE.json configs[0], not a fast path.
+// k_quirk_k1.cu -- FEC_SEM_FORGE_QUIRK kernels: the reference's literal secp256k1 and P-256 code paths, one lane per thread
+// (see quirk_k1.cuh, quirk_p256.cuh).  A parity artefact for BASELINE.json configs[0], not a fast path.
 #include "kernels.cuh"
 #include "quirk_k1.cuh"
+#include "quirk_p256.cuh"
 
 namespace fec {
 
@@ -23,6 +24,27 @@ k_quirk_k1(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status) {
   k_quirk_k1<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(scalars, points, n, out_fmt, out, status);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128)
+k_quirk_p256(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ points, size_t n, int out_fmt,
+             uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  const size_t lane = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (lane >= n) return;
+  uint8_t k[32], xy[64], o[65];
+  for (int i = 0; i < 32; i++) k[i] = scalars[lane * 32 + i];
+  if (points != nullptr)
+    for (int i = 0; i < 64; i++) xy[i] = points[lane * 64 + i];
+  const int st = quirk256::p_lane(k, points != nullptr ? xy : nullptr, out_fmt, o);
+  const int osz = out_size(out_fmt);
+  for (int i = 0; i < osz; i++) out[lane * osz + i] = o[i];
+  if (status != nullptr) status[lane] = (uint8_t)st;
+}
+
+cudaError_t quirk_p256_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
+                              uint8_t* status) {
+  k_quirk_p256<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(scalars, points, n, out_fmt, out, status);
   return cudaGetLastError();
 }
 

@@ -192,6 +192,8 @@ cudaError_t msm_pippenger_launch(int curve, cudaStream_t st, const uint8_t* scal
                                  uint8_t* scratch, int out_fmt, uint8_t* out, uint8_t* status, unsigned skew_limit, int* skewed);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
+cudaError_t quirk_p256_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
+                              uint8_t* status);
 cudaError_t wmul_fixed_setup();
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n,
                               int out_fmt, uint8_t* out, uint8_t* status);

@@ -62,11 +62,13 @@ typedef enum {
 typedef enum { FEC_PT_AFFINE_XY_BE = 0 /* 64 B */, FEC_PT_SEC1_COMPRESSED = 1 /* 33 B */ } fec_points_fmt;
 typedef enum {
   FEC_SEM_STD = 0,        /* SEC2 / FIPS 186-4 / RFC 7748 / RFC 8032 results (what the reference specifies) */
-  FEC_SEM_FORGE_QUIRK = 1 /* replay of the reference's LITERAL limb code and 256-step ladder (secp256k1.rs:442-507,
-                             634-713, 2635-2692), whose outputs are not SEC2 results.  secp256k1 with
-                             k*G or affine X||Y points only, anything else: FEC_ERR_UNSUPPORTED.  A parity artefact for
-                             BASELINE.json configs[0], one thread per lane, not a fast path.  Lane status: 1 scalar >= n,
-                             3 identity (all-zero record in both cases), no point validation (the reference does none). */
+  FEC_SEM_FORGE_QUIRK = 1 /* replay of the reference's LITERAL limb code: secp256k1 (secp256k1.rs:442-507, 634-713 and the
+                             256-step ladder :2635-2692) and P-256 (p256.rs:416-534, 544-704, the a = 0 doubling :1869-1912,
+                             Add with its projective equality test :1941-2067, MSB-first double-and-add :2120-2156), whose
+                             outputs are not SEC2 / FIPS 186-4 results.  k*G or affine X||Y points
+                             only, anything else: FEC_ERR_UNSUPPORTED.  A parity artefact (BASELINE.json configs[0]), one
+                             thread per lane, not a fast path.  Lane status: 1 scalar >= n, 3 identity (all-zero record in
+                             both cases), no point validation (the reference does none). */
 } fec_sem;
 typedef enum { FEC_FIELD_MUL = 0, FEC_FIELD_SQR = 1, FEC_FIELD_MULSQR = 2 } fec_field_op;
 

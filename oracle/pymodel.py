@@ -508,3 +508,93 @@ def random_field_le(prime_id: int, n: int, stream: int, sub: int = 0) -> np.ndar
         if v >= p:
             out[i] = np.frombuffer((v - p).to_bytes(32, "little"), dtype=np.uint8)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# forge-ec's LITERAL P-256 code path as big-integer semantics (forge-ec-curves/src/p256.rs): what oracle/ref/
+# oracle_ref_p256.c and FEC_SEM_FORGE_QUIRK replay limb by limb.  Add, Mul and pow are the field up to the corner
+# cases of reduce_wide_p256 (its closing +-p loops wrap modulo 2^256, :672-696); Sub (:470-496) adds p through `+=`,
+# which reduces it away again, so a < b gives a - b + 2^256; double (:1869-1912) is the a = 0 formula; Add
+# (:1941-2006) starts with a projective equality test; multiply (:2120-2156) is MSB-first double-and-add.
+# Reproduces the transliteration goldens of SURVEY.md Appendix A.2 (tests/golden/forge_ec_literal.json).
+# ----------------------------------------------------------------------------------------------
+p256lit_p = 2**256 - 2**224 + 2**192 + 2**96 - 1
+p256lit_n = 0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551
+p256lit_M = 2**256
+def p256lit_reduce_wide(T):
+    c = [(T >> (32*i)) & 0xFFFFFFFF for i in range(16)]
+    a = [0]*8
+    for i in range(8): a[i] += c[i]
+    a[3]+=2*c[11]; a[4]+=2*c[12]; a[5]+=2*c[13]; a[6]+=2*c[14]; a[7]+=2*c[15]
+    a[3]+=2*c[12]; a[4]+=2*c[13]; a[5]+=2*c[14]; a[6]+=2*c[15]
+    a[0]+=c[8]; a[1]+=c[9]; a[2]+=c[10]; a[6]+=c[14]; a[7]+=c[15]
+    a[0]+=c[9]; a[1]+=c[10]; a[2]+=c[11]; a[3]+=c[13]; a[4]+=c[14]; a[5]+=c[15]; a[6]+=c[13]; a[7]+=c[8]
+    a[0]-=c[11]; a[1]-=c[12]; a[2]-=c[13]; a[6]-=c[8]; a[7]-=c[10]
+    a[0]-=c[12]; a[1]-=c[13]; a[2]-=c[14]; a[3]-=c[15]; a[6]-=c[9]; a[7]-=c[11]
+    a[0]-=c[13]; a[1]-=c[14]; a[2]-=c[15]; a[3]-=c[8]; a[4]-=c[9]; a[5]-=c[10]; a[7]-=c[12]
+    a[0]-=c[14]; a[1]-=c[15]; a[3]-=c[9]; a[4]-=c[10]; a[5]-=c[11]; a[7]-=c[13]
+    V = sum(a[i] << (32*i) for i in range(8))
+    carry, L = V >> 256, V & (p256lit_M-1)       # floor semantics, as the arithmetic shifts give
+    R = (L - carry*p256lit_p) % p256lit_M
+    while R >= p256lit_p: R -= p256lit_p
+    return R
+def p256lit_mul(a,b): return p256lit_reduce_wide(a*b)
+def p256lit_sqr(a): return p256lit_mul(a,a)
+def p256lit_add(a,b): return (a+b) % p256lit_p
+def p256lit_sub(a,b):
+    if a < b: a = a % p256lit_p
+    return (a - b) % p256lit_M
+def p256lit_neg(a): return 0 if a == 0 else (p256lit_p - a) % p256lit_M
+def p256lit_powl(a, e):
+    r, base = 1, a
+    for i in range(256):
+        if (e >> i) & 1: r = p256lit_mul(r, base)
+        base = p256lit_sqr(base)
+    return r
+def p256lit_inv(a): return p256lit_powl(a, p256lit_p-2)
+p256lit_ID = (0,1,0)
+def p256lit_dbl(P):
+    x,y,z = P
+    if z == 0: return p256lit_ID
+    xx=p256lit_sqr(x); yy=p256lit_sqr(y); yyyy=p256lit_sqr(yy)
+    xy2=p256lit_sqr(p256lit_add(x,yy)); t=p256lit_sub(p256lit_sub(xy2,xx),yyyy); d=p256lit_add(t,t)
+    e=p256lit_mul(3,xx); ee=p256lit_sqr(e)
+    x3=p256lit_sub(p256lit_sub(ee,d),d)
+    y3=p256lit_sub(p256lit_mul(e,p256lit_sub(d,x3)), p256lit_mul(8,yyyy))
+    z3=p256lit_add(y,y)
+    if z != 1: z3 = p256lit_mul(z3, z)
+    return (x3,y3,z3)
+def p256lit_pt_eq(P,Q):
+    if P[2]==0 and Q[2]==0: return True
+    if P[2]==0 or Q[2]==0: return False
+    z1z1=p256lit_sqr(P[2]); z2z2=p256lit_sqr(Q[2])
+    u1=p256lit_mul(P[0],z2z2); u2=p256lit_mul(Q[0],z1z1)
+    s1=p256lit_mul(p256lit_mul(P[1],Q[2]),z2z2); s2=p256lit_mul(p256lit_mul(Q[1],P[2]),z1z1)
+    return u1==u2 and s1==s2
+def p256lit_padd(P,Q):
+    if P[2]==0: return Q
+    if Q[2]==0: return P
+    if p256lit_pt_eq(P,Q): return p256lit_dbl(P)
+    z1z1=p256lit_sqr(P[2]); z2z2=p256lit_sqr(Q[2])
+    u1=p256lit_mul(P[0],z2z2); u2=p256lit_mul(Q[0],z1z1)
+    s1=p256lit_mul(p256lit_mul(P[1],Q[2]),z2z2); s2=p256lit_mul(p256lit_mul(Q[1],P[2]),z1z1)
+    if u1==u2 and s1==p256lit_neg(s2): return p256lit_ID
+    h=p256lit_sub(u2,u1); i=p256lit_sqr(p256lit_add(h,h)); j=p256lit_mul(h,i)
+    r=p256lit_add(p256lit_sub(s2,s1),p256lit_sub(s2,s1)); v=p256lit_mul(u1,i)
+    x3=p256lit_sub(p256lit_sub(p256lit_sub(p256lit_sqr(r),j),v),v)
+    y3=p256lit_sub(p256lit_mul(r,p256lit_sub(v,x3)), p256lit_mul(p256lit_add(s1,s1),j))
+    z3=p256lit_mul(p256lit_sub(p256lit_sub(p256lit_sqr(p256lit_add(P[2],Q[2])),z1z1),z2z2),h)
+    return (x3,y3,z3)
+def p256lit_multiply(P,k):
+    if P[2]==0 or k==0: return p256lit_ID
+    R=p256lit_ID
+    for i in range(255,-1,-1):
+        R=p256lit_dbl(R)
+        if (k>>i)&1: R=p256lit_padd(R,P)
+    return R
+def p256lit_to_bytes(P):
+    if P[2]==0: return bytes(33)
+    zi=p256lit_inv(P[2]); zi2=p256lit_sqr(zi); zi3=p256lit_mul(zi2,zi)
+    x=p256lit_mul(P[0],zi2); y=p256lit_mul(P[1],zi3)
+    return bytes([3 if y&1 else 2])+x.to_bytes(32,'big')
+p256lit_G=(0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,1)

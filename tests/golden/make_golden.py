@@ -101,6 +101,13 @@ if __name__ == "__main__":
                                     "3735928559": "03413979fdc3541bd045e8b671d0505ae51528ac92557caa5c3867b673c744d4e8"},
         "secp256k1_generator_x_raw": "0239adf3970dbcab86dd8d9cb31d3988aa5e8ed55f112a5b203db8ccea164c84",
         "secp256k1_field_kats": {"mul_1_2_limb0": 12713681792961361445, "square_2_limb0": 4, "add_1_2_limb0": 3, "sub_3_1_limb0": 2},
+        # P256::to_affine(multiply(generator(), k)).to_bytes() (p256.rs:2092-2156, 1835-1857, 1558-1577), SURVEY.md Appendix A.2
+        "p256_kG_compressed": {"1": "036b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296",
+                               "2": "02661ed53e414c757a6e928a7e1f8e19288c85f5deff73d5334ebe35532d24167c",
+                               "3": "0243f28a513ce244ca16afe65f883be74907b350751b6da24a7fea2240f3285eec",
+                               "3735928559": "038a13e0ce3ba3c2c96b73193caa64250cd528da2f3425c71c4286622b3d7ac76c"},
+        # the small-operand checks of the reference's own field tests (p256.rs:2357-2393): 5+7, 7-5, 5*7, 5^2
+        "p256_field_kats": {"add_5_7": 12, "sub_7_5": 2, "mul_5_7": 35, "square_5": 25},
     }
     json.dump(ref, open(os.path.join(HERE, "forge_ec_literal.json"), "w"), indent=1)
     print("golden fixtures written")

@@ -328,7 +328,7 @@ def test_imad_peak_runs(engine):
 def test_forge_quirk_mode_replays_the_reference_literally(engine, fec, pm):
     """FEC_SEM_FORGE_QUIRK: BASELINE.json configs[0] (secp256k1 k*G over 2^16 synthetic scalars) and a k*P batch,
     byte for byte against oracle/ref (the literal restatement of forge-ec's own limb code) and the Appendix A.2
-    goldens; other curves / compressed input are refused."""
+    goldens; the same for P-256; compressed input is refused."""
     import ctypes
     import json
     import os
@@ -360,10 +360,33 @@ def test_forge_quirk_mode_replays_the_reference_literally(engine, fec, pm):
     oref.oref_secp256k1_batch_mul(ctypes.c_void_p(k.ctypes.data), ctypes.c_void_p(pc.ctypes.data), ctypes.c_size_t(m),
                                   ctypes.c_void_p(exp.ctypes.data), os.cpu_count() or 1)
     assert out.tobytes() == exp.tobytes()
-    for args in ((1, k[:4], None), (0, k[:4], pts[:4, :33].copy())):
-        with pytest.raises(fec.FecError):
-            engine.batch_mul(args[0], args[1], args[2], sem=fec.SEM_FORGE_QUIRK,
-                             points_fmt=fec.PT_SEC1_COMPRESSED if args[2] is not None else fec.PT_AFFINE_XY_BE)
+    with pytest.raises(fec.FecError):   # compressed input is refused: the reference's own decoder rejects its own encodings
+        engine.batch_mul(0, k[:4], pts[:4, :33].copy(), sem=fec.SEM_FORGE_QUIRK, points_fmt=fec.PT_SEC1_COMPRESSED)
+    # P-256: the same literal parity against oracle/ref/oracle_ref_p256.c -- k*G over 2^14 synthetic scalars (edge lanes
+    # included) and a k*P batch on true points and on arbitrary coordinates (the reference's from_affine validates nothing)
+    for ks, exp in lit["p256_kG_compressed"].items():
+        out, st = engine.batch_mul(1, _be(int(ks)), None, sem=fec.SEM_FORGE_QUIRK)
+        assert out.tobytes().hex() == exp and st[0] == 0
+    n = 1 << 14
+    k = pm.random_scalars_be(1, n, stream=1)
+    out, st = engine.batch_mul(1, k, None, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(n * 33, dtype=np.uint8)
+    oref.oref_p256_batch_mul(ctypes.c_void_p(k.ctypes.data), None, ctypes.c_size_t(n), ctypes.c_void_p(exp.ctypes.data), os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
+    kv = [int.from_bytes(k[i].tobytes(), "big") for i in range(n)]
+    assert st.tolist() == [1 if v >= pm.CURVES[1].n else 3 if v == 0 else 0 for v in kv]
+    m = 1024
+    r = pm.random_scalars_be(1, m, stream=3, sub=1, edge=False)
+    pts, _ = engine.batch_mul(1, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    pc = np.ascontiguousarray(pts)
+    pc[m // 2:] = np.frombuffer(pm.philox_bytes32(m, stream=9).tobytes(), dtype=np.uint8).reshape(m // 2, 64)   # arbitrary coordinates
+    pc[m // 2:, 0] &= 0x7F
+    pc[m // 2:, 32] &= 0x7F
+    out, st = engine.batch_mul(1, k[:m], pc, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(m * 33, dtype=np.uint8)
+    oref.oref_p256_batch_mul(ctypes.c_void_p(k.ctypes.data), ctypes.c_void_p(pc.ctypes.data), ctypes.c_size_t(m), ctypes.c_void_p(exp.ctypes.data),
+                             os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
 
 
 def test_multi_device_context_shards_lanes(fec, pm):

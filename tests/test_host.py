@@ -213,6 +213,38 @@ def test_quirk_device_code_on_host_matches_literal_oracle(hostsim, pm):
     assert (o64.raw[63] & 1) == o.raw[0] - 2
 
 
+def test_quirk_p256_device_code_on_host_matches_literal_oracle(hostsim, pm):
+    """FEC_SEM_FORGE_QUIRK for P-256 (csrc/quirk_p256.cuh, compiled for the host) against oracle/ref/oracle_ref_p256.c and
+    the transliteration goldens of SURVEY.md Appendix A.2; arbitrary (also off-curve) input points, as the reference's
+    from_affine validates nothing."""
+    import json
+    import random
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(ROOT, "tests", "golden", "forge_ec_literal.json")))
+    o = ctypes.create_string_buffer(33)
+    for ks, exp in lit["p256_kG_compressed"].items():
+        assert hostsim.hs_quirk_p256(int(ks).to_bytes(32, "big"), None, 0, o) == 0 and o.raw.hex() == exp
+    rnd = random.Random(6)
+    c = pm.CURVES[1]
+    ks = [0, 1, 2, c.n - 1, c.n, 2**256 - 1] + [rnd.randrange(c.n) for _ in range(6)]
+    for k in ks:
+        kb = k.to_bytes(32, "big")
+        P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
+        junk = rnd.randrange(c.p).to_bytes(32, "big") + rnd.randrange(c.p).to_bytes(32, "big")
+        for xy in (None, P[0].to_bytes(32, "big") + P[1].to_bytes(32, "big"), junk):
+            exp = ctypes.create_string_buffer(33)
+            oref.oref_p256_batch_mul(kb, xy, ctypes.c_size_t(1), exp, 1)
+            st = hostsim.hs_quirk_p256(kb, xy, 0, o)
+            assert o.raw == exp.raw, (hex(k), xy is None)
+            assert st == (1 if k >= c.n else 3 if o.raw == bytes(33) else 0)
+    kb = (0xDEADBEEF).to_bytes(32, "big")
+    o65, o64 = ctypes.create_string_buffer(65), ctypes.create_string_buffer(64)
+    hostsim.hs_quirk_p256(kb, None, 0, o); hostsim.hs_quirk_p256(kb, None, 1, o65); hostsim.hs_quirk_p256(kb, None, 2, o64)
+    assert o65.raw[0] == 4 and o65.raw[1:33] == o.raw[1:] == o64.raw[:32] and o65.raw[33:] == o64.raw[32:]
+    assert (o64.raw[63] & 1) == o.raw[0] - 2
+
+
 def _gloo_worker(rank, world, port, n, tmp):
     import importlib
     import sys

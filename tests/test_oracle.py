@@ -284,6 +284,54 @@ def test_oracle_ref_pinned_to_reference_kats(oref):
         assert out.tobytes().hex() == exp
 
 
+def test_oracle_ref_p256_pinned_to_survey_goldens_and_model(oref, pm):
+    """oracle/ref/oracle_ref_p256.c (the literal restatement of forge-ec's P-256 path) against the transliteration goldens
+    of SURVEY.md Appendix A.2, the small-operand values of the reference's own field tests (p256.rs:2357-2393) and the
+    big-integer model of the same semantics (pymodel.p256lit_*), including non-canonical operands and off-curve points
+    (from_affine validates nothing)."""
+    import itertools
+    import random
+    lit = _gold("forge_ec_literal.json")
+    limbs = lambda v: (ctypes.c_uint64 * 4)(*[(v >> (64 * i)) & (2**64 - 1) for i in range(4)])
+    val = lambda a: sum(int(a[i]) << (64 * i) for i in range(4))
+
+    def fop(op, a, b=0):
+        O = (ctypes.c_uint64 * 4)()
+        oref.oref_p256_field_op(op, limbs(a), limbs(b), O)
+        return val(O)
+
+    k = lit["p256_field_kats"]
+    assert (fop(2, 5, 7), fop(3, 7, 5), fop(0, 5, 7), fop(1, 5)) == (k["add_5_7"], k["sub_7_5"], k["mul_5_7"], k["square_5"])
+    p = pm.p256lit_p
+    rnd = random.Random(13)
+    vals = [0, 1, 2, p - 1, p, p + 1, 2**256 - 1, 2**255, 2**224, 2**256 - 2**224, 2**256 - 2**224 + 1] + [rnd.randrange(2**256) for _ in range(8)]
+    for a, b in itertools.product(vals, vals):
+        assert fop(0, a, b) == pm.p256lit_mul(a, b) and fop(2, a, b) == pm.p256lit_add(a, b) and fop(3, a, b) == pm.p256lit_sub(a, b)
+    for a in vals:
+        assert fop(4, a) == pm.p256lit_neg(a) and fop(1, a) == pm.p256lit_sqr(a)
+    assert fop(5, 5) * 5 % p == 1 and fop(5, 0) == 0
+    # the Sub defect in one line: 5 - 7 comes out as 2^256 - 2, not p - 2
+    assert fop(3, 5, 7) == 2**256 - 2
+    for ks, exp in lit["p256_kG_compressed"].items():
+        sc = np.frombuffer(int(ks).to_bytes(32, "big"), dtype=np.uint8).copy()
+        out = np.zeros(33, dtype=np.uint8)
+        oref.oref_p256_batch_mul(vp(sc.ctypes.data), None, sz(1), vp(out.ctypes.data), 1)
+        assert out.tobytes().hex() == exp
+        assert pm.p256lit_to_bytes(pm.p256lit_multiply(pm.p256lit_G, int(ks))).hex() == exp
+    n = pm.p256lit_n
+    ks = [0, 1, n - 1, n, 2**256 - 1] + [rnd.randrange(1, n) for _ in range(7)]
+    pts = [(rnd.randrange(p), rnd.randrange(p)) for _ in ks]
+    sc = np.frombuffer(b"".join(v.to_bytes(32, "big") for v in ks), dtype=np.uint8).copy()
+    xy = np.frombuffer(b"".join(x.to_bytes(32, "big") + y.to_bytes(32, "big") for x, y in pts), dtype=np.uint8).copy()
+    for points in (None, xy):
+        out = np.zeros(33 * len(ks), dtype=np.uint8)
+        oref.oref_p256_batch_mul(vp(sc.ctypes.data), vp(points.ctypes.data) if points is not None else None, sz(len(ks)), vp(out.ctypes.data), 2)
+        for i, v in enumerate(ks):
+            P = pm.p256lit_G if points is None else (pts[i][0], pts[i][1], 1)
+            exp = bytes(33) if v >= n else pm.p256lit_to_bytes(pm.p256lit_multiply(P, v))
+            assert out.tobytes()[33 * i : 33 * i + 33] == exp, (hex(v), points is None)
+
+
 def test_divergence_report_reference_vs_specified(oref, ostd, pm):
     """forge-ec's literal secp256k1 path does not produce SEC2 results.  The fraction of
     lanes on which it agrees with the specified behaviour is reported (expected: none)."""
@@ -295,3 +343,12 @@ def test_divergence_report_reference_vs_specified(oref, ostd, pm):
     agree = sum(lit.tobytes()[33 * i : 33 * i + 33] == std[33 * i : 33 * i + 33] for i in range(n))
     print(f"forge-ec literal secp256k1 k*G agrees with SEC2 on {agree}/{n} lanes")
     assert agree == 0
+    # P-256: the a = 0 doubling and the wrapping Sub leave only k = 1 (no arithmetic at all) in agreement with FIPS 186-4
+    k = pm.random_scalars_be(1, n, stream=1, edge=False)
+    k[0] = np.frombuffer((1).to_bytes(32, "big"), dtype=np.uint8)
+    lit = np.zeros(n * 33, dtype=np.uint8)
+    oref.oref_p256_batch_mul(vp(k.ctypes.data), None, sz(n), vp(lit.ctypes.data), 4)
+    std, _ = ostd.mul(1, k.tobytes(), None)
+    agree = [i for i in range(n) if lit.tobytes()[33 * i : 33 * i + 33] == std[33 * i : 33 * i + 33]]
+    print(f"forge-ec literal P-256 k*G agrees with FIPS 186-4 on lanes {agree} of {n}")
+    assert agree == [0]
