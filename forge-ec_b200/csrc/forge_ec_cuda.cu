@@ -171,10 +171,12 @@ int launch_ecdh(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uin
   FEC_CUDA(ctx, kdf_launch(st, kdf, dx, dst, n, info, info_len, out_len, dout));
   return FEC_OK;
 }
-int launch_x25519(fec_ctx* ctx, Device& d, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
+int launch_x25519(fec_ctx* ctx, Device& d, int sem, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
-  if (du == nullptr)  // base point u = 9: fixed-base path on the Edwards form of the curve (k_ed25519.cu, mode 2)
+  if (sem == FEC_SEM_FORGE_QUIRK)  // the reference's literal x25519(), one lane per thread (k_quirk_k1.cu)
+    FEC_CUDA(ctx, quirk_x25519_launch(st, ds, du, n, dout));
+  else if (du == nullptr)  // base point u = 9: fixed-base path on the Edwards form of the curve (k_ed25519.cu, mode 2)
     FEC_CUDA(ctx, ed25519_launch(d.sms, st, ds, 2, d.niels, n, dout));
   else
     FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
@@ -230,7 +232,7 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
       rc = launch_ecdh(ctx, d, job.curve, d.buf_in_a[slot], db, job.pfmt, m, job.kdf, job.info, job.info_len, job.out_len,
                        d.buf_out[slot], d.buf_st[slot], d.buf_x[slot], st);
     else if (job.kind == 1)
-      rc = launch_x25519(ctx, d, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
+      rc = launch_x25519(ctx, d, job.sem, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
     else
       rc = launch_ed(ctx, d, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
     if (rc) return rc;
@@ -561,19 +563,28 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
 }
 
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
+  return fec_batch_x25519_sem(ctx, FEC_SEM_STD, scalars, u, n, out);
+}
+int fec_batch_x25519_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  HostJob job{1, 0, 0, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};
+  if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
+  HostJob job{1, 0, (int)sem, 0, 0, 0, scalars, 32, u, 32, out, 32, nullptr};
   return run_host_job(ctx, job, n);
 }
 int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
                          uint8_t* d_out, void* stream) {
+  return fec_batch_x25519_sem_dev(ctx, dev_index, FEC_SEM_STD, d_scalars, d_u, n, d_out, stream);
+}
+int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+                             uint8_t* d_out, void* stream) {
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_u) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   int prev = 0;
   cudaGetDevice(&prev);
   FEC_CUDA(ctx, cudaSetDevice(d->id));
-  int rc = launch_x25519(ctx, *d, d_scalars, d_u, n, d_out, (cudaStream_t)stream);
+  int rc = launch_x25519(ctx, *d, (int)sem, d_scalars, d_u, n, d_out, (cudaStream_t)stream);
   cudaSetDevice(prev);
   return rc;
 }

@@ -1,8 +1,9 @@
-// k_quirk_k1.cu -- FEC_SEM_FORGE_QUIRK kernels: the reference's literal secp256k1 and P-256 code paths, one lane per thread
-// (see quirk_k1.cuh, quirk_p256.cuh).  A parity artefact for BASELINE.json configs[0], not a fast path.
+// k_quirk_k1.cu -- FEC_SEM_FORGE_QUIRK kernels: the reference's literal secp256k1, P-256 and x25519() code paths, one lane
+// per thread (see quirk_k1.cuh, quirk_p256.cuh, quirk_x25519.cuh).  A parity artefact for BASELINE.json configs[0], not a fast path.
 #include "kernels.cuh"
 #include "quirk_k1.cuh"
 #include "quirk_p256.cuh"
+#include "quirk_x25519.cuh"
 
 namespace fec {
 
@@ -45,6 +46,23 @@ k_quirk_p256(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ po
 cudaError_t quirk_p256_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                               uint8_t* status) {
   k_quirk_p256<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(scalars, points, n, out_fmt, out, status);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128)
+k_quirk_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, size_t n, uint8_t* __restrict__ out) {
+  const size_t lane = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (lane >= n) return;
+  uint8_t k[32], u[32], o[32];
+  for (int i = 0; i < 32; i++) k[i] = scalars[lane * 32 + i];
+  if (us != nullptr)
+    for (int i = 0; i < 32; i++) u[i] = us[lane * 32 + i];
+  quirk25519::x_lane(k, us != nullptr ? u : nullptr, o);
+  for (int i = 0; i < 32; i++) out[lane * 32 + i] = o[i];
+}
+
+cudaError_t quirk_x25519_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out) {
+  k_quirk_x25519<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(scalars, us, n, out);
   return cudaGetLastError();
 }
 

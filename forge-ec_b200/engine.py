@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "fec_ctx_last_cuda_error", "fec_batch_mul", "fec_batch_mul_dev", "fec_batch_x25519", "fec_batch_x25519_dev",
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
-    "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev",
+    "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev", "fec_batch_x25519_sem", "fec_batch_x25519_sem_dev",
 )
 
 
@@ -77,6 +77,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_batch_x25519.restype = ip
     lib.fec_batch_x25519_dev.argtypes = [vp, ip, u8, u8, sz, u8, vp]
     lib.fec_batch_x25519_dev.restype = ip
+    lib.fec_batch_x25519_sem.argtypes = [vp, ip, u8, u8, sz, u8]
+    lib.fec_batch_x25519_sem.restype = ip
+    lib.fec_batch_x25519_sem_dev.argtypes = [vp, ip, ip, u8, u8, sz, u8, vp]
+    lib.fec_batch_x25519_sem_dev.restype = ip
     lib.fec_batch_ed25519_pubkey.argtypes = [vp, u8, ip, sz, u8]
     lib.fec_batch_ed25519_pubkey.restype = ip
     lib.fec_batch_ed25519_pubkey_dev.argtypes = [vp, ip, u8, ip, sz, u8, vp]
@@ -255,13 +259,16 @@ class Engine:
         self._check(self._lib.fec_msm_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, out_fmt,
                                           _ptr(d_out), _ptr(d_status), stream))
 
-    def batch_x25519(self, scalars, us=None, *, n: Optional[int] = None) -> np.ndarray:
+    def batch_x25519(self, scalars, us=None, *, n: Optional[int] = None, sem: int = SEM_STD) -> np.ndarray:
         if n is None:
             n = (scalars.nbytes if isinstance(scalars, np.ndarray) else len(scalars)) // 32
         s = _host_in(scalars, n, 32, "scalars")
         u = None if us is None else _host_in(us, n, 32, "u")
         out = np.empty((n, 32), dtype=np.uint8)
-        self._check(self._lib.fec_batch_x25519(self._ctx, _ptr(s), _ptr(u), n, _ptr(out)))
+        if sem == SEM_STD:
+            self._check(self._lib.fec_batch_x25519(self._ctx, _ptr(s), _ptr(u), n, _ptr(out)))
+        else:
+            self._check(self._lib.fec_batch_x25519_sem(self._ctx, sem, _ptr(s), _ptr(u), n, _ptr(out)))
         return out
 
     def batch_ed25519_pubkey(self, data, input_is_seed: bool = True, *, n: Optional[int] = None) -> np.ndarray:
@@ -295,8 +302,8 @@ class Engine:
         self._check(self._lib.fec_batch_mul_dev(self._ctx, dev_index, curve, sem, _ptr(d_scalars), _ptr(d_points), points_fmt,
                                                 n, out_fmt, _ptr(d_out), _ptr(d_status), stream))
 
-    def batch_x25519_dev(self, d_scalars, d_us, n: int, d_out, *, stream: int = 0, dev_index: int = 0):
-        self._check(self._lib.fec_batch_x25519_dev(self._ctx, dev_index, _ptr(d_scalars), _ptr(d_us), n, _ptr(d_out), stream))
+    def batch_x25519_dev(self, d_scalars, d_us, n: int, d_out, *, stream: int = 0, dev_index: int = 0, sem: int = SEM_STD):
+        self._check(self._lib.fec_batch_x25519_sem_dev(self._ctx, dev_index, sem, _ptr(d_scalars), _ptr(d_us), n, _ptr(d_out), stream))
 
     def batch_ed25519_pubkey_dev(self, d_in, input_is_seed: bool, n: int, d_out, *, stream: int = 0, dev_index: int = 0):
         self._check(self._lib.fec_batch_ed25519_pubkey_dev(self._ctx, dev_index, _ptr(d_in), int(bool(input_is_seed)), n,

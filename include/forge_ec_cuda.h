@@ -136,6 +136,12 @@ int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_s
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
 int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
                          uint8_t* d_out, void* stream);
+/* The same with a semantics selector: FEC_SEM_FORGE_QUIRK replays the reference's LITERAL x25519() (curve25519.rs:1624-1716 on its
+ * own FieldElement, :50-494: limb arithmetic without carries, big-endian byte codec, A instead of a24, a hard-coded answer for
+ * the scalar 2), whose outputs are not RFC 7748 results.  A parity artefact, one thread per lane. */
+int fec_batch_x25519_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
+int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+                             uint8_t* d_out, void* stream);
 
 /* RFC 8032 5.1.5 public key.  input_is_seed != 0: 32-byte seeds (SHA-512 + clamp on device);
  * input_is_seed == 0: 32-byte little-endian scalars used as they are.  out n x 32 B (y || sign x). */

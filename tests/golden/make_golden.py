@@ -108,6 +108,11 @@ if __name__ == "__main__":
                                "3735928559": "038a13e0ce3ba3c2c96b73193caa64250cd528da2f3425c71c4286622b3d7ac76c"},
         # the small-operand checks of the reference's own field tests (p256.rs:2357-2393): 5+7, 7-5, 5*7, 5^2
         "p256_field_kats": {"add_5_7": 12, "sub_7_5": 2, "mul_5_7": 35, "square_5": 25},
+        # x25519(scalar, [9, 0, ..]) (curve25519.rs:1624-1716), SURVEY.md Appendix A.2: the RFC 7748 Alice scalar, the scalars 1 and 2
+        # (the latter is a hard-coded return value, :1626-1633)
+        "x25519_base_point": {"77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a": "5872689f4f0154963f579041b3cc745d9ab25f66dbb9e8c319d74a280fbba923",
+                              "01" + "00" * 31: "4ca04218e4464255382700d5d604394b0d009bc1220800f67fe03349fd9ff97a",
+                              "02" + "00" * 31: "1b7f9f7c276550bb3a3cecc8a5770c173f5831ed1bb28c0558aac4713f970822"},
     }
     json.dump(ref, open(os.path.join(HERE, "forge_ec_literal.json"), "w"), indent=1)
     print("golden fixtures written")

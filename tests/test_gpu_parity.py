@@ -389,6 +389,48 @@ def test_forge_quirk_mode_replays_the_reference_literally(engine, fec, pm):
     assert out.tobytes() == exp.tobytes()
 
 
+def test_forge_quirk_mode_replays_the_reference_x25519_literally(engine, fec, pm):
+    """FEC_SEM_FORGE_QUIRK for X25519: 2^14 synthetic (scalar, u) lanes and 2^12 base-point lanes byte for byte against
+    oracle/ref/oracle_ref_x25519.c, the Appendix A.2 goldens, and the device-pointer entry point."""
+    import ctypes
+    import json
+    import os
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(root, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(root, "tests", "golden", "forge_ec_literal.json")))
+    for ks, exp in lit["x25519_base_point"].items():
+        out = engine.batch_x25519(np.frombuffer(bytes.fromhex(ks), dtype=np.uint8), None, n=1, sem=fec.SEM_FORGE_QUIRK)
+        assert out.tobytes().hex() == exp
+    n = 1 << 14
+    ks = pm.philox_bytes32(n, stream=4).copy()
+    us = pm.philox_bytes32(n, stream=4, sub=1).copy()
+    ks[0] = 0
+    ks[0, 0] = 2                      # the hard-coded scalar
+    us[1] = 0                         # u = 0
+    us[2] = 255                       # u = 2^256 - 1 (bit 255 masked, the rest is not below p)
+    out = engine.batch_x25519(ks, us, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(n * 32, dtype=np.uint8)
+    kc, uc = np.ascontiguousarray(ks), np.ascontiguousarray(us)
+    oref.oref_x25519_batch(ctypes.c_void_p(kc.ctypes.data), ctypes.c_void_p(uc.ctypes.data), ctypes.c_size_t(n), ctypes.c_void_p(exp.ctypes.data),
+                           os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
+    m = 1 << 12
+    out = engine.batch_x25519(ks[:m], None, sem=fec.SEM_FORGE_QUIRK)
+    oref.oref_x25519_batch(ctypes.c_void_p(kc.ctypes.data), None, ctypes.c_size_t(m), ctypes.c_void_p(exp.ctypes.data), os.cpu_count() or 1)
+    assert out.tobytes() == exp[: 32 * m].tobytes()
+    dk, du = torch.from_numpy(kc[:m].copy()).cuda(), torch.from_numpy(uc[:m].copy()).cuda()
+    do = torch.empty(m * 32, dtype=torch.uint8, device="cuda")
+    engine.batch_x25519_dev(dk, du, m, do, sem=fec.SEM_FORGE_QUIRK)
+    torch.cuda.synchronize()
+    oref.oref_x25519_batch(ctypes.c_void_p(kc.ctypes.data), ctypes.c_void_p(uc.ctypes.data), ctypes.c_size_t(m), ctypes.c_void_p(exp.ctypes.data), 4)
+    assert do.cpu().numpy().tobytes() == exp[: 32 * m].tobytes()
+    # the standard semantics are untouched by the selector
+    assert engine.batch_x25519(ks[:64], us[:64]).tobytes() == engine.batch_x25519(ks[:64], us[:64], sem=fec.SEM_STD).tobytes()
+
+
 def test_multi_device_context_shards_lanes(fec, pm):
     """fec_ctx_create over every visible device: contiguous lane shards, one host thread and pipeline per device,
     results identical to the single-device run (skipped on a one-GPU box)."""

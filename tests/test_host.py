@@ -245,6 +245,28 @@ def test_quirk_p256_device_code_on_host_matches_literal_oracle(hostsim, pm):
     assert (o64.raw[63] & 1) == o.raw[0] - 2
 
 
+def test_quirk_x25519_device_code_on_host_matches_literal_oracle(hostsim):
+    """FEC_SEM_FORGE_QUIRK for X25519 (csrc/quirk_x25519.cuh, compiled for the host) against oracle/ref/oracle_ref_x25519.c
+    and the transliteration goldens of SURVEY.md Appendix A.2."""
+    import json
+    import random
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(ROOT, "tests", "golden", "forge_ec_literal.json")))
+    o, exp = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    for ks, want in lit["x25519_base_point"].items():
+        hostsim.hs_quirk_x25519(bytes.fromhex(ks), None, o)
+        assert o.raw.hex() == want
+    rnd = random.Random(8)
+    special_u = [bytes(32), (1).to_bytes(32, "little"), (9).to_bytes(32, "little"), b"\xff" * 32, (2**255 - 19).to_bytes(32, "big")]
+    for i in range(40):
+        k = bytes(rnd.randrange(256) for _ in range(32))
+        u = special_u[i] if i < len(special_u) else bytes(rnd.randrange(256) for _ in range(32))
+        oref.oref_x25519_batch(k, u, ctypes.c_size_t(1), exp, 1)
+        hostsim.hs_quirk_x25519(k, u, o)
+        assert o.raw == exp.raw, (k.hex(), u.hex())
+
+
 def _gloo_worker(rank, world, port, n, tmp):
     import importlib
     import sys

@@ -332,6 +332,43 @@ def test_oracle_ref_p256_pinned_to_survey_goldens_and_model(oref, pm):
             assert out.tobytes()[33 * i : 33 * i + 33] == exp, (hex(v), points is None)
 
 
+def test_oracle_ref_x25519_pinned_to_survey_goldens(oref, ostd):
+    """oracle/ref/oracle_ref_x25519.c (the literal restatement of forge-ec's x25519()) against the transliteration goldens
+    of SURVEY.md Appendix A.2 and the small-operand checks of the reference's own field tests (curve25519.rs:2012-2033:
+    1+2, 3-1, 1*2); it agrees with RFC 7748 on no random lane."""
+    lit = _gold("forge_ec_literal.json")
+    for ks, exp in lit["x25519_base_point"].items():
+        out = np.zeros(32, dtype=np.uint8)
+        sc = np.frombuffer(bytes.fromhex(ks), dtype=np.uint8).copy()
+        oref.oref_x25519_batch(vp(sc.ctypes.data), None, sz(1), vp(out.ctypes.data), 1)
+        assert out.tobytes().hex() == exp
+        nine = np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8).copy()   # the same through an explicit u
+        oref.oref_x25519_batch(vp(sc.ctypes.data), vp(nine.ctypes.data), sz(1), vp(out.ctypes.data), 1)
+        assert out.tobytes().hex() == exp
+
+    def fop(op, a, b=(0, 0, 0, 0)):
+        A, B, O = (ctypes.c_uint64 * 4)(*a), (ctypes.c_uint64 * 4)(*b), (ctypes.c_uint64 * 4)()
+        oref.oref_25519_field_op(op, A, B, O)
+        return list(O)
+
+    assert fop(2, (1, 0, 0, 0), (2, 0, 0, 0)) == [3, 0, 0, 0] and fop(3, (3, 0, 0, 0), (1, 0, 0, 0)) == [2, 0, 0, 0]
+    assert fop(0, (1, 0, 0, 0), (2, 0, 0, 0)) == [2, 0, 0, 0]
+    # no carries between limbs: (2^64 - 1) + 1 in limb 0 wraps to 0 instead of carrying into limb 1
+    assert fop(2, (2**64 - 1, 0, 0, 0), (1, 0, 0, 0)) == [0, 0, 0, 0]
+    n = 64
+    ks = np.frombuffer(hashlib.sha512(b"k").digest() * 32, dtype=np.uint8).copy()
+    us = np.frombuffer(hashlib.sha512(b"u").digest() * 32, dtype=np.uint8).copy()
+    for i in range(n):
+        ks[32 * i] ^= i
+        us[32 * i + 1] ^= i
+    out = np.zeros(32 * n, dtype=np.uint8)
+    oref.oref_x25519_batch(vp(ks.ctypes.data), vp(us.ctypes.data), sz(n), vp(out.ctypes.data), 4)
+    std = ostd.x25519(ks.tobytes(), us.tobytes())
+    agree = sum(out.tobytes()[32 * i : 32 * i + 32] == std[32 * i : 32 * i + 32] for i in range(n))
+    print(f"forge-ec literal x25519 agrees with RFC 7748 on {agree}/{n} lanes")
+    assert agree == 0
+
+
 def test_divergence_report_reference_vs_specified(oref, ostd, pm):
     """forge-ec's literal secp256k1 path does not produce SEC2 results.  The fraction of
     lanes on which it agrees with the specified behaviour is reported (expected: none)."""
