@@ -182,10 +182,13 @@ int launch_x25519(fec_ctx* ctx, Device& d, int sem, const uint8_t* ds, const uin
     FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
   return FEC_OK;
 }
-int launch_ed(fec_ctx* ctx, Device& d, const uint8_t* din, int is_seed, size_t n, uint8_t* dout, cudaStream_t st) {
+int launch_ed(fec_ctx* ctx, Device& d, int sem, const uint8_t* din, int is_seed, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
-  FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
+  if (sem == FEC_SEM_FORGE_QUIRK)  // the reference's literal derive_public_key (seeds only), one lane per thread
+    FEC_CUDA(ctx, quirk_ed25519_launch(st, din, n, dout));
+  else
+    FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
   return FEC_OK;
 }
 int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int iters, const uint8_t* a, const uint8_t* b,
@@ -234,7 +237,7 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
     else if (job.kind == 1)
       rc = launch_x25519(ctx, d, job.sem, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
     else
-      rc = launch_ed(ctx, d, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
+      rc = launch_ed(ctx, d, job.sem, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
     if (rc) return rc;
     FEC_CUDA(ctx, cudaMemcpyAsync(job.out + g0 * job.rec_out, d.buf_out[slot], m * job.rec_out, cudaMemcpyDeviceToHost, st));
     if (job.status) FEC_CUDA(ctx, cudaMemcpyAsync(job.status + g0, d.buf_st[slot], m, cudaMemcpyDeviceToHost, st));
@@ -590,19 +593,32 @@ int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uin
 }
 
 int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out) {
+  return fec_batch_ed25519_pubkey_sem(ctx, FEC_SEM_STD, seeds_or_scalars, input_is_seed, n, out);
+}
+// FEC_SEM_FORGE_QUIRK replays derive_public_key, which only exists for seeds
+static bool ed_sem_ok(int sem, int input_is_seed) { return sem == FEC_SEM_STD || (sem == FEC_SEM_FORGE_QUIRK && input_is_seed != 0); }
+int fec_batch_ed25519_pubkey_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out) {
   if (ctx == nullptr || (n > 0 && (seeds_or_scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  HostJob job{2, 0, 0, 0, 0, input_is_seed, seeds_or_scalars, 32, nullptr, 0, out, 32, nullptr};
+  if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
+  if (!ed_sem_ok((int)sem, input_is_seed)) return FEC_ERR_UNSUPPORTED;
+  HostJob job{2, 0, (int)sem, 0, 0, input_is_seed, seeds_or_scalars, 32, nullptr, 0, out, 32, nullptr};
   return run_host_job(ctx, job, n);
 }
 int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
                                  uint8_t* d_out, void* stream) {
+  return fec_batch_ed25519_pubkey_sem_dev(ctx, dev_index, FEC_SEM_STD, d_in, input_is_seed, n, d_out, stream);
+}
+int fec_batch_ed25519_pubkey_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_in, int input_is_seed, size_t n,
+                                     uint8_t* d_out, void* stream) {
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || (n > 0 && (d_in == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
+  if (!ed_sem_ok((int)sem, input_is_seed)) return FEC_ERR_UNSUPPORTED;
   if (!aligned16(d_in) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   int prev = 0;
   cudaGetDevice(&prev);
   FEC_CUDA(ctx, cudaSetDevice(d->id));
-  int rc = launch_ed(ctx, *d, d_in, input_is_seed, n, d_out, (cudaStream_t)stream);
+  int rc = launch_ed(ctx, *d, (int)sem, d_in, input_is_seed, n, d_out, (cudaStream_t)stream);
   cudaSetDevice(prev);
   return rc;
 }

@@ -192,6 +192,7 @@ cudaError_t msm_pippenger_launch(int curve, cudaStream_t st, const uint8_t* scal
                                  uint8_t* scratch, int out_fmt, uint8_t* out, uint8_t* status, unsigned skew_limit, int* skewed);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
+cudaError_t quirk_ed25519_launch(cudaStream_t st, const uint8_t* seeds, size_t n, uint8_t* out);
 cudaError_t quirk_x25519_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
 cudaError_t quirk_p256_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                               uint8_t* status);

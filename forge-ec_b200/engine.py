@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
     "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev", "fec_batch_x25519_sem", "fec_batch_x25519_sem_dev",
+    "fec_batch_ed25519_pubkey_sem", "fec_batch_ed25519_pubkey_sem_dev",
 )
 
 
@@ -81,6 +82,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_batch_x25519_sem.restype = ip
     lib.fec_batch_x25519_sem_dev.argtypes = [vp, ip, ip, u8, u8, sz, u8, vp]
     lib.fec_batch_x25519_sem_dev.restype = ip
+    lib.fec_batch_ed25519_pubkey_sem.argtypes = [vp, ip, u8, ip, sz, u8]
+    lib.fec_batch_ed25519_pubkey_sem.restype = ip
+    lib.fec_batch_ed25519_pubkey_sem_dev.argtypes = [vp, ip, ip, u8, ip, sz, u8, vp]
+    lib.fec_batch_ed25519_pubkey_sem_dev.restype = ip
     lib.fec_batch_ed25519_pubkey.argtypes = [vp, u8, ip, sz, u8]
     lib.fec_batch_ed25519_pubkey.restype = ip
     lib.fec_batch_ed25519_pubkey_dev.argtypes = [vp, ip, u8, ip, sz, u8, vp]
@@ -271,12 +276,15 @@ class Engine:
             self._check(self._lib.fec_batch_x25519_sem(self._ctx, sem, _ptr(s), _ptr(u), n, _ptr(out)))
         return out
 
-    def batch_ed25519_pubkey(self, data, input_is_seed: bool = True, *, n: Optional[int] = None) -> np.ndarray:
+    def batch_ed25519_pubkey(self, data, input_is_seed: bool = True, *, n: Optional[int] = None, sem: int = SEM_STD) -> np.ndarray:
         if n is None:
             n = (data.nbytes if isinstance(data, np.ndarray) else len(data)) // 32
         d = _host_in(data, n, 32, "seeds")
         out = np.empty((n, 32), dtype=np.uint8)
-        self._check(self._lib.fec_batch_ed25519_pubkey(self._ctx, _ptr(d), int(bool(input_is_seed)), n, _ptr(out)))
+        if sem == SEM_STD:
+            self._check(self._lib.fec_batch_ed25519_pubkey(self._ctx, _ptr(d), int(bool(input_is_seed)), n, _ptr(out)))
+        else:
+            self._check(self._lib.fec_batch_ed25519_pubkey_sem(self._ctx, sem, _ptr(d), int(bool(input_is_seed)), n, _ptr(out)))
         return out
 
     def field_bench(self, prime: int, op: int, a, b, iters: int, *, lanes: Optional[int] = None):
@@ -305,9 +313,9 @@ class Engine:
     def batch_x25519_dev(self, d_scalars, d_us, n: int, d_out, *, stream: int = 0, dev_index: int = 0, sem: int = SEM_STD):
         self._check(self._lib.fec_batch_x25519_sem_dev(self._ctx, dev_index, sem, _ptr(d_scalars), _ptr(d_us), n, _ptr(d_out), stream))
 
-    def batch_ed25519_pubkey_dev(self, d_in, input_is_seed: bool, n: int, d_out, *, stream: int = 0, dev_index: int = 0):
-        self._check(self._lib.fec_batch_ed25519_pubkey_dev(self._ctx, dev_index, _ptr(d_in), int(bool(input_is_seed)), n,
-                                                           _ptr(d_out), stream))
+    def batch_ed25519_pubkey_dev(self, d_in, input_is_seed: bool, n: int, d_out, *, stream: int = 0, dev_index: int = 0, sem: int = SEM_STD):
+        self._check(self._lib.fec_batch_ed25519_pubkey_sem_dev(self._ctx, dev_index, sem, _ptr(d_in), int(bool(input_is_seed)), n,
+                                                               _ptr(d_out), stream))
 
     def field_bench_dev(self, prime: int, op: int, lanes: int, iters: int, d_a, d_b, d_out, *, stream: int = 0, dev_index: int = 0):
         self._check(self._lib.fec_field_bench_dev(self._ctx, dev_index, prime, op, lanes, iters, _ptr(d_a), _ptr(d_b), _ptr(d_out),

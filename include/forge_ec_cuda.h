@@ -149,6 +149,13 @@ int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int 
                              uint8_t* out);
 int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
                                  uint8_t* d_out, void* stream);
+/* The same with a semantics selector: FEC_SEM_FORGE_QUIRK (seeds only, else FEC_ERR_UNSUPPORTED) replays the reference's LITERAL
+ * Ed25519Signature::derive_public_key (eddsa.rs:450-509 on ed25519.rs: the second half of the hash parsed big-endian, the
+ * fabricated base point, d for 2d, a hard-coded key for seeds starting with 0x9d, 32 bytes of a 33-byte SEC1-style record), whose
+ * outputs are not RFC 8032 keys.  A parity artefact, one thread per lane. */
+int fec_batch_ed25519_pubkey_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out);
+int fec_batch_ed25519_pubkey_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_in, int input_is_seed, size_t n,
+                                     uint8_t* d_out, void* stream);
 
 /* Field microbenchmark (config 2).  a, b, out: lanes x 32 B little-endian residues in [0,p).
  * Per lane: x = a; repeat iters times { MUL: x = x*b;  SQR: x = x^2;  MULSQR: x = (x*b)^2 }; out = x.

@@ -57,6 +57,8 @@ extern "C" {
     ) -> c_int;
     pub fn fec_batch_x25519(ctx: *mut fec_ctx, scalars: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     /// sem = 1 (FEC_SEM_FORGE_QUIRK): the reference's literal x25519(), a parity artefact
+    /// sem = 1 (FEC_SEM_FORGE_QUIRK, seeds only): the reference's literal derive_public_key, a parity artefact
+    pub fn fec_batch_ed25519_pubkey_sem(ctx: *mut fec_ctx, sem: c_int, seeds: *const u8, input_is_seed: c_int, n: usize, out: *mut u8) -> c_int;
     pub fn fec_batch_x25519_sem(ctx: *mut fec_ctx, sem: c_int, scalars: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn fec_batch_ed25519_pubkey(ctx: *mut fec_ctx, seeds_or_scalars: *const u8, input_is_seed: c_int, n: usize, out: *mut u8) -> c_int;
 }

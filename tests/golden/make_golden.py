@@ -113,6 +113,14 @@ if __name__ == "__main__":
         "x25519_base_point": {"77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a": "5872689f4f0154963f579041b3cc745d9ab25f66dbb9e8c319d74a280fbba923",
                               "01" + "00" * 31: "4ca04218e4464255382700d5d604394b0d009bc1220800f67fe03349fd9ff97a",
                               "02" + "00" * 31: "1b7f9f7c276550bb3a3cecc8a5770c173f5831ed1bb28c0558aac4713f970822"},
+        # Ed25519::to_affine(multiply(generator(), k)).to_bytes() (ed25519.rs:2015-2097, 1793-1811, 1505-1524) and
+        # Ed25519Signature::derive_public_key(seed) (eddsa.rs:450-509; the third seed hits the hard-coded return), SURVEY.md Appendix A.2
+        "ed25519_mul_generator_33": {"1": "03f28396fbfa62141a04c4308b8ba6e8d2631be7e9a1f3c0a0fe536ecdd3366921",
+                                     "2": "02b9ce7ad7c2bc7c79cfc9525020afb0626343f635000a672b8641c5058b67e871"},
+        "ed25519_derive_public_key": {bytes(range(32)).hex(): "030f4fbbae5405816d05f258a3510ad17216844c709b3934e5d613c5351e7c82",
+                                      "42" * 32: "025ac8d0d3f99edfc824e3aef017eddf81d09d0e55fb0fd722d351328d769ac3",
+                                      "9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60":
+                                          "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a"},
     }
     json.dump(ref, open(os.path.join(HERE, "forge_ec_literal.json"), "w"), indent=1)
     print("golden fixtures written")

@@ -11,6 +11,7 @@
 #include "../../forge-ec_b200/csrc/quirk_k1.cuh"
 #include "../../forge-ec_b200/csrc/quirk_p256.cuh"
 #include "../../forge-ec_b200/csrc/quirk_x25519.cuh"
+#include "../../forge-ec_b200/csrc/quirk_ed25519.cuh"
 #include "../../forge-ec_b200/csrc/kdf.cuh"
 
 using namespace fec;
@@ -161,6 +162,7 @@ void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t*
   else field_op<Fe25519>(op, a, b, o);
 }
 int hs_quirk_k1(const uint8_t* k_be, const uint8_t* xy_be, int ofmt, uint8_t* out) { return quirk::q_lane(k_be, xy_be, ofmt, out); }
+void hs_quirk_ed25519(const uint8_t* seed, uint8_t* out) { quirked::e_lane(seed, out); }
 void hs_quirk_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out) { quirk25519::x_lane(k, u, out); }
 int hs_quirk_p256(const uint8_t* k_be, const uint8_t* xy_be, int ofmt, uint8_t* out) { return quirk256::p_lane(k_be, xy_be, ofmt, out); }
 void hs_kdf(int kdf, const uint8_t* secret32, const uint8_t* info, int info_len, int out_len, uint8_t* okm) {

@@ -431,6 +431,39 @@ def test_forge_quirk_mode_replays_the_reference_x25519_literally(engine, fec, pm
     assert engine.batch_x25519(ks[:64], us[:64]).tobytes() == engine.batch_x25519(ks[:64], us[:64], sem=fec.SEM_STD).tobytes()
 
 
+def test_forge_quirk_mode_replays_the_reference_ed25519_keygen_literally(engine, fec, pm):
+    """FEC_SEM_FORGE_QUIRK for Ed25519 key generation: 2^13 synthetic seeds byte for byte against
+    oracle/ref/oracle_ref_ed25519.c, the Appendix A.2 goldens and the device-pointer entry point; scalars are refused (the
+    reference's derive_public_key only exists for seeds)."""
+    import ctypes
+    import json
+    import os
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(root, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(root, "tests", "golden", "forge_ec_literal.json")))
+    for seed, exp in lit["ed25519_derive_public_key"].items():
+        out = engine.batch_ed25519_pubkey(np.frombuffer(bytes.fromhex(seed), dtype=np.uint8), True, n=1, sem=fec.SEM_FORGE_QUIRK)
+        assert out.tobytes().hex() == exp
+    n = 1 << 13
+    seeds = np.ascontiguousarray(pm.philox_bytes32(n, stream=5))     # ~32 of them start with 0x9d: the hard-coded branch
+    out = engine.batch_ed25519_pubkey(seeds, True, sem=fec.SEM_FORGE_QUIRK)
+    exp = np.zeros(n * 32, dtype=np.uint8)
+    oref.oref_ed25519_batch_pubkey(ctypes.c_void_p(seeds.ctypes.data), ctypes.c_size_t(n), ctypes.c_void_p(exp.ctypes.data), os.cpu_count() or 1)
+    assert out.tobytes() == exp.tobytes()
+    assert sum(1 for i in range(n) if seeds[i, 0] == 0x9D) > 0
+    m = 1024
+    ds = torch.from_numpy(seeds[:m].copy()).cuda()
+    do = torch.empty(m * 32, dtype=torch.uint8, device="cuda")
+    engine.batch_ed25519_pubkey_dev(ds, True, m, do, sem=fec.SEM_FORGE_QUIRK)
+    torch.cuda.synchronize()
+    assert do.cpu().numpy().tobytes() == exp[: 32 * m].tobytes()
+    with pytest.raises(fec.FecError):
+        engine.batch_ed25519_pubkey(seeds[:4], False, sem=fec.SEM_FORGE_QUIRK)
+
+
 def test_multi_device_context_shards_lanes(fec, pm):
     """fec_ctx_create over every visible device: contiguous lane shards, one host thread and pipeline per device,
     results identical to the single-device run (skipped on a one-GPU box)."""

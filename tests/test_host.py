@@ -267,6 +267,26 @@ def test_quirk_x25519_device_code_on_host_matches_literal_oracle(hostsim):
         assert o.raw == exp.raw, (k.hex(), u.hex())
 
 
+def test_quirk_ed25519_device_code_on_host_matches_literal_oracle(hostsim):
+    """FEC_SEM_FORGE_QUIRK for Ed25519 key generation (csrc/quirk_ed25519.cuh, compiled for the host) against
+    oracle/ref/oracle_ref_ed25519.c and the transliteration goldens of SURVEY.md Appendix A.2."""
+    import json
+    import random
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    oref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
+    lit = json.load(open(os.path.join(ROOT, "tests", "golden", "forge_ec_literal.json")))
+    o, exp = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    for seed, want in lit["ed25519_derive_public_key"].items():
+        hostsim.hs_quirk_ed25519(bytes.fromhex(seed), o)
+        assert o.raw.hex() == want
+    rnd = random.Random(10)
+    for i in range(12):
+        seed = bytes(rnd.randrange(256) for _ in range(32)) if i else bytes(32)
+        oref.oref_ed25519_batch_pubkey(seed, ctypes.c_size_t(1), exp, 1)
+        hostsim.hs_quirk_ed25519(seed, o)
+        assert o.raw == exp.raw, seed.hex()
+
+
 def _gloo_worker(rank, world, port, n, tmp):
     import importlib
     import sys

@@ -369,6 +369,40 @@ def test_oracle_ref_x25519_pinned_to_survey_goldens(oref, ostd):
     assert agree == 0
 
 
+def test_oracle_ref_ed25519_pinned_to_survey_goldens(oref, ostd):
+    """oracle/ref/oracle_ref_ed25519.c (the literal restatement of forge-ec's Ed25519 key generation) against the
+    transliteration goldens of SURVEY.md Appendix A.2 and the small-operand values of the reference's own field tests
+    (ed25519.rs:2136-2179); apart from the hard-coded RFC 8032 key it agrees with RFC 8032 on no lane."""
+    lit = _gold("forge_ec_literal.json")
+    for ks, exp in lit["ed25519_mul_generator_33"].items():
+        out = ctypes.create_string_buffer(33)
+        oref.oref_ed25519_mul_generator((ctypes.c_uint64 * 4)(int(ks), 0, 0, 0), out)
+        assert out.raw.hex() == exp
+    for seed, exp in lit["ed25519_derive_public_key"].items():
+        out = np.zeros(32, dtype=np.uint8)
+        sd = np.frombuffer(bytes.fromhex(seed), dtype=np.uint8).copy()
+        oref.oref_ed25519_batch_pubkey(vp(sd.ctypes.data), sz(1), vp(out.ctypes.data), 1)
+        assert out.tobytes().hex() == exp
+
+    def fop(op, a, b=(0, 0, 0, 0)):
+        A, B, O = (ctypes.c_uint64 * 4)(*a), (ctypes.c_uint64 * 4)(*b), (ctypes.c_uint64 * 4)()
+        oref.oref_ed25519_field_op(op, A, B, O)
+        return list(O)
+
+    assert fop(2, (5, 0, 0, 0), (7, 0, 0, 0)) == [12, 0, 0, 0] and fop(3, (7, 0, 0, 0), (5, 0, 0, 0)) == [2, 0, 0, 0]
+    assert fop(0, (5, 0, 0, 0), (7, 0, 0, 0)) == [35, 0, 0, 0] and fop(1, (5, 0, 0, 0)) == [25, 0, 0, 0]
+    n = 48
+    seeds = np.frombuffer(hashlib.sha512(b"seeds").digest() * (n // 2), dtype=np.uint8).copy()
+    for i in range(n):
+        seeds[32 * i] = i            # none starts with 0x9d
+    out = np.zeros(32 * n, dtype=np.uint8)
+    oref.oref_ed25519_batch_pubkey(vp(seeds.ctypes.data), sz(n), vp(out.ctypes.data), 4)
+    std = ostd.ed(seeds.tobytes(), True)
+    agree = sum(out.tobytes()[32 * i : 32 * i + 32] == std[32 * i : 32 * i + 32] for i in range(n))
+    print(f"forge-ec literal Ed25519 key generation agrees with RFC 8032 on {agree}/{n} lanes")
+    assert agree == 0
+
+
 def test_divergence_report_reference_vs_specified(oref, ostd, pm):
     """forge-ec's literal secp256k1 path does not produce SEC2 results.  The fraction of
     lanes on which it agrees with the specified behaviour is reported (expected: none)."""
