@@ -320,6 +320,53 @@ def test_host_buffer_pipeline_spans_chunks(engine, fec, pm):
     assert engine.batch_ed25519_pubkey(hk, True).tobytes() == pk_dev.cpu().numpy().tobytes()
 
 
+def test_every_batch_size_regime_gives_the_same_lanes(engine, fec, pm):
+    """The deferred-inversion kernels run in three regimes -- one tile per warp with a warp-level inversion (small grids), a
+    block-level inversion shared by four warps (full grid, few tiles per warp), and 8-16 deferred tiles per warp-level
+    inversion (large batches).  Lanes are independent, so a call on the first n lanes must return the first n records of the
+    call on all of them, for every n; the head of the full result is checked against the model."""
+    import torch
+
+    st = torch.cuda.current_stream().cuda_stream
+    nmax = 1_100_009
+    sizes = [1, 37, 4101, 70_001, 300_007, 454_656, 454_688, 460_003, 757_760 + 33]
+    k = torch.empty(nmax * 32, dtype=torch.uint8, device="cuda")
+    u = torch.empty(nmax * 32, dtype=torch.uint8, device="cuda")
+    k2 = torch.empty(nmax * 32, dtype=torch.uint8, device="cuda")
+    engine.synth_dev(1, 7, 0, 0, nmax, k, edge=True, stream=st)
+    engine.synth_dev(2, 7, 0, 0, nmax, k2, edge=True, stream=st)
+    engine.synth_dev(0, 7, 1, 0, nmax, u, stream=st)
+    runs = {
+        "k1_kG": (33, lambda n, o: engine.batch_mul_dev(0, k, None, n, o, stream=st)),
+        "p256_kG": (33, lambda n, o: engine.batch_mul_dev(1, k2, None, n, o, stream=st)),
+        "x25519": (32, lambda n, o: engine.batch_x25519_dev(k, u, n, o, stream=st)),
+        "x25519_base": (32, lambda n, o: engine.batch_x25519_dev(k, None, n, o, stream=st)),
+        "ed25519": (32, lambda n, o: engine.batch_ed25519_pubkey_dev(k, True, n, o, stream=st)),
+    }
+    for name, (rec, fn) in runs.items():
+        full = torch.empty(nmax * rec, dtype=torch.uint8, device="cuda")
+        fn(nmax, full)
+        part = torch.empty(nmax * rec, dtype=torch.uint8, device="cuda")
+        for n in sizes:
+            if name == "x25519" and n > 310_000:
+                continue   # the ladder has no table: three sizes cover its regimes (X_DEFER = 8, 4 resident blocks)
+            part.zero_()
+            fn(n, part)
+            torch.cuda.synchronize()
+            assert torch.equal(part[: n * rec], full[: n * rec]), (name, n)
+            assert int(part[n * rec : n * rec + 64].sum()) == 0, (name, n)   # nothing written past the batch
+    kh, k2h, uh = k[: 32 * 24].cpu().numpy().tobytes(), k2[: 32 * 24].cpu().numpy().tobytes(), u[: 32 * 24].cpu().numpy().tobytes()
+    o = torch.empty(24 * 33, dtype=torch.uint8, device="cuda")
+    engine.batch_mul_dev(0, k, None, 24, o, stream=st); torch.cuda.synchronize()
+    assert o.cpu().numpy().tobytes() == pm.batch_mul(0, kh, None, 24, 0)[0]
+    engine.batch_mul_dev(1, k2, None, 24, o, stream=st); torch.cuda.synchronize()
+    assert o.cpu().numpy().tobytes() == pm.batch_mul(1, k2h, None, 24, 0)[0]
+    engine.batch_x25519_dev(k, u, 24, o, stream=st); torch.cuda.synchronize()
+    assert o[: 24 * 32].cpu().numpy().tobytes() == b"".join(pm.x25519(kh[32 * i : 32 * i + 32], uh[32 * i : 32 * i + 32]) for i in range(24))
+    engine.batch_ed25519_pubkey_dev(k, True, 24, o, stream=st); torch.cuda.synchronize()
+    assert o[: 24 * 32].cpu().numpy().tobytes() == b"".join(pm.ed25519_pubkey(kh[32 * i : 32 * i + 32]) for i in range(24))
+
+
 def test_imad_peak_runs(engine):
     rates = [engine.imad_peak(v) for v in (0, 1, 2)]
     assert all(r > 1e11 for r in rates), rates
