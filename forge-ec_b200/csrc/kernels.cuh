@@ -163,6 +163,8 @@ cudaError_t wmul_var_launch(int curve, int sms, cudaStream_t st, const uint8_t* 
 // FORGE_EC_SCRATCH_LG=18..24 overrides it (measurements)
 inline size_t glv_chunk_lanes() {
   static const size_t v = [] {
+    const char* x = getenv("FORGE_EC_SCRATCH_LANES");  // exact lane count (measurements)
+    if (x != nullptr && atoll(x) >= 1024) return (size_t)atoll(x) / 1024 * 1024;
     const char* e = getenv("FORGE_EC_SCRATCH_LG");
     const int lg = e != nullptr ? atoi(e) : 0;
     return size_t(1) << ((lg >= 18 && lg <= 24) ? lg : 22);
