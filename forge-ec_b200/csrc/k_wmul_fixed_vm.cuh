@@ -15,7 +15,7 @@ constexpr int FIXVM_BLOCKS = FEC_FIXVM_BLOCKS;
 constexpr int FIXVM_DEFER = 16;
 constexpr int FIXVM_SLOT_BYTES = VS_COUNT * 32 * FIXVM_THREADS;
 constexpr int FIXVM_IO_BYTES = (FIXVM_THREADS / 32) * 65 * 32;
-constexpr int FIXVM_SMEM = FIXVM_SLOT_BYTES + FIXVM_IO_BYTES + INV_SCRATCH_WORDS * 4;  // slots, staging, block-level inversion scratch
+constexpr int FIXVM_SMEM = FIXVM_SLOT_BYTES + FIXVM_IO_BYTES;  // slots + staging: 45 184 B, five blocks per SM (one more KB would leave four)
 
 struct GlobalCombEntry {
   const u32* base;
@@ -41,7 +41,7 @@ k_wmul_fixed_vm(const uint8_t* __restrict__ scalars, const u32* __restrict__ com
   int cnt = 0;
   size_t first_tile_of_batch = 0;
   const bool small = small_batch_mode(ntiles, nwarps, FIXVM_DEFER);  // kernel-uniform
-  u32* inv_scratch = smem + (FIXVM_SLOT_BYTES + FIXVM_IO_BYTES) / 4;
+  u32* inv_scratch = smem;  // the slot area: free once every warp of the block has left its last tile (barrier below)
   F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform
@@ -76,7 +76,10 @@ k_wmul_fixed_vm(const uint8_t* __restrict__ scalars, const u32* __restrict__ com
     }
     if (small ? !have : (cnt == FIXVM_DEFER || (!have && cnt > 0))) {
       u32 inv[8];
-      if (small) block_batch_inv<F, FIXVM_THREADS / 32>(inv, acc, inv_scratch);  // every warp of the block, exactly once
+      if (small) {  // every warp of the block, exactly once
+        __syncthreads();  // nobody is still working in the slots the scratch area overlays
+        block_batch_inv<F, FIXVM_THREADS / 32>(inv, acc, inv_scratch);
+      }
       else warp_batch_inv<F>(inv, acc);
 #pragma unroll 1
       for (int t = cnt - 1; t >= 0; t--) {
