@@ -431,6 +431,17 @@ struct FeP256 {
     u32 t[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) t[i] = c[i];
+#if defined(__CUDA_ARCH__) && !defined(FEC_P256_NO_SEQ)
+    // Keep the reduction behind the product: its first quotient digit is made to depend on the LAST word of the product
+    // (through a value that is always zero).  Otherwise ptxas starts the rounds while the multiplication's carry chains
+    // are still open, runs out of predicate registers and moves carries through register bits (55 of the 221
+    // instructions of the out-of-line multiplication were such LOP3s).
+    {
+      u32 dep;
+      asm volatile("{ .reg .pred pz; setp.eq.u32 pz, %1, 0xffffffff; selp.u32 %0, 1, 0, pz; }" : "=r"(dep) : "r"(c[15]));
+      t[0] |= dep;
+    }
+#endif
     u32 cy = 0u;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
