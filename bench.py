@@ -44,6 +44,7 @@ EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 2_809}
 # DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1f_*)
 LADDER_DRAM_BYTES_PER_LANE = 975  # 2^22-lane launch: 3.67 GB read + 0.42 GB written
 # canonical IMUL32 per operation of the secondary configurations
+CANON_FIELD = {"secp256k1": {"mul": 74, "sqr": 46}, "p256": {"mul": 64, "sqr": 36}, "25519": {"mul": 73, "sqr": 45}}
 CANON_OTHER = {"x25519_base_point": 153_576, "secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
 
 
@@ -205,6 +206,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development)")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configurations (development)")
+    ap.add_argument("--no-field", action="store_true", help="skip the field microbench (BASELINE.json configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -368,6 +370,26 @@ def main():
         others["secp256k1_msm"] = {"value": world * m / t, "unit": "points/s (one sum per GPU)", "lanes_per_gpu": m, "canonical_imad_frac": None}
         t = timed(lambda: eng.msm_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, stream=sp))
         others["p256_msm"] = {"value": world * m / t, "unit": "points/s (one sum per GPU)", "lanes_per_gpu": m, "canonical_imad_frac": None}
+        # BASELINE.json configs[1]: field mul / square microbench, 2^26 independent lanes, `iters` dependent operations per lane in
+        # registers (one operation per lane would measure HBM, not the multiply pipe); unit = field operations/s
+        if not args.no_field:
+            fl = 1 << 26
+            d_fa = torch.empty(fl * 32, dtype=torch.uint8, device=dev)
+            d_fb = torch.empty(fl * 32, dtype=torch.uint8, device=dev)
+            d_fo = torch.empty(fl * 32, dtype=torch.uint8, device=dev)
+            eng.synth_dev(0, 2, 0, first_lane, fl, d_fa, stream=sp)
+            eng.synth_dev(0, 2, 1, first_lane, fl, d_fb, stream=sp)
+            d_fa.view(fl, 32)[:, 31] &= 0x3F   # little-endian records below 2^254: canonical residues of all three primes
+            d_fb.view(fl, 32)[:, 31] &= 0x3F
+            torch.cuda.synchronize()
+            iters = 1024
+            for pname, prime in (("secp256k1", fec.PRIME_SECP256K1), ("p256", fec.PRIME_P256), ("25519", fec.PRIME_25519)):
+                for oname, op in (("mul", fec.FIELD_MUL), ("sqr", fec.FIELD_SQR)):
+                    t = timed(lambda: eng.field_bench_dev(prime, op, fl, iters, d_fa, d_fb, d_fo, stream=sp), reps=1)
+                    others[f"field_{pname}_{oname}"] = {
+                        "value": world * fl * iters / t, "unit": "field operations/s", "lanes_per_gpu": fl, "iters_per_lane": iters,
+                        "canonical_imad_frac": CANON_FIELD[pname][oname] * fl * iters / t / imad_peak}
+            del d_fa, d_fb, d_fo
         if world > 1:
             for v in others.values():  # max-over-ranks time -> min over ranks of the rate
                 if v["canonical_imad_frac"] is None:

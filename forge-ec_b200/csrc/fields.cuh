@@ -427,21 +427,15 @@ struct FeP256 {
   // o = c / 2^256 mod p for c < p * 2^256, canonical.  Four rounds on 64 bits: with q = the two lowest live words,
   // c += q p = q (2^96 - 1) + (q (2^64 - 2^32 + 1)) 2^192 clears them; the carry out of a round's chain (at word
   // o + 10) is folded into the next round's m (its word 2), so every chain is 7 words long.
-  FEC_DEV static void reduce512(u32 o[8], const u32 c[16]) {
+  // `dep` is a value that is always zero but that ptxas cannot prove to be: it is or-ed into the first quotient digit to
+  // keep the reduction behind whatever `dep` was computed from.  Without it ptxas starts the rounds while the
+  // multiplication's carry chains are still open, runs out of predicate registers and moves carries through register
+  // bits (55 of the 221 instructions of the out-of-line multiplication were such LOP3s).
+  FEC_DEV static void reduce512(u32 o[8], const u32 c[16], u32 dep = 0u) {
     u32 t[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) t[i] = c[i];
-#if defined(__CUDA_ARCH__) && !defined(FEC_P256_NO_SEQ)
-    // Keep the reduction behind the product: its first quotient digit is made to depend on the LAST word of the product
-    // (through a value that is always zero).  Otherwise ptxas starts the rounds while the multiplication's carry chains
-    // are still open, runs out of predicate registers and moves carries through register bits (55 of the 221
-    // instructions of the out-of-line multiplication were such LOP3s).
-    {
-      u32 dep;
-      asm volatile("{ .reg .pred pz; setp.eq.u32 pz, %1, 0xffffffff; selp.u32 %0, 1, 0, pz; }" : "=r"(dep) : "r"(c[15]));
-      t[0] |= dep;
-    }
-#endif
+    t[0] |= dep;
     u32 cy = 0u;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -468,15 +462,47 @@ struct FeP256 {
     const u32 bw = sub8(d, t + 8, p);
     select8(o, (0u - cy) | (bw - 1u), d, t + 8);
   }
+  // always-zero values for reduce512 (device code only).  top_is_ones: the top word of a product of two residues below p
+  // is at most 0xFFFFFFFE (p^2 < 2^512 - 2^481).  top_overflows: the two top partial words of the schoolbook product
+  // add up to the top word of a number below 2^512.
+  FEC_DEV static u32 top_is_ones(u32 c15) {
+#if defined(__CUDA_ARCH__)
+    u32 dep;
+    asm volatile("{ .reg .pred pz; setp.eq.u32 pz, %1, 0xffffffff; selp.u32 %0, 1, 0, pz; }" : "=r"(dep) : "r"(c15));
+    return dep;
+#else
+    return 0u;
+#endif
+  }
+  FEC_DEV static u32 top_overflows(u32 te, u32 to) {
+#if defined(__CUDA_ARCH__)
+    u32 dep;
+    asm volatile("{ .reg .u32 s; add.cc.u32 s, %1, %2; addc.u32 %0, 0, 0; }" : "=r"(dep) : "r"(te), "r"(to));
+    return dep;
+#else
+    return 0u;
+#endif
+  }
+#ifndef FEC_P256_FENCE_MUL
+#define FEC_P256_FENCE_MUL 1  // 0 none, 1 behind the merged product, 2 behind the product rows (merge and reduction may overlap)
+#endif
+#ifndef FEC_P256_FENCE_SQR
+#define FEC_P256_FENCE_SQR 1
+#endif
   FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
-    u32 r[16];
+    u32 r[16], te, to;
+#ifdef FEC_KARATSUBA
     mul_wide(r, a, b);
-    reduce512(o, r);
+    te = to = 0u;
+#else
+    mul_wide_school_tok(r, a, b, te, to);
+#endif
+    reduce512(o, r, FEC_P256_FENCE_MUL == 1 ? top_is_ones(r[15]) : FEC_P256_FENCE_MUL == 2 ? top_overflows(te, to) : 0u);
   }
   FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
     u32 r[16];
     sqr_wide(r, a);
-    reduce512(o, r);
+    reduce512(o, r, FEC_P256_FENCE_SQR == 1 ? top_is_ones(r[15]) : 0u);
   }
   // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
   FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<FeP256>(o, a, b); }

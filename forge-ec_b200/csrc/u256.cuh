@@ -85,7 +85,8 @@ FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b) {
 }
 
 // r[0..16) = a[0..8) * b[0..8), schoolbook
-FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
+// tok_e + tok_o (the two top partial words, final before the merge) never overflows 32 bits: see FeP256::mul_inl
+FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32& tok_e, u32& tok_o) {
   u32 ev[16];  // ev[k]: weight 2^(32k)
   u32 od[15];  // od[k]: weight 2^(32(k+1))
 #pragma unroll
@@ -110,6 +111,11 @@ FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
 #pragma unroll
   for (int k = 2; k < 15; k++) r[k] = addc_cc(ev[k], od[k - 1]);
   r[15] = addc(ev[15], od[14]);
+  tok_e = ev[15]; tok_o = od[14];
+}
+FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
+  u32 te, to;
+  mul_wide_school_tok(r, a, b, te, to);
 }
 
 // r[0..8) = a[0..4) * b[0..4): the same even/odd accumulation on half-size operands
