@@ -455,27 +455,33 @@ FEC_DEV void ed_add(EdExt& q, const EdExt& r) {
 // -------------------------------------------------------------------------------------
 // X25519 ladder step (RFC 7748 section 5; one bit): 5M + 4S + one multiplication by a24
 // -------------------------------------------------------------------------------------
-FEC_DEV void x25519_step(u32 x2[8], u32 z2[8], u32 x3[8], u32 z3[8], const u32 x1[8]) {
+// State: D = (xd, zd) and S = (xs, zs), the doubling and the differential addition of the previous step; which of them is
+// [m]P and which [m+1]P is the previous scalar bit.  The differential addition is symmetric in its two operands
+// (DA + CB is, DA - CB changes sign and is squared), so RFC 7748's two conditional swaps of whole points shrink to the
+// selection of the doubling's operand: sel = all-ones -> double S, else D.  (16 instead of 48 logic operations per bit.)
+FEC_DEV void x25519_step(u32 xd[8], u32 zd[8], u32 xs[8], u32 zs[8], const u32 x1[8], u32 sel) {
   typedef Fe25519 F;
   u32 A[8], AA[8], B[8], BB[8], E[8], Cc[8], D[8], DA[8], CB[8];
-  F::add(A, x2, z2);
-  F::sqr(AA, A);
-  F::sub(B, x2, z2);
-  F::sqr(BB, B);
-  F::sub(E, AA, BB);
-  F::add(Cc, x3, z3);
-  F::sub(D, x3, z3);
+  F::add(A, xd, zd);
+  F::sub(B, xd, zd);
+  F::add(Cc, xs, zs);
+  F::sub(D, xs, zs);
   F::mul(DA, D, A);
   F::mul(CB, Cc, B);
-  F::add(x3, DA, CB);
-  F::sqr(x3, x3);
-  F::sub(z3, DA, CB);
-  F::sqr(z3, z3);
-  F::mul(z3, x1, z3);
-  F::mul(x2, AA, BB);
-  F::mul_small(z2, E, 121665u);
-  F::add(z2, AA, z2);
-  F::mul(z2, E, z2);
+  F::add(xs, DA, CB);
+  F::sqr(xs, xs);
+  F::sub(zs, DA, CB);
+  F::sqr(zs, zs);
+  F::mul(zs, x1, zs);
+  select8(A, sel, Cc, A);
+  select8(B, sel, D, B);
+  F::sqr(AA, A);
+  F::sqr(BB, B);
+  F::sub(E, AA, BB);
+  F::mul(xd, AA, BB);
+  F::mul_small(zd, E, 121665u);
+  F::add(zd, AA, zd);
+  F::mul(zd, E, zd);
 }
 
 }  // namespace fec

@@ -87,6 +87,7 @@ int device_init(fec_ctx* ctx, Device& d) {
   FEC_CUDA(ctx, wmul_var_setup());
   FEC_CUDA(ctx, wmul_fixed_setup());
   FEC_CUDA(ctx, ed25519_setup());
+  FEC_CUDA(ctx, x25519_vm_setup());
   for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaStreamCreateWithFlags(&d.streams[s], cudaStreamNonBlocking));
   FEC_CUDA(ctx, cudaMalloc(&d.comb[0], COMB_WORDS * 4));
   FEC_CUDA(ctx, cudaMalloc(&d.comb[1], COMB_WORDS * 4));
@@ -171,6 +172,10 @@ int launch_ecdh(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uin
   FEC_CUDA(ctx, kdf_launch(st, kdf, dx, dst, n, info, info_len, out_len, dout));
   return FEC_OK;
 }
+static bool x_use_vm() {  // FORGE_EC_X_IMPL=vm: the accumulator-machine form of the ladder kernel (A/B: 45.0 against 48.9 M/s)
+  static const bool v = [] { const char* e = getenv("FORGE_EC_X_IMPL"); return e != nullptr && e[0] == 'v'; }();
+  return v;
+}
 int launch_x25519(fec_ctx* ctx, Device& d, int sem, const uint8_t* ds, const uint8_t* du, size_t n, uint8_t* dout, cudaStream_t st) {
   if (n == 0) return FEC_OK;
   ctx->launches++;
@@ -178,6 +183,8 @@ int launch_x25519(fec_ctx* ctx, Device& d, int sem, const uint8_t* ds, const uin
     FEC_CUDA(ctx, quirk_x25519_launch(st, ds, du, n, dout));
   else if (du == nullptr)  // base point u = 9: fixed-base path on the Edwards form of the curve (k_ed25519.cu, mode 2)
     FEC_CUDA(ctx, ed25519_launch(d.sms, st, ds, 2, d.niels, n, dout));
+  else if (x_use_vm())
+    FEC_CUDA(ctx, x25519_vm_launch(d.sms, st, ds, du, n, dout));
   else
     FEC_CUDA(ctx, x25519_launch(d.sms, st, ds, du, n, dout));
   return FEC_OK;

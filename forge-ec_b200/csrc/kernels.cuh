@@ -202,6 +202,9 @@ cudaError_t wmul_fixed_setup();
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n,
                               int out_fmt, uint8_t* out, uint8_t* status);
 cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
+// the same ladder on the accumulator machine (k_x25519_vm.cu); FORGE_EC_X_IMPL=regs|vm forces one form (measurements)
+cudaError_t x25519_vm_setup();
+cudaError_t x25519_vm_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
 cudaError_t ed25519_setup();
 cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode /* 0 scalars, 1 seeds, 2 X25519 base point */, const u32* niels, size_t n,
                            uint8_t* out);

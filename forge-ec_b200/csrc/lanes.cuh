@@ -534,21 +534,20 @@ FEC_DEV void x25519_core(u32 x2[8], u32 z2[8], const u32 k_le[8], const u32 u_le
 #pragma unroll
   for (int i = 7; i >= 1; i--) k[i] = funnel_l(k[i - 1], k[i], 1);
   k[0] <<= 1;
-  u32 swap = 0u;
+  // (x2, z2) is the doubling of the previous step, (x3, z3) its differential addition (see x25519_step); prev = the
+  // previous bit: the pair that holds [m]P is (x3, z3) iff prev is set
+  u32 prev = 0u;
 #pragma unroll 1
   for (int t = 254; t >= 0; t--) {
     u32 kt = 0u - (k[7] >> 31);
 #pragma unroll
     for (int i = 7; i >= 1; i--) k[i] = funnel_l(k[i - 1], k[i], 1);
     k[0] <<= 1;
-    swap ^= kt;
-    cswap8(x2, x3, swap);
-    cswap8(z2, z3, swap);
-    swap = kt;
-    x25519_step(x2, z2, x3, z3, x1);
+    x25519_step(x2, z2, x3, z3, x1, prev ^ kt);
+    prev = kt;
   }
-  cswap8(x2, x3, swap);
-  cswap8(z2, z3, swap);
+  select8(x2, prev, x3, x2);
+  select8(z2, prev, z3, z2);
 }
 
 // -------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 #include "../../forge-ec_b200/csrc/quirk_k1.cuh"
 #include "../../forge-ec_b200/csrc/quirk_p256.cuh"
 #include "../../forge-ec_b200/csrc/quirk_x25519.cuh"
+#include "../../forge-ec_b200/csrc/x25519_vm.cuh"
 #include "../../forge-ec_b200/csrc/quirk_ed25519.cuh"
 #include "../../forge-ec_b200/csrc/kdf.cuh"
 
@@ -183,6 +184,21 @@ void hs_x25519(const uint8_t* k, const uint8_t* u, uint8_t* out) {
   u32 kk[8], uu[8], x2[8], z2[8], zi[8], t[8], r[8], one[8];
   load_le32(kk, k); load_le32(uu, u);
   x25519_core(x2, z2, kk, uu);
+  set_small(one, 1u);
+  u32 zz = Fe25519::is_zero(z2);
+  select8(t, zz, one, z2);
+  Fe25519::inv(zi, t);
+  Fe25519::mul(t, x2, zi);
+  Fe25519::canon(r, t);
+  for (int i = 0; i < 8; i++) r[i] &= ~zz;
+  store_le32(out, r);
+}
+// the accumulator-machine form of the ladder (x25519_vm.cuh; k_x25519_vm on the device), one lane, T = 1
+void hs_x25519_vm(const uint8_t* k, const uint8_t* u, uint8_t* out) {
+  u32 kk[8], uu[8], x2[8], z2[8], zi[8], t[8], r[8], one[8];
+  u32 slots[XS_COUNT * 8];
+  load_le32(kk, k); load_le32(uu, u);
+  x25519_vm_core<1>(slots, x2, z2, kk, uu);
   set_small(one, 1u);
   u32 zz = Fe25519::is_zero(z2);
   select8(t, zz, one, z2);

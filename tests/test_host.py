@@ -137,6 +137,8 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         o = ctypes.create_string_buffer(32)
         hostsim.hs_x25519(k, u, o)
         assert o.raw == pm.x25519(k, u)
+        hostsim.hs_x25519_vm(k, u, o)
+        assert o.raw == pm.x25519(k, u)
         hostsim.hs_ed25519_pubkey(k, 1, o)
         assert o.raw == pm.ed25519_pubkey(k)
         hostsim.hs_ed25519_pubkey(k, 0, o)
