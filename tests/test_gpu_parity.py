@@ -665,3 +665,56 @@ def test_cpp_host_side_on_gpu():
     r = subprocess.run([_build_cpp_traits_test()], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+_AB_CHILD = r"""
+import hashlib, importlib, os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+fec = importlib.import_module("forge-ec_b200")
+eng = fec.Engine()
+n = 4096
+h = hashlib.sha256()
+rng = np.random.default_rng(20261018)
+for curve in (0, 1):
+    order = (0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141, 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551)[curve]
+    k = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    k[:, 0] &= 0x7F                                   # below both group orders
+    for i, v in enumerate((0, 1, 2, order - 1, order - 2, (order + 1) // 2)):
+        k[i] = np.frombuffer(v.to_bytes(32, "big"), dtype=np.uint8)
+    r = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    r[:, 0] &= 0x7F
+    r[:, 31] |= 1
+    pts, st0 = eng.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    out1, st1 = eng.batch_mul(curve, k, None)
+    out2, st2 = eng.batch_mul(curve, k, pts)
+    for a in (pts, st0, out1, st1, out2, st2):
+        h.update(np.ascontiguousarray(a).tobytes())
+ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+us = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+us[0] = 0
+us[1] = 255
+h.update(np.ascontiguousarray(eng.batch_x25519(ks, us)).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_every_kernel_form_returns_the_same_bytes(tmp_path):
+    """The forms kept for A/B measurements (single-kernel k*P, register-resident / accumulator-machine fixed base, the
+    accumulator-machine X25519 ladder) against the default kernels on 4096 seeded lanes per entry point, edge scalars included.
+    The switches are read once per process, so each form runs in a child process and reports a digest of all outputs."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ab_child.py"
+    script.write_text(_AB_CHILD)
+    digests = {}
+    for name, env in (("default", {}), ("var_mono", {"FORGE_EC_VAR_IMPL": "mono"}), ("fixed_regs", {"FORGE_EC_FIXED_IMPL": "regs"}),
+                      ("fixed_vm", {"FORGE_EC_FIXED_IMPL": "vm"}), ("x_vm", {"FORGE_EC_X_IMPL": "vm"})):
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, env=e)
+        assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
+        digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0]
+    assert len(set(digests.values())) == 1, digests
