@@ -16,7 +16,10 @@
 namespace fec {
 
 constexpr int GLV_PREP_THREADS = 128;
-constexpr int GLV_LAD_THREADS = 128;
+#ifndef FEC_GLV_LAD_THREADS
+#define FEC_GLV_LAD_THREADS 128
+#endif
+constexpr int GLV_LAD_THREADS = FEC_GLV_LAD_THREADS;
 #ifndef FEC_GLV_LAD_BLOCKS
 #define FEC_GLV_LAD_BLOCKS 5
 #endif
@@ -87,7 +90,11 @@ k_glv_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
   sc.flags[lane] = flags | (st << 8);
 }
 
+#ifdef FEC_GLV_LAD_MAXNREG  // A/B: an explicit register cap instead of a resident-block count
+__global__ void __maxnreg__(FEC_GLV_LAD_MAXNREG)
+#else
 __global__ void __launch_bounds__(GLV_LAD_THREADS, FEC_GLV_LAD_BLOCKS)
+#endif
 k_glv_ladder(size_t n, GlvScratch sc) {
   extern __shared__ __align__(16) u32 smem[];
   size_t lane = (size_t)blockIdx.x * GLV_LAD_THREADS + threadIdx.x;

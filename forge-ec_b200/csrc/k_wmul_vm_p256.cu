@@ -16,7 +16,10 @@ constexpr int P3_PREP_THREADS = 128;
 #ifndef FEC_P3_PREP_BLOCKS
 #define FEC_P3_PREP_BLOCKS 4
 #endif
-constexpr int P3_LAD_THREADS = 128;
+#ifndef FEC_P3_LAD_THREADS
+#define FEC_P3_LAD_THREADS 128
+#endif
+constexpr int P3_LAD_THREADS = FEC_P3_LAD_THREADS;
 #ifndef FEC_P3_LAD_BLOCKS
 #define FEC_P3_LAD_BLOCKS 6  // 80 registers: 31.5 -> 31.8 M/s once the multiplication lost its predicate spills (4: 30.9)
 #endif
@@ -84,7 +87,11 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   }
 }
 
+#ifdef FEC_P3_LAD_MAXNREG  // A/B: an explicit register cap instead of a resident-block count
+__global__ void __maxnreg__(FEC_P3_LAD_MAXNREG)
+#else
 __global__ void __launch_bounds__(P3_LAD_THREADS, FEC_P3_LAD_BLOCKS)
+#endif
 k_p3_ladder(size_t n, P3Scratch sc) {
   extern __shared__ __align__(16) u32 smem[];
   size_t lane = (size_t)blockIdx.x * P3_LAD_THREADS + threadIdx.x;
