@@ -64,8 +64,23 @@ FEC_DEV u32 funnel_l(u32 lo, u32 hi, u32 s) { return s ? ((hi << s) | (lo >> (32
 // acc[0..2*NP) += {a0,a1,..}[k] * b laid out as NP (lo,hi) pairs, one carry chain.
 // `fresh` = how many of the top words of the span have never been written (their old value is
 // taken as 0); when fresh==0 the chain's carry-out is returned (else 0 -- it cannot carry).
+// An always-zero value that ptxas cannot fold (two byte permutations that select the same byte), or plain 0.  The zero
+// half of a (carry word, 0) addend pair is then `z0 & carry word`, a LOP3 on the ALU pipe written straight into the
+// pair's register, where ptxas would otherwise place an IMAD.MOV -- on the multiply pipe, the one that bounds the
+// kernels (9 of the 136 instructions of a secp256k1 multiplication).
+FEC_DEV u32 opaque_zero(u32 x) {
+#if defined(__CUDA_ARCH__) && defined(FEC_ZERO_ON_ALU)
+  u32 p, q;
+  asm("prmt.b32 %0, %1, %1, 0x0000;" : "=r"(p) : "r"(x));
+  asm("prmt.b32 %0, %1, %1, 0x4444;" : "=r"(q) : "r"(x));
+  return p ^ q;
+#else
+  (void)x;
+  return 0u;
+#endif
+}
 template <int NP, int FRESH>
-FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b) {
+FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b, u32 z0 = 0u) {
   static_assert(FRESH >= 0 && FRESH <= 2, "fresh words");
 #pragma unroll
   for (int k = 0; k < NP; k++) {
@@ -73,7 +88,8 @@ FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b) {
     const bool lo_fresh = (2 * k >= 2 * NP - FRESH);
     const bool hi_fresh = (2 * k + 1 >= 2 * NP - FRESH);
     const u32 lo_in = lo_fresh ? 0u : acc[2 * k];
-    const u32 hi_in = hi_fresh ? 0u : acc[2 * k + 1];
+    // FRESH == 1: the pair is (carry word of an earlier row, never written).  See opaque_zero.
+    const u32 hi_in = hi_fresh ? ((FRESH == 1) ? (z0 & acc[2 * k]) : 0u) : acc[2 * k + 1];
     acc[2 * k] = (k == 0) ? mad_lo_cc(ak, b, lo_in) : madc_lo_cc(ak, b, lo_in);
     if (k == NP - 1 && FRESH > 0)
       acc[2 * k + 1] = madc_hi(ak, b, hi_in);
@@ -87,6 +103,7 @@ FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b) {
 // r[0..16) = a[0..8) * b[0..8), schoolbook
 // tok_e + tok_o (the two top partial words, final before the merge) never overflows 32 bits: see FeP256::mul_inl
 FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32& tok_e, u32& tok_o) {
+  const u32 z0 = opaque_zero(a[0]);
   u32 ev[16];  // ev[k]: weight 2^(32k)
   u32 od[15];  // od[k]: weight 2^(32(k+1))
 #pragma unroll
@@ -99,12 +116,12 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
   // odd rows: a_odd*b[i] -> even positions, a_even*b[i] -> odd positions (full -> carry word)
   // even rows: a_even*b[i] -> even positions (full -> carry word), a_odd*b[i] -> odd positions
   mad_row<4, 2>(ev + 2, a + 1, b[1]);  od[8]  = mad_row<4, 0>(od + 0, a, b[1]);
-  ev[10] = mad_row<4, 0>(ev + 2, a, b[2]);  mad_row<4, 1>(od + 2, a + 1, b[2]);
-  mad_row<4, 1>(ev + 4, a + 1, b[3]);  od[10] = mad_row<4, 0>(od + 2, a, b[3]);
-  ev[12] = mad_row<4, 0>(ev + 4, a, b[4]);  mad_row<4, 1>(od + 4, a + 1, b[4]);
-  mad_row<4, 1>(ev + 6, a + 1, b[5]);  od[12] = mad_row<4, 0>(od + 4, a, b[5]);
-  ev[14] = mad_row<4, 0>(ev + 6, a, b[6]);  mad_row<4, 1>(od + 6, a + 1, b[6]);
-  mad_row<4, 1>(ev + 8, a + 1, b[7]);  od[14] = mad_row<4, 0>(od + 6, a, b[7]);
+  ev[10] = mad_row<4, 0>(ev + 2, a, b[2]);  mad_row<4, 1>(od + 2, a + 1, b[2], z0);
+  mad_row<4, 1>(ev + 4, a + 1, b[3], z0);  od[10] = mad_row<4, 0>(od + 2, a, b[3]);
+  ev[12] = mad_row<4, 0>(ev + 4, a, b[4]);  mad_row<4, 1>(od + 4, a + 1, b[4], z0);
+  mad_row<4, 1>(ev + 6, a + 1, b[5], z0);  od[12] = mad_row<4, 0>(od + 4, a, b[5]);
+  ev[14] = mad_row<4, 0>(ev + 6, a, b[6]);  mad_row<4, 1>(od + 6, a + 1, b[6], z0);
+  mad_row<4, 1>(ev + 8, a + 1, b[7], z0);  od[14] = mad_row<4, 0>(od + 6, a, b[7]);
   // merge: r = ev + (od << 32).  ev[15] was written by row 7 (fresh), od[14] by row 7's carry.
   r[0] = ev[0];
   r[1] = add_cc(ev[1], od[0]);
@@ -120,14 +137,15 @@ FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
 
 // r[0..8) = a[0..4) * b[0..4): the same even/odd accumulation on half-size operands
 FEC_DEV void mul_wide4(u32 r[8], const u32 a[4], const u32 b[4]) {
+  const u32 z0 = 0u;  // (Karatsuba halves: A/B variant only)
   u32 ev[8], od[7];
   ev[0] = mul_lo(a[0], b[0]); ev[1] = mul_hi(a[0], b[0]);
   ev[2] = mul_lo(a[2], b[0]); ev[3] = mul_hi(a[2], b[0]);
   od[0] = mul_lo(a[1], b[0]); od[1] = mul_hi(a[1], b[0]);
   od[2] = mul_lo(a[3], b[0]); od[3] = mul_hi(a[3], b[0]);
   mad_row<2, 2>(ev + 2, a + 1, b[1]);  od[4] = mad_row<2, 0>(od + 0, a, b[1]);
-  ev[6] = mad_row<2, 0>(ev + 2, a, b[2]);  mad_row<2, 1>(od + 2, a + 1, b[2]);
-  mad_row<2, 1>(ev + 4, a + 1, b[3]);  od[6] = mad_row<2, 0>(od + 2, a, b[3]);
+  ev[6] = mad_row<2, 0>(ev + 2, a, b[2]);  mad_row<2, 1>(od + 2, a + 1, b[2], z0);
+  mad_row<2, 1>(ev + 4, a + 1, b[3], z0);  od[6] = mad_row<2, 0>(od + 2, a, b[3]);
   r[0] = ev[0];
   r[1] = add_cc(ev[1], od[0]);
 #pragma unroll
@@ -183,6 +201,7 @@ FEC_DEV void mul_wide_karatsuba(u32 r[16], const u32 a[8], const u32 b[8]) {
 
 // r[0..16) = a[0..8)^2 : 28 off-diagonal products (doubled by a 1-bit funnel shift) + 8 diagonals.
 FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
+  const u32 z0 = opaque_zero(a[0]);
   // off-diagonal sum S = sum_{i<j} a[i]a[j] 2^(32(i+j)); positions 1..14 (+carry word 15 stays 0)
   u32 ev[16];  // even positions 2..14 used: ev[k] weight 2^(32k)
   u32 od[15];  // odd positions: od[k] weight 2^(32(k+1)), positions 1..13 -> od[0..13]
@@ -200,20 +219,20 @@ FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
   mad_row<3, 2>(ev + 4, a + 3, a[1]);
   // row 2: a2*a3 (5,6) a2*a5 (7,8) a2*a7 (9,10) -> od[4..9], od[9] fresh;
   //        a2*a4 (6,7) a2*a6 (8,9) -> ev[6..9] full -> carry ev[10]
-  mad_row<3, 1>(od + 4, a + 3, a[2]);
+  mad_row<3, 1>(od + 4, a + 3, a[2], z0);
   ev[10] = mad_row<2, 0>(ev + 6, a + 4, a[2]);
   // row 3: a3*a4 (7,8) a3*a6 (9,10) -> od[6..9] full -> carry od[10];
   //        a3*a5 (8,9) a3*a7 (10,11) -> ev[8..11], ev[11] fresh
   od[10] = mad_row<2, 0>(od + 6, a + 4, a[3]);
-  mad_row<2, 1>(ev + 8, a + 5, a[3]);
+  mad_row<2, 1>(ev + 8, a + 5, a[3], z0);
   // row 4: a4*a5 (9,10) a4*a7 (11,12) -> od[8..11], od[11] fresh;  a4*a6 (10,11) -> ev[10..11] full -> carry ev[12]
-  mad_row<2, 1>(od + 8, a + 5, a[4]);
+  mad_row<2, 1>(od + 8, a + 5, a[4], z0);
   ev[12] = mad_row<1, 0>(ev + 10, a + 6, a[4]);
   // row 5: a5*a6 (11,12) -> od[10..11] full -> carry od[12];  a5*a7 (12,13) -> ev[12..13], ev[13] fresh
   od[12] = mad_row<1, 0>(od + 10, a + 6, a[5]);
-  mad_row<1, 1>(ev + 12, a + 7, a[5]);
+  mad_row<1, 1>(ev + 12, a + 7, a[5], z0);
   // row 6: a6*a7 (13,14) -> od[12..13], od[13] fresh
-  mad_row<1, 1>(od + 12, a + 7, a[6]);
+  mad_row<1, 1>(od + 12, a + 7, a[6], z0);
   // merge off-diagonals: s[1..14] (s[0]=0, s[15] = 0); s fits in 15 words (sum < 2^480)
   u32 s[16];
   s[1] = od[0];
