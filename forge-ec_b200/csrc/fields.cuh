@@ -484,25 +484,26 @@ struct FeP256 {
 #endif
   }
 #ifndef FEC_P256_FENCE_MUL
-#define FEC_P256_FENCE_MUL 1  // 0 none, 1 behind the merged product, 2 behind the product rows (merge and reduction may overlap)
+#define FEC_P256_FENCE_MUL 3  // 0 none, 1 top word all ones, 2 behind the product rows (merge and reduction may overlap), 3 carry out of the merge
 #endif
 #ifndef FEC_P256_FENCE_SQR
-#define FEC_P256_FENCE_SQR 1
+#define FEC_P256_FENCE_SQR 3  // 0 none, 1 top word all ones, 3 carry out of the last chain
 #endif
+  // Variants 2 and 3 are zero for EVERY input; variant 1 relies on operands below p (all field routines return them).
   FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
-    u32 r[16], te, to;
+    u32 r[16], te, to, tc;
 #ifdef FEC_KARATSUBA
     mul_wide(r, a, b);
-    te = to = 0u;
+    te = to = tc = 0u;
 #else
-    mul_wide_school_tok(r, a, b, te, to);
+    mul_wide_school_tok<FEC_P256_FENCE_MUL == 3>(r, a, b, te, to, tc);
 #endif
-    reduce512(o, r, FEC_P256_FENCE_MUL == 1 ? top_is_ones(r[15]) : FEC_P256_FENCE_MUL == 2 ? top_overflows(te, to) : 0u);
+    reduce512(o, r, FEC_P256_FENCE_MUL == 1 ? top_is_ones(r[15]) : FEC_P256_FENCE_MUL == 2 ? top_overflows(te, to) : FEC_P256_FENCE_MUL == 3 ? tc : 0u);
   }
   FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
-    u32 r[16];
-    sqr_wide(r, a);
-    reduce512(o, r, FEC_P256_FENCE_SQR == 1 ? top_is_ones(r[15]) : 0u);
+    u32 r[16], tc;
+    sqr_wide_tok<FEC_P256_FENCE_SQR == 3>(r, a, tc);
+    reduce512(o, r, FEC_P256_FENCE_SQR == 1 ? top_is_ones(r[15]) : FEC_P256_FENCE_SQR == 3 ? tc : 0u);
   }
   // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
   FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<FeP256>(o, a, b); }

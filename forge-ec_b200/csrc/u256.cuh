@@ -101,8 +101,11 @@ FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b, u32 z0 = 0u) {
 }
 
 // r[0..16) = a[0..8) * b[0..8), schoolbook
-// tok_e + tok_o (the two top partial words, final before the merge) never overflows 32 bits: see FeP256::mul_inl
-FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32& tok_e, u32& tok_o) {
+// Tokens for callers that want to order later work behind the product (FeP256::mul_inl): tok_e + tok_o (the two top partial
+// words, final before the merge) never overflows 32 bits; with TOKC, tok_c is the carry out of the merge chain -- zero
+// for every input, because the product is below 2^512.
+template <bool TOKC>
+FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32& tok_e, u32& tok_o, u32& tok_c) {
   const u32 z0 = opaque_zero(a[0]);
   u32 ev[16];  // ev[k]: weight 2^(32k)
   u32 od[15];  // od[k]: weight 2^(32(k+1))
@@ -127,12 +130,18 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
   r[1] = add_cc(ev[1], od[0]);
 #pragma unroll
   for (int k = 2; k < 15; k++) r[k] = addc_cc(ev[k], od[k - 1]);
-  r[15] = addc(ev[15], od[14]);
+  tok_c = 0u;
+  if (TOKC) {
+    r[15] = addc_cc(ev[15], od[14]);
+    tok_c = addc(0u, 0u);
+  } else {
+    r[15] = addc(ev[15], od[14]);
+  }
   tok_e = ev[15]; tok_o = od[14];
 }
 FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
-  u32 te, to;
-  mul_wide_school_tok(r, a, b, te, to);
+  u32 te, to, tc;
+  mul_wide_school_tok<false>(r, a, b, te, to, tc);
 }
 
 // r[0..8) = a[0..4) * b[0..4): the same even/odd accumulation on half-size operands
@@ -200,7 +209,9 @@ FEC_DEV void mul_wide_karatsuba(u32 r[16], const u32 a[8], const u32 b[8]) {
 }
 
 // r[0..16) = a[0..8)^2 : 28 off-diagonal products (doubled by a 1-bit funnel shift) + 8 diagonals.
-FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
+// (TOKC: tok_c receives the carry out of the final chain -- zero for every input, the square is below 2^512)
+template <bool TOKC>
+FEC_DEV void sqr_wide_tok(u32 r[16], const u32 a[8], u32& tok_c) {
   const u32 z0 = opaque_zero(a[0]);
   // off-diagonal sum S = sum_{i<j} a[i]a[j] 2^(32(i+j)); positions 1..14 (+carry word 15 stays 0)
   u32 ev[16];  // even positions 2..14 used: ev[k] weight 2^(32k)
@@ -252,11 +263,16 @@ FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
 #pragma unroll
   for (int i = 1; i < 8; i++) {
     r[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
-    if (i < 7)
+    if (i < 7 || TOKC)
       r[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
     else
       r[2 * i + 1] = madc_hi(a[i], a[i], t[2 * i + 1]);
   }
+  tok_c = TOKC ? addc(0u, 0u) : 0u;
+}
+FEC_DEV void sqr_wide(u32 r[16], const u32 a[8]) {
+  u32 tc;
+  sqr_wide_tok<false>(r, a, tc);
 }
 
 FEC_DEV void mul_wide(u32 r[16], const u32 a[8], const u32 b[8]) {
