@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development)")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configurations (development)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the optional NCCL gather measurement (N > 1)")
     ap.add_argument("--no-field", action="store_true", help="skip the field microbench (BASELINE.json configs[1])")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -314,6 +315,29 @@ def main():
         e2e = {"value": world * n * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 96,
                "d2h_bytes_per_step": n * 34, "steps": e2e_steps, "timer": "host wall clock around the synchronous fec_batch_mul call",
                "matches_device_resident_run": same}
+
+    # ---- SURVEY 8e, optional and outside every timed throughput figure: the device-side gather of the shards' results over
+    # NVLink / NVSwitch (ncclAllGather of n x 33 B per rank), timed on the device, max over ranks
+    gather = None
+    if world > 1 and not args.no_gather:
+        g_all = torch.empty(world * n * 33, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(g_all, d_out)   # warm-up (communicator set-up)
+        torch.cuda.synchronize()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            dist.all_gather_into_tensor(g_all, d_out)
+        g1.record()
+        torch.cuda.synchronize()
+        gt = torch.tensor([g0.elapsed_time(g1) / 3.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(g_all[rank * n * 33:(rank + 1) * n * 33], d_out))
+        gather = {"collective": "ncclAllGather (torch.distributed all_gather_into_tensor)", "bytes_per_rank": n * 33, "ms": float(gt.item()),
+                  "algorithmic_GBps_per_gpu": (world - 1) * n * 33 / (float(gt.item()) * 1e-3) / 1e9,
+                  "share_of_step": float(gt.item()) / (total_ms_max / args.steps), "own_shard_intact": ok,
+                  "note": "not part of value / e2e: the path has no exchange step, results normally leave by per-device D2H copies"}
+        del g_all
 
     # ---- the other configurations of BASELINE.json, device-resident, a few repetitions each (reported, not the headline)
     others = None
@@ -474,7 +498,8 @@ def main():
                      "hbm": {"bound": "hbm", "achieved": IO_BYTES_PER_OP * n / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": IO_BYTES_PER_OP * n / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_op": IO_BYTES_PER_OP}},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world, "other_configs": others, "clocks": clocks,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world, "device_gather": gather, "other_configs": others,
+        "clocks": clocks,
     }
     sys.stdout.flush()
     os.write(result_fd, (json.dumps(line) + "\n").encode())
