@@ -1,9 +1,13 @@
 // x25519_vm.cuh -- the RFC 7748 ladder (x25519(), forge-ec-curves/src/curve25519.rs:1624-1716) on the accumulator
 // machine of vm.cuh (host-compilable for tests/hostsim).
 //
-// Why.  With x1, (x2, z2), (x3, z3) and the temporaries of a step in registers the ladder needs 128 registers per thread
-// (16 warps per SM); here one field element is in registers and the lane's nine others are shared-memory slots, so the
-// kernel runs 20 warps per SM at 96 registers like the Weierstrass ladders.
+// Why it exists, and why it is NOT the default.  With x1, (x2, z2), (x3, z3) and the temporaries of a step in registers the
+// ladder needs 128 registers per thread (16 warps per SM); here one field element is in registers and the lane's nine
+// others are shared-memory slots, so the kernel runs 20 warps per SM at 96 registers like the Weierstrass ladders.
+// Measured (B200, 2^22 lanes): 45.0 M/s against 48.9 M/s for the register-resident kernel -- this loop has no table and
+// fits its registers, and with the field routines in line ptxas overlaps one product's reduction with the next product's
+// rows, which calls through a single accumulator forbid.  Kept behind FORGE_EC_X_IMPL=vm for A/B and as the host-sim
+// cross-check of the ladder (two independent formulations of the conditional swap must agree).
 //
 // Slot map of a lane: 0 = x1, 1..4 and 5..8 = two sets {x2, z2, x3, z3}.  A step reads set P and writes set Q, then the
 // sets change roles (no copies).  The conditional swap of RFC 7748 costs no instruction: lane-private slots of the
