@@ -104,6 +104,34 @@ template <class F> FEC_VMOP fe vm_sqr(fe a) {
   F::sqr_inl(r.v, a.v);
   return r;
 }
+// Two INDEPENDENT operations in one routine (FEC_VM_DUAL).  A warp executes in order: alone, a product
+// is ~70 IMAD.WIDE followed by ~60 dependent additions, and only other warps fill the multiply pipe during the second phase.
+// With two independent data flows in one straight-line routine ptxas interleaves the reduction of one with the rows of the
+// other (as it does in the in-line X25519 step), so a single warp keeps both pipes busy.
+struct fe2 { fe a, b; };
+template <class F, int T> FEC_VMOP fe2 vm_mul2(fe a0, saddr p0, fe a1, saddr p1) {  // a0 * [p0], a1 * [p1]
+  u32 b0[8], b1[8];
+  Vm<F, T>::ldv(b0, p0);
+  Vm<F, T>::ldv(b1, p1);
+  fe2 r;
+  F::mul_inl(r.a.v, a0.v, b0);
+  F::mul_inl(r.b.v, a1.v, b1);
+  return r;
+}
+template <class F> FEC_VMOP fe2 vm_sqr2(fe a0, fe a1) {  // a0^2, a1^2
+  fe2 r;
+  F::sqr_inl(r.a.v, a0.v);
+  F::sqr_inl(r.b.v, a1.v);
+  return r;
+}
+template <class F, int T> FEC_VMOP fe2 vm_mulsqr(fe a0, saddr p0, fe a1) {  // a0 * [p0], a1^2
+  u32 b0[8];
+  Vm<F, T>::ldv(b0, p0);
+  fe2 r;
+  F::mul_inl(r.a.v, a0.v, b0);
+  F::sqr_inl(r.b.v, a1.v);
+  return r;
+}
 template <class F, int T> FEC_VMLIN fe vm_add(fe a, saddr p) {  // a + [p]
   u32 b[8];
   Vm<F, T>::ldv(b, p);
@@ -158,6 +186,34 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
               Cs = V::slot(S, VS_C), D = V::slot(S, VS_D);
+#ifdef FEC_VM_DUAL
+  {  // the same 2M + 5S as two paired squarings, a multiplication next to a squaring, and one multiplication
+    fe a0 = V::ld(X), a1 = V::ld(Y);
+    fe2 s = vm_sqr2<F>(a0, a1);
+    V::st(A, s.a); V::st(B, s.b);                  // A = X^2, B = Y^2
+    a1 = V::ld(X);
+    a1 = vm_add<F, T>(a1, B);
+    fe2 t = vm_sqr2<F>(s.b, a1);
+    V::st(Cs, t.a);                                // C = B^2
+    a1 = vm_sub<F, T>(t.b, A);
+    a1 = vm_sub<F, T>(a1, Cs);
+    a1 = vm_small<F, 2>(a1); V::st(D, a1);         // D = 2((X+B)^2 - A - C)
+    a1 = V::ld(A);
+    a1 = vm_small<F, 3>(a1); V::st(A, a1);         // E = 3A
+    a0 = V::ld(Y);
+    fe2 u = vm_mulsqr<F, T>(a0, Z, a1);            // Y Z, E^2
+    a0 = vm_small<F, 2>(u.a); V::st(Z, a0);        // Z3 = 2YZ
+    a1 = vm_sub<F, T>(u.b, D);
+    a1 = vm_sub<F, T>(a1, D); V::st(X, a1);        // X3 = E^2 - 2D
+    a1 = vm_rsub<F, T>(a1, D);                     // D - X3
+    a1 = vm_mul<F, T>(a1, A);                      // E (D - X3)
+    a0 = V::ld(Cs);
+    a0 = vm_small<F, 8>(a0);
+    fe y;
+    F::sub(y.v, a1.v, a0.v); V::st(Y, y);          // Y3 = E(D - X3) - 8C
+    return;
+  }
+#endif
 #ifdef FEC_K1_DBL_3M4S
   // A/B variant: D = 4 X B by a multiplication (3M + 4S, 8 linear operations instead of 11)
   {
@@ -260,6 +316,24 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
               R = V::slot(S, VS_C), TX = V::slot(S, VS_TX), TY = V::slot(S, VS_TY);
+#ifdef FEC_VM_DUAL
+  if (!SUBS_ONLY) {  // (secp256k1 form) Z1Z1; U2 next to Z1^3; S2 next to HH
+    fe a = V::ld(Z);
+    const u32 q_inf = F::is_zero(a.v);
+    a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
+    fe2 m = vm_mul2<F, T>(a, TX, a, Z);            // U2 = x2 Z1Z1, Z1^3
+    fe h = vm_sub<F, T>(m.a, X); V::st(H, h);      // H = U2 - X1
+    const u32 h_zero = F::is_zero(h.v);
+    fe2 n = vm_mulsqr<F, T>(m.b, TY, h);           // y2 Z1^3, HH
+    V::st(V::slot(S, VS_D), n.b);                  // HH
+    a = vm_cneg<F>(n.a, neg_y);                    // S2 = +-y2 Z1^3
+    a = vm_sub<F, T>(a, Y);
+    const u32 r_zero = F::is_zero(a.v);
+    a = vm_small<F, 2>(a);
+    V::st(R, a);                                   // r = 2(S2 - Y1)
+    return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+  }
+#endif
   fe a = V::ld(Z);
   const u32 q_inf = F::is_zero(a.v);
   a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
@@ -301,6 +375,31 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
     a = vm_rsub<F, T>(a, R); V::st(Y, a);          // Y3
     return;
   }
+#ifdef FEC_VM_DUAL
+  {  // HH is in its slot already (vm_jac_madd_1);  (Z1+H)^2 next to r^2;  J next to V;  r (V - X3) next to Y1 J
+    fe a0 = V::ld(Z);
+    a0 = vm_add<F, T>(a0, H);
+    fe a1 = V::ld(R);
+    fe2 q = vm_sqr2<F>(a0, a1);
+    a0 = vm_sub<F, T>(q.a, A);
+    a0 = vm_sub<F, T>(a0, HH); V::st(Z, a0);       // Z3 = (Z1+H)^2 - Z1Z1 - HH
+    a0 = V::ld(HH);
+    a0 = vm_small<F, 4>(a0);                       // I = 4 HH
+    V::st(HH, q.b);                                // r^2 (HH is dead)
+    fe2 jv = vm_mul2<F, T>(a0, H, a0, X);          // J = H I, V = X1 I
+    V::st(H, jv.a); V::st(A, jv.b);
+    a0 = V::ld(HH);
+    a0 = vm_sub<F, T>(a0, H);
+    a0 = vm_sub<F, T>(a0, A);
+    a0 = vm_sub<F, T>(a0, A); V::st(X, a0);        // X3 = r^2 - J - 2V
+    a0 = vm_rsub<F, T>(a0, A);                     // V - X3
+    fe2 w = vm_mul2<F, T>(a0, R, jv.a, Y);         // r (V - X3), Y1 J
+    a1 = vm_small<F, 2>(w.b);
+    fe y;
+    F::sub(y.v, w.a.v, a1.v); V::st(Y, y);         // Y3 = r (V - X3) - 2 Y1 J
+    return;
+  }
+#endif
   fe a = V::ld(H);
   a = vm_sqr<F>(a); V::st(HH, a);                // HH
 #ifdef FEC_K1_MADD_Z_MUL

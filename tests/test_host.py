@@ -145,6 +145,29 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.ed25519_pubkey(k, False)
 
 
+def test_dual_operation_programs_of_the_accumulator_machine(pm):
+    """FEC_VM_DUAL (vm.cuh): the secp256k1 doubling / mixed addition written with two independent field operations per
+    routine call (A/B form) must give the same k*P as the model, edge scalars included."""
+    import random
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libhostsim_dual.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DFEC_VM_DUAL", "-x", "c++", "-shared", "-fPIC", "-o", so, src], check=True)
+    hs = ctypes.CDLL(so)
+    rnd = random.Random(23)
+    be = lambda v: v.to_bytes(32, "big")
+    c = pm.CURVES[0]
+    hs.hs_set_var_impl(1)
+    o = ctypes.create_string_buffer(33)
+    ks = [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, (30 << 252) - c.n, 15 << 252] + [rnd.randrange(c.n) for _ in range(12)]
+    for k in ks:
+        P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
+        for pt in (be(P[0]) + be(P[1]), be(c.gx) + be(c.gy)):
+            st = hs.hs_wmul(0, be(k), pt, 0, 0, 0, o)
+            assert (o.raw, bytes([st])) == pm.batch_mul(0, be(k), pt, 1, 0, 0), hex(k)
+
+
 def test_karatsuba_variant_of_the_multiplier(pm):
     """u256.cuh keeps a one-level Karatsuba 8x8 multiplier behind FEC_KARATSUBA (measured slower on B200: it trades 16
     IMAD.WIDE for ~70 additions); it must stay correct, including equal and extreme halves."""
