@@ -462,6 +462,72 @@ struct FeP256 {
     const u32 bw = sub8(d, t + 8, p);
     select8(o, (0u - cy) | (bw - 1u), d, t + 8);
   }
+  // reduce512 in stages (see mul2_inl): one 64-bit round, and the conditional subtraction
+  template <int R>
+  FEC_DEV static void red_round(u32 t[16], u32& cy) {
+    const int b = 2 * R;
+    const u32 q0 = t[b], q1 = t[b + 1];
+    u32 s2, s3;
+    if (R == 0) { s2 = q0; s3 = q1; } else { s2 = add_cc(q0, cy); s3 = addc(q1, 0u); }
+    const u32 m1 = sub_cc(q1, q0);
+    const u32 m2 = subc_cc(s2, q1);
+    const u32 m3 = subc(s3, 0u);
+    t[b + 3] = add_cc(t[b + 3], q0);
+    t[b + 4] = addc_cc(t[b + 4], q1);
+    t[b + 5] = addc_cc(t[b + 5], 0u);
+    t[b + 6] = addc_cc(t[b + 6], q0);
+    t[b + 7] = addc_cc(t[b + 7], m1);
+    t[b + 8] = addc_cc(t[b + 8], m2);
+    t[b + 9] = addc_cc(t[b + 9], m3);
+    cy = addc(0u, 0u);
+  }
+  FEC_DEV static void red_final(u32 o[8], const u32 t[16], u32 cy) {
+    u32 p[8], d[8];
+    P(p);
+    const u32 bw = sub8(d, t + 8, p);
+    select8(o, (0u - cy) | (bw - 1u), d, t + 8);
+  }
+  // Two independent multiplications, INTERLEAVED at carry-chain granularity (FEC_VM_DUAL): all rows of
+  // the first product, then the rows of the second one between the merge, the four reduction rounds and the final
+  // subtraction of the first (between two chains the carry flag is dead, so the order is legal in PTX), then the tail of the
+  // second.  A multiplication is 64 IMAD.WIDE (multiply pipe) and ~88 dependent additions (ALU pipe): alone, a warp uses
+  // the two pipes one after the other.  Without the tokens below ptxas regroups the stages (all 128 IMAD.WIDE first).
+  FEC_DEV static void mul2_inl(u32 o0[8], const u32 a0[8], const u32 b0[8], u32 o1[8], const u32 a1[8], const u32 b1[8]) {
+    ProdSt A, B;
+    u32 t[16], tc, cy = 0u;
+    const u32 z0 = opaque_zero_always(a1[0]);
+    prod_row<0>(A, a0, b0); prod_row<1>(A, a0, b0); prod_row<2>(A, a0, b0); prod_row<3>(A, a0, b0);
+    prod_row<4>(A, a0, b0); prod_row<5>(A, a0, b0); prod_row<6>(A, a0, b0); prod_row<7>(A, a0, b0);
+    // row k + 2 of the second product waits for tail stage k of the first one: its multiplier word is or-ed with an
+    // always-zero value computed from the stage's last result (the carry out of the merge; `carry & z0` afterwards)
+    u32 bb[8];
+    copy8(bb, b1);
+    bb[0] |= A.ev[15] & z0;   // rows 0 and 1 behind the first product's last row: they run next to its merge
+    prod_row<0>(B, a1, bb);
+    prod_merge(t, tc, A);
+    t[0] |= tc;
+    bb[1] |= A.od[14] & z0;
+    prod_row<1>(B, a1, bb);
+    red_round<0>(t, cy);
+    bb[2] |= tc;
+    prod_row<2>(B, a1, bb);
+    red_round<1>(t, cy);
+    bb[3] |= cy & z0;
+    prod_row<3>(B, a1, bb);
+    red_round<2>(t, cy);
+    bb[4] |= cy & z0;
+    prod_row<4>(B, a1, bb);
+    red_round<3>(t, cy);
+    bb[5] |= cy & z0;
+    prod_row<5>(B, a1, bb);
+    red_final(o0, t, cy);
+    bb[6] |= cy & z0;
+    prod_row<6>(B, a1, bb);
+    bb[7] |= o0[7] & z0;
+    prod_row<7>(B, a1, bb);
+    prod_merge(t, tc, B);
+    reduce512(o1, t, tc);
+  }
   // always-zero values for reduce512 (device code only).  top_is_ones: the top word of a product of two residues below p
   // is at most 0xFFFFFFFE (p^2 < 2^512 - 2^481).  top_overflows: the two top partial words of the schoolbook product
   // add up to the top word of a number below 2^512.

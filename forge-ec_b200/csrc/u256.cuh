@@ -79,6 +79,17 @@ FEC_DEV u32 opaque_zero(u32 x) {
   return 0u;
 #endif
 }
+FEC_DEV u32 opaque_zero_always(u32 x) {  // the same, not switched by FEC_ZERO_ON_ALU (ordering tokens of FeP256::mul2_inl)
+#if defined(__CUDA_ARCH__)
+  u32 p, q;
+  asm("prmt.b32 %0, %1, %1, 0x0000;" : "=r"(p) : "r"(x));
+  asm("prmt.b32 %0, %1, %1, 0x4444;" : "=r"(q) : "r"(x));
+  return p ^ q;
+#else
+  (void)x;
+  return 0u;
+#endif
+}
 template <int NP, int FRESH>
 FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b, u32 z0 = 0u) {
   static_assert(FRESH >= 0 && FRESH <= 2, "fresh words");
@@ -142,6 +153,47 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
 FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
   u32 te, to, tc;
   mul_wide_school_tok<false>(r, a, b, te, to, tc);
+}
+
+// The same product in STAGES, for routines that interleave two independent field operations at carry-chain granularity
+// (FeP256::mul2_inl): stage 0 = row b[0] (plain products), stages 1..7 = rows b[1..7] (two carry chains each),
+// prod_merge = r = ev + (od << 32) with the carry out of the chain in tok_c (zero for every input).
+struct ProdSt { u32 ev[16]; u32 od[15]; };
+template <int R>
+FEC_DEV void prod_row(ProdSt& s, const u32 a[8], const u32 b[8]) {
+  u32* ev = s.ev;
+  u32* od = s.od;
+  if (R == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      ev[j] = mul_lo(a[j], b[0]);
+      ev[j + 1] = mul_hi(a[j], b[0]);
+      od[j] = mul_lo(a[j + 1], b[0]);
+      od[j + 1] = mul_hi(a[j + 1], b[0]);
+    }
+  } else if (R == 1) {
+    mad_row<4, 2>(ev + 2, a + 1, b[1]);  od[8] = mad_row<4, 0>(od + 0, a, b[1]);
+  } else if (R == 2) {
+    ev[10] = mad_row<4, 0>(ev + 2, a, b[2]);  mad_row<4, 1>(od + 2, a + 1, b[2]);
+  } else if (R == 3) {
+    mad_row<4, 1>(ev + 4, a + 1, b[3]);  od[10] = mad_row<4, 0>(od + 2, a, b[3]);
+  } else if (R == 4) {
+    ev[12] = mad_row<4, 0>(ev + 4, a, b[4]);  mad_row<4, 1>(od + 4, a + 1, b[4]);
+  } else if (R == 5) {
+    mad_row<4, 1>(ev + 6, a + 1, b[5]);  od[12] = mad_row<4, 0>(od + 4, a, b[5]);
+  } else if (R == 6) {
+    ev[14] = mad_row<4, 0>(ev + 6, a, b[6]);  mad_row<4, 1>(od + 6, a + 1, b[6]);
+  } else {
+    mad_row<4, 1>(ev + 8, a + 1, b[7]);  od[14] = mad_row<4, 0>(od + 6, a, b[7]);
+  }
+}
+FEC_DEV void prod_merge(u32 r[16], u32& tok_c, const ProdSt& s) {
+  r[0] = s.ev[0];
+  r[1] = add_cc(s.ev[1], s.od[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) r[k] = addc_cc(s.ev[k], s.od[k - 1]);
+  r[15] = addc_cc(s.ev[15], s.od[14]);
+  tok_c = addc(0u, 0u);
 }
 
 // r[0..8) = a[0..4) * b[0..4): the same even/odd accumulation on half-size operands

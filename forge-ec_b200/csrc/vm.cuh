@@ -109,13 +109,20 @@ template <class F> FEC_VMOP fe vm_sqr(fe a) {
 // With two independent data flows in one straight-line routine ptxas interleaves the reduction of one with the rows of the
 // other (as it does in the in-line X25519 step), so a single warp keeps both pipes busy.
 struct fe2 { fe a, b; };
+// two multiplications: the field's interleaved routine where it has one (FeP256::mul2_inl), else one after the other
+template <class F> FEC_DEV void field_mul2(F, u32 o0[8], const u32 a0[8], const u32 b0[8], u32 o1[8], const u32 a1[8], const u32 b1[8]) {
+  F::mul_inl(o0, a0, b0);
+  F::mul_inl(o1, a1, b1);
+}
+FEC_DEV void field_mul2(FeP256, u32 o0[8], const u32 a0[8], const u32 b0[8], u32 o1[8], const u32 a1[8], const u32 b1[8]) {
+  FeP256::mul2_inl(o0, a0, b0, o1, a1, b1);
+}
 template <class F, int T> FEC_VMOP fe2 vm_mul2(fe a0, saddr p0, fe a1, saddr p1) {  // a0 * [p0], a1 * [p1]
   u32 b0[8], b1[8];
   Vm<F, T>::ldv(b0, p0);
   Vm<F, T>::ldv(b1, p1);
   fe2 r;
-  F::mul_inl(r.a.v, a0.v, b0);
-  F::mul_inl(r.b.v, a1.v, b1);
+  field_mul2(F(), r.a.v, a0.v, b0, r.b.v, a1.v, b1);
   return r;
 }
 template <class F> FEC_VMOP fe2 vm_sqr2(fe a0, fe a1) {  // a0^2, a1^2
@@ -273,6 +280,34 @@ FEC_DEV void vm_jac_dbl_am3(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
               Cs = V::slot(S, VS_C), D = V::slot(S, VS_D);
+#ifdef FEC_VM_DUAL
+  {  // alpha's product next to Z3 = 2Y Z (one interleaved routine); the rest as below
+    fe a = V::ld(Z);
+    a = vm_sqr<F>(a); V::st(A, a);                 // delta = Z^2
+    a = vm_rsub<F, T>(a, X); V::st(D, a);          // X - delta
+    fe a0 = V::ld(X);
+    a0 = vm_add<F, T>(a0, A);
+    fe a1 = V::ld(Y);
+    a1 = vm_small<F, 2>(a1); V::st(B, a1);         // 2Y
+    fe2 m = vm_mul2<F, T>(a0, D, a1, Z);           // (X + delta)(X - delta), 2Y Z
+    V::st(Z, m.b);                                 // Z3
+    a = vm_small<F, 3>(m.a); V::st(D, a);          // alpha
+    a = V::ld(B);
+    a = vm_sqr<F>(a); V::st(B, a);                 // 4 gamma
+    a = vm_mul<F, T>(a, X); V::st(Cs, a);          // 4 beta
+    a = V::ld(D);
+    a = vm_sqr<F>(a);
+    a = vm_sub<F, T>(a, Cs);
+    a = vm_sub<F, T>(a, Cs); V::st(X, a);          // X3 = alpha^2 - 8 beta
+    a = vm_rsub<F, T>(a, Cs);                      // 4 beta - X3
+    a = vm_mul<F, T>(a, D); V::st(A, a);           // alpha (4 beta - X3)
+    a = V::ld(B);
+    a = vm_sqr<F>(a);
+    a = vm_half<F>(a);                             // 8 gamma^2
+    a = vm_rsub<F, T>(a, A); V::st(Y, a);          // Y3
+    return;
+  }
+#endif
   fe a = V::ld(Z);
   a = vm_sqr<F>(a); V::st(A, a);                 // delta = Z^2
   a = vm_rsub<F, T>(a, X); V::st(D, a);          // X - delta
@@ -332,6 +367,19 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
     a = vm_small<F, 2>(a);
     V::st(R, a);                                   // r = 2(S2 - Y1)
     return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+  } else {  // (P-256 form) U2 next to Z1^3 in one interleaved routine
+    fe a = V::ld(Z);
+    const u32 q_inf = F::is_zero(a.v);
+    a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
+    fe2 m = vm_mul2<F, T>(a, TX, a, Z);            // U2 = x2 Z1Z1, Z1^3
+    fe h = vm_sub<F, T>(m.a, X); V::st(H, h);      // H = U2 - X1
+    const u32 h_zero = F::is_zero(h.v);
+    a = vm_mul<F, T>(m.b, TY);
+    a = vm_cneg<F>(a, neg_y);                      // S2 = +-y2 Z1^3
+    a = vm_sub<F, T>(a, Y);
+    const u32 r_zero = F::is_zero(a.v);
+    V::st(R, a);                                   // r = S2 - Y1
+    return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
   }
 #endif
   fe a = V::ld(Z);
@@ -355,6 +403,27 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
               R = V::slot(S, VS_C), HH = V::slot(S, VS_D);
+#ifdef FEC_VM_DUAL
+  if (SUBS_ONLY) {  // Z3 next to HHH, r (V - X3) next to Y1 HHH (interleaved routines)
+    fe a = V::ld(H);
+    a = vm_sqr<F>(a); V::st(HH, a);                // HH
+    fe a0 = V::ld(Z);
+    fe2 m = vm_mul2<F, T>(a0, H, a, H);            // Z3 = Z1 H, HHH
+    V::st(Z, m.a); V::st(H, m.b);
+    a = V::ld(X);
+    a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 HH
+    a = V::ld(R);
+    a = vm_sqr<F>(a);
+    a = vm_sub<F, T>(a, H);
+    a = vm_sub<F, T>(a, A);
+    a = vm_sub<F, T>(a, A); V::st(X, a);           // X3 = r^2 - HHH - 2V
+    a = vm_rsub<F, T>(a, A);                       // V - X3
+    fe2 w = vm_mul2<F, T>(a, R, m.b, Y);           // r (V - X3), Y1 HHH
+    fe y;
+    F::sub(y.v, w.a.v, w.b.v); V::st(Y, y);        // Y3
+    return;
+  }
+#endif
   if (SUBS_ONLY) {
     fe a = V::ld(Z);
     a = vm_mul<F, T>(a, H); V::st(Z, a);           // Z3 = Z1 H
