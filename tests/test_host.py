@@ -139,6 +139,19 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.x25519(k, u)
         hostsim.hs_x25519_vm(k, u, o)
         assert o.raw == pm.x25519(k, u)
+    # edge inputs of the ladder (both formulations of the conditional swap): u = 0, 1, p - 1, p, p + 1, 2^255 - 1, 2^256 - 1
+    # (non-canonical and bit 255 set: masked / reduced as RFC 7748 says), a point of order 8, scalars of all zeros / all ones
+    p25519 = 2**255 - 19
+    us = [0, 1, p25519 - 1, p25519, p25519 + 1, 2**255 - 1, 2**256 - 1, 9,
+          0x00b8495f16056286fdb1329ceb8d09da6ac49ff1fae35616aeb8413b7c7aebe0]
+    for uv in us:
+        for k in (bytes(32), b"\xff" * 32, bytes(range(32)), bytes([rnd.randrange(256) for _ in range(32)])):
+            u = uv.to_bytes(32, "little")
+            o = ctypes.create_string_buffer(32)
+            hostsim.hs_x25519(k, u, o)
+            assert o.raw == pm.x25519(k, u), (hex(uv), k.hex())
+            hostsim.hs_x25519_vm(k, u, o)
+            assert o.raw == pm.x25519(k, u), (hex(uv), k.hex())
         hostsim.hs_ed25519_pubkey(k, 1, o)
         assert o.raw == pm.ed25519_pubkey(k)
         hostsim.hs_ed25519_pubkey(k, 0, o)
