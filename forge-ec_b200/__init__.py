@@ -30,6 +30,7 @@ from .engine import (  # noqa: F401
     OUT_AFFINE_XY_BE,
     OUT_X_BE,
     OUT_SEC1_COMPRESSED,
+    OUT_SEC1_HYBRID,
     OUT_SEC1_UNCOMPRESSED,
     OUT_SIZE,
     PRIME_25519,

@@ -276,9 +276,11 @@ int run_host_job(fec_ctx* ctx, const HostJob& job, size_t n) {
 
 // FEC_SEM_FORGE_QUIRK replays the reference's literal limb code; restated for both Weierstrass curves, affine X||Y input only
 // (the reference's own SEC1 decoder rejects its own encodings, test_summary.md:77-85, so there is nothing to replay)
-bool sem_supported(int sem, int curve, int points_fmt) {
+bool sem_supported(int sem, int curve, int points_fmt, int out_fmt) {
   if (sem == FEC_SEM_STD) return true;
-  return sem == FEC_SEM_FORGE_QUIRK && (curve == FEC_SECP256K1 || curve == FEC_P256) && points_fmt == FEC_PT_AFFINE_XY_BE;
+  // (the literal replay encodes compressed / uncompressed / X||Y records only)
+  return sem == FEC_SEM_FORGE_QUIRK && (curve == FEC_SECP256K1 || curve == FEC_P256) && points_fmt == FEC_PT_AFFINE_XY_BE &&
+         out_fmt <= FEC_OUT_AFFINE_XY_BE;
 }
 
 Device* dev_at(fec_ctx* ctx, int dev_index) {
@@ -370,9 +372,9 @@ const char* fec_ctx_last_cuda_error(const fec_ctx* ctx) { return ctx ? ctx->last
 int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
                   fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status) {
   if (ctx == nullptr || (n > 0 && (scalars == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
-  if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
+  if (!sem_supported(sem, curve, points_fmt, (int)out_fmt)) return FEC_ERR_UNSUPPORTED;
   HostJob job{0, (int)curve, (int)sem, (int)points_fmt, (int)out_fmt, 0, scalars, 32, points,
               (size_t)(points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64), out, (size_t)out_size(out_fmt), status};
   return run_host_job(ctx, job, n);
@@ -383,10 +385,10 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
                       uint8_t* d_status, void* stream) {
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
-  if (!sem_supported(sem, curve, points_fmt)) return FEC_ERR_UNSUPPORTED;
+  if (!sem_supported(sem, curve, points_fmt, (int)out_fmt)) return FEC_ERR_UNSUPPORTED;
   int prev = 0;
   cudaGetDevice(&prev);
   FEC_CUDA(ctx, cudaSetDevice(d->id));
@@ -498,7 +500,7 @@ int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_s
                 fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream) {
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || n == 0 || d_scalars == nullptr || d_points == nullptr || d_out == nullptr) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points)) return FEC_ERR_INVALID_ARG;
   int prev = 0;
@@ -512,7 +514,7 @@ int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_s
 int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
             fec_out out_fmt, uint8_t* out, uint8_t* status) {
   if (ctx == nullptr || n == 0 || scalars == nullptr || points == nullptr || out == nullptr) return FEC_ERR_INVALID_ARG;
-  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 3 || (int)points_fmt < 0 || (int)points_fmt > 1)
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   const size_t G = ctx->devs.size();

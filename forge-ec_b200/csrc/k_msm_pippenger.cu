@@ -52,23 +52,24 @@ k_pip_digits(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ po
   const size_t lane = (size_t)blockIdx.x * PIP_THREADS + threadIdx.x;
   const bool live = lane < n;
   const size_t ld = live ? lane : n - 1;
-  u32 k[8], px[8], py[8], ok;
+  u32 k[8], px[8], py[8], ok, idn = 0u;
   load_rec32_be(k, scalars + ld * 32);
   if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
     uint8_t rec[33];
     for (int i = 0; i < 33; i++) rec[i] = points[ld * 33 + i];
-    ok = sec1_decompress<C>(px, py, rec);
+    ok = sec1_decompress_id<C>(px, py, rec, idn);
   } else {
     load_rec32_be(px, points + ld * 64);
     load_rec32_be(py, points + ld * 64 + 32);
-    ok = affine_from_plain<C>(px, py);
+    ok = affine_from_plain_id<C>(px, py, idn);
   }
   u32 nn[8];
   C::N(nn);
   const u32 range_bad = geq8(k, nn);
   if (!live) return;  // no warp-collective operation follows
   if (range_bad) atomicOr(sc.bad, (u32)LANE_SCALAR_RANGE);
-  else if (!ok) atomicOr(sc.bad, (u32)LANE_POINT_INVALID);
+  else if (!ok && !idn) atomicOr(sc.bad, (u32)LANE_POINT_INVALID);
+  if (idn) set_small(k, 0u);  // the identity as an input point contributes nothing: all digits zero (lib.rs:934-951 simply adds it)
   g_st8(sc.aff + lane * 16, px);
   g_st8(sc.aff + lane * 16 + 8, py);
   // k >= 2^255: use (n - k) (-P) instead, so that the top chunk stays below 2^15 and the 17th window (which has a single

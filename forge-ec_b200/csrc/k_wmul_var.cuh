@@ -60,19 +60,19 @@ k_wmul_var(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
       const size_t lane = first + lane_in_warp;
       const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
       const bool live = (int)lane_in_warp < cnt_lanes;
-      u32 k[8], px[8], py[8], st, ok = 0xFFFFFFFFu;
+      u32 k[8], px[8], py[8], st, ok = 0xFFFFFFFFu, idn = 0u;
       set_small(k, 1u);
       C::G(px, py);
       if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
         __syncwarp();
         warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
         __syncwarp();
-        if (live) ok = sec1_decompress<C>(px, py, io + lane_in_warp * 33);
+        if (live) ok = sec1_decompress_id<C>(px, py, io + lane_in_warp * 33, idn);
         __syncwarp();
       } else if (live) {
         load_rec32_be(px, points + lane * 64);
         load_rec32_be(py, points + lane * 64 + 32);
-        ok = affine_from_plain<C>(px, py);
+        ok = affine_from_plain_id<C>(px, py, idn);
       }
       if (live) load_rec32_be(k, scalars + lane * 32);
       {
@@ -99,7 +99,7 @@ k_wmul_var(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ poin
         scalar_prepare<C>(K, negm, st, k);
         wmul_var_core<C>(Q, K, px, py, tab, inv);
       }
-      if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);  // range > invalid point > k = 0
+      st = lane_status(st, ok, idn);  // range > invalid point > identity (k = 0, or the identity as the input point)
       const u32 zz = F::is_zero(Q.Z);
       st |= (st == 0u ? zz & LANE_INFINITY : 0u);
       if (status != nullptr && live) status[lane] = (uint8_t)st;

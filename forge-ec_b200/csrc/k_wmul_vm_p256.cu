@@ -58,15 +58,15 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   // lanes past the end recompute the last lane (the whole warp takes part in the inversion) into 32 spare table rows
   const size_t lane = live ? first + lane_in_warp : n - 1;
   const size_t row = live ? lane : n + lane_in_warp;
-  u32 k[8], px[8], py[8], ok;
+  u32 k[8], px[8], py[8], ok, idn = 0u;
   if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
     warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
     __syncwarp();
-    ok = sec1_decompress<C>(px, py, io + (lane - first) * 33);
+    ok = sec1_decompress_id<C>(px, py, io + (lane - first) * 33, idn);
   } else {
     load_rec32_be(px, points + lane * 64);
     load_rec32_be(py, points + lane * 64 + 32);
-    ok = affine_from_plain<C>(px, py);
+    ok = affine_from_plain_id<C>(px, py, idn);
   }
   load_rec32_be(k, scalars + lane * 32);
   {
@@ -77,7 +77,7 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   }
   u32 K[8], negm, st;
   scalar_prepare<C>(K, negm, st, k);
-  if (st != LANE_SCALAR_RANGE) st = (~ok & LANE_POINT_INVALID) | (ok & st);  // range > invalid point > k = 0
+  st = lane_status(st, ok, idn);  // range > invalid point > identity (k = 0, or the identity as the input point)
   GlobalLaneTab tab{sc.tab + row * P3_TAB_WORDS};
   P3WarpInv inv;
   wmul_var_table<C>(tab, px, py, inv);

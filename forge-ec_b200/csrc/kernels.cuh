@@ -52,7 +52,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, size
   for (size_t i = (nw << 2) + l; i < bytes; i += 32) dst[i] = src[i];
 }
 
-__host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : (fmt == 2 ? 64 : 32)); }
+__host__ __device__ constexpr int out_size(int fmt) { return fmt == 0 ? 33 : ((fmt == 1 || fmt == 4) ? 65 : (fmt == 2 ? 64 : 32)); }
 
 // per-lane table of 8 affine points in shared memory, word-interleaved across the block:
 // word w of entry j of thread t at [(j*16 + w) * THREADS + t]  (conflict-free for any digits)

@@ -455,9 +455,24 @@ FEC_DEV u32 affine_from_plain(u32 x[8], u32 y[8]) {
   F::from_plain(y, y);
   return ok & on_curve<C>(x, y);
 }
+// The same for callers that accept the identity as an input point: `idn` is set for the all-zero X || Y record, the engine's own
+// encoding of the identity (point.rs:41-47), which never satisfies the curve equation (b != 0) -- the ok mask is clear for it.
+// Curve::multiply(identity, k) is the identity and multi_scalar_multiply simply adds it (forge-ec-core/src/lib.rs:820-832,
+// 934-951), so such a lane is reported as LANE_INFINITY, not as an invalid point.
+template <class C>
+FEC_DEV u32 affine_from_plain_id(u32 x[8], u32 y[8], u32& idn) {
+  idn = is_zero8(x) & is_zero8(y);
+  return affine_from_plain<C>(x, y);
+}
+// lane status from the three masks, priority: scalar range > invalid point > identity (k = 0 or identity input)
+FEC_DEV u32 lane_status(u32 st_scalar, u32 ok, u32 idn) {
+  if (st_scalar == LANE_SCALAR_RANGE) return st_scalar;
+  return (idn & LANE_INFINITY) | (~idn & ((~ok & LANE_POINT_INVALID) | (ok & st_scalar)));
+}
 
 // SEC1 / raw affine encodings.  fmt: 0 = 02|03 || X (33 B), 1 = 04 || X || Y (65 B), 2 = X || Y (64 B), 3 = X (32 B,
-// the ECDH shared secret of KeyExchange::derive_shared_secret, secp256k1.rs:1885-1905).
+// the ECDH shared secret of KeyExchange::derive_shared_secret, secp256k1.rs:1885-1905), 4 = 06|07 || X || Y (65 B,
+// PointFormat::Hybrid, secp256k1.rs:1048-1066 / p256.rs:1704-1722).
 // dead != 0 -> all-zero record (the reference's identity encoding, point.rs:41-47).
 FEC_DEV void sec1_encode(uint8_t* o, int fmt, const u32 x[8], const u32 y[8], u32 dead) {
   u32 xx[8], yy[8];
@@ -473,12 +488,24 @@ FEC_DEV void sec1_encode(uint8_t* o, int fmt, const u32 x[8], const u32 y[8], u3
   } else if (fmt == 2) {
     store_be32(o, xx);
     store_be32(o + 32, yy);
+  } else if (fmt == 4) {
+    o[0] = (uint8_t)((6u | (y[0] & 1u)) & ~dead);
+    store_be32(o + 1, xx);
+    store_be32(o + 33, yy);
   } else {
     store_be32(o, xx);
   }
 }
 
 // SEC1 compressed -> affine candidate (decode half of point.rs:70-144): returns the ok mask.
+// sec1_decompress_id additionally reports the identity record (prefix 0x00, point.rs:82-87) in `idn` (ok is clear for it).
+template <class C>
+FEC_DEV u32 sec1_decompress(u32 x[8], u32 y[8], const uint8_t* rec);
+template <class C>
+FEC_DEV u32 sec1_decompress_id(u32 x[8], u32 y[8], const uint8_t* rec, u32& idn) {
+  idn = rec[0] == 0u ? 0xFFFFFFFFu : 0u;
+  return sec1_decompress<C>(x, y, rec);
+}
 template <class C>
 FEC_DEV u32 sec1_decompress(u32 x[8], u32 y[8], const uint8_t* rec) {
   typedef typename C::F F;

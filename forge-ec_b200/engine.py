@@ -10,9 +10,9 @@ import numpy as np
 
 CURVE_SECP256K1, CURVE_P256 = 0, 1
 PRIME_SECP256K1, PRIME_P256, PRIME_25519 = 0, 1, 2
-OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE = 0, 1, 2, 3
+OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE, OUT_SEC1_HYBRID = 0, 1, 2, 3, 4
 KDF_NONE, KDF_HKDF_SHA256, KDF_XOR_INFO = 0, 1, 2
-OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32}
+OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32, 4: 65}
 PT_AFFINE_XY_BE, PT_SEC1_COMPRESSED = 0, 1
 PT_SIZE = {0: 64, 1: 33}
 SEM_STD, SEM_FORGE_QUIRK = 0, 1

@@ -75,6 +75,8 @@ class AffinePoint:
             return bytes(33) if self.infinity else bytes([2 | (self.xy[63] & 1)]) + self.xy[:32]
         if fmt == "uncompressed":
             return bytes(65) if self.infinity else b"\x04" + self.xy
+        if fmt == "hybrid":  # PointFormat::Hybrid (forge-ec-core/src/lib.rs:536-543, secp256k1.rs:1048-1066)
+            return bytes(65) if self.infinity else bytes([6 | (self.xy[63] & 1)]) + self.xy
         raise ValueError("UnsupportedOperation: format")
 
 

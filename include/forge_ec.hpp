@@ -77,7 +77,7 @@ struct Scalar {
   const std::array<uint8_t, 32>& to_bytes() const { return be; }
 };
 
-enum class PointFormat { Compressed, Uncompressed };
+enum class PointFormat { Compressed, Uncompressed, Hybrid };  // forge-ec-core/src/lib.rs:536-543
 struct AffinePoint {
   std::array<uint8_t, 64> xy{};  // X || Y big-endian (FieldElement::to_bytes twice); all zero = the identity
   bool infinity = true;
@@ -92,7 +92,8 @@ struct AffinePoint {
   bool is_identity() const { return infinity; }
   std::array<uint8_t, 32> x() const { std::array<uint8_t, 32> r; std::memcpy(r.data(), xy.data(), 32); return r; }
   std::array<uint8_t, 32> y() const { std::array<uint8_t, 32> r; std::memcpy(r.data(), xy.data() + 32, 32); return r; }
-  // SEC1: 02|03 || X (33 B) or 04 || X || Y (65 B); the identity is all zero (secp256k1.rs:875-894, point.rs:41-47)
+  // SEC1: 02|03 || X (33 B), 04 || X || Y (65 B) or the hybrid 06|07 || X || Y (65 B, secp256k1.rs:1048-1066); the identity
+  // is all zero (secp256k1.rs:875-894, point.rs:41-47)
   std::vector<uint8_t> to_bytes_with_format(PointFormat f) const {
     std::vector<uint8_t> o(f == PointFormat::Compressed ? 33 : 65, 0);
     if (infinity) return o;
@@ -100,7 +101,7 @@ struct AffinePoint {
       o[0] = (uint8_t)(2 | (xy[63] & 1));
       std::memcpy(o.data() + 1, xy.data(), 32);
     } else {
-      o[0] = 4;
+      o[0] = f == PointFormat::Hybrid ? (uint8_t)(6 | (xy[63] & 1)) : (uint8_t)4;
       std::memcpy(o.data() + 1, xy.data(), 64);
     }
     return o;
@@ -120,8 +121,8 @@ struct WeierstrassCurve {
     if (points != nullptr) {
       p.resize(n * 64);
       for (size_t i = 0; i < n; i++) {
-        if ((*points)[i].infinity) throw Error(ErrorKind::PointNotOnCurve, "batch_mul: the identity is not a valid input point");
-        std::memcpy(&p[i * 64], (*points)[i].xy.data(), 64);
+        // the identity travels as the all-zero record and k * identity is the identity (Curve::multiply, lib.rs:820-832)
+        if (!(*points)[i].infinity) std::memcpy(&p[i * 64], (*points)[i].xy.data(), 64);
       }
     }
     if (n == 0) return {};
@@ -148,7 +149,7 @@ struct WeierstrassCurve {
     std::vector<uint8_t> k(n * 32), p(n * 64);
     for (size_t i = 0; i < n; i++) {
       std::memcpy(&k[i * 32], scalars[i].be.data(), 32);
-      std::memcpy(&p[i * 64], points[i].xy.data(), 64);
+      if (!points[i].infinity) std::memcpy(&p[i * 64], points[i].xy.data(), 64);  // identity: all-zero record, adds nothing
     }
     uint8_t out[64], st = 0;
     check(fec_msm(e.ctx(), C, k.data(), p.data(), FEC_PT_AFFINE_XY_BE, n, FEC_OUT_AFFINE_XY_BE, out, &st), "fec_msm");

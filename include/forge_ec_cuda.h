@@ -52,7 +52,9 @@ typedef enum {
   FEC_OUT_SEC1_COMPRESSED = 0,   /* 33 B: 02|03 || X          (PointFormat::Compressed)   */
   FEC_OUT_SEC1_UNCOMPRESSED = 1, /* 65 B: 04 || X || Y        (PointFormat::Uncompressed) */
   FEC_OUT_AFFINE_XY_BE = 2,      /* 64 B: X || Y, big-endian  (FieldElement::to_bytes x2) */
-  FEC_OUT_X_BE = 3               /* 32 B: X, big-endian       (the ECDH shared secret, secp256k1.rs:1885-1905) */
+  FEC_OUT_X_BE = 3,              /* 32 B: X, big-endian       (the ECDH shared secret, secp256k1.rs:1885-1905) */
+  FEC_OUT_SEC1_HYBRID = 4        /* 65 B: 06|07 || X || Y     (PointFormat::Hybrid, forge-ec-core/src/lib.rs:536-543;
+                                    secp256k1.rs:1048-1066, p256.rs:1704-1722) */
 } fec_out;
 typedef enum {
   FEC_KDF_NONE = 0,        /* the 32-byte shared secret itself (KeyExchange::derive_shared_secret)                       */
@@ -105,7 +107,7 @@ void fec_shard_range(size_t n, int n_shards, int index, size_t* first, size_t* c
 
 /* k_i*G when points == NULL, else k_i*P_i.
  * scalars: n x 32 B big-endian (Scalar::from_bytes layout); points: n x 64 B (X||Y big-endian) or
- * n x 33 B SEC1 compressed; out: n x {33,65,64} B; status: n x u8 or NULL. */
+ * n x 33 B SEC1 compressed; out: n x {33,65,64,32,65} B by out_fmt; status: n x u8 or NULL. */
 int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
                   fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status);
 int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,

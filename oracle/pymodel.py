@@ -156,8 +156,8 @@ def w_is_on_curve(c: WeierstrassCurve, P) -> bool:
 # identity -> 0x00 followed by zero padding)
 # --------------------------------------------------------------------------------------
 
-OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE = 0, 1, 2, 3
-OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32}
+OUT_SEC1_COMPRESSED, OUT_SEC1_UNCOMPRESSED, OUT_AFFINE_XY_BE, OUT_X_BE, OUT_SEC1_HYBRID = 0, 1, 2, 3, 4
+OUT_SIZE = {0: 33, 1: 65, 2: 64, 3: 32, 4: 65}
 
 
 def sec1_encode(P, fmt: int = OUT_SEC1_COMPRESSED) -> bytes:
@@ -170,6 +170,8 @@ def sec1_encode(P, fmt: int = OUT_SEC1_COMPRESSED) -> bytes:
         return b"\x04" + x.to_bytes(32, "big") + y.to_bytes(32, "big")
     if fmt == OUT_X_BE:
         return x.to_bytes(32, "big")
+    if fmt == OUT_SEC1_HYBRID:  # PointFormat::Hybrid (secp256k1.rs:1048-1066, p256.rs:1704-1722)
+        return bytes([6 | (y & 1)]) + x.to_bytes(32, "big") + y.to_bytes(32, "big")
     return x.to_bytes(32, "big") + y.to_bytes(32, "big")
 
 
@@ -209,6 +211,11 @@ def batch_mul(curve, scalars: bytes, points: bytes | None, n: int, fmt: int = 0,
             P = (c.gx, c.gy)
         else:
             raw = points[psz * i : psz * (i + 1)]
+            # the identity as an input point: the all-zero X || Y record (the engine's own identity encoding, point.rs:41-47)
+            # resp. prefix 0x00 (point.rs:82-87); Curve::multiply(identity, k) is the identity (lib.rs:820-832)
+            if (points_fmt == 0 and raw == bytes(64)) or (points_fmt != 0 and raw[0] == 0):
+                st[i] = ST_INFINITY
+                continue
             if points_fmt == 0:
                 P = (int.from_bytes(raw[:32], "big"), int.from_bytes(raw[32:], "big"))
                 if not w_is_on_curve(c, P):

@@ -234,7 +234,7 @@ static int w_mul(const wcurve_t* c, const u64* k, const u64* xm, const u64* ym, 
   f_mul(f, ox, q.X, zi2); f_mul(f, zi2, zi2, zi); f_mul(f, oy, q.Y, zi2);
   return 1;
 }
-static int out_size(int fmt) { return fmt == 0 ? 33 : (fmt == 1 ? 65 : 64); }
+static int out_size(int fmt) { return fmt == 0 ? 33 : ((fmt == 1 || fmt == 4) ? 65 : (fmt == 3 ? 32 : 64)); }
 
 /* one lane of fec_batch_mul; returns the status byte */
 static int w_lane(int curve, const uint8_t* sc, const uint8_t* pt, int pfmt, int ofmt, uint8_t* out) {
@@ -249,10 +249,12 @@ static int w_lane(int curve, const uint8_t* sc, const uint8_t* pt, int pfmt, int
     cpy4(xm, c->gx); cpy4(ym, c->gy);
   } else if (pfmt == 0) {
     from_be(x, pt); from_be(y, pt + 32);
+    if (is_zero4(x) && is_zero4(y)) return 3;                 /* the identity as an input point (all-zero record, point.rs:41-47): k * O = O */
     if (cmp4(x, f->p) >= 0 || cmp4(y, f->p) >= 0) return 2;
     f_to(f, xm, x); f_to(f, ym, y);
     if (!w_on_curve(c, xm, ym)) return 2;
   } else {
+    if (pt[0] == 0) return 3;                                 /* identity marker, point.rs:82-87 */
     if (pt[0] != 2 && pt[0] != 3) return 2;
     from_be(x, pt + 1);
     if (cmp4(x, f->p) >= 0) return 2;
@@ -273,6 +275,8 @@ static int w_lane(int curve, const uint8_t* sc, const uint8_t* pt, int pfmt, int
   f_from(f, x, rx); f_from(f, y, ry);
   if (ofmt == 0) { out[0] = (uint8_t)(2 | (y[0] & 1)); to_be(out + 1, x); }
   else if (ofmt == 1) { out[0] = 4; to_be(out + 1, x); to_be(out + 33, y); }
+  else if (ofmt == 4) { out[0] = (uint8_t)(6 | (y[0] & 1)); to_be(out + 1, x); to_be(out + 33, y); }  /* PointFormat::Hybrid, secp256k1.rs:1048-1066 */
+  else if (ofmt == 3) { to_be(out, x); }                                                              /* x only: the ECDH shared secret */
   else { to_be(out, x); to_be(out + 32, y); }
   return 0;
 }

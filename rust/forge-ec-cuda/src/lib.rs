@@ -26,6 +26,7 @@ pub const FEC_OUT_SEC1_COMPRESSED: c_int = 0;
 pub const FEC_OUT_SEC1_UNCOMPRESSED: c_int = 1;
 pub const FEC_OUT_AFFINE_XY_BE: c_int = 2;
 pub const FEC_OUT_X_BE: c_int = 3;
+pub const FEC_OUT_SEC1_HYBRID: c_int = 4;
 pub const FEC_KDF_NONE: c_int = 0;
 pub const FEC_KDF_HKDF_SHA256: c_int = 1;
 pub const FEC_KDF_XOR_INFO: c_int = 2;

@@ -18,7 +18,7 @@ def _edge_scalars(c):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-@pytest.mark.parametrize("out_fmt", [0, 1, 2])
+@pytest.mark.parametrize("out_fmt", [0, 1, 2, 3, 4])  # compressed, uncompressed, X || Y, X, hybrid (PointFormat::Hybrid)
 def test_fixed_base_matches_model(engine, pm, curve, out_fmt):
     c = pm.CURVES[curve]
     n = 300
@@ -71,7 +71,8 @@ def test_variable_base_matches_model(engine, pm, curve, points_fmt):
     exp, est = pm.batch_mul(curve, sc.tobytes(), pts, n, 0, points_fmt)
     assert st.tobytes() == est
     assert out.tobytes() == exp
-    assert est[60] == 2 and est[63] == 2 and est[64] == 2
+    # lane 63 is the identity as an input point (all-zero X || Y resp. prefix 0x00): k * O = O, status 3
+    assert est[60] == 2 and est[63] == 3 and est[64] == 2
 
 
 def test_golden_weierstrass(engine, fec, pm):

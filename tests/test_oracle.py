@@ -29,7 +29,7 @@ def ostd():
             s = np.frombuffer(bytes(sc), dtype=np.uint8)
             n = s.size // 32
             p = None if pts is None else np.frombuffer(bytes(pts), dtype=np.uint8)
-            out = np.empty(n * {0: 33, 1: 65, 2: 64}[ofmt], dtype=np.uint8)
+            out = np.empty(n * {0: 33, 1: 65, 2: 64, 3: 32, 4: 65}[ofmt], dtype=np.uint8)
             st = np.empty(n, dtype=np.uint8)
             lib.ostd_batch_mul(curve, vp(s.ctypes.data), vp(p.ctypes.data) if p is not None else None, pfmt, sz(n), ofmt,
                                vp(out.ctypes.data), vp(st.ctypes.data), threads)
@@ -146,12 +146,21 @@ def test_invalid_inputs(ostd, pm):
     be = lambda v: v.to_bytes(32, "big")
     for c in (0, 1):
         cv = pm.CURVES[c]
-        bad_pts = [be(1) + be(1), be(cv.p) + be(cv.gy), bytes(64), b"\xff" * 64]
+        bad_pts = [be(1) + be(1), be(cv.p) + be(cv.gy), be(0) + be(1), b"\xff" * 64]
         for p in bad_pts:
             assert ostd.mul(c, be(5), p) == (bytes(33), b"\x02")
             assert pm.batch_mul(c, be(5), p, 1) == (bytes(33), b"\x02")
-        for rec in (b"\x04" + be(cv.gx), b"\x02" + be(cv.p), bytes(33)):
+        for rec in (b"\x04" + be(cv.gx), b"\x02" + be(cv.p), b"\x05" + bytes(32)):
             assert ostd.mul(c, be(5), rec, 1) == (bytes(33), b"\x02")
+            assert pm.batch_mul(c, be(5), rec, 1, 0, 1) == (bytes(33), b"\x02")
+        # the identity as an INPUT point -- the all-zero X || Y record (the engine's own identity encoding, point.rs:41-47) or the
+        # SEC1 prefix 0x00 (point.rs:82-87): Curve::multiply(identity, k) is the identity (lib.rs:820-832), status 3; an
+        # out-of-range scalar still wins
+        for pts, pfmt in ((bytes(64), 0), (bytes(33), 1), (b"\x00" + be(cv.gx), 1)):
+            assert ostd.mul(c, be(5), pts, pfmt) == (bytes(33), b"\x03")
+            assert pm.batch_mul(c, be(5), pts, 1, 0, pfmt) == (bytes(33), b"\x03")
+            assert ostd.mul(c, be(cv.n), pts, pfmt) == (bytes(33), b"\x01")
+            assert pm.batch_mul(c, be(cv.n), pts, 1, 0, pfmt) == (bytes(33), b"\x01")
         for k in (cv.n, cv.n + 1, 2**256 - 1):
             assert ostd.mul(c, be(k), None) == (bytes(33), b"\x01")
 
@@ -227,6 +236,62 @@ def test_field_small_operand_kats(ostd, pm):
         a = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % p
         assert int.from_bytes(ostd.field(prime, 0, 1, le(a), le(pow(a, -1, p))), "little") == 1
         assert int.from_bytes(ostd.field(prime, 0, 1, le(p - 1), le(p - 1)), "little") == 1
+
+
+def test_p256_large_operand_field_kats(ostd, oref, pm):
+    """The only large-operand field known-answer values the reference holds (p256.rs:2454-2480, quoted there as u64 limbs
+    'expected from Python'): Gx^2, Gx^3, 3 Gx and Gx^3 - 3 Gx + b = Gy^2.  P-256 `mul` is the one reference field
+    operation that is correct on full-size operands, so the values pin oracle/std (Montgomery field behind the
+    microbenchmark model), oracle/ref/oracle_ref_p256.c (the literal restatement) and the big-integer model at once."""
+    val = lambda l: sum(v << (64 * i) for i, v in enumerate(l))
+    X2 = val([12074202155401100, 3726334282074508753, 9331909631644438744, 11022199779588240050])
+    X3 = val([6985818112209442057, 5293983511093485517, 13285487596276262425, 4350650246863171228])
+    TX = val([15988812018543642563, 7280764249650076386, 16876875322344915671, 4703857913423513302])
+    Y2 = val([13753198298469232017, 5299206390010787296, 9373276401007028734, 6187767046927055789])
+    c = pm.CURVES[1]
+    # big-integer model
+    assert (c.gx * c.gx % c.p, pow(c.gx, 3, c.p), 3 * c.gx % c.p, c.gy * c.gy % c.p) == (X2, X3, TX, Y2)
+    assert (X3 - TX + c.b) % c.p == Y2
+    # oracle/std through the field microbenchmark entry point (x = a; iters x { x = x * b | x = x^2 })
+    le = lambda v: v.to_bytes(32, "little")
+    f = lambda op, iters, a, b: int.from_bytes(ostd.field(1, op, iters, le(a), le(b)), "little")
+    assert f(0, 1, c.gx, c.gx) == X2 and f(1, 1, c.gx, 0) == X2
+    assert f(0, 2, c.gx, c.gx) == X3 and f(0, 1, X2, c.gx) == X3
+    assert f(0, 1, 3, c.gx) == TX and f(1, 1, c.gy, 0) == Y2
+    # oracle/ref (literal P-256 field): mul is exact; square / add / sub as the reference's own test uses them (:2446-2478)
+    limbs = lambda v: (ctypes.c_uint64 * 4)(*[(v >> (64 * i)) & (2**64 - 1) for i in range(4)])
+
+    def fop(op, a, b=0):
+        O = (ctypes.c_uint64 * 4)()
+        oref.oref_p256_field_op(op, limbs(a), limbs(b), O)
+        return sum(int(O[i]) << (64 * i) for i in range(4))
+
+    assert fop(1, c.gx) == X2 and fop(0, X2, c.gx) == X3 and fop(0, 3, c.gx) == TX and fop(1, c.gy) == Y2
+    # Gx^3 < 3 Gx as integers, so the reference's `x_cubed - three_x` (:2466) takes the branch of Sub that adds P through the
+    # reducing Add (a no-op) and then wraps modulo 2^256 (p256.rs:473-495, SURVEY.md section 0): the literal restatement is off by
+    # 2^256 - p there, exactly as the big-integer model of the literal semantics says, while the specified value is Gy^2.
+    d = fop(3, X3, TX)
+    assert X3 < TX and d == pm.p256lit_sub(X3, TX) == (X3 - TX) % 2**256
+    assert (d - (2**256 - c.p)) % 2**256 == (X3 - TX) % c.p and ((X3 - TX) % c.p + c.b) % c.p == Y2
+
+
+def test_hybrid_point_format(ostd, pm):
+    """PointFormat::Hybrid (forge-ec-core/src/lib.rs:536-543; secp256k1.rs:1048-1066, p256.rs:1704-1722): 06|07 || X || Y"""
+    be = lambda v: v.to_bytes(32, "big")
+    for c in (0, 1):
+        cv = pm.CURVES[c]
+        ks = b"".join(be(k) for k in (1, 2, 3, 0xDEADBEEF, cv.n - 1, 0))
+        unc, st = ostd.mul(c, ks, None, 0, 1)
+        hyb, st2 = ostd.mul(c, ks, None, 0, 4)
+        assert st == st2 == bytes(5) + b"\x03"
+        for i in range(6):
+            u, h = unc[65 * i : 65 * i + 65], hyb[65 * i : 65 * i + 65]
+            assert h[1:] == u[1:] and (h[0] == (6 | (u[64] & 1)) if i < 5 else h == bytes(65))
+        assert pm.batch_mul(c, ks, None, 6, 4) == (hyb, st2)
+        assert hyb[0] == (6 | (cv.gy & 1)) and hyb[1:33] == be(cv.gx) and hyb[33:65] == be(cv.gy)
+        # x only (the ECDH shared secret record)
+        xo, _ = ostd.mul(c, ks, None, 0, 3)
+        assert xo == b"".join(unc[65 * i + 1 : 65 * i + 33] for i in range(6)) == pm.batch_mul(c, ks, None, 6, 3)[0]
 
 
 def test_c_oracle_matches_python_model_on_philox_inputs(ostd, pm):
