@@ -24,6 +24,9 @@ from .engine import (  # noqa: F401
     LANE_OK,
     LANE_POINT_INVALID,
     LANE_SCALAR_RANGE,
+    NONCE_BIP340,
+    NONCE_ECDSA,
+    NONCE_EDDSA,
     KDF_HKDF_SHA256,
     KDF_NONE,
     KDF_XOR_INFO,

@@ -55,32 +55,53 @@ struct fec_ctx {
   std::vector<cudaEvent_t> stage_ev;
   int stage_used = 0;
   std::vector<Device> devs;
-  std::mutex mu;
+  std::mutex mu;       // serialises the host-buffer entry points (they own the per-device pipeline buffers)
+  std::mutex err_mu;   // the per-device host threads of one call may fail at the same time
   std::atomic<uint64_t> launches{0};
   char last_err[256] = {0};
 };
 
 namespace {
 
-thread_local int tl_err_line = 0;
+void set_err(fec_ctx* ctx, const char* file, int line, const char* what, const char* msg) {
+  std::lock_guard<std::mutex> lock(ctx->err_mu);
+  snprintf(ctx->last_err, sizeof(ctx->last_err), "%s:%d %s: %s", file, line, what, msg);
+}
 #define FEC_CUDA(ctx, call)                                                                     \
   do {                                                                                          \
     cudaError_t e_ = (call);                                                                    \
     if (e_ != cudaSuccess) {                                                                    \
-      snprintf((ctx)->last_err, sizeof((ctx)->last_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
-               cudaGetErrorString(e_));                                                         \
-      tl_err_line = __LINE__;                                                                   \
+      set_err((ctx), __FILE__, __LINE__, #call, cudaGetErrorString(e_));                        \
       return e_ == cudaErrorMemoryAllocation ? FEC_ERR_OOM : FEC_ERR_CUDA;                      \
     }                                                                                           \
   } while (0)
+
+// scope guards for the early-return paths of FEC_CUDA: the caller's device is restored, stream-ordered scratch is given back,
+// and a device's pipeline streams are drained before the caller may touch (or free) its buffers again
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+struct AsyncBuf {
+  uint8_t* p = nullptr;
+  cudaStream_t st = nullptr;
+  ~AsyncBuf() { if (p != nullptr) cudaFreeAsync(p, st); }
+};
+struct DrainGuard {
+  Device& d;
+  explicit DrainGuard(Device& dev) : d(dev) {}
+  ~DrainGuard();
+};
 
 int device_init(fec_ctx* ctx, Device& d) {
   FEC_CUDA(ctx, cudaSetDevice(d.id));
   cudaDeviceProp prop;
   FEC_CUDA(ctx, cudaGetDeviceProperties(&prop, d.id));
   if (prop.major < 10) {
-    snprintf(ctx->last_err, sizeof(ctx->last_err), "device %d is sm_%d%d; this library is built for sm_100a only", d.id,
-             prop.major, prop.minor);
+    char msg[96];
+    snprintf(msg, sizeof(msg), "device %d is sm_%d%d; this library is built for sm_100a only", d.id, prop.major, prop.minor);
+    set_err(ctx, __FILE__, __LINE__, "device_init", msg);
     return FEC_ERR_NO_DEVICE;
   }
   d.sms = prop.multiProcessorCount;
@@ -128,6 +149,10 @@ void device_free(Device& d) {
   cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels);
 }
 
+
+DrainGuard::~DrainGuard() {
+  for (int s = 0; s < N_PIPE; s++) if (d.streams[s]) cudaStreamSynchronize(d.streams[s]);
+}
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -198,6 +223,24 @@ int launch_ed(fec_ctx* ctx, Device& d, int sem, const uint8_t* din, int is_seed,
     FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
   return FEC_OK;
 }
+// signing-side nonce commitment (k_nonce.cu).  Weierstrass modes: R = k G as affine X || Y into `dxy` with its lane status into
+// `dst_tmp`, then the tail kernel (r = x(R) / the even-y rule) writes dR, dr and dst (dst may be dst_tmp).  EdDSA: the 64-byte
+// value mod L into dr, then [r]B from the fixed-base table into dR.
+int launch_nonce(fec_ctx* ctx, Device& d, int curve, int mode, const uint8_t* dnonce, size_t n, uint8_t* dR, uint8_t* dr, uint8_t* dst,
+                 uint8_t* dxy, uint8_t* dst_tmp, cudaStream_t st) {
+  if (n == 0) return FEC_OK;
+  if (mode == FEC_NONCE_EDDSA) {
+    ctx->launches++;
+    FEC_CUDA(ctx, sc_reduce64_launch(st, dnonce, n, dr));
+    if (dst != nullptr) FEC_CUDA(ctx, cudaMemsetAsync(dst, 0, n, st));
+    return launch_ed(ctx, d, FEC_SEM_STD, dr, 0, n, dR, st);
+  }
+  int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, dnonce, nullptr, FEC_PT_AFFINE_XY_BE, n, FEC_OUT_AFFINE_XY_BE, dxy, dst_tmp, st);
+  if (rc) return rc;
+  ctx->launches++;
+  FEC_CUDA(ctx, nonce_tail_launch(curve, mode, st, dxy, dnonce, dst_tmp, n, dR, dr, dst));
+  return FEC_OK;
+}
 int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int iters, const uint8_t* a, const uint8_t* b,
                  uint8_t* o, cudaStream_t st) {
   if (lanes == 0) return FEC_OK;
@@ -208,28 +251,34 @@ int launch_field(fec_ctx* ctx, Device& d, int prime, int op, size_t lanes, int i
 
 // ---- host-buffer pipeline: H2D -> kernel -> D2H in CHUNK_LANES granules over N_PIPE streams ----
 struct HostJob {
-  int kind;  // 0 mul, 1 x25519, 2 ed25519, 3 ecdh (mul + key derivation)
+  int kind;  // 0 mul, 1 x25519, 2 ed25519, 3 ecdh (mul + key derivation), 4 nonce commitment (two outputs)
   int curve, sem, pfmt, ofmt, is_seed;
-  const uint8_t* in_a; size_t rec_a;
+  const uint8_t* in_a; size_t rec_a;  // kind 4: the nonces (32 or 64 B per lane)
   const uint8_t* in_b; size_t rec_b;
   uint8_t* out; size_t rec_out;
   uint8_t* status;
   int kdf = 0, info_len = 0, out_len = 0;  // kind 3 only
   const uint8_t* info = nullptr;
+  int mode = 0;                            // kind 4 only
+  uint8_t* out2 = nullptr;                 // kind 4: out_r, 32 B per lane
 };
+int launch_nonce(fec_ctx* ctx, Device& d, int curve, int mode, const uint8_t* dnonce, size_t n, uint8_t* dR, uint8_t* dr, uint8_t* dst,
+                 uint8_t* dxy, uint8_t* dst_tmp, cudaStream_t st);
 
 int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t count) {
   if (count == 0) return FEC_OK;
   int rc = device_pipe_init(ctx, d);
   if (rc) return rc;
   FEC_CUDA(ctx, cudaSetDevice(d.id));
+  DrainGuard drain(d);  // whatever happens below, no copy into the caller's buffers is in flight when this function returns
   int slot = 0;
   for (size_t off = 0; off < count; off += CHUNK_LANES, slot = (slot + 1) % N_PIPE) {
     const size_t m = (count - off) < CHUNK_LANES ? (count - off) : CHUNK_LANES;
     const size_t g0 = first + off;
     cudaStream_t st = d.streams[slot];
     FEC_CUDA(ctx, cudaStreamSynchronize(st));  // slot's previous chunk fully drained
-    FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_a[slot], job.in_a + g0 * job.rec_a, m * job.rec_a, cudaMemcpyHostToDevice, st));
+    uint8_t* da = job.rec_a > 32 ? d.buf_in_b[slot] : d.buf_in_a[slot];  // 64-byte input records live in the larger buffer
+    FEC_CUDA(ctx, cudaMemcpyAsync(da, job.in_a + g0 * job.rec_a, m * job.rec_a, cudaMemcpyHostToDevice, st));
     const uint8_t* db = nullptr;
     if (job.in_b != nullptr) {
       FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_b[slot], job.in_b + g0 * job.rec_b, m * job.rec_b, cudaMemcpyHostToDevice, st));
@@ -243,10 +292,14 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
                        d.buf_out[slot], d.buf_st[slot], d.buf_x[slot], st);
     else if (job.kind == 1)
       rc = launch_x25519(ctx, d, job.sem, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
+    else if (job.kind == 4)  // R -> buf_out, r -> buf_x; the affine R of the Weierstrass modes passes through buf_in_b (unused there)
+      rc = launch_nonce(ctx, d, job.curve, job.mode, da, m, d.buf_out[slot], d.buf_x[slot], d.buf_st[slot], d.buf_in_b[slot],
+                        d.buf_st[slot], st);
     else
       rc = launch_ed(ctx, d, job.sem, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
     if (rc) return rc;
     FEC_CUDA(ctx, cudaMemcpyAsync(job.out + g0 * job.rec_out, d.buf_out[slot], m * job.rec_out, cudaMemcpyDeviceToHost, st));
+    if (job.out2) FEC_CUDA(ctx, cudaMemcpyAsync(job.out2 + g0 * 32, d.buf_x[slot], m * 32, cudaMemcpyDeviceToHost, st));
     if (job.status) FEC_CUDA(ctx, cudaMemcpyAsync(job.status + g0, d.buf_st[slot], m, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[s]));
@@ -389,12 +442,10 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   if (!sem_supported(sem, curve, points_fmt, (int)out_fmt)) return FEC_ERR_UNSUPPORTED;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   int rc = launch_mul(ctx, *d, (int)curve, (int)sem, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status,
                       (cudaStream_t)stream);
-  cudaSetDevice(prev);
   return rc;
 }
 
@@ -448,53 +499,46 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
   if (!ecdh_args_ok((int)curve, (int)points_fmt, (int)kdf, info, info_len, out_len)) return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   if (n == 0) return FEC_OK;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* tmp = nullptr;  // shared secrets (kdf != NONE) and lane status when the caller wants none
+  AsyncBuf tmp;  // shared secrets (kdf != NONE) and lane status when the caller wants none; given back to the pool on return
+  tmp.st = st;
   const size_t xbytes = kdf == FEC_KDF_NONE ? 0 : n * 32, sbytes = d_status == nullptr ? (n + 15) / 16 * 16 : 0;
-  if (xbytes + sbytes > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp, xbytes + sbytes, st));
-  uint8_t* dx = tmp;
-  uint8_t* dst = d_status != nullptr ? d_status : tmp + xbytes;
-  int rc = launch_ecdh(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)kdf, info, (int)info_len, (int)out_len,
-                       d_out, dst, dx, st);
-  if (tmp != nullptr) cudaFreeAsync(tmp, st);
-  cudaSetDevice(prev);
-  return rc;
+  if (xbytes + sbytes > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xbytes + sbytes, st));
+  uint8_t* dx = tmp.p;
+  uint8_t* dst = d_status != nullptr ? d_status : tmp.p + xbytes;
+  return launch_ecdh(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)kdf, info, (int)info_len, (int)out_len,
+                     d_out, dst, dx, st);
 }
 
 // sum_i k_i * P_i on one device: products through the batched k*P path (affine X || Y + lane status), then the reduction
 static int msm_on_device(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, const uint8_t* dp, int pfmt, size_t n, int ofmt,
                          uint8_t* dout, uint8_t* dstatus, cudaStream_t st) {
   static const bool no_pippenger = getenv("FORGE_EC_MSM_IMPL") != nullptr && getenv("FORGE_EC_MSM_IMPL")[0] == 'p';  // "products": A/B
-  if (n >= (curve == FEC_SECP256K1 ? MSM_PIPPENGER_MIN_K1 : MSM_PIPPENGER_MIN_P256) && n < (size_t(1) << 31) && !no_pippenger) {
-    uint8_t* scratch = nullptr;
-    FEC_CUDA(ctx, cudaMallocAsync(&scratch, msm_pippenger_scratch_bytes(n), st));
+  // the bucket method indexes its 17 n (window, lane) entries with 32-bit counters and offsets (k_msm_pippenger.cu): above
+  // (2^32 - 1) / 17 = 252 645 135 points the products + reduction path below takes over
+  if (n >= (curve == FEC_SECP256K1 ? MSM_PIPPENGER_MIN_K1 : MSM_PIPPENGER_MIN_P256) && n <= MSM_PIPPENGER_MAX && !no_pippenger) {
+    AsyncBuf scratch;
+    scratch.st = st;
+    FEC_CUDA(ctx, cudaMallocAsync(&scratch.p, msm_pippenger_scratch_bytes(n), st));
     int skewed = 0;
     const unsigned limit = (unsigned)(64 * (n >> 15) + 4096);
-    const cudaError_t e = msm_pippenger_launch(curve, st, ds, dp, pfmt, n, scratch, ofmt, dout, dstatus, limit, &skewed);
-    cudaFreeAsync(scratch, st);
-    FEC_CUDA(ctx, e);
+    FEC_CUDA(ctx, msm_pippenger_launch(curve, st, ds, dp, pfmt, n, scratch.p, ofmt, dout, dstatus, limit, &skewed));
     ctx->launches += skewed ? 3 : 9;
     if (!skewed) return FEC_OK;  // otherwise: pathologically repeated digits, use the products + reduction path below
   }
   const int blocks = msm_blocks(d.sms, n);
   const size_t xy_bytes = n * 64, st_bytes = (n + 15) / 16 * 16, sc_bytes = ((size_t)blocks * 24 + 4) * 4;
-  uint8_t* tmp = nullptr;
-  FEC_CUDA(ctx, cudaMallocAsync(&tmp, xy_bytes + st_bytes + sc_bytes, st));
-  int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, ds, dp, pfmt, n, FEC_OUT_AFFINE_XY_BE, tmp, tmp + xy_bytes, st);
-  if (rc == FEC_OK) {
-    ctx->launches += 2;
-    cudaError_t e = msm_reduce_launch(curve, d.sms, st, tmp, tmp + xy_bytes, n, reinterpret_cast<u32*>(tmp + xy_bytes + st_bytes), ofmt,
-                                      dout, dstatus);
-    if (e != cudaSuccess) {
-      snprintf(ctx->last_err, sizeof(ctx->last_err), "msm_reduce: %s", cudaGetErrorString(e));
-      rc = FEC_ERR_CUDA;
-    }
-  }
-  cudaFreeAsync(tmp, st);
-  return rc;
+  AsyncBuf tmp;
+  tmp.st = st;
+  FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xy_bytes + st_bytes + sc_bytes, st));
+  int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, ds, dp, pfmt, n, FEC_OUT_AFFINE_XY_BE, tmp.p, tmp.p + xy_bytes, st);
+  if (rc) return rc;
+  ctx->launches += 2;
+  FEC_CUDA(ctx, msm_reduce_launch(curve, d.sms, st, tmp.p, tmp.p + xy_bytes, n, reinterpret_cast<u32*>(tmp.p + xy_bytes + st_bytes), ofmt,
+                                  dout, dstatus));
+  return FEC_OK;
 }
 int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
                 fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream) {
@@ -503,11 +547,9 @@ int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_s
   if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
     return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_points)) return FEC_ERR_INVALID_ARG;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   int rc = msm_on_device(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status, (cudaStream_t)stream);
-  cudaSetDevice(prev);
   return rc;
 }
 // host buffers: every device of the context sums its contiguous lane range, the per-device sums are added on device 0
@@ -521,8 +563,7 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
   const size_t psz = points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64;
   std::vector<uint8_t> part(G * 64, 0), pst(G, (uint8_t)FEC_LANE_INFINITY);
   std::vector<int> rcs(G, FEC_OK);
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;
   auto shard = [&](size_t i) -> int {
     size_t first = 0, count = 0;
     fec_shard_range(n, (int)G, (int)i, &first, &count);
@@ -530,19 +571,20 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
     Device& d = ctx->devs[i];
     FEC_CUDA(ctx, cudaSetDevice(d.id));
     cudaStream_t st = d.streams[0];
-    uint8_t* buf = nullptr;
+    struct Sync { cudaStream_t s; ~Sync() { cudaStreamSynchronize(s); } } sync{st};  // (declared first: runs after the free below)
+    AsyncBuf buf;
+    buf.st = st;
     const size_t sb = count * 32, pb = (count * psz + 15) / 16 * 16;
-    FEC_CUDA(ctx, cudaMallocAsync(&buf, sb + pb + 128, st));
-    FEC_CUDA(ctx, cudaMemcpyAsync(buf, scalars + first * 32, sb, cudaMemcpyHostToDevice, st));
-    FEC_CUDA(ctx, cudaMemcpyAsync(buf + sb, points + first * psz, count * psz, cudaMemcpyHostToDevice, st));
-    int rc = msm_on_device(ctx, d, (int)curve, buf, buf + sb, (int)points_fmt, count, FEC_OUT_AFFINE_XY_BE, buf + sb + pb, buf + sb + pb + 64, st);
-    if (rc == FEC_OK) {
-      FEC_CUDA(ctx, cudaMemcpyAsync(&part[i * 64], buf + sb + pb, 64, cudaMemcpyDeviceToHost, st));
-      FEC_CUDA(ctx, cudaMemcpyAsync(&pst[i], buf + sb + pb + 64, 1, cudaMemcpyDeviceToHost, st));
-    }
-    cudaFreeAsync(buf, st);
+    FEC_CUDA(ctx, cudaMallocAsync(&buf.p, sb + pb + 128, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(buf.p, scalars + first * 32, sb, cudaMemcpyHostToDevice, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(buf.p + sb, points + first * psz, count * psz, cudaMemcpyHostToDevice, st));
+    int rc = msm_on_device(ctx, d, (int)curve, buf.p, buf.p + sb, (int)points_fmt, count, FEC_OUT_AFFINE_XY_BE, buf.p + sb + pb,
+                           buf.p + sb + pb + 64, st);
+    if (rc) return rc;
+    FEC_CUDA(ctx, cudaMemcpyAsync(&part[i * 64], buf.p + sb + pb, 64, cudaMemcpyDeviceToHost, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(&pst[i], buf.p + sb + pb + 64, 1, cudaMemcpyDeviceToHost, st));
     FEC_CUDA(ctx, cudaStreamSynchronize(st));
-    return rc;
+    return FEC_OK;
   };
   if (G == 1) {
     rcs[0] = shard(0);
@@ -551,27 +593,60 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
     for (size_t i = 0; i < G; i++) th.emplace_back([&, i]() { rcs[i] = shard(i); });
     for (auto& t : th) t.join();
   }
-  for (int rc : rcs) if (rc) { cudaSetDevice(prev); return rc; }
+  for (int rc : rcs) if (rc) return rc;
   // combine: the G partial sums are G more "products" for the same reduction (status 3 = identity contributes nothing)
   Device& d0 = ctx->devs[0];
   FEC_CUDA(ctx, cudaSetDevice(d0.id));
   cudaStream_t st = d0.streams[0];
-  uint8_t* buf = nullptr;
+  struct Sync { cudaStream_t s; ~Sync() { cudaStreamSynchronize(s); } } sync{st};
+  AsyncBuf buf;
+  buf.st = st;
   const size_t sc_off = (G * 64 + G + 15) / 16 * 16;
-  FEC_CUDA(ctx, cudaMallocAsync(&buf, sc_off + (24 + 4) * 4 + 128, st));
-  FEC_CUDA(ctx, cudaMemcpyAsync(buf, part.data(), G * 64, cudaMemcpyHostToDevice, st));
-  FEC_CUDA(ctx, cudaMemcpyAsync(buf + G * 64, pst.data(), G, cudaMemcpyHostToDevice, st));
-  uint8_t* dres = buf + sc_off + (24 + 4) * 4;
+  FEC_CUDA(ctx, cudaMallocAsync(&buf.p, sc_off + (24 + 4) * 4 + 128, st));
+  FEC_CUDA(ctx, cudaMemcpyAsync(buf.p, part.data(), G * 64, cudaMemcpyHostToDevice, st));
+  FEC_CUDA(ctx, cudaMemcpyAsync(buf.p + G * 64, pst.data(), G, cudaMemcpyHostToDevice, st));
+  uint8_t* dres = buf.p + sc_off + (24 + 4) * 4;
   ctx->launches += 2;
-  FEC_CUDA(ctx, msm_reduce_launch((int)curve, 1, st, buf, buf + G * 64, G, reinterpret_cast<u32*>(buf + sc_off), (int)out_fmt, dres, dres + 80));
+  FEC_CUDA(ctx, msm_reduce_launch((int)curve, 1, st, buf.p, buf.p + G * 64, G, reinterpret_cast<u32*>(buf.p + sc_off), (int)out_fmt, dres,
+                                  dres + 80));
   uint8_t hst = 0;
   FEC_CUDA(ctx, cudaMemcpyAsync(out, dres, (size_t)out_size(out_fmt), cudaMemcpyDeviceToHost, st));
   FEC_CUDA(ctx, cudaMemcpyAsync(&hst, dres + 80, 1, cudaMemcpyDeviceToHost, st));
-  cudaFreeAsync(buf, st);
   FEC_CUDA(ctx, cudaStreamSynchronize(st));
   if (status) *status = hst;
-  cudaSetDevice(prev);
   return FEC_OK;
+}
+
+static bool nonce_args_ok(int curve, int mode) {
+  if (mode < 0 || mode > 2) return false;
+  if (mode == FEC_NONCE_EDDSA) return true;
+  return mode == FEC_NONCE_BIP340 ? curve == FEC_SECP256K1 : (curve == FEC_SECP256K1 || curve == FEC_P256);
+}
+int fec_batch_nonce_commit(fec_ctx* ctx, fec_curve curve, fec_nonce_mode mode, const uint8_t* nonces, size_t n, uint8_t* out_R,
+                           uint8_t* out_r, uint8_t* status) {
+  if (ctx == nullptr || (n > 0 && (nonces == nullptr || out_R == nullptr || out_r == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!nonce_args_ok((int)curve, (int)mode)) return FEC_ERR_INVALID_ARG;
+  HostJob job{4, (int)curve, FEC_SEM_STD, 0, 0, 0, nonces, (size_t)(mode == FEC_NONCE_EDDSA ? 64 : 32), nullptr, 0, out_R,
+              (size_t)(mode == FEC_NONCE_ECDSA ? 33 : 32), status};
+  job.mode = (int)mode;
+  job.out2 = out_r;
+  return run_host_job(ctx, job, n);
+}
+int fec_batch_nonce_commit_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_nonce_mode mode, const uint8_t* d_nonces, size_t n,
+                               uint8_t* d_out_R, uint8_t* d_out_r, uint8_t* d_status, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_nonces == nullptr || d_out_R == nullptr || d_out_r == nullptr))) return FEC_ERR_INVALID_ARG;
+  if (!nonce_args_ok((int)curve, (int)mode)) return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_nonces) || !aligned16(d_out_R) || !aligned16(d_out_r)) return FEC_ERR_INVALID_ARG;
+  if (n == 0) return FEC_OK;
+  DeviceGuard restore;
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  cudaStream_t st = (cudaStream_t)stream;
+  AsyncBuf tmp;  // affine R and the lane status of the multiplication (Weierstrass modes)
+  tmp.st = st;
+  const size_t xyb = mode == FEC_NONCE_EDDSA ? 0 : n * 64, stb = mode == FEC_NONCE_EDDSA ? 0 : (n + 15) / 16 * 16;
+  if (xyb + stb > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xyb + stb, st));
+  return launch_nonce(ctx, *d, (int)curve, (int)mode, d_nonces, n, d_out_R, d_out_r, d_status, tmp.p, tmp.p + xyb, st);
 }
 
 int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out) {
@@ -593,11 +668,9 @@ int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uin
   if (d == nullptr || (n > 0 && (d_scalars == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
   if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_scalars) || !aligned16(d_u) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   int rc = launch_x25519(ctx, *d, (int)sem, d_scalars, d_u, n, d_out, (cudaStream_t)stream);
-  cudaSetDevice(prev);
   return rc;
 }
 
@@ -624,11 +697,9 @@ int fec_batch_ed25519_pubkey_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, c
   if (sem != FEC_SEM_STD && sem != FEC_SEM_FORGE_QUIRK) return FEC_ERR_INVALID_ARG;
   if (!ed_sem_ok((int)sem, input_is_seed)) return FEC_ERR_UNSUPPORTED;
   if (!aligned16(d_in) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   int rc = launch_ed(ctx, *d, (int)sem, d_in, input_is_seed, n, d_out, (cudaStream_t)stream);
-  cudaSetDevice(prev);
   return rc;
 }
 
@@ -639,11 +710,9 @@ int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_
     return FEC_ERR_INVALID_ARG;
   if ((int)prime < 0 || (int)prime > 2 || (int)op < 0 || (int)op > 2) return FEC_ERR_INVALID_ARG;
   if (!aligned16(d_a) || !aligned16(d_b) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   int rc = launch_field(ctx, *d, (int)prime, (int)op, lanes, iters, d_a, d_b, d_out, (cudaStream_t)stream);
-  cudaSetDevice(prev);
   return rc;
 }
 
@@ -669,7 +738,7 @@ int fec_field_bench(fec_ctx* ctx, fec_prime prime, fec_field_op op, size_t lanes
   do {                                                                                                  \
     cudaError_t e_ = (call);                                                                            \
     if (e_ != cudaSuccess) {                                                                            \
-      snprintf(ctx->last_err, sizeof(ctx->last_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      set_err(ctx, __FILE__, __LINE__, #call, cudaGetErrorString(e_));                                    \
       cleanup();                                                                                        \
       return e_ == cudaErrorMemoryAllocation ? FEC_ERR_OOM : FEC_ERR_CUDA;                              \
     }                                                                                                   \
@@ -703,8 +772,7 @@ int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_se
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || instr_per_sec == nullptr || variant < 0 || variant > 2) return FEC_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   const int blocks = d->sms * 8, trips = 4096;
   u32* sink = nullptr;
@@ -713,7 +781,6 @@ int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_se
     cudaFree(sink);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaSetDevice(prev);
   };
   FEC_TRY(cudaMalloc(&sink, (size_t)blocks * PEAK_THREADS * 4));
   FEC_TRY(cudaEventCreate(&e0));
@@ -744,18 +811,12 @@ int fec_synth_dev(fec_ctx* ctx, int dev_index, int mode, uint32_t stream_id, uin
   Device* d = dev_at(ctx, dev_index);
   if (d == nullptr || (n > 0 && d_out == nullptr) || mode < 0 || mode > 2 || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
   if (n == 0) return FEC_OK;
-  int prev = 0;
-  cudaGetDevice(&prev);
+  DeviceGuard restore;  // the caller's current device comes back on every return path
   FEC_CUDA(ctx, cudaSetDevice(d->id));
   const unsigned long long seed = 0x666F7267652D6563ULL;  // "forge-ec"
   ctx->launches++;
-  cudaError_t e = synth_launch(d->sms, (cudaStream_t)stream, d_out, n, (u32)seed, (u32)(seed >> 32), stream_id, sub,
-                               (unsigned long long)first_lane, mode, edge);
-  cudaSetDevice(prev);
-  if (e != cudaSuccess) {
-    snprintf(ctx->last_err, sizeof(ctx->last_err), "k_synth: %s", cudaGetErrorString(e));
-    return FEC_ERR_CUDA;
-  }
+  FEC_CUDA(ctx, synth_launch(d->sms, (cudaStream_t)stream, d_out, n, (u32)seed, (u32)(seed >> 32), stream_id, sub,
+                             (unsigned long long)first_lane, mode, edge));
   return FEC_OK;
 }
 

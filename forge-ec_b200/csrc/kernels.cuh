@@ -189,9 +189,14 @@ cudaError_t msm_reduce_launch(int curve, int sms, cudaStream_t st, const uint8_t
 // bucket method for n >= MSM_PIPPENGER_MIN_* points (k_msm_pippenger.cu); *skewed = 1 (and nothing else done) when some bucket holds
 // more than skew_limit points, in which case the caller uses the products + reduction path
 constexpr size_t MSM_PIPPENGER_MIN_K1 = size_t(1) << 17, MSM_PIPPENGER_MIN_P256 = size_t(1) << 16;  // measured crossovers
+constexpr size_t MSM_PIPPENGER_MAX = 0xFFFFFFFFull / 17;  // 17 n (window, lane) entries are counted and addressed in 32 bits
 size_t msm_pippenger_scratch_bytes(size_t n);
 cudaError_t msm_pippenger_launch(int curve, cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n,
                                  uint8_t* scratch, int out_fmt, uint8_t* out, uint8_t* status, unsigned skew_limit, int* skewed);
+// signing-side nonce commitment tails (k_nonce.cu): r = x(R) / the even-y rule behind R = k G; 64-byte value mod L in front of [r]B
+cudaError_t nonce_tail_launch(int curve, int mode, cudaStream_t st, const uint8_t* xy, const uint8_t* k_be, const uint8_t* st_in, size_t n,
+                              uint8_t* out_R, uint8_t* out_r, uint8_t* status);
+cudaError_t sc_reduce64_launch(cudaStream_t st, const uint8_t* in64, size_t n, uint8_t* out_le);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t quirk_ed25519_launch(cudaStream_t st, const uint8_t* seeds, size_t n, uint8_t* out);

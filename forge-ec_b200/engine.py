@@ -18,6 +18,7 @@ PT_SIZE = {0: 64, 1: 33}
 SEM_STD, SEM_FORGE_QUIRK = 0, 1
 FIELD_MUL, FIELD_SQR, FIELD_MULSQR = 0, 1, 2
 LANE_OK, LANE_SCALAR_RANGE, LANE_POINT_INVALID, LANE_INFINITY = 0, 1, 2, 3
+NONCE_ECDSA, NONCE_BIP340, NONCE_EDDSA = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "fec_ctx_create", "fec_ctx_destroy", "fec_ctx_device_count", "fec_ctx_launch_count", "fec_strerror",
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "fec_batch_ed25519_pubkey", "fec_batch_ed25519_pubkey_dev", "fec_field_bench", "fec_field_bench_dev",
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
     "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev", "fec_batch_x25519_sem", "fec_batch_x25519_sem_dev",
-    "fec_batch_ed25519_pubkey_sem", "fec_batch_ed25519_pubkey_sem_dev",
+    "fec_batch_ed25519_pubkey_sem", "fec_batch_ed25519_pubkey_sem_dev", "fec_batch_nonce_commit", "fec_batch_nonce_commit_dev",
 )
 
 
@@ -108,6 +109,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_msm.restype = ip
     lib.fec_msm_dev.argtypes = [vp, ip, ip, u8, u8, ip, sz, ip, u8, u8, vp]
     lib.fec_msm_dev.restype = ip
+    lib.fec_batch_nonce_commit.argtypes = [vp, ip, ip, u8, sz, u8, u8, u8]
+    lib.fec_batch_nonce_commit.restype = ip
+    lib.fec_batch_nonce_commit_dev.argtypes = [vp, ip, ip, ip, u8, sz, u8, u8, u8, vp]
+    lib.fec_batch_nonce_commit_dev.restype = ip
     lib.fec_ctx_stage_timing.argtypes = [vp, ip]
     lib.fec_ctx_stage_timing.restype = ip
     lib.fec_ctx_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
@@ -263,6 +268,24 @@ class Engine:
                 stream: int = 0, dev_index: int = 0):
         self._check(self._lib.fec_msm_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, out_fmt,
                                           _ptr(d_out), _ptr(d_status), stream))
+
+    def batch_nonce_commit(self, curve: int, mode: int, nonces, *, n: Optional[int] = None):
+        """Signing-side nonce commitment (ECDSA r = x(k G), BIP-340 even-y rule, EdDSA [r mod L]B).
+        Returns (out_R[n, 33 | 32], out_r[n, 32], status[n])."""
+        rec_in = 64 if mode == NONCE_EDDSA else 32
+        if n is None:
+            n = (nonces.nbytes if isinstance(nonces, np.ndarray) else len(nonces)) // rec_in
+        a = _host_in(nonces, n, rec_in, "nonces")
+        R = np.empty((n, 33 if mode == NONCE_ECDSA else 32), dtype=np.uint8)
+        r = np.empty((n, 32), dtype=np.uint8)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.fec_batch_nonce_commit(self._ctx, curve, mode, _ptr(a), n, _ptr(R), _ptr(r), _ptr(st)))
+        return R, r, st
+
+    def batch_nonce_commit_dev(self, curve: int, mode: int, d_nonces, n: int, d_out_R, d_out_r, d_status=None, *, stream: int = 0,
+                               dev_index: int = 0):
+        self._check(self._lib.fec_batch_nonce_commit_dev(self._ctx, dev_index, curve, mode, _ptr(d_nonces), n, _ptr(d_out_R),
+                                                         _ptr(d_out_r), _ptr(d_status), stream))
 
     def batch_x25519(self, scalars, us=None, *, n: Optional[int] = None, sem: int = SEM_STD) -> np.ndarray:
         if n is None:

@@ -17,6 +17,8 @@
  *                                                                   point.rs:70-144; forge-ec-core/src/lib.rs:905-923
  *   fec_batch_x25519         n x   x25519(scalar, u)             curve25519.rs:1624-1716  (RFC 7748)
  *   fec_batch_ed25519_pubkey n x   Ed25519Signature::derive_public_key   forge-ec-signature/src/eddsa.rs:450-509 (RFC 8032 5.1.5)
+ *   fec_batch_nonce_commit   n x   the R = k*G step of EcdsaSignature / BipSchnorr / EdDSA sign   ecdsa.rs:108-131, schnorr.rs:372-385,
+ *                                                                eddsa.rs:120-131
  *   fec_field_bench          n x   FieldElement::mul / square    secp256k1.rs:442-507, 634-713; p256.rs:498-534, 772-776;
  *                                                                curve25519.rs:227-314, 490-494
  *
@@ -73,6 +75,11 @@ typedef enum {
                              both cases), no point validation (the reference does none). */
 } fec_sem;
 typedef enum { FEC_FIELD_MUL = 0, FEC_FIELD_SQR = 1, FEC_FIELD_MULSQR = 2 } fec_field_op;
+typedef enum {
+  FEC_NONCE_ECDSA = 0,  /* R = k G, r = x(R) as a scalar            (forge-ec-signature/src/ecdsa.rs:108-131)  */
+  FEC_NONCE_BIP340 = 1, /* R = k G, x-only R, k <- n - k if y odd   (schnorr.rs:372-385; secp256k1 only)       */
+  FEC_NONCE_EDDSA = 2   /* r = 64-byte hash value mod L, R = [r]B   (eddsa.rs:120-131, 322-330; RFC 8032 5.1.6) */
+} fec_nonce_mode;
 
 typedef enum {
   FEC_OK = 0,
@@ -132,6 +139,20 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
             fec_out out_fmt, uint8_t* out, uint8_t* status);
 int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
                 fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream);
+
+/* Signing-side nonce commitment: the fixed-base multiplication of a signature and the scalar that goes with it.
+ *   FEC_NONCE_ECDSA   nonces n x 32 B big-endian k;  out_R n x 33 B SEC1 compressed R = k G;  out_r n x 32 B big-endian r = x(R).
+ *                     status: 1 if k >= n or x(R) >= n (where the reference's Scalar::from_bytes fails, ecdsa.rs:116-121), 3 if k = 0
+ *                     or r = 0 (ecdsa.rs:125-129); records of such lanes are all zero.
+ *   FEC_NONCE_BIP340  (curve must be FEC_SECP256K1) nonces n x 32 B big-endian k;  out_R n x 32 B x(R);  out_r n x 32 B big-endian
+ *                     k' = k if y(R) is even, n - k otherwise (the nonce the signer continues with).  status as above (1: k >= n, 3: k = 0).
+ *   FEC_NONCE_EDDSA   (curve ignored) nonces n x 64 B: the SHA-512 output r = H(prefix || M) as a little-endian integer;
+ *                     out_r n x 32 B little-endian r mod L;  out_R n x 32 B RFC 8032 encoding of [r mod L]B.  status all zero.
+ * status may be NULL. */
+int fec_batch_nonce_commit(fec_ctx* ctx, fec_curve curve, fec_nonce_mode mode, const uint8_t* nonces, size_t n, uint8_t* out_R,
+                           uint8_t* out_r, uint8_t* status);
+int fec_batch_nonce_commit_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_nonce_mode mode, const uint8_t* d_nonces, size_t n,
+                               uint8_t* d_out_R, uint8_t* d_out_r, uint8_t* d_status, void* stream);
 
 /* RFC 7748 X25519: scalars n x 32 B (clamped inside), u n x 32 B little-endian (NULL = base point 9),
  * out n x 32 B little-endian. */

@@ -415,6 +415,50 @@ PRIMES = {0: SECP256K1.p, 1: P256.p, 2: P25519}
 FIELD_OP_MUL, FIELD_OP_SQR, FIELD_OP_MULSQR_CHAIN = 0, 1, 2
 
 
+# --------------------------------------------------------------------------------------
+# Signing-side nonce commitment: the R = k*G / [r]B step of a signature and the scalar that goes with it
+# --------------------------------------------------------------------------------------
+NONCE_ECDSA, NONCE_BIP340, NONCE_EDDSA = 0, 1, 2
+
+
+def nonce_commit(curve, mode: int, nonces: bytes, n: int):
+    """Model of fec_batch_nonce_commit: (out_R, out_r, status).
+    ECDSA (forge-ec-signature/src/ecdsa.rs:108-131): R = k G compressed, r = x(R) as a scalar -- rejected (status 1) where the
+    reference's Scalar::from_bytes fails (x >= n), status 3 for k = 0 or r = 0.  BIP-340 (schnorr.rs:372-385): x-only R and
+    k' = n - k when y(R) is odd.  EdDSA (RFC 8032 5.1.6; eddsa.rs:120-131 shape): r = 64-byte little-endian value mod L, R = [r]B."""
+    if mode == NONCE_EDDSA:
+        R, r = bytearray(32 * n), bytearray(32 * n)
+        for i in range(n):
+            v = int.from_bytes(nonces[64 * i : 64 * i + 64], "little") % ED_L
+            r[32 * i : 32 * i + 32] = v.to_bytes(32, "little")
+            R[32 * i : 32 * i + 32] = ed_encode(ed_scalar_mul_base(v))
+        return bytes(R), bytes(r), bytes(n)
+    c = CURVES[curve]
+    xy, st = batch_mul(curve, nonces, None, n, OUT_AFFINE_XY_BE)
+    st = bytearray(st)
+    rsz = 33 if mode == NONCE_ECDSA else 32
+    R, r = bytearray(rsz * n), bytearray(32 * n)
+    for i in range(n):
+        if st[i]:
+            continue
+        x = int.from_bytes(xy[64 * i : 64 * i + 32], "big")
+        y = int.from_bytes(xy[64 * i + 32 : 64 * i + 64], "big")
+        k = int.from_bytes(nonces[32 * i : 32 * i + 32], "big")
+        if mode == NONCE_ECDSA:
+            if x >= c.n:
+                st[i] = ST_SCALAR_RANGE
+                continue
+            if x == 0:
+                st[i] = ST_INFINITY
+                continue
+            R[33 * i : 33 * i + 33] = bytes([2 | (y & 1)]) + x.to_bytes(32, "big")
+            r[32 * i : 32 * i + 32] = x.to_bytes(32, "big")
+        else:
+            R[32 * i : 32 * i + 32] = x.to_bytes(32, "big")
+            r[32 * i : 32 * i + 32] = ((c.n - k) if (y & 1) else k).to_bytes(32, "big")
+    return bytes(R), bytes(r), bytes(st)
+
+
 def field_bench_model(prime_id: int, op: int, iters: int, a: int, b: int) -> int:
     """What fec_field_bench computes per lane (little-endian 32-byte in/out):
     op=mul: x=a; repeat iters: x = x*b.   op=sqr: x=a; repeat: x = x^2.

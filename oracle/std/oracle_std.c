@@ -461,6 +461,104 @@ void ostd_batch_mul(int curve, const uint8_t* scalars, const uint8_t* points, in
   job_t j = {0, curve, points_fmt, out_fmt, 0, 0, scalars, points, out, status, 0, 0};
   run(j, n, threads);
 }
+/* Curve::multi_scalar_multiply (forge-ec-core/src/lib.rs:934-951): the products multiply(points[i], scalars[i]) added one by one.
+ * out: ONE record of out_fmt, status: ONE byte -- 1 / 2 if some lane has an out-of-range scalar / an invalid point (all-zero
+ * record), 3 if the sum is the identity.  ostd_msm_products adds products that ostd_batch_mul has already computed (n x 64 B
+ * X || Y + n status bytes); ostd_msm computes them with `threads` workers first.  The additions run in order. */
+void ostd_msm_products(int curve, const uint8_t* xy, const uint8_t* st, size_t n, int out_fmt, uint8_t* out, uint8_t* status) {
+  ostd_init_once();
+  const wcurve_t* c = &W[curve];
+  const field_t* f = &c->F;
+  memset(out, 0, (size_t)out_size(out_fmt));
+  int worst = 0;
+  for (size_t i = 0; i < n; i++) if (st[i] == 1 || st[i] == 2) { if (worst != 1) worst = st[i]; }
+  if (worst) { *status = (uint8_t)worst; return; }
+  jac_t acc, t;
+  cpy4(acc.X, f->one); cpy4(acc.Y, f->one); set4(acc.Z, 0);
+  for (size_t i = 0; i < n; i++) {
+    if (st[i] != 0) continue;                                   /* identity products add nothing */
+    u64 x[4], y[4];
+    from_be(x, xy + 64 * i); from_be(y, xy + 64 * i + 32);
+    f_to(f, t.X, x); f_to(f, t.Y, y); cpy4(t.Z, f->one);
+    jac_add(c, &acc, &acc, &t);
+  }
+  if (is_zero4(acc.Z)) { *status = 3; return; }
+  u64 zi[4], zi2[4], ax[4], ay[4], x[4], y[4];
+  f_inv(f, zi, acc.Z); f_sqr(f, zi2, zi);
+  f_mul(f, ax, acc.X, zi2); f_mul(f, zi2, zi2, zi); f_mul(f, ay, acc.Y, zi2);
+  f_from(f, x, ax); f_from(f, y, ay);
+  if (out_fmt == 0) { out[0] = (uint8_t)(2 | (y[0] & 1)); to_be(out + 1, x); }
+  else if (out_fmt == 1) { out[0] = 4; to_be(out + 1, x); to_be(out + 33, y); }
+  else if (out_fmt == 4) { out[0] = (uint8_t)(6 | (y[0] & 1)); to_be(out + 1, x); to_be(out + 33, y); }
+  else if (out_fmt == 3) { to_be(out, x); }
+  else { to_be(out, x); to_be(out + 32, y); }
+  *status = 0;
+}
+void ostd_msm(int curve, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt, uint8_t* out,
+              uint8_t* status, int threads) {
+  uint8_t* xy = (uint8_t*)malloc(n * 64 + 1);
+  uint8_t* st = (uint8_t*)malloc(n + 1);
+  ostd_batch_mul(curve, scalars, points, points_fmt, n, 2, xy, st, threads);
+  ostd_msm_products(curve, xy, st, n, out_fmt, out, status);
+  free(xy); free(st);
+}
+void ostd_batch_ed25519_pubkey(const uint8_t* in, int input_is_seed, size_t n, uint8_t* out, int threads);
+/* Signing-side nonce commitment.  mode 0 ECDSA (forge-ec-signature/src/ecdsa.rs:108-131): R = k G (33 B SEC1
+ * compressed), r = x(R) as a scalar, status 1 where Scalar::from_bytes(x) fails (x >= n) and 3 for r = 0; mode 1 BIP-340
+ * (schnorr.rs:372-385): x-only R (32 B), k' = n - k when y(R) is odd; mode 2 EdDSA (RFC 8032 5.1.6): r = the 64-byte little-endian
+ * value mod L, R = [r]B.  out_r: 32 B per lane (big-endian for the Weierstrass modes, little-endian for EdDSA). */
+static const u64 ED_L[4] = {0x5812631A5CF5D3EDull, 0x14DEF9DEA2F79CD6ull, 0, 0x1000000000000000ull};
+static void sc_reduce64(const uint8_t* in, uint8_t* out_le) {   /* byte-wise Horner: r = (256 r + b) mod L */
+  u64 r[4] = {0, 0, 0, 0};
+  for (int i = 63; i >= 0; i--) {
+    u64 v[5];
+    v[4] = r[3] >> 56;
+    v[3] = (r[3] << 8) | (r[2] >> 56); v[2] = (r[2] << 8) | (r[1] >> 56); v[1] = (r[1] << 8) | (r[0] >> 56); v[0] = (r[0] << 8) | in[i];
+    /* v < 2^261: subtract L while v >= L (at most 2^9 + 1 times would be slow): q = v >> 252, v -= q L, then fix the sign */
+    u64 q = (v[3] >> 60) | (v[4] << 4);
+    u64 t[4] = {v[0], v[1], v[2], v[3] & 0x0FFFFFFFFFFFFFFFull};
+    u128 m0 = (u128)q * ED_L[0], m1 = (u128)q * ED_L[1] + (u64)(m0 >> 64);
+    u64 s[4] = {(u64)m0, (u64)m1, (u64)(m1 >> 64), 0};
+    u64 d[4];
+    if (sub4(d, t, s)) add4(d, d, ED_L);
+    memcpy(r, d, 32);
+  }
+  to_le(out_le, r);
+}
+void ostd_batch_nonce_commit(int curve, int mode, const uint8_t* nonces, size_t n, uint8_t* out_R, uint8_t* out_r, uint8_t* status,
+                             int threads) {
+  ostd_init_once();
+  if (mode == 2) {
+    for (size_t i = 0; i < n; i++) sc_reduce64(nonces + 64 * i, out_r + 32 * i);
+    ostd_batch_ed25519_pubkey(out_r, 0, n, out_R, threads);
+    if (status) memset(status, 0, n);
+    return;
+  }
+  const wcurve_t* c = &W[curve];
+  uint8_t* xy = (uint8_t*)malloc(n * 64 + 1);
+  uint8_t* st = (uint8_t*)malloc(n + 1);
+  ostd_batch_mul(curve, nonces, NULL, 0, n, 2, xy, st, threads);
+  const size_t rsz = mode == 0 ? 33 : 32;
+  memset(out_R, 0, n * rsz); memset(out_r, 0, n * 32);
+  for (size_t i = 0; i < n; i++) {
+    int s = st[i];
+    u64 x[4], y[4], k[4];
+    from_be(x, xy + 64 * i); from_be(y, xy + 64 * i + 32); from_be(k, nonces + 32 * i);
+    if (s == 0 && mode == 0) s = cmp4(x, c->n) >= 0 ? 1 : (is_zero4(x) ? 3 : 0);
+    if (s == 0) {
+      if (mode == 0) {
+        out_R[33 * i] = (uint8_t)(2 | (y[0] & 1)); to_be(out_R + 33 * i + 1, x); to_be(out_r + 32 * i, x);
+      } else {
+        u64 nk[4];
+        sub4(nk, c->n, k);
+        to_be(out_R + 32 * i, x); to_be(out_r + 32 * i, (y[0] & 1) ? nk : k);
+      }
+    }
+    if (status) status[i] = (uint8_t)s;
+  }
+  free(xy); free(st);
+}
+
 void ostd_batch_x25519(const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out, int threads) {
   job_t j = {1, 0, 0, 0, 0, 0, scalars, us, out, NULL, 0, 0};
   run(j, n, threads);

@@ -576,24 +576,22 @@ def test_batched_ecdh_matches_model(engine, fec, pm, curve):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_multi_scalar_multiply_matches_model(engine, fec, pm, curve):
-    """sum_i k_i*P_i = the batched products + a device-wide reduction, against the model that adds the
-    products one by one (lib.rs:934-951); cancellations, repeated points (the doubling case of the reduction), identity
-    lanes, rejected lanes, one to several thousand points."""
+def test_multi_scalar_multiply_matches_model(engine, fec, ostd, pm, curve):
+    """sum_i k_i*P_i = the batched products + a device-wide reduction, against the oracle that adds the
+    products one by one (lib.rs:934-951; oracle/std `ostd_msm`, and the Python model on a small case); cancellations,
+    repeated points (the doubling case of the reduction), identity lanes, rejected lanes, one to several thousand points.
+    The expected values never come from the GPU (the bucket method and 2^17 points: test_gpu_parity_large.py)."""
     c = pm.CURVES[curve]
     for n in (1, 2, 33, 257, 5000):
         k = pm.random_scalars_be(curve, n, stream=7, edge=(n >= 33))
         r = pm.random_scalars_be(curve, n, stream=7, sub=1, edge=False)
-        pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
-        prods = engine.batch_mul(curve, k, pts, out_fmt=fec.OUT_AFFINE_XY_BE)     # checked against the oracle elsewhere
-        exp, est = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0, products=(prods[0].tobytes(), prods[1].tobytes()))
-        got, st = engine.msm(curve, k, pts)
-        assert (got, st) == (exp, est), (curve, n)
-    # a small case entirely in the model
+        pts = np.frombuffer(ostd.mul(curve, r.tobytes(), None, 0, 2)[0], dtype=np.uint8).reshape(n, 64)
+        assert engine.msm(curve, k, pts) == ostd.msm(curve, k.tobytes(), pts.tobytes(), 0, 0), (curve, n)
+    # a small case entirely in the Python model
     n = 6
     k = pm.random_scalars_be(curve, n, stream=8, edge=False)
     r = pm.random_scalars_be(curve, n, stream=8, sub=1, edge=False)
-    pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
+    pts = np.frombuffer(pm.batch_mul(curve, r.tobytes(), None, n, pm.OUT_AFFINE_XY_BE)[0], dtype=np.uint8).reshape(n, 64)
     assert engine.msm(curve, k, pts, out_fmt=fec.OUT_SEC1_UNCOMPRESSED) == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 1)
     # k P + (n - k) P = identity; P + P + P + P (every combine step is a doubling); identity lanes only
     kk = int.from_bytes(k[0].tobytes(), "big")
@@ -606,6 +604,10 @@ def test_multi_scalar_multiply_matches_model(engine, fec, pm, curve):
     assert rec == exp and st == 0
     rec, st = engine.msm(curve, np.zeros(96, dtype=np.uint8), pts[:3])
     assert rec == bytes(33) and st == 3
+    # the identity as an input point is simply added (lib.rs:934-951): it changes nothing
+    withid = np.concatenate([pts[:3].reshape(-1), np.zeros(64, dtype=np.uint8), pts[3:].reshape(-1)])
+    kid = np.concatenate([k[:3].reshape(-1), k[0], k[3:].reshape(-1)])
+    assert engine.msm(curve, kid, withid) == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0)
     # rejected lanes
     bad = np.frombuffer(_be(5) + _be(c.n), dtype=np.uint8)
     assert engine.msm(curve, bad, pts[:2]) == (bytes(33), 1)
@@ -616,45 +618,24 @@ def test_multi_scalar_multiply_matches_model(engine, fec, pm, curve):
     P = cls.multi_scalar_multiply([fec.AffinePoint(pts[i].tobytes()) for i in range(n)], [fec.Scalar(k[i].tobytes()) for i in range(n)], engine)
     assert P.to_bytes() == pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0)[0]
     assert cls.multi_scalar_multiply([], [], engine).is_identity()
+    # Curve::multiply(identity, k) is the identity (lib.rs:820-832): a k = 0 result fed back into multiply
+    O = cls.multiply(None, fec.Scalar.from_int(0), engine)
+    assert O.is_identity() and cls.multiply(O, fec.Scalar.from_int(5), engine).is_identity()
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_msm_bucket_method_matches_model(engine, fec, pm, curve):
-    """n >= 2^17 takes the bucket (Pippenger) path: against the model that adds the per-lane products (themselves
-    checked against the oracle elsewhere) one by one; SEC1 compressed input; a rejected lane; repeated scalars, which
-    overflow one bucket and must fall back to the products path with the same result."""
+def test_msm_bucket_method_negation_property(engine, fec, ostd, pm, curve):
+    """the bucket (Pippenger) path at n >= 10^5 (oracle comparison: test_gpu_parity_large.py): sum_i k_i P_i with every k_i
+    negated is the negated point -- same x, other y parity"""
     c = pm.CURVES[curve]
     n = 140000
-    k = pm.random_scalars_be(curve, n, stream=9)                       # edge lanes: 0, 1, 2, 3, n-1, n-2, ...
+    k = pm.random_scalars_be(curve, n, stream=9)
     r = pm.random_scalars_be(curve, n, stream=9, sub=1, edge=False)
     pts, _ = engine.batch_mul(curve, r, None, out_fmt=fec.OUT_AFFINE_XY_BE)
-    prods = engine.batch_mul(curve, k, pts, out_fmt=fec.OUT_AFFINE_XY_BE)
-    exp, est = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 0, products=(prods[0].tobytes(), prods[1].tobytes()))
-    assert engine.msm(curve, k, pts) == (exp, est) and est == 0
-    comp, _ = engine.batch_mul(curve, r, None)
-    assert engine.msm(curve, k, comp, points_fmt=fec.PT_SEC1_COMPRESSED) == (exp, est)
-    exp65, _ = pm.msm(curve, k.tobytes(), pts.tobytes(), n, 1, products=(prods[0].tobytes(), prods[1].tobytes()))
-    assert engine.msm(curve, k, pts, out_fmt=fec.OUT_SEC1_UNCOMPRESSED)[0] == exp65
-    # sum_i k_i P_i with every k_i negated is the negated point: same x, other y parity
     kneg = np.frombuffer(b"".join(_be((c.n - int.from_bytes(k[i].tobytes(), "big")) % c.n) for i in range(n)), dtype=np.uint8)
-    rec, st = engine.msm(curve, kneg, pts)
-    assert st == 0 and rec[1:] == exp[1:] and rec[0] == exp[0] ^ 1
-    bad = k.copy()
-    bad[777] = np.frombuffer(_be(c.n + 5), dtype=np.uint8)
-    assert engine.msm(curve, bad, pts) == (bytes(33), 1)
-    offp = pts.copy()
-    offp[12345, 63] ^= 1
-    assert engine.msm(curve, k, offp) == (bytes(33), 2)
-    # every lane the SAME point with random scalars: each bucket then adds P + P (doubling inside the mixed addition),
-    # 2P + P, and P + (-P) whenever both signs meet; the sum is (sum_i k_i mod n) P
-    onep = np.tile(pts[5], n)
-    ksum = sum(int.from_bytes(k[i].tobytes(), "big") for i in range(n)) % c.n
-    exp_one, _ = pm.batch_mul(curve, _be(ksum), pts[5].tobytes(), 1, 0)
-    assert engine.msm(curve, k, onep) == (exp_one, 0)
-    same = np.tile(np.frombuffer(_be(0x1234567 << 200 | 0xABCDEF), dtype=np.uint8), n)   # one bucket per window holds everything
-    exp1, _ = pm.msm(curve, same.tobytes(), pts.tobytes(), n, 0,
-                     products=tuple(x.tobytes() for x in engine.batch_mul(curve, same, pts, out_fmt=fec.OUT_AFFINE_XY_BE)))
-    assert engine.msm(curve, same, pts) == (exp1, 0)
+    a, sa = engine.msm(curve, k, pts)
+    b, sb = engine.msm(curve, kneg, pts)
+    assert sa == sb == 0 and a[1:] == b[1:] and a[0] == b[0] ^ 1
 
 
 def test_cpp_host_side_on_gpu():
@@ -719,3 +700,32 @@ def test_every_kernel_form_returns_the_same_bytes(tmp_path):
         assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
         digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_nonce_commit_matches_oracle_and_published_vectors(engine, fec, ostd, pm):
+    """the signing-side fixed-base step through fec_batch_nonce_commit -- ECDSA r = x(k G) (ecdsa.rs:108-131),
+    BIP-340 even-y rule (schnorr.rs:372-385), EdDSA [r mod L]B from the 64-byte hash value (RFC 8032 5.1.6) -- against RFC 6979 /
+    BIP-340 / RFC 8032 vectors and the C oracle, rejected lanes included"""
+    from test_oracle import nonce_commit_goldens
+
+    def commit(curve, mode, nonces):
+        R, r, st = engine.batch_nonce_commit(curve, mode, np.frombuffer(nonces, dtype=np.uint8))
+        return R.tobytes(), r.tobytes(), st.tobytes()
+
+    nonce_commit_goldens(pm, commit)
+    n = 3000
+    for curve in (0, 1):
+        c = pm.CURVES[curve]
+        k = pm.random_scalars_be(curve, n, stream=12)
+        for i, v in enumerate(_edge_scalars(c)):
+            k[8 + i] = np.frombuffer(_be(v % 2**256), dtype=np.uint8)
+        for mode in ((fec.NONCE_ECDSA, fec.NONCE_BIP340) if curve == 0 else (fec.NONCE_ECDSA,)):
+            assert commit(curve, mode, k.tobytes()) == ostd.nonce_commit(curve, mode, k.tobytes()), (curve, mode)
+    h = pm.philox_bytes32(2 * n, stream=13).reshape(n, 64).copy()
+    L = pm.ED_L
+    for i, v in enumerate([0, 2**512 - 1, L, L - 1, 2**252, (L << 200) + 5, 2**511, (L << 259) - 1, 2**252 - 1, L + 1]):
+        h[i] = np.frombuffer(v.to_bytes(64, "little"), dtype=np.uint8)
+    assert commit(0, fec.NONCE_EDDSA, h.tobytes()) == ostd.nonce_commit(0, 2, h.tobytes())
+    # the BIP-340 mode belongs to secp256k1
+    with pytest.raises(fec.FecError):
+        engine.batch_nonce_commit(1, fec.NONCE_BIP340, k)

@@ -19,58 +19,6 @@ def _gold(name):
 
 
 @pytest.fixture(scope="session")
-def ostd():
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_std.so"))
-
-    class O:
-        @staticmethod
-        def mul(curve, sc, pts=None, pfmt=0, ofmt=0, threads=4):
-            s = np.frombuffer(bytes(sc), dtype=np.uint8)
-            n = s.size // 32
-            p = None if pts is None else np.frombuffer(bytes(pts), dtype=np.uint8)
-            out = np.empty(n * {0: 33, 1: 65, 2: 64, 3: 32, 4: 65}[ofmt], dtype=np.uint8)
-            st = np.empty(n, dtype=np.uint8)
-            lib.ostd_batch_mul(curve, vp(s.ctypes.data), vp(p.ctypes.data) if p is not None else None, pfmt, sz(n), ofmt,
-                               vp(out.ctypes.data), vp(st.ctypes.data), threads)
-            return out.tobytes(), st.tobytes()
-
-        @staticmethod
-        def x25519(ks, us=None, threads=4):
-            k = np.frombuffer(bytes(ks), dtype=np.uint8)
-            n = k.size // 32
-            u = None if us is None else np.frombuffer(bytes(us), dtype=np.uint8)
-            out = np.empty(n * 32, dtype=np.uint8)
-            lib.ostd_batch_x25519(vp(k.ctypes.data), vp(u.ctypes.data) if u is not None else None, sz(n), vp(out.ctypes.data), threads)
-            return out.tobytes()
-
-        @staticmethod
-        def ed(data, is_seed=True, threads=4):
-            d = np.frombuffer(bytes(data), dtype=np.uint8)
-            n = d.size // 32
-            out = np.empty(n * 32, dtype=np.uint8)
-            lib.ostd_batch_ed25519_pubkey(vp(d.ctypes.data), int(is_seed), sz(n), vp(out.ctypes.data), threads)
-            return out.tobytes()
-
-        @staticmethod
-        def field(prime, op, iters, a, b, threads=2):
-            aa = np.frombuffer(bytes(a), dtype=np.uint8)
-            bb = np.frombuffer(bytes(b), dtype=np.uint8)
-            n = aa.size // 32
-            out = np.empty(n * 32, dtype=np.uint8)
-            lib.ostd_field_bench(prime, op, sz(n), iters, vp(aa.ctypes.data), vp(bb.ctypes.data), vp(out.ctypes.data), threads)
-            return out.tobytes()
-
-        @staticmethod
-        def sha512(m):
-            d = ctypes.create_string_buffer(64)
-            lib.ostd_sha512(m, sz(len(m)), d)
-            return d.raw
-
-    return O
-
-
-@pytest.fixture(scope="session")
 def oref():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
     return ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "liboracle_ref.so"))
@@ -488,3 +436,60 @@ def test_divergence_report_reference_vs_specified(oref, ostd, pm):
     agree = [i for i in range(n) if lit.tobytes()[33 * i : 33 * i + 33] == std[33 * i : 33 * i + 33]]
     print(f"forge-ec literal P-256 k*G agrees with FIPS 186-4 on lanes {agree} of {n}")
     assert agree == [0]
+
+
+def _tagged(tag, msg):
+    t = hashlib.sha256(tag.encode()).digest()
+    return hashlib.sha256(t + t + msg).digest()
+
+
+# published signing vectors restated as (nonce, expected commitment): RFC 6979 A.2.5 (P-256, SHA-256, "sample"), BIP-340 test
+# vector 0 (nonce and signature equation recomputed from the specification with hashlib), RFC 8032 7.1 TEST 1
+RFC6979_P256_K = 0xA6E3C57DD01ABE90086538398355DD4C3B17AA873382B0F24D6129493D8AAD60
+RFC6979_P256_R = 0xEFD48B2AACB6A8FD1140DD9CD45E81D69D2C877B56AAF991C34D0EA84EAF3716
+BIP340_V0_SIG = bytes.fromhex("E907831F80848D1069A5371B402410364BDF1C5F8307B0084C55F1CE2DCA8215"
+                              "25F66A4A85EA8B71E482A74F382D2CE5EBEEE8FDB2172F477DF4900D310536C0")
+RFC8032_T1_SEED = bytes.fromhex("9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60")
+RFC8032_T1_R = bytes.fromhex("e5564300c360ac729086e2cc806e828a84877f1eb8e5d974d873e06522490155")
+
+
+def nonce_commit_goldens(pm, commit):
+    """checks `commit(curve, mode, nonces) -> (R, r, status)` against the three published vectors"""
+    be = lambda v: v.to_bytes(32, "big")
+    # ECDSA: r = x(k G) (ecdsa.rs:108-131)
+    R, r, st = commit(1, 0, be(RFC6979_P256_K))
+    assert st == b"\x00" and r == be(RFC6979_P256_R) and R[1:] == r and R[0] in (2, 3)
+    # BIP-340 (schnorr.rs:372-385): d = 3, aux = 0, m = 0
+    c = pm.CURVES[0]
+    d, m = 3, bytes(32)
+    P = pm.w_mul(c, d, (c.gx, c.gy))
+    dd = d if P[1] % 2 == 0 else c.n - d
+    t = (dd ^ int.from_bytes(_tagged("BIP0340/aux", bytes(32)), "big")).to_bytes(32, "big")
+    k0 = int.from_bytes(_tagged("BIP0340/nonce", t + be(P[0]) + m), "big") % c.n
+    R, kk, st = commit(0, 1, be(k0))
+    assert st == b"\x00" and R == BIP340_V0_SIG[:32]
+    e = int.from_bytes(_tagged("BIP0340/challenge", R + be(P[0]) + m), "big") % c.n
+    assert be((int.from_bytes(kk, "big") + e * dd) % c.n) == BIP340_V0_SIG[32:]
+    # EdDSA: r = SHA-512(prefix || M) mod L, R = [r]B (RFC 8032 5.1.6; eddsa.rs:120-131)
+    h = hashlib.sha512(RFC8032_T1_SEED).digest()
+    nonce = hashlib.sha512(h[32:] + b"").digest()
+    R, r, st = commit(0, 2, nonce)
+    assert st == b"\x00" and R == RFC8032_T1_R and int.from_bytes(r, "little") == int.from_bytes(nonce, "little") % pm.ED_L
+
+
+def test_nonce_commit_oracles_against_published_vectors(ostd, pm):
+    """both oracles on RFC 6979 / BIP-340 / RFC 8032 vectors, on each other, and on the rejected lanes"""
+    nonce_commit_goldens(pm, lambda c, m, x: pm.nonce_commit(c, m, x, len(x) // (64 if m == 2 else 32)))
+    nonce_commit_goldens(pm, ostd.nonce_commit)
+    n = 48
+    for curve in (0, 1):
+        k = pm.random_scalars_be(curve, n, stream=12)
+        k[9] = np.frombuffer(pm.CURVES[curve].n.to_bytes(32, "big"), dtype=np.uint8)
+        for mode in ((0, 1) if curve == 0 else (0,)):
+            got = ostd.nonce_commit(curve, mode, k.tobytes())
+            assert got == pm.nonce_commit(curve, mode, k.tobytes(), n)
+            assert got[2][0] == 3 and got[2][9] == 1 and got[0][: len(got[0]) // n] == bytes(len(got[0]) // n)
+    h = b"".join(hashlib.sha512(bytes([i])).digest() for i in range(n))
+    edge = [0, 2**512 - 1, pm.ED_L, pm.ED_L - 1, 2**252, (pm.ED_L << 200) + 5, 2**511, (pm.ED_L << 259) - 1]
+    h = b"".join(v.to_bytes(64, "little") for v in edge) + h
+    assert ostd.nonce_commit(0, 2, h) == pm.nonce_commit(0, 2, h, len(h) // 64)
