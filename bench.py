@@ -39,10 +39,21 @@ CANON_IMUL32_PER_OP = 172_562   # SURVEY.md 8d, config 3 (fixed 4-bit window, Ja
 IO_BYTES_PER_OP = 32 + 64 + 33  # scalar + affine point in, SEC1 compressed out
 SYNTH_STREAM = 3
 # What the implemented algorithm (GLV split, 2 x 32 signed 4-bit digits, effective-affine table, shared inversion) really
-# executes, from ncu (profiles/r1f_*): IMAD.WIDE warp instructions x 32 / lanes.  Used for `pipe_utilisation` only.
-EXEC_IMUL32_PER_OP = {"prepare": 8_855, "ladder": 88_914, "finish": 2_809}
-# DRAM bytes per lane of the dominant kernel (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1f_*)
-LADDER_DRAM_BYTES_PER_LANE = 975  # 2^22-lane launch: 3.67 GB read + 0.42 GB written
+# executes is NOT a constant of this file: it is read from profiles/exec_counts.json, the artefact tools/ncu_opcounts.py writes
+# from the round's `ncu --set full --import-source on` capture of the same kernels (per kernel: IMAD.WIDE and total warp
+# instructions per lane, DRAM bytes).  Without the artefact the executed-instruction figures are reported as null.
+EXEC_COUNTS_PATH = os.path.join(ROOT, "profiles", "exec_counts.json")
+ISSUE_CYCLES_IMAD_WIDE = 4  # measured (tools/ubench.cu, profiles/r2a_ubench_issue_model.log): an IMAD.WIDE holds the issue port 4 clk
+
+
+def load_exec_counts():
+    try:
+        d = json.load(open(EXEC_COUNTS_PATH))
+        k = d["kernels"]
+        return {"source": d.get("source"), "note": d.get("note"),
+                "prepare": k["k_glv_prep"], "ladder": k["k_glv_ladder"], "finish": k["k_glv_finish"]}
+    except Exception:
+        return None
 # canonical IMUL32 per operation of the secondary configurations
 CANON_FIELD = {"secp256k1": {"mul": 74, "sqr": 46}, "p256": {"mul": 64, "sqr": 36}, "25519": {"mul": 73, "sqr": 45}}
 CANON_OTHER = {"x25519_base_point": 153_576, "secp256k1_kG": 44_716, "p256_kG": 37_716, "p256_kP": 142_992, "x25519": 153_576, "ed25519_keygen": 32_631}
@@ -208,6 +219,8 @@ def main():
     ap.add_argument("--no-others", action="store_true", help="skip the secondary configurations (development)")
     ap.add_argument("--no-gather", action="store_true", help="skip the optional NCCL gather measurement (N > 1)")
     ap.add_argument("--no-field", action="store_true", help="skip the field microbench (BASELINE.json configs[1])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (2^24 lanes in total over the N GPUs)")
+    ap.add_argument("--no-single-process", action="store_true", help="skip the one-process multi-device leg (N > 1, rank 0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -232,6 +245,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    failures = []  # anything that must make this run exit non-zero (a number next to a wrong result is worthless)
     fec = importlib.import_module("forge-ec_b200")  # raises loudly if the CUDA library is missing
     eng = fec.Engine()                               # current device; no CPU fallback exists
     n = args.lanes
@@ -314,7 +328,59 @@ def main():
         same = bool(torch.equal(h_out, d_out.cpu())) and bool(torch.equal(h_st, d_st.cpu()))
         e2e = {"value": world * n * e2e_steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 96,
                "d2h_bytes_per_step": n * 34, "steps": e2e_steps, "timer": "host wall clock around the synchronous fec_batch_mul call",
-               "matches_device_resident_run": same}
+               "host_buffers": "pinned (torch pin_memory)", "matches_device_resident_run": same}
+        if not same:
+            failures.append("e2e: the host-buffer call returned different bytes than the device-resident run")
+        # the same call on PAGEABLE host memory -- what a Rust Vec<u8> or a numpy array is: cudaMemcpyAsync stages such copies
+        # through the driver's own pinned buffer and blocks the calling thread, so the three-stream pipeline overlaps less
+        p_k, p_p = h_k.numpy().copy(), h_p.numpy().copy()
+        p_out, p_st = np.empty(n * 33, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        eng.batch_mul_ptr(fec.CURVE_SECP256K1, p_k.ctypes.data, p_p.ctypes.data, n, p_out.ctypes.data, p_st.ctypes.data)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.batch_mul_ptr(fec.CURVE_SECP256K1, p_k.ctypes.data, p_p.ctypes.data, n, p_out.ctypes.data, p_st.ctypes.data)
+        barrier()
+        dtp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        e2e["pageable"] = {"value": world * n * e2e_steps / float(dtp.item()), "unit": UNIT,
+                           "matches_device_resident_run": bool(np.array_equal(p_out, h_out.numpy())) and bool(np.array_equal(p_st, h_st.numpy()))}
+        del p_k, p_p, p_out, p_st
+
+    # ---- strong scaling (BASELINE.json configs[2] read as 2^24 pairs IN TOTAL at 1/2/4/8 GPUs): every rank takes 2^24 / N lanes
+    strong = None
+    if not args.no_strong:
+        ns = max(1024, (1 << 24) // world)
+        ns = min(ns, n)
+
+        def strong_step():
+            eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, d_p, ns, d_out, d_st, stream=sp)
+
+        strong_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            strong_step()
+        s1.record(stream)
+        barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "lanes_total": ns * world, "lanes_per_gpu": ns, "value": world * ns * args.steps / (float(ts.item()) * 1e-3),
+                  "unit": UNIT, "ms_per_step": float(ts.item()) / args.steps}
+        if not args.no_e2e:
+            eng.batch_mul_ptr(fec.CURVE_SECP256K1, h_k.data_ptr(), h_p.data_ptr(), ns, h_out.data_ptr(), h_st.data_ptr())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                eng.batch_mul_ptr(fec.CURVE_SECP256K1, h_k.data_ptr(), h_p.data_ptr(), ns, h_out.data_ptr(), h_st.data_ptr())
+            barrier()
+            dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+            strong["e2e"] = {"value": world * ns * args.steps / float(dts.item()), "unit": UNIT, "host_buffers": "pinned"}
 
     # ---- SURVEY 8e, optional and outside every timed throughput figure: the device-side gather of the shards' results over
     # NVLink / NVSwitch (ncclAllGather of n x 33 B per rank), timed on the device, max over ranks
@@ -371,16 +437,49 @@ def main():
         t = timed(lambda: eng.batch_mul_dev(fec.CURVE_SECP256K1, d_k, None, m0, d_o, stream=sp), reps=10)
         others["secp256k1_kG_2p16"] = {"value": world * m0 / t, "unit": "ops/s", "lanes_per_gpu": m0,
                                        "canonical_imad_frac": CANON_OTHER["secp256k1_kG"] * m0 / t / imad_peak}
-        # BASELINE.json configs[3]: one key exchange = X25519(a,9), X25519(b,9), X25519(a,B), X25519(b,A) = 2 base-point + 2 ladders
-        t_ex = 2.0 / others["x25519"]["value"] + 2.0 / others["x25519_base_point"]["value"]
-        others["x25519_key_exchange"] = {"value": 4.0 / t_ex, "unit": "scalar-mults/s (4 per exchange)", "lanes_per_gpu": m,
-                                         "canonical_imad_frac": 4.0 / t_ex / world * CANON_OTHER["x25519"] / imad_peak}
+        # BASELINE.json configs[3], as stated: X25519 key exchange over 2^24 random keypairs (per GPU).  One exchange = the four
+        # calls A = X25519(a, 9), B = X25519(b, 9), s1 = X25519(a, B), s2 = X25519(b, A); the two shared secrets must be equal.
+        mx = min(n, 1 << 24)
+        d_A = torch.empty(mx * 32, dtype=torch.uint8, device=dev)
+        d_B = torch.empty(mx * 32, dtype=torch.uint8, device=dev)
+        d_s1 = torch.empty(mx * 32, dtype=torch.uint8, device=dev)
+        d_s2 = torch.empty(mx * 32, dtype=torch.uint8, device=dev)
+
+        def exchange():
+            eng.batch_x25519_dev(d_k, None, mx, d_A, stream=sp)
+            eng.batch_x25519_dev(d_r, None, mx, d_B, stream=sp)
+            eng.batch_x25519_dev(d_k, d_B, mx, d_s1, stream=sp)
+            eng.batch_x25519_dev(d_r, d_A, mx, d_s2, stream=sp)
+
+        t = timed(exchange, reps=2)
+        agree = bool(torch.equal(d_s1, d_s2)) and bool(d_s1.view(mx, 32).any(dim=1).all())
+        others["x25519_key_exchange"] = {"value": world * 4 * mx / t, "unit": "scalar-mults/s (4 per exchange)", "keypairs_per_gpu": mx,
+                                         "exchanges_per_s": world * mx / t, "shared_secrets_agree": agree,
+                                         "canonical_imad_frac": 4 * mx / t * CANON_OTHER["x25519"] / imad_peak}
+        del d_A, d_B, d_s1, d_s2
+        if not agree:
+            failures.append("x25519_key_exchange: the two parties' shared secrets differ")
         # P-256 needs scalars below its own order and points on its own curve
         d_k2 = torch.empty(m * 32, dtype=torch.uint8, device=dev)
         d_p2 = torch.empty(m * 64, dtype=torch.uint8, device=dev)
         eng.synth_dev(2, 5, 0, first_lane, m, d_k2, edge=True, stream=sp)
         t = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k2, None, m, d_p2, out_fmt=fec.OUT_AFFINE_XY_BE, stream=sp))
         others["p256_kG"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": CANON_OTHER["p256_kG"] * m / t / imad_peak}
+        # BASELINE.json configs[4], as stated: P-256 k*G + Ed25519 key generation with COMPRESSED-point encoding, 2^26 scalars over
+        # 8 GPUs = 2^23 lanes per GPU (SEC1 compressed 33 B for P-256, the RFC 8032 32-byte encoding for Ed25519)
+        m4 = min(n, 1 << 23)
+        d_k4 = torch.empty(m4 * 32, dtype=torch.uint8, device=dev)
+        d_o4 = torch.empty(m4 * 33, dtype=torch.uint8, device=dev)
+        eng.synth_dev(2, 5, 0, rank * m4, m4, d_k4, edge=True, stream=sp)
+        t1 = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k4, None, m4, d_o4, out_fmt=fec.OUT_SEC1_COMPRESSED, stream=sp))
+        t2 = timed(lambda: eng.batch_ed25519_pubkey_dev(d_k4, True, m4, d_o4, stream=sp))
+        others["p256_kG_2p23_compressed"] = {"value": world * m4 / t1, "unit": "ops/s", "lanes_per_gpu": m4,
+                                             "canonical_imad_frac": CANON_OTHER["p256_kG"] * m4 / t1 / imad_peak}
+        others["ed25519_keygen_2p23"] = {"value": world * m4 / t2, "unit": "ops/s", "lanes_per_gpu": m4,
+                                         "canonical_imad_frac": CANON_OTHER["ed25519_keygen"] * m4 / t2 / imad_peak}
+        others["config4_p256_kG_plus_ed25519_keygen"] = {"value": world * 2 * m4 / (t1 + t2), "unit": "ops/s (both key types for every scalar)",
+                                                         "lanes_per_gpu": m4, "canonical_imad_frac": None}
+        del d_k4, d_o4
         t = timed(lambda: eng.batch_mul_dev(fec.CURVE_P256, d_k2, d_p2, m, d_o, stream=sp))
         others["p256_kP"] = {"value": world * m / t, "unit": "ops/s", "lanes_per_gpu": m, "canonical_imad_frac": CANON_OTHER["p256_kP"] * m / t / imad_peak}
         # SURVEY 8f rows next to the path: ECDH (k*P, x-coordinate, HKDF-SHA-256 on the device) and the multi-scalar
@@ -429,6 +528,38 @@ def main():
                           "base-point X25519 through the Edwards table)")
         del d_o, d_k2, d_p2
 
+    # ---- the ONE-PROCESS multi-device form (fec_ctx_create with a device list, one fec_batch_mul call on
+    # host buffers, the library shards the lanes over its devices with one host thread each).  Rank 0 alone runs it on all N
+    # GPUs while the other ranks wait at the barrier; 2^24 lanes in total, pinned and pageable host buffers.
+    single = None
+    if world > 1 and not args.no_single_process and not args.no_e2e:
+        barrier()
+        if rank == 0:
+            tot = min(n, 1 << 24)
+            with fec.Engine(devices=list(range(world))) as many:
+                res = {}
+                for kind in ("pinned", "pageable"):
+                    if kind == "pinned":
+                        a_k, a_p, a_o, a_s = h_k.data_ptr(), h_p.data_ptr(), h_out.data_ptr(), h_st.data_ptr()
+                    else:
+                        q_k, q_p = h_k.numpy()[: tot * 32].copy(), h_p.numpy()[: tot * 64].copy()
+                        q_o, q_s = np.empty(tot * 33, dtype=np.uint8), np.empty(tot, dtype=np.uint8)
+                        a_k, a_p, a_o, a_s = q_k.ctypes.data, q_p.ctypes.data, q_o.ctypes.data, q_s.ctypes.data
+                    many.batch_mul_ptr(fec.CURVE_SECP256K1, a_k, a_p, tot, a_o, a_s)  # warm-up: allocates every device's pipeline
+                    t0 = time.perf_counter()
+                    for _ in range(max(1, args.steps)):
+                        many.batch_mul_ptr(fec.CURVE_SECP256K1, a_k, a_p, tot, a_o, a_s)
+                    dt1 = time.perf_counter() - t0
+                    res[kind] = tot * max(1, args.steps) / dt1
+                ok = bool(np.array_equal(q_o, h_out.numpy()[: tot * 33])) and bool(torch.equal(h_out[: tot * 33], d_out[: tot * 33].cpu()))
+                single = {"value": res["pinned"], "pageable_value": res["pageable"], "unit": UNIT, "lanes_total": tot, "devices": world,
+                          "what": "fec.Engine(devices=range(N)) in rank 0's process: one fec_batch_mul call on host buffers, lanes sharded "
+                                  "by the library (one host thread, three streams per device)",
+                          "matches_per_rank_results": ok}
+                if not ok:
+                    failures.append("e2e_single_process: the multi-device context returned different bytes")
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -458,6 +589,7 @@ def main():
                "std_value": rate_std, "gpu_bit_exact_on_sample": parity}
         if not parity:
             print("PARITY FAILURE: GPU output differs from the CPU oracle on the sampled lanes", file=sys.stderr)
+            failures.append("gpu_bit_exact_on_sample is false")
 
     hbm_peak = None
     try:
@@ -469,24 +601,56 @@ def main():
     stage_total = ms_prep + ms_lad + ms_fin
     lanes_per_launch = n / max(chunks, 1)
     ladder_ms = ms_lad / max(chunks, 1)
+    ex = load_exec_counts()
     stages = {
         "kernels": ["k_glv_prep", "k_glv_ladder", "k_glv_finish"], "launches_per_step": 3 * chunks, "lanes_per_launch": lanes_per_launch,
         "ms_per_step": [ms_prep, ms_lad, ms_fin], "share_of_step": [ms_prep / stage_total, ms_lad / stage_total, ms_fin / stage_total],
-        "executed_imul32_per_op": EXEC_IMUL32_PER_OP,
-        # IMAD.WIDE instructions the kernels really issue / measured IMAD.WIDE issue rate: how busy the multiply pipe is
-        "pipe_utilisation": {"ladder": EXEC_IMUL32_PER_OP["ladder"] * n / (ms_lad * 1e-3) / imad_peak,
-                             "step": sum(EXEC_IMUL32_PER_OP.values()) * n / kernel_s / imad_peak},
-        "source": "CUDA events between the kernels of one extra step (fec_ctx_stage_timing); instruction counts from ncu, profiles/",
+        "source": "CUDA events between the kernels of one extra step (fec_ctx_stage_timing)",
     }
+    frac_executed = issue = ladder_traffic = None
+    if ex is not None:
+        names = ("prepare", "ladder", "finish")
+        wide = {k: ex[k]["imad_wide_per_lane"] for k in names}
+        tot = {k: ex[k]["total_per_lane"] for k in names}
+        stages["executed_imul32_per_op"] = wide
+        stages["executed_instructions_per_op"] = tot
+        stages["counts_source"] = f"{os.path.relpath(EXEC_COUNTS_PATH, ROOT)}: {ex['source']}; {ex['note']}"
+        # IMAD.WIDE instructions the kernels really issue / measured IMAD.WIDE issue rate: how busy the multiply pipe is
+        stages["pipe_utilisation"] = {"ladder": wide["ladder"] * n / (ms_lad * 1e-3) / imad_peak,
+                                      "step": sum(wide.values()) * n / kernel_s / imad_peak}
+        frac_executed = stages["pipe_utilisation"]["step"]
+        # The issue port, not the multiply pipe, is what the kernels saturate: an IMAD.WIDE holds an SM sub-partition's issue port
+        # for 4 cycles and every other instruction for 1 (tools/ubench.cu).  cycles needed = (4 W + others) warp instructions per
+        # warp-operation; cycles available = SMSPs x clock x time.
+        sm_hz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        smsps = 4 * torch.cuda.get_device_properties(local).multi_processor_count
+
+        def port(k, ms):
+            need = (ISSUE_CYCLES_IMAD_WIDE * wide[k] + (tot[k] - wide[k])) * n / 32.0
+            return need / (smsps * sm_hz * 1e6 * ms * 1e-3)
+
+        issue = {"model": "issue cycles = 4 x IMAD.WIDE + 1 x every other warp instruction (measured: profiles/r2a_ubench_issue_model.log)",
+                 "issue_port_utilisation": {"prepare": port("prepare", ms_prep), "ladder": port("ladder", ms_lad), "finish": port("finish", ms_fin)},
+                 "imad_wide_share_of_issue_cycles": {k: ISSUE_CYCLES_IMAD_WIDE * wide[k] / (ISSUE_CYCLES_IMAD_WIDE * wide[k] + tot[k] - wide[k]) for k in names},
+                 "sm_mhz_used": sm_hz,
+                 "reading": "the ladder fills its issue slots; its IMAD.WIDE share of them is what pipe_utilisation reports, so more "
+                            "multiply throughput needs fewer non-multiply instructions per multiplication, not more overlap"}
+        dram = ex["ladder"].get("dram_bytes_per_lane")
+        ladder_traffic = dram * lanes_per_launch if dram else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 limbs (8 x 32-bit, IMAD.WIDE.U32 carry chains)", "data": "synthetic (device Philox-4x32-10, seed 'forge-ec')",
         "config": {"workload": "secp256k1 variable-base k*P + batch affine normalisation + SEC1 compressed [BASELINE.json configs[2]]",
-                   "lanes_per_gpu": n, "sharding": "contiguous lane ranges, one rank per GPU, no collective on the data path",
+                   "lanes_per_gpu": n, "sharding": "contiguous lane ranges, one rank per GPU, no collective on the data path (weak scaling: "
+                                                   "2^24 lanes per GPU; the `strong` key holds 2^24 lanes in total)",
                    "l2": "inputs 1.5 GiB + outputs 0.55 GiB per step exceed the 126 MB L2; no flush needed"},
         "roofline": {"bound": "imad", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMUL32/s", "frac": achieved / imad_peak,
-                     "traffic": LADDER_DRAM_BYTES_PER_LANE * lanes_per_launch,
+                     "frac_executed": frac_executed,
+                     "frac_note": "frac counts SURVEY 8d's canonical 172 562 IMUL32 per operation (the GLV split executes fewer, hence > 1); "
+                                  "frac_executed counts the IMAD.WIDE instructions the kernels execute (ncu) and is the multiply pipe's real load",
+                     "issue_port": issue,
+                     "traffic": ladder_traffic,
                      "traffic_note": "k_glv_ladder, bytes per launch, from one ncu --set full capture (profiles/); its algorithmic "
                                      "traffic is 64 table entries x 64 B + 36 B in + 96 B out = 4.2 KB per lane, most of it served by L2",
                      "kernel": "k_glv_prep + k_glv_ladder + k_glv_finish (the canonical figure covers the whole operation; "
@@ -498,13 +662,16 @@ def main():
                      "hbm": {"bound": "hbm", "achieved": IO_BYTES_PER_OP * n / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": IO_BYTES_PER_OP * n / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_op": IO_BYTES_PER_OP}},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world, "device_gather": gather, "other_configs": others,
-        "clocks": clocks,
+        "cpu_baseline": cpu, "e2e": e2e, "strong": strong, "e2e_single_process": single, "gpu_launches": int(launches) * world,
+        "device_gather": gather, "other_configs": others, "clocks": clocks, "failures": failures,
     }
     sys.stdout.flush()
     os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    if failures:  # a throughput next to a wrong result is worthless: make the run fail
+        print("BENCH FAILED: " + "; ".join(failures), file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

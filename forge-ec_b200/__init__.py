@@ -55,6 +55,7 @@ from .traits import (  # noqa: F401
     P256,
     Scalar,
     Secp256k1,
+    batch_nonce_commit,
     batch_x25519,
     default_engine,
     x25519,

@@ -46,14 +46,18 @@ struct FeK1 {
     u32 acc[8];
     copy8(acc, r);
     u32 ca = mad_row<4, 0>(acc, h, C977);  // += {h0,h2,h4,h6}*977 at limb pairs (0,1)..(6,7)
-    u32 od[8];                             // {h1,h3,h5,h7}*977 at weight 2^32
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      od[2 * k] = mul_lo(h[2 * k + 1], C977);
-      od[2 * k + 1] = mul_hi(h[2 * k + 1], C977);
-    }
+    // s = {h1,h3,h5,h7}*977 + hi, both at weight 2^32 (the "<< 32" half of the fold): hi enters as the 64-bit ADDEND of the four
+    // products -- (h[2k], h[2k+1]) is the pair the product of h[2k+1] lands on -- so the sum costs no additions of its own
+    // (ptxas finds the same fusion when the sum is written as products + an 8-word addition)
     u32 s[8];
-    u32 s8 = add8(s, od, h);  // (od + hi) at weight 2^32  (the "<< 32" half of the fold)
+    s[0] = mad_lo_cc(h[1], C977, h[0]);
+    s[1] = madc_hi_cc(h[1], C977, h[1]);
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+      s[2 * k] = madc_lo_cc(h[2 * k + 1], C977, h[2 * k]);
+      s[2 * k + 1] = madc_hi_cc(h[2 * k + 1], C977, h[2 * k + 1]);
+    }
+    u32 s8 = addc(0u, 0u);
     acc[1] = add_cc(acc[1], s[0]);
 #pragma unroll
     for (int i = 2; i < 8; i++) acc[i] = addc_cc(acc[i], s[i - 1]);

@@ -135,14 +135,70 @@ FEC_DEV void glv_ladder(saddr S, const u32* tab, const u32 KK[8], u32 flags) {
       const u32 neg_y = sgn ^ (h == 0 ? neg1 : neg2);
       const u32 cur = idx;
       cp_async_wait();
-      const u32 fl = vm_jac_madd_1<F, T>(S, neg_y);
+#ifndef FEC_K1_MADD_7M4S  // the 8M + 3S form (8 linear operations instead of 14; r2: 59.7 -> 60.2 M/s); A/B: madd-2007-bl
+      constexpr bool LEAN = true;
+#else
+      constexpr bool LEAN = false;
+#endif
+      const u32 fl = vm_jac_madd_1<F, T, LEAN>(S, neg_y);
       // the addend slots are free again: start fetching the next addend (none after the very last addition)
       if (!(i == 31 && h == 1)) {
         if (h == 0) next_digit4(K2r, idx, sgn); else next_digit4(K1r, idx, sgn);
         glv_prefetch<T>(S, tab, idx, h ^ 1);
       }
-      vm_jac_madd_2<F, T>(S);
+      vm_jac_madd_2<F, T, LEAN>(S);
       if (warp_any(fl)) glv_madd_fix<T>(S, tab, cur, h, neg_y, fl);
+    }
+  }
+}
+
+// The same loop with the point in REGISTERS and the field operations expanded in line (A/B against the accumulator machine,
+// FORGE_EC_GLV_LADDER=regs): no slots, no calls, no shared memory -- the instruction scheduler sees whole point formulas, as in
+// the X25519 step -- at the price of a loop body (one doubling, one mixed addition) of ~2.9 k instructions and ~150 registers.
+// Table entries arrive by 128-bit loads one addition ahead of their use.
+template <class CH>
+FEC_DEV void glv_ladder_regs(Jac& Q, const u32* tab, const u32 KK[8], u32 flags) {
+  typedef FeK1 F;
+  u32 K1r[4], K2r[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { K1r[i] = KK[i]; K2r[i] = KK[4 + i]; }
+  const u32 neg1 = 0u - (flags & 1u), neg2 = 0u - ((flags >> 1) & 1u);
+  u32 idx, sgn, tx[8], ty[8];
+  next_digit4(K1r, idx, sgn);
+  g_ld8(Q.X, tab + idx * 24);
+  g_ld8(ty, tab + idx * 24 + 16);
+  {
+    u32 ny[8];
+    F::neg(ny, ty);
+    select8(Q.Y, sgn ^ neg1, ny, ty);
+  }
+  set_small(Q.Z, 1u);
+  next_digit4(K2r, idx, sgn);
+  g_ld8(tx, tab + idx * 24 + 8);
+  g_ld8(ty, tab + idx * 24 + 16);
+#pragma unroll 1
+  for (int i = 0; i < 32; i++) {
+    if (i > 0) {
+#pragma unroll 1
+      for (int d = 0; d < 4; d++) jac_dbl<CH>(Q);
+    }
+#pragma unroll 1
+    for (int h = (i == 0 ? 1 : 0); h < 2; h++) {
+      const u32 neg_y = sgn ^ (h == 0 ? neg1 : neg2);
+      u32 cx[8], cy[8];
+      copy8(cx, tx);
+      {
+        u32 ny[8];
+        F::neg(ny, ty);
+        select8(cy, neg_y, ny, ty);
+      }
+      if (!(i == 31 && h == 1)) {  // the next addend: its loads overlap this addition
+        if (h == 0) next_digit4(K2r, idx, sgn); else next_digit4(K1r, idx, sgn);
+        g_ld8(tx, tab + idx * 24 + (h == 0 ? 8 : 0));
+        g_ld8(ty, tab + idx * 24 + 16);
+      }
+      const u32 fl = jac_madd_lean<CH>(Q, cx, cy);
+      if (warp_any(fl)) jac_madd_fix<CurveK1>(Q, cx, cy, fl);
     }
   }
 }

@@ -114,6 +114,40 @@ k_glv_ladder(size_t n, GlvScratch sc) {
   }
 }
 
+// A/B form of the ladder (FORGE_EC_GLV_LADDER=regs): the point in registers, field operations in line (glv_ladder_regs)
+#ifndef FEC_GLV_LADR_BLOCKS
+#define FEC_GLV_LADR_BLOCKS 3
+#endif
+#ifndef FEC_GLV_LADR_INLINE
+#define FEC_GLV_LADR_INLINE 2  // 2: multiplication and squaring in line, 1: squaring only, 0: both called
+#endif
+__global__ void __launch_bounds__(GLV_LAD_THREADS, FEC_GLV_LADR_BLOCKS)
+k_glv_ladder_regs(size_t n, GlvScratch sc) {
+  size_t lane = (size_t)blockIdx.x * GLV_LAD_THREADS + threadIdx.x;
+  const bool live = lane < n;
+  if (!live) lane = n - 1;
+  u32 KK[8];
+  g_ld8(KK, sc.kk + lane * 8);
+  const u32 flags = sc.flags[lane];
+  Jac Q;
+#if FEC_GLV_LADR_INLINE == 2
+  glv_ladder_regs<CurveK1Inl>(Q, sc.tab + lane * GLV_TAB_WORDS, KK, flags);
+#elif FEC_GLV_LADR_INLINE == 1
+  glv_ladder_regs<CurveK1InlSqr>(Q, sc.tab + lane * GLV_TAB_WORDS, KK, flags);
+#else
+  glv_ladder_regs<CurveK1>(Q, sc.tab + lane * GLV_TAB_WORDS, KK, flags);
+#endif
+  if (live) {
+    g_st8(sc.q + lane * 24, Q.X);
+    g_st8(sc.q + lane * 24 + 8, Q.Y);
+    g_st8(sc.q + lane * 24 + 16, Q.Z);
+  }
+}
+static bool ladder_regs() {  // development switch (A/B measurements only)
+  static const bool v = [] { const char* e = getenv("FORGE_EC_GLV_LADDER"); return e != nullptr && e[0] == 'r'; }();
+  return v;
+}
+
 // Warp-independent: every warp walks tiles of 32 lanes, applies the corrections, keeps the Jacobian results of
 // GLV_FIN_DEFER tiles in thread-local memory with the running product of their Z and then inverts once per warp
 // (Montgomery's trick along the tile axis; no __syncthreads, no idle warps while one lane set is being inverted).
@@ -236,7 +270,10 @@ cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const ui
     k_glv_prep<<<(unsigned)((m + GLV_PREP_THREADS - 1) / GLV_PREP_THREADS), GLV_PREP_THREADS, 0, st>>>(
         scalars + off * 32, points + off * psz, points_fmt, m, sc);
     mark();
-    k_glv_ladder<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, GLV_LAD_SMEM, st>>>(m, sc);
+    if (ladder_regs())
+      k_glv_ladder_regs<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, 0, st>>>(m, sc);
+    else
+      k_glv_ladder<<<(unsigned)((m + GLV_LAD_THREADS - 1) / GLV_LAD_THREADS), GLV_LAD_THREADS, GLV_LAD_SMEM, st>>>(m, sc);
     mark();
     k_glv_finish<<<fin_grid(m), GLV_FIN_THREADS, GLV_FIN_SMEM, st>>>(
         m, sc, out_fmt, out + off * osz, status ? status + off : nullptr);

@@ -12,9 +12,15 @@
 
 namespace fec {
 
-constexpr int P3_PREP_THREADS = 128;
+#ifndef FEC_P3_PREP_THREADS
+#define FEC_P3_PREP_THREADS 128  // (r2: 128 threads 32.97, 256 threads 32.84, 512 threads 32.86 M/s; one inversion per warp 31.84)
+#endif
+constexpr int P3_PREP_THREADS = FEC_P3_PREP_THREADS;
 #ifndef FEC_P3_PREP_BLOCKS
-#define FEC_P3_PREP_BLOCKS 4
+#define FEC_P3_PREP_BLOCKS (512 / FEC_P3_PREP_THREADS)  // 128 registers
+#endif
+#ifndef FEC_P3_PREP_BLOCK_INV
+#define FEC_P3_PREP_BLOCK_INV 1  // the warps of a block share ONE inversion (0: one per warp, the form before r2)
 #endif
 #ifndef FEC_P3_LAD_THREADS
 #define FEC_P3_LAD_THREADS 128
@@ -52,17 +58,34 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* io = io_all + warp * (33 * 32);
   const size_t first = ((size_t)blockIdx.x * (P3_PREP_THREADS / 32) + warp) * 32;
+#if FEC_P3_PREP_BLOCK_INV
+  // The inversion of the table's common denominator is the expensive part of this kernel (255 squarings: as much as the
+  // table itself) and a warp pays for it whether one lane or 32 need it.  The warps of a block therefore share ONE inversion
+  // (block_batch_inv: products across the warps through shared memory, warp 0 inverts, everybody multiplies back), and a
+  // warp past the end of the batch stays for the barriers and recomputes the last lane into the spare rows.
+  __shared__ u32 inv_scratch[INV_SCRATCH_WORDS];
+  const int cnt_lanes = first >= n ? 0 : (int)((n - first) < 32 ? (n - first) : 32);
+#else
   if (first >= n) return;  // warp-uniform
   const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+#endif
   const bool live = (int)lane_in_warp < cnt_lanes;
   // lanes past the end recompute the last lane (the whole warp takes part in the inversion) into 32 spare table rows
   const size_t lane = live ? first + lane_in_warp : n - 1;
   const size_t row = live ? lane : n + lane_in_warp;
   u32 k[8], px[8], py[8], ok, idn = 0u;
   if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
+    // (a lane past the end reads the record of the batch's last lane, which lives in another warp's staging area or nowhere:
+    // it takes the record from global memory instead)
     warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
     __syncwarp();
-    ok = sec1_decompress_id<C>(px, py, io + (lane - first) * 33, idn);
+    if (live) {
+      ok = sec1_decompress_id<C>(px, py, io + lane_in_warp * 33, idn);
+    } else {
+      uint8_t rec[33];
+      for (int i = 0; i < 33; i++) rec[i] = points[lane * 33 + i];
+      ok = sec1_decompress_id<C>(px, py, rec, idn);
+    }
   } else {
     load_rec32_be(px, points + lane * 64);
     load_rec32_be(py, points + lane * 64 + 32);
@@ -79,7 +102,11 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   scalar_prepare<C>(K, negm, st, k);
   st = lane_status(st, ok, idn);  // range > invalid point > identity (k = 0, or the identity as the input point)
   GlobalLaneTab tab{sc.tab + row * P3_TAB_WORDS};
+#if FEC_P3_PREP_BLOCK_INV
+  BlockInv<F, P3_PREP_THREADS / 32> inv{inv_scratch};
+#else
   P3WarpInv inv;
+#endif
   wmul_var_table<C>(tab, px, py, inv);
   if (live) {
     g_st8(sc.kk + lane * 8, K);

@@ -154,6 +154,20 @@ class _WeierstrassCurve:
         return cls.batch_ecdh([private_key], [public_key], None, 32, engine)[0]
 
 
+def batch_nonce_commit(curve: int, mode: int, nonces: Sequence[bytes], engine: Optional[_e.Engine] = None):
+    """The fixed-base step of `sign` for a batch of nonces: ECDSA r = x(k G) (ecdsa.rs:108-131), BIP-340
+    x-only R with k negated when y(R) is odd (schnorr.rs:372-385), EdDSA R = [r mod L]B from 64-byte hash values
+    (eddsa.rs:120-131, RFC 8032 5.1.6).  Returns a list of (R bytes, scalar bytes); raises ValueError where the reference
+    returns Err (nonce out of range / zero, x(R) not a scalar)."""
+    eng = engine or default_engine()
+    R, r, st = eng.batch_nonce_commit(curve, mode, np.frombuffer(b"".join(nonces), dtype=np.uint8), n=len(nonces))
+    if np.any(st == _e.LANE_SCALAR_RANGE):
+        raise ValueError("InvalidScalar")
+    if np.any(st == _e.LANE_INFINITY):
+        raise ValueError("InvalidSignature")
+    return [(R[i].tobytes(), r[i].tobytes()) for i in range(len(nonces))]
+
+
 class Secp256k1(_WeierstrassCurve):
     CURVE_ID = _e.CURVE_SECP256K1
 

@@ -201,6 +201,24 @@ inline std::array<uint8_t, 32> x25519(Engine& e, const std::array<uint8_t, 32>& 
   return batch_x25519(e, {scalar}, &us)[0];
 }
 
+// The fixed-base step of `sign` for a batch of nonces: ECDSA r = x(k G) (forge-ec-signature/src/ecdsa.rs:108-131),
+// BIP-340 x-only R and the even-y rule (schnorr.rs:372-385), EdDSA R = [r mod L]B from 64-byte hash values (eddsa.rs:120-131).
+struct NonceCommit {
+  std::vector<uint8_t> R, r, status;  // n x {33 | 32} B, n x 32 B, n lane status bytes
+};
+inline NonceCommit batch_nonce_commit(Engine& e, fec_curve curve, fec_nonce_mode mode, const std::vector<uint8_t>& nonces) {
+  const size_t rec_in = mode == FEC_NONCE_EDDSA ? 64 : 32;
+  if (nonces.size() % rec_in != 0) throw Error(ErrorKind::InvalidEncoding, "batch_nonce_commit: ragged nonce buffer");
+  const size_t n = nonces.size() / rec_in;
+  NonceCommit o;
+  o.R.resize(n * (mode == FEC_NONCE_ECDSA ? 33 : 32));
+  o.r.resize(n * 32);
+  o.status.resize(n);
+  if (n == 0) return o;
+  check(fec_batch_nonce_commit(e.ctx(), curve, mode, nonces.data(), n, o.R.data(), o.r.data(), o.status.data()), "fec_batch_nonce_commit");
+  return o;
+}
+
 struct Ed25519Signature {
   // seed -> SHA-512 -> clamp -> [s]B -> 32 bytes (forge-ec-signature/src/eddsa.rs:450-509, RFC 8032 5.1.5)
   static std::vector<std::array<uint8_t, 32>> batch_derive_public_key(Engine& e, const std::vector<std::array<uint8_t, 32>>& seeds) {

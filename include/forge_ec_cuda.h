@@ -34,7 +34,14 @@
  *   - A lane whose status is not FEC_LANE_OK has an all-zero output record, which is also the
  *     reference's encoding of the identity (point.rs:41-47).
  *   - There is no CPU fallback: without a usable CUDA device fec_ctx_create fails.
- *   - A context serialises its calls on an internal mutex; several contexts may coexist.
+ *   - Threads: the host entry points of one context are serialised on an internal mutex (they share the context's pipeline
+ *     buffers); several contexts may coexist.  The `*_dev` entry points take no lock: they only enqueue work on the caller's
+ *     stream and may be called concurrently for different streams (the launch counter is atomic).  fec_ctx_stage_timing /
+ *     fec_ctx_stage_ms are single-threaded measurement aids and must not overlap other calls on the same context.
+ *   - `*_dev` calls never synchronise, with one exception: fec_msm_dev with n >= 2^16 points waits once for the stream (the
+ *     bucket method reads back its largest bucket size to decide on the fallback), so it cannot be captured in a CUDA graph.
+ *   - Scratch memory comes from the device's default stream-ordered pool (cudaMallocAsync), whose release threshold the
+ *     context raises so that the pool keeps its memory between calls.
  */
 #ifndef FORGE_EC_CUDA_H
 #define FORGE_EC_CUDA_H
@@ -44,6 +51,13 @@
 
 #ifdef __cplusplus
 extern "C" {
+#endif
+
+/* The library is linked with hidden default visibility: exactly the functions declared here are exported. */
+#if defined(__GNUC__)
+#define FEC_API __attribute__((visibility("default")))
+#else
+#define FEC_API
 #endif
 
 typedef struct fec_ctx fec_ctx;
@@ -99,25 +113,25 @@ enum {
 };
 
 /* device_ids == NULL or n_devices <= 0: use the current CUDA device only. */
-int fec_ctx_create(const int* device_ids, int n_devices, fec_ctx** out);
-void fec_ctx_destroy(fec_ctx* ctx);
-int fec_ctx_device_count(const fec_ctx* ctx);
+FEC_API int fec_ctx_create(const int* device_ids, int n_devices, fec_ctx** out);
+FEC_API void fec_ctx_destroy(fec_ctx* ctx);
+FEC_API int fec_ctx_device_count(const fec_ctx* ctx);
 /* number of kernels this context has launched since creation (for bench.py's gpu_launches) */
-uint64_t fec_ctx_launch_count(const fec_ctx* ctx);
-const char* fec_strerror(int err);
+FEC_API uint64_t fec_ctx_launch_count(const fec_ctx* ctx);
+FEC_API const char* fec_strerror(int err);
 /* last CUDA error string seen by this context (thread-unsafe diagnostic) */
-const char* fec_ctx_last_cuda_error(const fec_ctx* ctx);
+FEC_API const char* fec_ctx_last_cuda_error(const fec_ctx* ctx);
 
 /* Sharding rule used by the host entry points (and by bench.py across ranks): shard `index` of `n_shards` owns
  * the contiguous lanes [first, first+count); cuts are multiples of 1024 lanes.  Needs no device. */
-void fec_shard_range(size_t n, int n_shards, int index, size_t* first, size_t* count);
+FEC_API void fec_shard_range(size_t n, int n_shards, int index, size_t* first, size_t* count);
 
 /* k_i*G when points == NULL, else k_i*P_i.
  * scalars: n x 32 B big-endian (Scalar::from_bytes layout); points: n x 64 B (X||Y big-endian) or
  * n x 33 B SEC1 compressed; out: n x {33,65,64,32,65} B by out_fmt; status: n x u8 or NULL. */
-int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
+FEC_API int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint8_t* scalars, const uint8_t* points,
                   fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* out, uint8_t* status);
-int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
+FEC_API int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
                       const uint8_t* d_points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out,
                       uint8_t* d_status, void* stream);
 
@@ -125,9 +139,9 @@ int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem,
  * kdf == FEC_KDF_NONE: out = n x 32 B shared secrets; otherwise out = n x out_len bytes (1 <= out_len <= 64, info_len <= 256;
  * `info` is host memory in both variants).  A lane whose scalar is out of range, whose point is invalid or whose result is
  * the identity gets an all-zero record and its status byte (the reference returns Err for it). */
-int fec_batch_ecdh(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+FEC_API int fec_batch_ecdh(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
                    fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len, uint8_t* out, uint8_t* status);
-int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+FEC_API int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
                        fec_points_fmt points_fmt, size_t n, fec_kdf kdf, const uint8_t* info, size_t info_len, size_t out_len,
                        uint8_t* d_out, uint8_t* d_status, void* stream);
 
@@ -135,9 +149,9 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
  * the batched k*P kernels followed by a device-wide reduction.  out: ONE record of out_fmt; status: ONE byte -- 0 ok, 1 / 2 some
  * lane had an out-of-range scalar / an invalid point (out is all-zero), 3 the sum is the identity.  n >= 1.  The host variant
  * sums contiguous lane ranges on every device of the context and adds the per-device sums on the first one. */
-int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+FEC_API int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
             fec_out out_fmt, uint8_t* out, uint8_t* status);
-int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
+FEC_API int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_scalars, const uint8_t* d_points,
                 fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream);
 
 /* Signing-side nonce commitment: the fixed-base multiplication of a signature and the scalar that goes with it.
@@ -149,63 +163,63 @@ int fec_msm_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_s
  *   FEC_NONCE_EDDSA   (curve ignored) nonces n x 64 B: the SHA-512 output r = H(prefix || M) as a little-endian integer;
  *                     out_r n x 32 B little-endian r mod L;  out_R n x 32 B RFC 8032 encoding of [r mod L]B.  status all zero.
  * status may be NULL. */
-int fec_batch_nonce_commit(fec_ctx* ctx, fec_curve curve, fec_nonce_mode mode, const uint8_t* nonces, size_t n, uint8_t* out_R,
+FEC_API int fec_batch_nonce_commit(fec_ctx* ctx, fec_curve curve, fec_nonce_mode mode, const uint8_t* nonces, size_t n, uint8_t* out_R,
                            uint8_t* out_r, uint8_t* status);
-int fec_batch_nonce_commit_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_nonce_mode mode, const uint8_t* d_nonces, size_t n,
+FEC_API int fec_batch_nonce_commit_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_nonce_mode mode, const uint8_t* d_nonces, size_t n,
                                uint8_t* d_out_R, uint8_t* d_out_r, uint8_t* d_status, void* stream);
 
 /* RFC 7748 X25519: scalars n x 32 B (clamped inside), u n x 32 B little-endian (NULL = base point 9),
  * out n x 32 B little-endian. */
-int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
-int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+FEC_API int fec_batch_x25519(fec_ctx* ctx, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
+FEC_API int fec_batch_x25519_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
                          uint8_t* d_out, void* stream);
 /* The same with a semantics selector: FEC_SEM_FORGE_QUIRK replays the reference's LITERAL x25519() (curve25519.rs:1624-1716 on its
  * own FieldElement, :50-494: limb arithmetic without carries, big-endian byte codec, A instead of a24, a hard-coded answer for
  * the scalar 2), whose outputs are not RFC 7748 results.  A parity artefact, one thread per lane. */
-int fec_batch_x25519_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
-int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
+FEC_API int fec_batch_x25519_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* scalars, const uint8_t* u, size_t n, uint8_t* out);
+FEC_API int fec_batch_x25519_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_scalars, const uint8_t* d_u, size_t n,
                              uint8_t* d_out, void* stream);
 
 /* RFC 8032 5.1.5 public key.  input_is_seed != 0: 32-byte seeds (SHA-512 + clamp on device);
  * input_is_seed == 0: 32-byte little-endian scalars used as they are.  out n x 32 B (y || sign x). */
-int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n,
+FEC_API int fec_batch_ed25519_pubkey(fec_ctx* ctx, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n,
                              uint8_t* out);
-int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
+FEC_API int fec_batch_ed25519_pubkey_dev(fec_ctx* ctx, int dev_index, const uint8_t* d_in, int input_is_seed, size_t n,
                                  uint8_t* d_out, void* stream);
 /* The same with a semantics selector: FEC_SEM_FORGE_QUIRK (seeds only, else FEC_ERR_UNSUPPORTED) replays the reference's LITERAL
  * Ed25519Signature::derive_public_key (eddsa.rs:450-509 on ed25519.rs: the second half of the hash parsed big-endian, the
  * fabricated base point, d for 2d, a hard-coded key for seeds starting with 0x9d, 32 bytes of a 33-byte SEC1-style record), whose
  * outputs are not RFC 8032 keys.  A parity artefact, one thread per lane. */
-int fec_batch_ed25519_pubkey_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out);
-int fec_batch_ed25519_pubkey_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_in, int input_is_seed, size_t n,
+FEC_API int fec_batch_ed25519_pubkey_sem(fec_ctx* ctx, fec_sem sem, const uint8_t* seeds_or_scalars, int input_is_seed, size_t n, uint8_t* out);
+FEC_API int fec_batch_ed25519_pubkey_sem_dev(fec_ctx* ctx, int dev_index, fec_sem sem, const uint8_t* d_in, int input_is_seed, size_t n,
                                      uint8_t* d_out, void* stream);
 
 /* Field microbenchmark (config 2).  a, b, out: lanes x 32 B little-endian residues in [0,p).
  * Per lane: x = a; repeat iters times { MUL: x = x*b;  SQR: x = x^2;  MULSQR: x = (x*b)^2 }; out = x.
  * *seconds (may be NULL) receives the kernel time measured with CUDA events (host variant only). */
-int fec_field_bench(fec_ctx* ctx, fec_prime prime, fec_field_op op, size_t lanes, int iters, const uint8_t* a,
+FEC_API int fec_field_bench(fec_ctx* ctx, fec_prime prime, fec_field_op op, size_t lanes, int iters, const uint8_t* a,
                     const uint8_t* b, uint8_t* out, double* seconds);
-int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_op op, size_t lanes, int iters,
+FEC_API int fec_field_bench_dev(fec_ctx* ctx, int dev_index, fec_prime prime, fec_field_op op, size_t lanes, int iters,
                         const uint8_t* d_a, const uint8_t* d_b, uint8_t* d_out, void* stream);
 
 /* Roofline calibration: a register-resident loop of independent 32x32->64 multiply-adds.
  * variant 0 = IMAD.WIDE.U32 (one instruction per IMUL32), 1 = mad.lo + mad.hi (two IMAD per IMUL32),
  * 2 = carry-chained IMAD.WIDE.X as used by the field code.
  * Returns multiply-add *instructions* per second over the whole device. */
-int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec);
+FEC_API int fec_imad_peak(fec_ctx* ctx, int dev_index, int variant, double* instr_per_sec);
 
 /* Measurement aid: while enabled, fec_batch_mul_dev(FEC_SECP256K1, points != NULL) records CUDA events between its three
  * kernels (prepare / ladder / finish).  fec_ctx_stage_ms waits for them, returns the summed milliseconds per stage and
  * the number of timed chunks, and forgets them. */
-int fec_ctx_stage_timing(fec_ctx* ctx, int enable);
-int fec_ctx_stage_ms(fec_ctx* ctx, double ms[3], int* chunks);
+FEC_API int fec_ctx_stage_timing(fec_ctx* ctx, int enable);
+FEC_API int fec_ctx_stage_ms(fec_ctx* ctx, double ms[3], int* chunks);
 
 /* Synthetic benchmark inputs: Philox-4x32-10, key "forge-ec", counter = (lane, block, stream_id);
  * lane i of the call is global lane first_lane + i and receives 32 bytes (blocks 2*sub, 2*sub+1).
  * mode 0: raw bytes; mode 1 / 2: big-endian scalar below the secp256k1 / P-256 group order (what
  * Scalar::random -> from_bytes_reduced yields, secp256k1.rs:2256-2263, forge-ec-core/src/lib.rs:326-332);
  * edge != 0 overwrites global lanes 0..7 with {0,1,2,3,n-1,n-2,(n+1)/2,2^255 mod n}. */
-int fec_synth_dev(fec_ctx* ctx, int dev_index, int mode, uint32_t stream_id, uint32_t sub, uint64_t first_lane, int edge,
+FEC_API int fec_synth_dev(fec_ctx* ctx, int dev_index, int mode, uint32_t stream_id, uint32_t sub, uint64_t first_lane, int edge,
                   size_t n, uint8_t* d_out, void* stream);
 
 #ifdef __cplusplus

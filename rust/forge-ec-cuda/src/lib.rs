@@ -30,6 +30,9 @@ pub const FEC_OUT_SEC1_HYBRID: c_int = 4;
 pub const FEC_KDF_NONE: c_int = 0;
 pub const FEC_KDF_HKDF_SHA256: c_int = 1;
 pub const FEC_KDF_XOR_INFO: c_int = 2;
+pub const FEC_NONCE_ECDSA: c_int = 0;
+pub const FEC_NONCE_BIP340: c_int = 1;
+pub const FEC_NONCE_EDDSA: c_int = 2;
 pub const FEC_LANE_OK: u8 = 0;
 pub const FEC_LANE_SCALAR_RANGE: u8 = 1;
 pub const FEC_LANE_POINT_INVALID: u8 = 2;
@@ -55,6 +58,10 @@ extern "C" {
     pub fn fec_msm(
         ctx: *mut fec_ctx, curve: c_int, scalars: *const u8, points: *const u8, points_fmt: c_int, n: usize, out_fmt: c_int,
         out: *mut u8, status: *mut u8,
+    ) -> c_int;
+    pub fn fec_batch_nonce_commit(
+        ctx: *mut fec_ctx, curve: c_int, mode: c_int, nonces: *const u8, n: usize, out_r_point: *mut u8, out_r_scalar: *mut u8,
+        status: *mut u8,
     ) -> c_int;
     pub fn fec_batch_x25519(ctx: *mut fec_ctx, scalars: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     /// sem = 1 (FEC_SEM_FORGE_QUIRK): the reference's literal x25519(), a parity artefact
@@ -116,6 +123,10 @@ pub trait BatchMul: CudaCurve {
         let pts: Option<Vec<u8>> = points.map(|ps| {
             let mut v = Vec::with_capacity(64 * n);
             for p in ps {
+                if bool::from(p.is_identity()) {            // the identity travels as the all-zero record: k * O = O
+                    v.extend_from_slice(&[0u8; 64]);
+                    continue;
+                }
                 v.extend_from_slice(&<Self::Field as FieldElement>::to_bytes(&p.x()));
                 v.extend_from_slice(&<Self::Field as FieldElement>::to_bytes(&p.y()));
             }
@@ -147,6 +158,9 @@ pub trait BatchMul: CudaCurve {
     /// `info = None` returns the 32-byte x-coordinates, otherwise `out_len` bytes of the curve's key derivation.
     fn batch_ecdh(engine: &Engine, scalars_be: &[u8], points_xy_be: &[u8], kdf: c_int, info: Option<&[u8]>, out_len: usize) -> Result<(Vec<u8>, Vec<u8>)> {
         let n = scalars_be.len() / 32;
+        // the C side reads n x 32 and n x 64 bytes: a short or ragged slice must not cross the FFI from safe code
+        if scalars_be.len() % 32 != 0 || points_xy_be.len() != 64 * n { return Err(Error::InvalidEncoding); }
+        if info.is_some() && (out_len == 0 || out_len > 64 || info.map_or(0, |v| v.len()) > 256) { return Err(Error::InvalidEncoding); }
         let rec = if info.is_none() { 32 } else { out_len };
         let mut out = vec![0u8; rec * n];
         let mut status = vec![0u8; n];
@@ -161,6 +175,7 @@ pub trait BatchMul: CudaCurve {
     /// `Curve::multi_scalar_multiply` (forge-ec-core/src/lib.rs:934-951) on the GPU: X || Y of the sum and its status.
     fn multi_scalar_multiply_xy(engine: &Engine, scalars_be: &[u8], points_xy_be: &[u8]) -> Result<([u8; 64], u8)> {
         let n = scalars_be.len() / 32;
+        if n == 0 || scalars_be.len() % 32 != 0 || points_xy_be.len() != 64 * n { return Err(Error::InvalidEncoding); }
         let (mut out, mut st) = ([0u8; 64], 0u8);
         let rc = unsafe {
             fec_msm(engine.ctx, Self::CURVE_ID, scalars_be.as_ptr(), points_xy_be.as_ptr(), FEC_PT_AFFINE_XY_BE, n, FEC_OUT_AFFINE_XY_BE,
@@ -172,6 +187,7 @@ pub trait BatchMul: CudaCurve {
     /// SEC1 compressed bytes straight from the GPU (what `CompressedPoint::from_affine` would produce).
     fn batch_mul_compressed(engine: &Engine, points_xy_be: Option<&[u8]>, scalars_be: &[u8]) -> Result<(Vec<u8>, Vec<u8>)> {
         let n = scalars_be.len() / 32;
+        if scalars_be.len() % 32 != 0 || points_xy_be.map_or(false, |p| p.len() != 64 * n) { return Err(Error::InvalidEncoding); }
         let mut out = vec![0u8; 33 * n];
         let mut status = vec![0u8; n];
         let rc = unsafe {
@@ -180,6 +196,23 @@ pub trait BatchMul: CudaCurve {
         };
         if rc != 0 { Err(map_err(rc)) } else { Ok((out, status)) }
     }
+}
+
+/// Signing-side nonce commitment, the fixed-base step of `sign`:
+/// ECDSA `r = x(k G)` (forge-ec-signature/src/ecdsa.rs:108-131), BIP-340 x-only R with the even-y rule (schnorr.rs:372-385),
+/// EdDSA `R = [r mod L]B` from the 64-byte hash value (eddsa.rs:120-131, RFC 8032 5.1.6).
+/// Returns (R records, scalar records, lane status).
+pub fn batch_nonce_commit(engine: &Engine, curve: c_int, mode: c_int, nonces: &[u8]) -> Result<(Vec<u8>, Vec<u8>, Vec<u8>)> {
+    let rec_in = if mode == FEC_NONCE_EDDSA { 64 } else { 32 };
+    if nonces.len() % rec_in != 0 { return Err(Error::InvalidEncoding); }
+    let n = nonces.len() / rec_in;
+    let mut r_point = vec![0u8; n * if mode == FEC_NONCE_ECDSA { 33 } else { 32 }];
+    let mut r_scalar = vec![0u8; n * 32];
+    let mut status = vec![0u8; n];
+    let rc = unsafe {
+        fec_batch_nonce_commit(engine.ctx, curve, mode, nonces.as_ptr(), n, r_point.as_mut_ptr(), r_scalar.as_mut_ptr(), status.as_mut_ptr())
+    };
+    if rc != 0 { Err(map_err(rc)) } else { Ok((r_point, r_scalar, status)) }
 }
 
 impl CudaCurve for forge_ec_curves::secp256k1::Secp256k1 {

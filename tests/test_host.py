@@ -21,6 +21,11 @@ def test_library_exports_every_declared_symbol(fec):
     for sym in declared:
         assert hasattr(lib, sym), f"libforge_ec_cuda.so does not export {sym}"
     assert sorted(fec.EXPORTED_SYMBOLS) == declared
+    # ... and nothing else: the kernels' launchers (namespace fec) stay internal (hidden default visibility)
+    nm = subprocess.run(["nm", "-D", "--defined-only", fec.library_path()], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in nm.splitlines() if len(l.split()) == 3 and l.split()[1] in "TW")
+    assert [s for s in exported if s.startswith("fec_")] == declared
+    assert not [s for s in exported if "3fec" in s], "internal launchers are exported"
 
 
 def test_strerror_and_argument_checks_need_no_device(fec):
