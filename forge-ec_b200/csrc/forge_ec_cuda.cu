@@ -37,6 +37,7 @@ struct Device {
   int id = -1;
   int sms = 0;
   u32* comb[2] = {nullptr, nullptr};  // secp256k1, P-256
+  u32* comb_ct[2] = {nullptr, nullptr};  // the 4-bit combs of the constant-time table form (32 KiB each)
   u32* niels = nullptr;
   cudaStream_t streams[N_PIPE] = {};
   uint8_t* buf_in_a[N_PIPE] = {};   // scalars / seeds / field a
@@ -45,7 +46,11 @@ struct Device {
   uint8_t* buf_st[N_PIPE] = {};
   uint8_t* buf_x[N_PIPE] = {};      // ECDH: the 32-byte shared secrets before key derivation
   bool pipe_ready = false;
+  // pinned staging for callers that pass PAGEABLE host memory (a Rust Vec<u8>, a numpy array): in a, in b, out, x, status per slot
+  uint8_t* stage[N_PIPE] = {};
+  bool stage_ready = false;
 };
+constexpr size_t STAGE_OFF_B = 64, STAGE_OFF_OUT = 128, STAGE_OFF_X = 128 + 66, STAGE_OFF_ST = 128 + 66 + 32, STAGE_BYTES_PER_LANE = 128 + 66 + 32 + 1;
 
 }  // namespace
 
@@ -118,7 +123,11 @@ int device_init(fec_ctx* ctx, Device& d) {
   FEC_CUDA(ctx, build_comb_launch(FEC_SECP256K1, d.streams[0], d.comb[0], bases));
   FEC_CUDA(ctx, build_comb_launch(FEC_P256, d.streams[0], d.comb[1], bases + COMB_WINDOWS * 32));
   FEC_CUDA(ctx, build_niels_launch(d.streams[0], d.niels, bases + COMB_WINDOWS * 64));
-  ctx->launches += 6;
+  for (int c = 0; c < 2; c++) {
+    FEC_CUDA(ctx, cudaMalloc(&d.comb_ct[c], (size_t)CT_TABLE_WORDS * 4));
+    FEC_CUDA(ctx, build_comb_ct_launch(c, d.streams[0], d.comb_ct[c]));
+  }
+  ctx->launches += 8;
   FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[0]));
   cudaFree(bases);
   return FEC_OK;
@@ -138,15 +147,40 @@ int device_pipe_init(fec_ctx* ctx, Device& d) {
   return FEC_OK;
 }
 
+// cudaMemcpyAsync on pageable host memory is staged through the driver's own pinned buffer and BLOCKS the calling thread, so the
+// three-stream pipeline of run_shard degenerates to copy -> compute -> copy (measured: 59.4 -> 35.8 M/s end to end on 2^24 lanes).
+// For such buffers the library stages through its own pinned memory: the host thread copies chunk i+1 in (and chunk i-2 out)
+// while the GPU works on the chunks in between.  FORGE_EC_STAGE=0 disables it (A/B).
+int device_stage_init(fec_ctx* ctx, Device& d) {
+  if (d.stage_ready) return FEC_OK;
+  for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaHostAlloc(&d.stage[s], CHUNK_LANES * STAGE_BYTES_PER_LANE + 256, cudaHostAllocDefault));
+  d.stage_ready = true;
+  return FEC_OK;
+}
+bool is_pageable(const void* p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+bool staging_enabled() {
+  static const bool v = [] { const char* e = getenv("FORGE_EC_STAGE"); return !(e != nullptr && e[0] == '0'); }();
+  return v;
+}
+
 void device_free(Device& d) {
   if (d.id < 0) return;
   cudaSetDevice(d.id);
   for (int s = 0; s < N_PIPE; s++) {
+    if (d.stage[s]) cudaFreeHost(d.stage[s]);
     if (d.streams[s]) cudaStreamSynchronize(d.streams[s]);
     cudaFree(d.buf_in_a[s]); cudaFree(d.buf_in_b[s]); cudaFree(d.buf_out[s]); cudaFree(d.buf_st[s]); cudaFree(d.buf_x[s]);
     if (d.streams[s]) cudaStreamDestroy(d.streams[s]);
   }
-  cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels);
+  cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels); cudaFree(d.comb_ct[0]); cudaFree(d.comb_ct[1]);
 }
 
 
@@ -165,7 +199,8 @@ int launch_mul(fec_ctx* ctx, Device& d, int curve, int sem, const uint8_t* ds, c
     FEC_CUDA(ctx, curve == FEC_SECP256K1 ? quirk_k1_launch(st, ds, dp, n, ofmt, dout, dst) : quirk_p256_launch(st, ds, dp, n, ofmt, dout, dst));
   } else if (dp == nullptr) {
     ctx->launches++;
-    FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
+    if (fixed_ct_table()) FEC_CUDA(ctx, wmul_fixed_ct_launch(curve, d.sms, st, ds, d.comb_ct[curve], n, ofmt, dout, dst));
+    else FEC_CUDA(ctx, wmul_fixed_launch(curve, d.sms, st, ds, d.comb[curve], n, ofmt, dout, dst));
   } else {
     int launches = 0;
     StageEvents se{nullptr, 0, 0}, *sep = nullptr;
@@ -271,17 +306,41 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
   if (rc) return rc;
   FEC_CUDA(ctx, cudaSetDevice(d.id));
   DrainGuard drain(d);  // whatever happens below, no copy into the caller's buffers is in flight when this function returns
+  // pageable caller memory goes through the device's pinned staging slots (see device_stage_init)
+  const bool staged = staging_enabled() && count > 0 &&
+                      (is_pageable(job.in_a) || is_pageable(job.in_b) || is_pageable(job.out) || is_pageable(job.out2) || is_pageable(job.status));
+  if (staged && (rc = device_stage_init(ctx, d)) != FEC_OK) return rc;
+  struct Pending { size_t g0 = 0, m = 0; bool live = false; } pend[N_PIPE];
+  auto flush = [&](int s) {  // a finished chunk's results: staging -> the caller's buffers
+    if (!pend[s].live) return;
+    const size_t g0 = pend[s].g0, m = pend[s].m;
+    memcpy(job.out + g0 * job.rec_out, d.stage[s] + CHUNK_LANES * STAGE_OFF_OUT, m * job.rec_out);
+    if (job.out2) memcpy(job.out2 + g0 * 32, d.stage[s] + CHUNK_LANES * STAGE_OFF_X, m * 32);
+    if (job.status) memcpy(job.status + g0, d.stage[s] + CHUNK_LANES * STAGE_OFF_ST, m);
+    pend[s].live = false;
+  };
   int slot = 0;
   for (size_t off = 0; off < count; off += CHUNK_LANES, slot = (slot + 1) % N_PIPE) {
     const size_t m = (count - off) < CHUNK_LANES ? (count - off) : CHUNK_LANES;
     const size_t g0 = first + off;
     cudaStream_t st = d.streams[slot];
     FEC_CUDA(ctx, cudaStreamSynchronize(st));  // slot's previous chunk fully drained
+    const uint8_t* ha = job.in_a + g0 * job.rec_a;
+    const uint8_t* hb = job.in_b != nullptr ? job.in_b + g0 * job.rec_b : nullptr;
+    if (staged) {
+      flush(slot);
+      memcpy(d.stage[slot], ha, m * job.rec_a);
+      ha = d.stage[slot];
+      if (hb != nullptr) {
+        memcpy(d.stage[slot] + CHUNK_LANES * STAGE_OFF_B, hb, m * job.rec_b);
+        hb = d.stage[slot] + CHUNK_LANES * STAGE_OFF_B;
+      }
+    }
     uint8_t* da = job.rec_a > 32 ? d.buf_in_b[slot] : d.buf_in_a[slot];  // 64-byte input records live in the larger buffer
-    FEC_CUDA(ctx, cudaMemcpyAsync(da, job.in_a + g0 * job.rec_a, m * job.rec_a, cudaMemcpyHostToDevice, st));
+    FEC_CUDA(ctx, cudaMemcpyAsync(da, ha, m * job.rec_a, cudaMemcpyHostToDevice, st));
     const uint8_t* db = nullptr;
-    if (job.in_b != nullptr) {
-      FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_b[slot], job.in_b + g0 * job.rec_b, m * job.rec_b, cudaMemcpyHostToDevice, st));
+    if (hb != nullptr) {
+      FEC_CUDA(ctx, cudaMemcpyAsync(d.buf_in_b[slot], hb, m * job.rec_b, cudaMemcpyHostToDevice, st));
       db = d.buf_in_b[slot];
     }
     if (job.kind == 0)
@@ -298,11 +357,19 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
     else
       rc = launch_ed(ctx, d, job.sem, d.buf_in_a[slot], job.is_seed, m, d.buf_out[slot], st);
     if (rc) return rc;
-    FEC_CUDA(ctx, cudaMemcpyAsync(job.out + g0 * job.rec_out, d.buf_out[slot], m * job.rec_out, cudaMemcpyDeviceToHost, st));
-    if (job.out2) FEC_CUDA(ctx, cudaMemcpyAsync(job.out2 + g0 * 32, d.buf_x[slot], m * 32, cudaMemcpyDeviceToHost, st));
-    if (job.status) FEC_CUDA(ctx, cudaMemcpyAsync(job.status + g0, d.buf_st[slot], m, cudaMemcpyDeviceToHost, st));
+    uint8_t* ho = staged ? d.stage[slot] + CHUNK_LANES * STAGE_OFF_OUT : job.out + g0 * job.rec_out;
+    uint8_t* hx = staged ? d.stage[slot] + CHUNK_LANES * STAGE_OFF_X : (job.out2 ? job.out2 + g0 * 32 : nullptr);
+    uint8_t* hs = staged ? d.stage[slot] + CHUNK_LANES * STAGE_OFF_ST : (job.status ? job.status + g0 : nullptr);
+    FEC_CUDA(ctx, cudaMemcpyAsync(ho, d.buf_out[slot], m * job.rec_out, cudaMemcpyDeviceToHost, st));
+    if (job.out2) FEC_CUDA(ctx, cudaMemcpyAsync(hx, d.buf_x[slot], m * 32, cudaMemcpyDeviceToHost, st));
+    if (job.status) FEC_CUDA(ctx, cudaMemcpyAsync(hs, d.buf_st[slot], m, cudaMemcpyDeviceToHost, st));
+    if (staged) { pend[slot].g0 = g0; pend[slot].m = m; pend[slot].live = true; }
   }
-  for (int s = 0; s < N_PIPE; s++) FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[s]));
+  for (int k = 0; k < N_PIPE; k++) {  // oldest slot first
+    const int s = (slot + k) % N_PIPE;
+    FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[s]));
+    if (staged) flush(s);
+  }
   return FEC_OK;
 }
 

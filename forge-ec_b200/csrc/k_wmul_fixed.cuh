@@ -1,5 +1,6 @@
 // k_wmul_fixed.cuh -- fixed-base kernel template and comb-table builder; instantiated per curve
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace fec {
@@ -15,7 +16,8 @@ namespace fec {
 constexpr int FIX_DEFER = 16;
 constexpr int FIX_SLOT_WORDS = 36;  // X, Y, Z, prefix (8 words each) + status + padding
 
-template <class C>
+// CT = true: the constant-time table form (ScanComb, lanes.cuh): comb_g is the 32 KiB 4-bit comb, copied to shared memory first
+template <class C, bool CT = false>
 __global__ void __launch_bounds__(FIX_THREADS, FIX_BLOCKS_PER_SM)
 k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g, size_t n, int out_fmt,
              uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
@@ -23,7 +25,13 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
   extern __shared__ __align__(16) u32 smem[];
   const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* io = reinterpret_cast<uint8_t*>(smem) + warp * FIX_IO_BYTES_PER_WARP;
-  GlobalComb comb{comb_g};
+  typename std::conditional<CT, ScanComb, GlobalComb>::type comb{comb_g};
+  if (CT) {
+    u32* tab = smem + FIX_SMEM_BYTES / 4;
+    for (int i = threadIdx.x; i < CT_TABLE_WORDS; i += FIX_THREADS) tab[i] = comb_g[i];
+    __syncthreads();
+    comb.base = tab;
+  }
   const int osz = out_size(out_fmt);
   const size_t ntiles = (n + 31) / 32;
   const size_t gwarp = (size_t)blockIdx.x * (FIX_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (FIX_THREADS / 32);
@@ -44,7 +52,8 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
       if (live) load_rec32_be(k, scalars + lane * 32);
       scalar_prepare<C>(K, negm, st, k);
       Jac Q;
-      wmul_fixed_core<C>(Q, K, comb);
+      if (CT) wmul_fixed_core<C, decltype(comb), CT_W>(Q, K, comb);
+      else wmul_fixed_core<C>(Q, K, comb);
       const u32 zz = F::is_zero(Q.Z);
       st |= (st == 0u ? zz & LANE_INFINITY : 0u);
       if (status != nullptr && live) status[lane] = (uint8_t)st;
@@ -118,15 +127,47 @@ __global__ void __launch_bounds__(128) k_build_comb(u32* __restrict__ comb_g, co
   for (int w = 0; w < 8; w++) { o[w] = x[w]; o[8 + w] = y[w]; }
 }
 
+// the 4-bit comb of the constant-time form: one thread per entry (i, j) = (2j+1) 2^(4i) G, affine (its own Fermat inversion)
+template <class C>
+__global__ void __launch_bounds__(128) k_build_comb_ct(u32* __restrict__ comb4) {
+  typedef typename C::F F;
+  const int e = blockIdx.x * 128 + threadIdx.x;  // the grid covers the 512 entries exactly
+  const int i = e / CT_ENTRIES, j = e % CT_ENTRIES;
+  u32 bx[8], by[8];
+  comb_base<C, CT_W>(bx, by, i);
+  Jac R;
+  comb_entry_jac<C>(R, bx, by, j);
+  u32 zi[8], x[8], y[8];
+  F::inv(zi, R.Z);
+  jac_to_affine<C>(x, y, R, zi, 0u);
+  u32* o = comb4 + (size_t)e * 16;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { o[w] = x[w]; o[8 + w] = y[w]; }
+}
+constexpr int FIX_CT_SMEM_BYTES = FIX_SMEM_BYTES + CT_TABLE_WORDS * 4;
 template <class C>
 cudaError_t wmul_fixed_setup_t() {
-  return cudaFuncSetAttribute(k_wmul_fixed<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIX_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(k_wmul_fixed<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIX_CT_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_wmul_fixed<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIX_SMEM_BYTES);
 }
 template <class C>
 cudaError_t wmul_fixed_launch_t(int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n, int out_fmt,
                                 uint8_t* out, uint8_t* status) {
   const int g = persistent_grid(sms, FIX_BLOCKS_PER_SM, (n + FIX_THREADS - 1) / FIX_THREADS);
-  k_wmul_fixed<C><<<g, FIX_THREADS, FIX_SMEM_BYTES, st>>>(scalars, comb, n, out_fmt, out, status);
+  k_wmul_fixed<C, false><<<g, FIX_THREADS, FIX_SMEM_BYTES, st>>>(scalars, comb, n, out_fmt, out, status);
+  return cudaGetLastError();
+}
+template <class C>
+cudaError_t wmul_fixed_ct_launch_t(int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb4, size_t n, int out_fmt,
+                                   uint8_t* out, uint8_t* status) {
+  const int g = persistent_grid(sms, FIX_BLOCKS_PER_SM, (n + FIX_THREADS - 1) / FIX_THREADS);
+  k_wmul_fixed<C, true><<<g, FIX_THREADS, FIX_CT_SMEM_BYTES, st>>>(scalars, comb4, n, out_fmt, out, status);
+  return cudaGetLastError();
+}
+template <class C>
+cudaError_t build_comb_ct_launch_t(cudaStream_t st, u32* comb4) {
+  k_build_comb_ct<C><<<CT_WINDOWS * CT_ENTRIES / 128, 128, 0, st>>>(comb4);
   return cudaGetLastError();
 }
 template <class C>
@@ -145,5 +186,9 @@ cudaError_t wmul_fixed_vm_launch_k1(int, cudaStream_t, const uint8_t*, const u32
 cudaError_t wmul_fixed_vm_launch_p256(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
 cudaError_t build_comb_launch_k1(cudaStream_t, u32*, u32*);
 cudaError_t build_comb_launch_p256(cudaStream_t, u32*, u32*);
+cudaError_t wmul_fixed_ct_launch_k1(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
+cudaError_t wmul_fixed_ct_launch_p256(int, cudaStream_t, const uint8_t*, const u32*, size_t, int, uint8_t*, uint8_t*);
+cudaError_t build_comb_ct_launch_k1(cudaStream_t, u32*);
+cudaError_t build_comb_ct_launch_p256(cudaStream_t, u32*);
 
 }  // namespace fec

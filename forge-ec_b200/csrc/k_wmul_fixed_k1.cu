@@ -6,6 +6,24 @@ cudaError_t wmul_fixed_launch_k1(int sms, cudaStream_t st, const uint8_t* s, con
   return wmul_fixed_launch_t<CurveK1>(sms, st, s, comb, n, of, o, status);
 }
 cudaError_t build_comb_launch_k1(cudaStream_t st, u32* comb, u32* bases) { return build_comb_launch_t<CurveK1>(st, comb, bases); }
+cudaError_t wmul_fixed_ct_launch_k1(int sms, cudaStream_t st, const uint8_t* s, const u32* comb4, size_t n, int of, uint8_t* o,
+                                    uint8_t* status) {
+  return wmul_fixed_ct_launch_t<CurveK1>(sms, st, s, comb4, n, of, o, status);
+}
+cudaError_t build_comb_ct_launch_k1(cudaStream_t st, u32* comb4) { return build_comb_ct_launch_t<CurveK1>(st, comb4); }
+// FORGE_EC_CT_TABLE=1: the constant-time table form of k*G (4-bit comb in shared memory, masked scans): see lanes.cuh, DESIGN.md
+bool fixed_ct_table() {
+  static const bool v = [] { const char* e = getenv("FORGE_EC_CT_TABLE"); return e != nullptr && e[0] == '1'; }();
+  return v;
+}
+cudaError_t wmul_fixed_ct_launch(int curve, int sms, cudaStream_t st, const uint8_t* s, const u32* comb4, size_t n, int of, uint8_t* o,
+                                 uint8_t* status) {
+  return curve == FEC_SECP256K1 ? wmul_fixed_ct_launch_k1(sms, st, s, comb4, n, of, o, status)
+                                : wmul_fixed_ct_launch_p256(sms, st, s, comb4, n, of, o, status);
+}
+cudaError_t build_comb_ct_launch(int curve, cudaStream_t st, u32* comb4) {
+  return curve == FEC_SECP256K1 ? build_comb_ct_launch_k1(st, comb4) : build_comb_ct_launch_p256(st, comb4);
+}
 cudaError_t wmul_fixed_setup() {
   cudaError_t e = wmul_fixed_setup_k1();
   if (e == cudaSuccess) e = wmul_fixed_vm_setup_k1();

@@ -206,6 +206,12 @@ cudaError_t quirk_p256_launch(cudaStream_t st, const uint8_t* scalars, const uin
 cudaError_t wmul_fixed_setup();
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb, size_t n,
                               int out_fmt, uint8_t* out, uint8_t* status);
+// constant-time table form of k*G (FORGE_EC_CT_TABLE=1): a 64 x 8 comb of odd multiples (32 KiB per curve) in shared memory,
+// every addend read by a masked scan of its window (lanes.cuh: ScanComb)
+bool fixed_ct_table();
+cudaError_t build_comb_ct_launch(int curve, cudaStream_t st, u32* comb4 /* CT_TABLE_WORDS words */);
+cudaError_t wmul_fixed_ct_launch(int curve, int sms, cudaStream_t st, const uint8_t* scalars, const u32* comb4, size_t n, int out_fmt,
+                                 uint8_t* out, uint8_t* status);
 cudaError_t x25519_launch(int sms, cudaStream_t st, const uint8_t* scalars, const uint8_t* us, size_t n, uint8_t* out);
 // the same ladder on the accumulator machine (k_x25519_vm.cu); FORGE_EC_X_IMPL=regs|vm forces one form (measurements)
 cudaError_t x25519_vm_setup();

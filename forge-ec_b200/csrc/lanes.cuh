@@ -205,22 +205,23 @@ FEC_DEV void next_digit_w(u32 K[8], u32& idx, u32& sgn) {
   sgn = (u >> (W - 1)) - 1u;
   idx = (u ^ sgn) & ((1u << (W - 1)) - 1u);
 }
-template <class C, class Comb>
+template <class C, class Comb, int W = COMB_W>
 FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
   typedef typename C::F F;
+  constexpr int WINDOWS = 256 / W;
   u32 idx, sgn, nx[8], ny2[8];
-  next_digit_w<COMB_W>(K, idx, sgn);  // top digit: always positive
-  comb(COMB_WINDOWS - 1, idx, Q.X, Q.Y);
+  next_digit_w<W>(K, idx, sgn);  // top digit: always positive
+  comb(WINDOWS - 1, idx, Q.X, Q.Y);
   F::one(Q.Z);
-  next_digit_w<COMB_W>(K, idx, sgn);
-  comb(COMB_WINDOWS - 2, idx, nx, ny2);
+  next_digit_w<W>(K, idx, sgn);
+  comb(WINDOWS - 2, idx, nx, ny2);
 #pragma unroll 1
-  for (int i = COMB_WINDOWS - 2; i >= 0; i--) {
+  for (int i = WINDOWS - 2; i >= 0; i--) {
     u32 tx[8], ty[8], ny[8];
     const u32 sg = sgn;
     copy8(tx, nx); copy8(ty, ny2);
     if (i > 0) {  // fetch the next addend while this addition runs
-      next_digit_w<COMB_W>(K, idx, sgn);
+      next_digit_w<W>(K, idx, sgn);
       comb(i - 1, idx, nx, ny2);
     }
     F::neg(ny, ty);
@@ -228,6 +229,28 @@ FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
     jac_madd_safe<C>(Q, tx, ty);
   }
 }
+// The constant-time form of the same (FORGE_EC_CT_TABLE=1): 4-bit windows, 64 x 8 odd multiples = 32 KiB per curve, staged in
+// SHARED memory, and an addend is read by scanning ALL 8 entries of its window under masks -- the addresses a lane touches do
+// not depend on its scalar (the 16-bit-window table is indexed by secret digits: no divergence, but a data-dependent address
+// stream into the L2).  63 additions instead of 15.
+constexpr int CT_W = 4;
+constexpr int CT_WINDOWS = 256 / CT_W;
+constexpr int CT_ENTRIES = 1 << (CT_W - 1);
+constexpr int CT_TABLE_WORDS = CT_WINDOWS * CT_ENTRIES * 16;
+struct ScanComb {
+  const u32* base;  // shared memory: entry (i, j) at word (i * 8 + j) * 16
+  FEC_DEV void operator()(int i, u32 idx, u32 x[8], u32 y[8]) const {
+#pragma unroll
+    for (int w = 0; w < 8; w++) { x[w] = 0u; y[w] = 0u; }
+#pragma unroll
+    for (u32 j = 0; j < (u32)CT_ENTRIES; j++) {
+      const u32* e = base + ((size_t)i * CT_ENTRIES + j) * 16;  // the same address in every lane: a broadcast read
+      const u32 m = (j == idx) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { x[w] |= e[w] & m; y[w] |= e[8 + w] & m; }
+    }
+  }
+};
 
 // -------------------------------------------------------------------------------------
 // secp256k1 only: GLV endomorphism phi(x,y) = (beta x, y) = lambda (x,y).
@@ -694,13 +717,13 @@ FEC_DEV void ed_encode(u32 out_le[8], const EdExt& Q, const u32 zi[8]) {
 // comb table entries (context set-up only; control flow depends on the public indices i, j)
 // -------------------------------------------------------------------------------------
 // window base 2^(W i) G, affine (one Fermat inversion; 16 of them per curve)
-template <class C>
+template <class C, int W = COMB_W>
 FEC_DEV void comb_base(u32 bx[8], u32 by[8], int i) {
   typedef typename C::F F;
   Jac R;
   C::G(R.X, R.Y);
   F::one(R.Z);
-  for (int d = 0; d < COMB_W * i; d++) jac_dbl<C>(R);
+  for (int d = 0; d < W * i; d++) jac_dbl<C>(R);
   u32 zi[8];
   F::inv(zi, R.Z);
   jac_to_affine<C>(bx, by, R, zi, 0u);

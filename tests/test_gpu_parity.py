@@ -693,7 +693,8 @@ def test_every_kernel_form_returns_the_same_bytes(tmp_path):
     script.write_text(_AB_CHILD)
     digests = {}
     for name, env in (("default", {}), ("var_mono", {"FORGE_EC_VAR_IMPL": "mono"}), ("fixed_regs", {"FORGE_EC_FIXED_IMPL": "regs"}),
-                      ("fixed_vm", {"FORGE_EC_FIXED_IMPL": "vm"}), ("x_vm", {"FORGE_EC_X_IMPL": "vm"})):
+                      ("fixed_vm", {"FORGE_EC_FIXED_IMPL": "vm"}), ("x_vm", {"FORGE_EC_X_IMPL": "vm"}),
+                      ("fixed_ct_table", {"FORGE_EC_CT_TABLE": "1"}), ("ladder_regs", {"FORGE_EC_GLV_LADDER": "regs"})):
         e = dict(os.environ)
         e.update(env)
         r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, env=e)
