@@ -40,7 +40,9 @@ static int fixed_impl() {
 cudaError_t wmul_fixed_launch(int curve, int sms, cudaStream_t st, const uint8_t* s, const u32* comb, size_t n, int of, uint8_t* o,
                               uint8_t* status) {
   const int impl = fixed_impl();
-  const bool vm = impl == 2 || (impl == 0 && curve == FEC_P256);
+  // (r2) below 2^17 lanes the register-resident kernel also wins for P-256: a batch that does not fill the device is bound by
+  // the latency of a lane, not by a pipe (2^14 lanes: 135 against 113 M/s, 2^16: 266 against 246, 2^18: 367 against 378)
+  const bool vm = impl == 2 || (impl == 0 && curve == FEC_P256 && n >= (size_t(1) << 17));
   if (vm)
     return curve == FEC_SECP256K1 ? wmul_fixed_vm_launch_k1(sms, st, s, comb, n, of, o, status)
                                   : wmul_fixed_vm_launch_p256(sms, st, s, comb, n, of, o, status);

@@ -189,6 +189,27 @@ def test_field_bench_matches_model(engine, pm, prime, op):
             assert int.from_bytes(out[i].tobytes(), "little") == pm.field_bench_model(prime, op, iters, ai, bi), (i, iters)
 
 
+def test_p256_large_operand_field_kats_on_gpu(engine, fec, pm):
+    """the reference's own large-operand field values (p256.rs:2454-2480: Gx^2, Gx^3, 3 Gx, Gy^2 as u64 limbs) through the GPU
+    field kernels -- the same constants tests/test_oracle.py pins both oracles to"""
+    val = lambda l: sum(v << (64 * i) for i, v in enumerate(l))
+    X2 = val([12074202155401100, 3726334282074508753, 9331909631644438744, 11022199779588240050])
+    X3 = val([6985818112209442057, 5293983511093485517, 13285487596276262425, 4350650246863171228])
+    TX = val([15988812018543642563, 7280764249650076386, 16876875322344915671, 4703857913423513302])
+    Y2 = val([13753198298469232017, 5299206390010787296, 9373276401007028734, 6187767046927055789])
+    c = pm.CURVES[1]
+    le = lambda v: np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+    a = np.stack([le(c.gx), le(c.gx), le(3), le(c.gy), le(X2)])
+    b = np.stack([le(c.gx), le(c.gx), le(c.gx), le(c.gy), le(c.gx)])
+    mul1, _ = engine.field_bench(fec.PRIME_P256, fec.FIELD_MUL, a, b, 1)
+    mul2, _ = engine.field_bench(fec.PRIME_P256, fec.FIELD_MUL, a, b, 2)
+    sqr1, _ = engine.field_bench(fec.PRIME_P256, fec.FIELD_SQR, a, b, 1)
+    g = lambda o, i: int.from_bytes(o[i].tobytes(), "little")
+    assert g(mul1, 0) == X2 and g(sqr1, 0) == X2 and g(mul2, 1) == X3 and g(mul1, 4) == X3
+    assert g(mul1, 2) == TX and g(mul1, 3) == Y2 and g(sqr1, 3) == Y2
+    assert (X3 - TX + c.b) % c.p == Y2
+
+
 def test_ragged_and_empty(engine, pm):
     """n = 0, n = 1, n not a multiple of any tile size; outputs beyond n untouched."""
     out, st = engine.batch_mul(0, np.empty(0, dtype=np.uint8), None, n=0)
