@@ -237,8 +237,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group for the one wait that must not occupy the GPUs: while rank 0 drives all N devices from its own process,
+        # an NCCL barrier kernel spinning on the other ranks' GPUs would time-slice with rank 0's work there
+        cpu_pg = dist.new_group(backend="gloo")
 
     def barrier():
         if world > 1:
@@ -534,6 +538,7 @@ def main():
     single = None
     if world > 1 and not args.no_single_process and not args.no_e2e:
         barrier()
+        torch.cuda.synchronize()
         if rank == 0:
             tot = min(n, 1 << 24)
             with fec.Engine(devices=list(range(world))) as many:
@@ -558,6 +563,7 @@ def main():
                           "matches_per_rank_results": ok}
                 if not ok:
                     failures.append("e2e_single_process: the multi-device context returned different bytes")
+        dist.barrier(group=cpu_pg)  # the other ranks wait here on the CPU (gloo), their GPUs idle
         barrier()
 
     if rank != 0:

@@ -351,7 +351,11 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
                        d.buf_out[slot], d.buf_st[slot], d.buf_x[slot], st);
     else if (job.kind == 1)
       rc = launch_x25519(ctx, d, job.sem, d.buf_in_a[slot], db, m, d.buf_out[slot], st);
-    else if (job.kind == 4)  // R -> buf_out, r -> buf_x; the affine R of the Weierstrass modes passes through buf_in_b (unused there)
+    else if (job.kind == 5) {  // point decoding: the records arrive in buf_in_b (33 or 64 B per lane)
+      ctx->launches++;
+      const cudaError_t e = point_decode_launch(job.curve, st, da, job.pfmt, m, job.ofmt, d.buf_out[slot], job.status ? d.buf_st[slot] : nullptr);
+      if (e != cudaSuccess) { set_err(ctx, __FILE__, __LINE__, "point_decode_launch", cudaGetErrorString(e)); rc = FEC_ERR_CUDA; }
+    } else if (job.kind == 4)  // R -> buf_out, r -> buf_x; the affine R of the Weierstrass modes passes through buf_in_b (unused there)
       rc = launch_nonce(ctx, d, job.curve, job.mode, da, m, d.buf_out[slot], d.buf_x[slot], d.buf_st[slot], d.buf_in_b[slot],
                         d.buf_st[slot], st);
     else
@@ -681,6 +685,31 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
   FEC_CUDA(ctx, cudaMemcpyAsync(&hst, dres + 80, 1, cudaMemcpyDeviceToHost, st));
   FEC_CUDA(ctx, cudaStreamSynchronize(st));
   if (status) *status = hst;
+  return FEC_OK;
+}
+
+int fec_batch_point_decode(fec_ctx* ctx, fec_curve curve, const uint8_t* points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt,
+                           uint8_t* out, uint8_t* status) {
+  if (ctx == nullptr || (n > 0 && (points == nullptr || out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  // the records travel as "input a" of the pipeline; 33- and 64-byte records use the larger device buffer (rec_a > 32)
+  HostJob job{5, (int)curve, FEC_SEM_STD, (int)points_fmt, (int)out_fmt, 0, points, (size_t)(points_fmt == FEC_PT_SEC1_COMPRESSED ? 33 : 64),
+              nullptr, 0, out, (size_t)out_size(out_fmt), status};
+  return run_host_job(ctx, job, n);
+}
+int fec_batch_point_decode_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_points, fec_points_fmt points_fmt, size_t n,
+                               fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream) {
+  Device* d = dev_at(ctx, dev_index);
+  if (d == nullptr || (n > 0 && (d_points == nullptr || d_out == nullptr))) return FEC_ERR_INVALID_ARG;
+  if ((int)curve < 0 || (int)curve > 1 || (int)out_fmt < 0 || (int)out_fmt > 4 || (int)points_fmt < 0 || (int)points_fmt > 1)
+    return FEC_ERR_INVALID_ARG;
+  if (!aligned16(d_points) || !aligned16(d_out)) return FEC_ERR_INVALID_ARG;
+  if (n == 0) return FEC_OK;
+  DeviceGuard restore;
+  FEC_CUDA(ctx, cudaSetDevice(d->id));
+  ctx->launches++;
+  FEC_CUDA(ctx, point_decode_launch((int)curve, (cudaStream_t)stream, d_points, (int)points_fmt, n, (int)out_fmt, d_out, d_status));
   return FEC_OK;
 }
 

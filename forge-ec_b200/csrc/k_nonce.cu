@@ -113,6 +113,52 @@ k_sc_reduce64(const uint8_t* __restrict__ in64, size_t n, uint8_t* __restrict__ 
   store_rec32_le(out_le + lane * 32, r);
 }
 
+// Standalone point decoding / validation (CompressedPoint::to_affine, forge-ec-encoding/src/point.rs:70-144, and
+// Curve::validate_point, forge-ec-core/src/lib.rs:905-923 -- on these cofactor-1 curves "on the curve" is the whole check):
+// n x {33 B SEC1 compressed | 64 B X || Y} -> n records of out_fmt + status (0 valid, 2 rejected, 3 the identity record).
+template <class C>
+__global__ void __launch_bounds__(NONCE_THREADS)
+k_point_decode(const uint8_t* __restrict__ points, int points_fmt, size_t n, int out_fmt, uint8_t* __restrict__ out,
+               uint8_t* __restrict__ status) {
+  typedef typename C::F F;
+  __shared__ __align__(16) uint8_t in_all[(NONCE_THREADS / 32) * 33 * 32 + 16];
+  __shared__ __align__(16) uint8_t out_all[(NONCE_THREADS / 32) * 65 * 32 + 16];
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* in = in_all + warp * (33 * 32);
+  uint8_t* io = out_all + warp * (65 * 32);
+  const size_t first = ((size_t)blockIdx.x * (NONCE_THREADS / 32) + warp) * 32;
+  if (first >= n) return;  // warp-uniform
+  const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+  const bool live = (int)lane_in_warp < cnt_lanes;
+  const size_t lane = first + (live ? lane_in_warp : 0u);
+  u32 px[8], py[8], ok, idn = 0u;
+  if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
+    warp_copy(in, points + first * 33, (size_t)cnt_lanes * 33);
+    __syncwarp();
+    ok = sec1_decompress_id<C>(px, py, in + (live ? lane_in_warp : 0u) * 33, idn);
+  } else {
+    load_rec32_be(px, points + lane * 64);
+    load_rec32_be(py, points + lane * 64 + 32);
+    ok = affine_from_plain_id<C>(px, py, idn);
+  }
+  const u32 st = lane_status(0u, ok, idn);
+  u32 x[8], y[8];
+  F::to_plain(x, px);
+  F::to_plain(y, py);
+  const int osz = out_size(out_fmt);
+  if (live) sec1_encode(io + lane_in_warp * osz, out_fmt, x, y, st != 0u ? 0xFFFFFFFFu : 0u);
+  __syncwarp();
+  warp_copy(out + first * osz, io, (size_t)cnt_lanes * osz);
+  if (live && status != nullptr) status[lane] = (uint8_t)st;
+}
+
+cudaError_t point_decode_launch(int curve, cudaStream_t st, const uint8_t* points, int points_fmt, size_t n, int out_fmt, uint8_t* out,
+                                uint8_t* status) {
+  const unsigned g = (unsigned)((n + NONCE_THREADS - 1) / NONCE_THREADS);
+  if (curve == FEC_SECP256K1) k_point_decode<CurveK1><<<g, NONCE_THREADS, 0, st>>>(points, points_fmt, n, out_fmt, out, status);
+  else k_point_decode<CurveP256><<<g, NONCE_THREADS, 0, st>>>(points, points_fmt, n, out_fmt, out, status);
+  return cudaGetLastError();
+}
 cudaError_t nonce_tail_launch(int curve, int mode, cudaStream_t st, const uint8_t* xy, const uint8_t* k_be, const uint8_t* st_in, size_t n,
                               uint8_t* out_R, uint8_t* out_r, uint8_t* status) {
   const unsigned g = (unsigned)((n + NONCE_THREADS - 1) / NONCE_THREADS);

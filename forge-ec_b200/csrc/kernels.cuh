@@ -197,6 +197,9 @@ cudaError_t msm_pippenger_launch(int curve, cudaStream_t st, const uint8_t* scal
 cudaError_t nonce_tail_launch(int curve, int mode, cudaStream_t st, const uint8_t* xy, const uint8_t* k_be, const uint8_t* st_in, size_t n,
                               uint8_t* out_R, uint8_t* out_r, uint8_t* status);
 cudaError_t sc_reduce64_launch(cudaStream_t st, const uint8_t* in64, size_t n, uint8_t* out_le);
+// standalone SEC1 decoding + curve membership (k_nonce.cu)
+cudaError_t point_decode_launch(int curve, cudaStream_t st, const uint8_t* points, int points_fmt, size_t n, int out_fmt, uint8_t* out,
+                                uint8_t* status);
 cudaError_t quirk_k1_launch(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, size_t n, int out_fmt, uint8_t* out,
                             uint8_t* status);
 cudaError_t quirk_ed25519_launch(cudaStream_t st, const uint8_t* seeds, size_t n, uint8_t* out);

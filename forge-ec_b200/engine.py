@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "fec_imad_peak", "fec_synth_dev", "fec_shard_range", "fec_ctx_stage_timing", "fec_ctx_stage_ms",
     "fec_batch_ecdh", "fec_batch_ecdh_dev", "fec_msm", "fec_msm_dev", "fec_batch_x25519_sem", "fec_batch_x25519_sem_dev",
     "fec_batch_ed25519_pubkey_sem", "fec_batch_ed25519_pubkey_sem_dev", "fec_batch_nonce_commit", "fec_batch_nonce_commit_dev",
+    "fec_batch_point_decode", "fec_batch_point_decode_dev",
 )
 
 
@@ -109,6 +110,10 @@ def load_library() -> ctypes.CDLL:
     lib.fec_msm.restype = ip
     lib.fec_msm_dev.argtypes = [vp, ip, ip, u8, u8, ip, sz, ip, u8, u8, vp]
     lib.fec_msm_dev.restype = ip
+    lib.fec_batch_point_decode.argtypes = [vp, ip, u8, ip, sz, ip, u8, u8]
+    lib.fec_batch_point_decode.restype = ip
+    lib.fec_batch_point_decode_dev.argtypes = [vp, ip, ip, u8, ip, sz, ip, u8, u8, vp]
+    lib.fec_batch_point_decode_dev.restype = ip
     lib.fec_batch_nonce_commit.argtypes = [vp, ip, ip, u8, sz, u8, u8, u8]
     lib.fec_batch_nonce_commit.restype = ip
     lib.fec_batch_nonce_commit_dev.argtypes = [vp, ip, ip, ip, u8, sz, u8, u8, u8, vp]
@@ -268,6 +273,22 @@ class Engine:
                 stream: int = 0, dev_index: int = 0):
         self._check(self._lib.fec_msm_dev(self._ctx, dev_index, curve, _ptr(d_scalars), _ptr(d_points), points_fmt, n, out_fmt,
                                           _ptr(d_out), _ptr(d_status), stream))
+
+    def batch_point_decode(self, curve: int, points, *, n: Optional[int] = None, points_fmt: int = PT_SEC1_COMPRESSED,
+                           out_fmt: int = OUT_AFFINE_XY_BE):
+        """SEC1 decoding / curve-membership validation of n points, re-encoded in out_fmt.  Returns (out[n, rec], status[n])."""
+        if n is None:
+            n = (points.nbytes if isinstance(points, np.ndarray) else len(points)) // PT_SIZE[points_fmt]
+        p = _host_in(points, n, PT_SIZE[points_fmt], "points")
+        out = np.empty((n, OUT_SIZE[out_fmt]), dtype=np.uint8)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.fec_batch_point_decode(self._ctx, curve, _ptr(p), points_fmt, n, out_fmt, _ptr(out), _ptr(st)))
+        return out, st
+
+    def batch_point_decode_dev(self, curve: int, d_points, n: int, d_out, d_status=None, *, points_fmt: int = PT_SEC1_COMPRESSED,
+                               out_fmt: int = OUT_AFFINE_XY_BE, stream: int = 0, dev_index: int = 0):
+        self._check(self._lib.fec_batch_point_decode_dev(self._ctx, dev_index, curve, _ptr(d_points), points_fmt, n, out_fmt, _ptr(d_out),
+                                                         _ptr(d_status), stream))
 
     def batch_nonce_commit(self, curve: int, mode: int, nonces, *, n: Optional[int] = None):
         """Signing-side nonce commitment (ECDSA r = x(k G), BIP-340 even-y rule, EdDSA [r mod L]B).

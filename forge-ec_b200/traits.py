@@ -127,6 +127,16 @@ class _WeierstrassCurve:
             raise ValueError("PointNotOnCurve")
         return AffinePoint(rec, st == _e.LANE_INFINITY)
 
+    @classmethod
+    def batch_decode(cls, records: Sequence[bytes], engine: Optional[_e.Engine] = None):
+        """CompressedPoint::to_affine for a batch of 33-byte SEC1 records (forge-ec-encoding/src/point.rs:70-144), validated as
+        Curve::validate_point does (forge-ec-core/src/lib.rs:905-923).  Raises ValueError("InvalidEncoding") for a rejected record."""
+        eng = engine or default_engine()
+        out, st = eng.batch_point_decode(cls.CURVE_ID, np.frombuffer(b"".join(records), dtype=np.uint8), n=len(records))
+        if np.any(st == _e.LANE_POINT_INVALID):
+            raise ValueError("InvalidEncoding")
+        return [AffinePoint(out[i].tobytes(), bool(st[i] == _e.LANE_INFINITY)) for i in range(len(records))]
+
     # ---- KeyExchange (secp256k1.rs:1843-1906, p256.rs:2278-2345) ------------------------------------------
     KDF = _e.KDF_HKDF_SHA256
 

@@ -136,6 +136,20 @@ struct WeierstrassCurve {
     return r;
   }
   static AffinePoint generator(Engine& e) { return multiply(e, nullptr, Scalar::from_u64(1)); }
+  // CompressedPoint::to_affine + Curve::validate_point for a batch of 33-byte SEC1 records (point.rs:70-144, lib.rs:905-923)
+  static std::vector<AffinePoint> batch_decode(Engine& e, const std::vector<std::array<uint8_t, 33>>& records) {
+    const size_t n = records.size();
+    std::vector<uint8_t> out(n * 64), st(n);
+    std::vector<AffinePoint> r(n);
+    if (n == 0) return r;
+    check(fec_batch_point_decode(e.ctx(), C, records[0].data(), FEC_PT_SEC1_COMPRESSED, n, FEC_OUT_AFFINE_XY_BE, out.data(), st.data()),
+          "fec_batch_point_decode");
+    for (size_t i = 0; i < n; i++) {
+      if (st[i] == FEC_LANE_POINT_INVALID) throw Error(ErrorKind::InvalidEncoding, "batch_decode: not a point of the curve");
+      if (st[i] == FEC_LANE_OK) r[i] = AffinePoint::from_xy(&out[i * 64]);
+    }
+    return r;
+  }
   // Curve::multiply + to_affine (lib.rs:820-832), one lane
   static AffinePoint multiply(Engine& e, const AffinePoint* point, const Scalar& k) {
     if (point == nullptr) return batch_mul(e, nullptr, {k})[0];

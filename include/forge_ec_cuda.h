@@ -17,6 +17,7 @@
  *                                                                   point.rs:70-144; forge-ec-core/src/lib.rs:905-923
  *   fec_batch_x25519         n x   x25519(scalar, u)             curve25519.rs:1624-1716  (RFC 7748)
  *   fec_batch_ed25519_pubkey n x   Ed25519Signature::derive_public_key   forge-ec-signature/src/eddsa.rs:450-509 (RFC 8032 5.1.5)
+ *   fec_batch_point_decode   n x   CompressedPoint::to_affine / Curve::validate_point   point.rs:70-144; forge-ec-core/src/lib.rs:905-923
  *   fec_batch_nonce_commit   n x   the R = k*G step of EcdsaSignature / BipSchnorr / EdDSA sign   ecdsa.rs:108-131, schnorr.rs:372-385,
  *                                                                eddsa.rs:120-131
  *   fec_field_bench          n x   FieldElement::mul / square    secp256k1.rs:442-507, 634-713; p256.rs:498-534, 772-776;
@@ -134,6 +135,16 @@ FEC_API int fec_batch_mul(fec_ctx* ctx, fec_curve curve, fec_sem sem, const uint
 FEC_API int fec_batch_mul_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec_sem sem, const uint8_t* d_scalars,
                       const uint8_t* d_points, fec_points_fmt points_fmt, size_t n, fec_out out_fmt, uint8_t* d_out,
                       uint8_t* d_status, void* stream);
+
+/* Standalone point decoding and validation: n x { CompressedPoint::to_affine (forge-ec-encoding/src/point.rs:70-144) |
+ * PointAffine::new + is_on_curve; Curve::validate_point (forge-ec-core/src/lib.rs:905-923: on these cofactor-1 curves membership
+ * of the curve is the whole check) }.  points: n x 33 B SEC1 compressed or n x 64 B X || Y; out: n records of out_fmt (so the same
+ * call also converts between the encodings); status: 0 valid, 2 rejected (bad prefix, coordinate >= p, no square root, not on
+ * the curve), 3 the identity record (prefix 0x00 / all-zero X || Y); rejected and identity lanes give all-zero records. */
+FEC_API int fec_batch_point_decode(fec_ctx* ctx, fec_curve curve, const uint8_t* points, fec_points_fmt points_fmt, size_t n,
+                                   fec_out out_fmt, uint8_t* out, uint8_t* status);
+FEC_API int fec_batch_point_decode_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8_t* d_points, fec_points_fmt points_fmt,
+                                       size_t n, fec_out out_fmt, uint8_t* d_out, uint8_t* d_status, void* stream);
 
 /* Batched ECDH: shared_i = x(k_i * P_i), 32 bytes big-endian, then the reference's key derivation.
  * kdf == FEC_KDF_NONE: out = n x 32 B shared secrets; otherwise out = n x out_len bytes (1 <= out_len <= 64, info_len <= 256;

@@ -234,6 +234,30 @@ def batch_mul(curve, scalars: bytes, points: bytes | None, n: int, fmt: int = 0,
     return bytes(out), bytes(st)
 
 
+def point_decode(curve, points: bytes, n: int, fmt: int = OUT_AFFINE_XY_BE, points_fmt: int = 1):
+    """Model of fec_batch_point_decode: CompressedPoint::to_affine (forge-ec-encoding/src/point.rs:70-144) / on-curve validation
+    (Curve::validate_point, forge-ec-core/src/lib.rs:905-923, cofactor 1) and re-encoding: (out_bytes, status_bytes)."""
+    c = CURVES[curve]
+    osz, psz = OUT_SIZE[fmt], (64 if points_fmt == 0 else 33)
+    out, st = bytearray(n * osz), bytearray(n)
+    for i in range(n):
+        raw = points[psz * i : psz * (i + 1)]
+        if (points_fmt == 0 and raw == bytes(64)) or (points_fmt != 0 and raw[0] == 0):
+            st[i] = ST_INFINITY
+            continue
+        if points_fmt == 0:
+            P = (int.from_bytes(raw[:32], "big"), int.from_bytes(raw[32:], "big"))
+            if not w_is_on_curve(c, P):
+                P = None
+        else:
+            P = sec1_decompress(c, raw)
+        if P is None:
+            st[i] = ST_POINT_INVALID
+            continue
+        out[osz * i : osz * (i + 1)] = sec1_encode(P, fmt)
+    return bytes(out), bytes(st)
+
+
 def w_add_affine(c: WeierstrassCurve, P, Q):
     """affine addition with every special case (None = identity)"""
     if P is None:

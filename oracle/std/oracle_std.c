@@ -502,6 +502,16 @@ void ostd_msm(int curve, const uint8_t* scalars, const uint8_t* points, int poin
   ostd_msm_products(curve, xy, st, n, out_fmt, out, status);
   free(xy); free(st);
 }
+/* Standalone point decoding / validation (CompressedPoint::to_affine, forge-ec-encoding/src/point.rs:70-144; Curve::validate_point,
+ * forge-ec-core/src/lib.rs:905-923): k = 1 times the decoded point is the point itself, so this is w_lane with the scalar 1 --
+ * status 2 for a rejected record, 3 for the identity record. */
+void ostd_batch_point_decode(int curve, const uint8_t* points, int points_fmt, size_t n, int out_fmt, uint8_t* out, uint8_t* status,
+                             int threads) {
+  uint8_t* one = (uint8_t*)calloc(n ? n : 1, 32);
+  for (size_t i = 0; i < n; i++) one[32 * i + 31] = 1;
+  ostd_batch_mul(curve, one, points, points_fmt, n, out_fmt, out, status, threads);
+  free(one);
+}
 void ostd_batch_ed25519_pubkey(const uint8_t* in, int input_is_seed, size_t n, uint8_t* out, int threads);
 /* Signing-side nonce commitment.  mode 0 ECDSA (forge-ec-signature/src/ecdsa.rs:108-131): R = k G (33 B SEC1
  * compressed), r = x(R) as a scalar, status 1 where Scalar::from_bytes(x) fails (x >= n) and 3 for r = 0; mode 1 BIP-340

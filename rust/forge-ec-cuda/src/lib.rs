@@ -59,6 +59,9 @@ extern "C" {
         ctx: *mut fec_ctx, curve: c_int, scalars: *const u8, points: *const u8, points_fmt: c_int, n: usize, out_fmt: c_int,
         out: *mut u8, status: *mut u8,
     ) -> c_int;
+    pub fn fec_batch_point_decode(
+        ctx: *mut fec_ctx, curve: c_int, points: *const u8, points_fmt: c_int, n: usize, out_fmt: c_int, out: *mut u8, status: *mut u8,
+    ) -> c_int;
     pub fn fec_batch_nonce_commit(
         ctx: *mut fec_ctx, curve: c_int, mode: c_int, nonces: *const u8, n: usize, out_r_point: *mut u8, out_r_scalar: *mut u8,
         status: *mut u8,
@@ -182,6 +185,20 @@ pub trait BatchMul: CudaCurve {
                     out.as_mut_ptr(), &mut st)
         };
         if rc != 0 { Err(map_err(rc)) } else { Ok((out, st)) }
+    }
+
+    /// Batched `CompressedPoint::to_affine` + `Curve::validate_point` (forge-ec-encoding/src/point.rs:70-144,
+    /// forge-ec-core/src/lib.rs:905-923): 33-byte SEC1 records -> validated `X || Y` (64 B) and the lane status.
+    fn batch_decode_compressed(engine: &Engine, records: &[u8]) -> Result<(Vec<u8>, Vec<u8>)> {
+        if records.len() % 33 != 0 { return Err(Error::InvalidEncoding); }
+        let n = records.len() / 33;
+        let mut out = vec![0u8; 64 * n];
+        let mut status = vec![0u8; n];
+        let rc = unsafe {
+            fec_batch_point_decode(engine.ctx, Self::CURVE_ID, records.as_ptr(), FEC_PT_SEC1_COMPRESSED, n, FEC_OUT_AFFINE_XY_BE,
+                                   out.as_mut_ptr(), status.as_mut_ptr())
+        };
+        if rc != 0 { Err(map_err(rc)) } else { Ok((out, status)) }
     }
 
     /// SEC1 compressed bytes straight from the GPU (what `CompressedPoint::from_affine` would produce).

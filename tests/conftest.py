@@ -95,6 +95,15 @@ def ostd():
             return out.tobytes(), int(s1[0])
 
         @staticmethod
+        def point_decode(curve, pts, pfmt=1, ofmt=2, threads=ncpu):
+            p = np.frombuffer(bytes(pts), dtype=np.uint8)
+            n = p.size // (33 if pfmt == 1 else 64)
+            out = np.empty(n * {0: 33, 1: 65, 2: 64, 3: 32, 4: 65}[ofmt], dtype=np.uint8)
+            st = np.empty(n, dtype=np.uint8)
+            lib.ostd_batch_point_decode(curve, vp(p.ctypes.data), pfmt, sz(n), ofmt, vp(out.ctypes.data), vp(st.ctypes.data), threads)
+            return out.tobytes(), st.tobytes()
+
+        @staticmethod
         def nonce_commit(curve, mode, nonces, threads=ncpu):
             """(out_R, out_r, status) of the signing-side nonce commitment"""
             a = np.frombuffer(bytes(nonces), dtype=np.uint8)

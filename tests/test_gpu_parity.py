@@ -751,3 +751,27 @@ def test_nonce_commit_matches_oracle_and_published_vectors(engine, fec, ostd, pm
     # the BIP-340 mode belongs to secp256k1
     with pytest.raises(fec.FecError):
         engine.batch_nonce_commit(1, fec.NONCE_BIP340, k)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_point_decode_matches_oracle(engine, fec, ostd, pm, curve):
+    """the missing standalone decode of round 1: fec_batch_point_decode = CompressedPoint::to_affine (point.rs:70-144) +
+    Curve::validate_point (lib.rs:905-923) without a scalar multiplication; every input and output format"""
+    c = pm.CURVES[curve]
+    n = 1500
+    r = pm.random_scalars_be(curve, n, stream=14, edge=False)
+    comp = np.frombuffer(ostd.mul(curve, r.tobytes(), None, 0, 0)[0], dtype=np.uint8).reshape(n, 33).copy()
+    comp[3, 0] = 4; comp[5, 0] = 0; comp[7, 1:] = 0xFF; comp[9, 32] ^= 1; comp[11] = 0
+    for ofmt in (0, 1, 2, 3, 4):
+        out, st = engine.batch_point_decode(curve, comp, out_fmt=ofmt)
+        assert (out.tobytes(), st.tobytes()) == ostd.point_decode(curve, comp.tobytes(), 1, ofmt)
+    assert {0, 2, 3} <= set(st.tolist())
+    xy = np.frombuffer(ostd.mul(curve, r.tobytes(), None, 0, 2)[0], dtype=np.uint8).reshape(n, 64).copy()
+    xy[3, 63] ^= 1; xy[5] = 0; xy[7] = 0xFF
+    out, st = engine.batch_point_decode(curve, xy, points_fmt=fec.PT_AFFINE_XY_BE, out_fmt=fec.OUT_SEC1_COMPRESSED)
+    assert (out.tobytes(), st.tobytes()) == ostd.point_decode(curve, xy.tobytes(), 0, 0)
+    cls = fec.Secp256k1 if curve == 0 else fec.P256
+    pts = cls.batch_decode([comp[0].tobytes(), comp[1].tobytes(), comp[5].tobytes()], engine)
+    assert pts[0].to_bytes() == comp[0].tobytes() and pts[2].is_identity()
+    with pytest.raises(ValueError):
+        cls.batch_decode([comp[3].tobytes()], engine)

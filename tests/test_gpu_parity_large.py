@@ -174,3 +174,14 @@ def test_nonce_commit_2p16_matches_c_oracle(engine, ostd, pm, mode):
     R, r, st = engine.batch_nonce_commit(0, mode, nonces)
     eR, er, est = ostd.nonce_commit(0, mode, nonces.tobytes())
     assert st.tobytes() == est and r.tobytes() == er and R.tobytes() == eR
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_point_decode_2p16_matches_c_oracle(engine, ostd, pm, curve):
+    """8f.1 on its own: 2^16 SEC1 compressed keys -> validated affine X || Y"""
+    r = pm.random_scalars_be(curve, N, stream=14, edge=False)
+    comp = np.frombuffer(ostd.mul(curve, r.tobytes(), None, 0, 0)[0], dtype=np.uint8).reshape(N, 33).copy()
+    comp[2000, 0] = 4; comp[2041, 0] = 0; comp[2082, 1:] = 0xFF; comp[3000:3100, 32] ^= 1
+    out, st = engine.batch_point_decode(curve, comp)
+    exp, est = ostd.point_decode(curve, comp.tobytes(), 1, 2)
+    assert st.tobytes() == est and out.tobytes() == exp and {0, 2, 3} <= set(est)

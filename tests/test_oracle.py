@@ -493,3 +493,22 @@ def test_nonce_commit_oracles_against_published_vectors(ostd, pm):
     edge = [0, 2**512 - 1, pm.ED_L, pm.ED_L - 1, 2**252, (pm.ED_L << 200) + 5, 2**511, (pm.ED_L << 259) - 1]
     h = b"".join(v.to_bytes(64, "little") for v in edge) + h
     assert ostd.nonce_commit(0, 2, h) == pm.nonce_commit(0, 2, h, len(h) // 64)
+
+
+def test_point_decode_oracles_agree(ostd, pm):
+    """CompressedPoint::to_affine / validate_point (point.rs:70-144, lib.rs:905-923): the C oracle against the Python model and
+    against the OpenSSL fixtures (compressed -> uncompressed), rejected and identity records included"""
+    be = lambda v: v.to_bytes(32, "big")
+    for name, cid in CURVE_ID.items():
+        g = _gold("weierstrass.json")[name]
+        comp = b"".join(bytes.fromhex(e["compressed"]) for e in g["fixed_base"])
+        unc = b"".join(bytes.fromhex(e["uncompressed"]) for e in g["fixed_base"])
+        n = len(g["fixed_base"])
+        assert ostd.point_decode(cid, comp, 1, 1) == (unc, bytes(n)) == pm.point_decode(cid, comp, n, 1, 1)
+        xy = b"".join(unc[65 * i + 1 : 65 * i + 65] for i in range(n))
+        assert ostd.point_decode(cid, xy, 0, 0) == (comp, bytes(n)) == pm.point_decode(cid, xy, n, 0, 0)
+        cv = pm.CURVES[cid]
+        bad = [b"\x04" + be(cv.gx), b"\x02" + be(cv.p), b"\x02" + be(5 if cid == 0 else 1), bytes(33), b"\x00" + be(cv.gx), b"\x03" + be(cv.gx)]
+        recs = b"".join(bad)
+        got = ostd.point_decode(cid, recs, 1, 2)
+        assert got == pm.point_decode(cid, recs, len(bad), 2, 1) and got[1] == bytes([2, 2, 2, 3, 3, 0])
