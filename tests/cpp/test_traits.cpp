@@ -3,6 +3,7 @@
 // ECDH commutes, n-1 and out-of-range scalars, an off-curve point, multi_scalar_multiply, the RFC 7748 6.1 exchange
 // (curve25519.rs:2061-2089) and RFC 8032 7.1 TEST 1 (eddsa.rs:572-585).
 // Exit code 0: all checks passed on the GPU; 77: no usable device and the library said so loudly (UnsupportedOperation).
+#include <algorithm>
 #include <cstdio>
 #include <string>
 
@@ -87,6 +88,24 @@ static void weierstrass(Engine& e, const char* g1, const char* g2, const char* g
   const auto k2 = Curve::batch_ecdh(e, std::vector<Scalar>(ks.size(), a), pub, info, 32, &st2);
   CHECK(k1 == k2);
   for (uint8_t s : st1) CHECK(s == 0);
+  // r2: the hybrid encoding (PointFormat::Hybrid, secp256k1.rs:1048-1066): 06|07 || X || Y with the parity of y
+  const auto hyb = G.to_bytes_with_format(PointFormat::Hybrid);
+  CHECK(hyb.size() == 65 && hyb[0] == (6 | (G.xy[63] & 1)) && std::equal(hyb.begin() + 1, hyb.end(), G.xy.begin()));
+  // r2: the identity as an input point: k * O = O (Curve::multiply, lib.rs:820-832), and a sum simply skips it
+  CHECK(Curve::multiply(e, &O, Scalar::from_u64(5)).is_identity());
+  CHECK(Curve::multi_scalar_multiply(e, {G, O, G2}, {Scalar::from_u64(2), Scalar::from_u64(7), Scalar::from_u64(3)}).xy ==
+        Curve::multiply(e, nullptr, Scalar::from_u64(8)).xy);
+  // r2: CompressedPoint::to_affine for a batch (point.rs:70-144): compressed -> affine round trip, a bad prefix is refused
+  std::array<uint8_t, 33> c1{}, c2{};
+  const auto gb = G.to_bytes(), g2b = G2.to_bytes();
+  std::copy(gb.begin(), gb.end(), c1.begin());
+  std::copy(g2b.begin(), g2b.end(), c2.begin());
+  const auto dec = Curve::batch_decode(e, {c1, c2});
+  CHECK(dec[0].xy == G.xy && dec[1].xy == G2.xy);
+  c2[0] = 5;
+  threw = false;
+  try { Curve::batch_decode(e, {c1, c2}); } catch (const Error& err) { threw = err.kind() == ErrorKind::InvalidEncoding; }
+  CHECK(threw);
 }
 
 int main() {
@@ -115,6 +134,13 @@ int main() {
     // RFC 8032 7.1 TEST 1 (eddsa.rs:572-585)
     const auto seed = hex<32>("9d61b19deffd5a60ba844af492ec2cc44449c5697b326919703bac031cae7f60");
     CHECK(to_hex(Ed25519Signature::derive_public_key(e, seed)) == "d75a980182b10ab7d54bfed3c964073a0ee172f3daa62325af021a68f707511a");
+    // r2: the nonce commitment of sign(): RFC 6979 A.2.5 (P-256, SHA-256, "sample"): k -> r = x(k G) (ecdsa.rs:108-131)
+    {
+      const auto k = hex<32>("a6e3c57dd01abe90086538398355dd4c3b17aa873382b0f24d6129493d8aad60");
+      const NonceCommit nc = batch_nonce_commit(e, FEC_P256, FEC_NONCE_ECDSA, std::vector<uint8_t>(k.begin(), k.end()));
+      CHECK(nc.status[0] == 0 && to_hex(nc.r) == "efd48b2aacb6a8fd1140dd9cd45e81d69d2c877b56aaf991c34d0ea84eaf3716");
+      CHECK(nc.R.size() == 33 && std::equal(nc.r.begin(), nc.r.end(), nc.R.begin() + 1));
+    }
     CHECK(e.launch_count() > 0);
   } catch (const Error& err) {
     if (err.kind() == ErrorKind::UnsupportedOperation) {
