@@ -111,6 +111,22 @@ FEC_DEV u32 mad_row(u32* acc, const u32* a /*stride 2*/, u32 b, u32 z0 = 0u) {
   return 0u;
 }
 
+// The same row on a span whose top pair has been written before (FRESH == 0), with the chain's carry-out ABSORBED into `sink`
+// instead of being materialised as a word of its own: `sink` is the word of the OTHER column parity at the carry's position,
+// which this row has just written as the high word of a fresh top pair -- at most 2^32 - 2 ((2^32-1)^2 + 1 = 2^64 - 2^33 + 2),
+// so the +1 cannot overflow.  Saves, per carry, the SEL that makes the carry word and the zeroed partner register the next
+// row's top product would need (14 of the 65 non-multiply instructions of a multiplication were such pairs).
+template <int NP>
+FEC_DEV void mad_row_absorb(u32* acc, const u32* a /*stride 2*/, u32 b, u32& sink) {
+#pragma unroll
+  for (int k = 0; k < NP; k++) {
+    const u32 ak = a[2 * k];
+    acc[2 * k] = (k == 0) ? mad_lo_cc(ak, b, acc[2 * k]) : madc_lo_cc(ak, b, acc[2 * k]);
+    acc[2 * k + 1] = madc_hi_cc(ak, b, acc[2 * k + 1]);
+  }
+  sink = addc(sink, 0u);
+}
+
 // r[0..16) = a[0..8) * b[0..8), schoolbook
 // Tokens for callers that want to order later work behind the product (FeP256::mul_inl): tok_e + tok_o (the two top partial
 // words, final before the merge) never overflows 32 bits; with TOKC, tok_c is the carry out of the merge chain -- zero
@@ -127,6 +143,7 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
     od[j] = mul_lo(a[j + 1], b[0]);
     od[j + 1] = mul_hi(a[j + 1], b[0]);
   }
+#ifdef FEC_CARRY_WORDS  // the form before r2: every full chain's carry becomes a word of its own (A/B)
   // odd rows: a_odd*b[i] -> even positions, a_even*b[i] -> odd positions (full -> carry word)
   // even rows: a_even*b[i] -> even positions (full -> carry word), a_odd*b[i] -> odd positions
   mad_row<4, 2>(ev + 2, a + 1, b[1]);  od[8]  = mad_row<4, 0>(od + 0, a, b[1]);
@@ -136,7 +153,21 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
   mad_row<4, 1>(ev + 6, a + 1, b[5], z0);  od[12] = mad_row<4, 0>(od + 4, a, b[5]);
   ev[14] = mad_row<4, 0>(ev + 6, a, b[6]);  mad_row<4, 1>(od + 6, a + 1, b[6], z0);
   mad_row<4, 1>(ev + 8, a + 1, b[7], z0);  od[14] = mad_row<4, 0>(od + 6, a, b[7]);
-  // merge: r = ev + (od << 32).  ev[15] was written by row 7 (fresh), od[14] by row 7's carry.
+#else
+  // Row i = two carry chains: the products that land on the parity whose top pair is NEW this row (a_odd * b[i]: fresh pair,
+  // no carry out), then the others over a span that is full (a_even * b[i]), whose carry-out sits exactly at the position of the
+  // fresh pair's high word in the other parity and is absorbed there (mad_row_absorb).  No carry words, no zeroed partners.
+  (void)z0;
+  mad_row<4, 2>(ev + 2, a + 1, b[1]);  mad_row_absorb<4>(od + 0, a, b[1], ev[9]);
+  mad_row<4, 2>(od + 2, a + 1, b[2]);  mad_row_absorb<4>(ev + 2, a, b[2], od[9]);
+  mad_row<4, 2>(ev + 4, a + 1, b[3]);  mad_row_absorb<4>(od + 2, a, b[3], ev[11]);
+  mad_row<4, 2>(od + 4, a + 1, b[4]);  mad_row_absorb<4>(ev + 4, a, b[4], od[11]);
+  mad_row<4, 2>(ev + 6, a + 1, b[5]);  mad_row_absorb<4>(od + 4, a, b[5], ev[13]);
+  mad_row<4, 2>(od + 6, a + 1, b[6]);  mad_row_absorb<4>(ev + 6, a, b[6], od[13]);
+  mad_row<4, 2>(ev + 8, a + 1, b[7]);  mad_row_absorb<4>(od + 6, a, b[7], ev[15]);
+  od[14] = 0u;  // (no word of the odd parity exists at position 15 any more)
+#endif
+  // merge: r = ev + (od << 32).  ev[15] was written by row 7 (fresh), od[14] by row 7's carry (zero in the absorbing form).
   r[0] = ev[0];
   r[1] = add_cc(ev[1], od[0]);
 #pragma unroll
@@ -276,6 +307,7 @@ FEC_DEV void sqr_wide_tok(u32 r[16], const u32 a[8], u32& tok_c) {
   ev[2] = mul_lo(a[0], a[2]); ev[3] = mul_hi(a[0], a[2]);
   ev[4] = mul_lo(a[0], a[4]); ev[5] = mul_hi(a[0], a[4]);
   ev[6] = mul_lo(a[0], a[6]); ev[7] = mul_hi(a[0], a[6]);
+#ifdef FEC_CARRY_WORDS  // the form before r2 (A/B): carry words
   // row 1: a1*a2 (3,4) a1*a4 (5,6) a1*a6 (7,8) -> od[2..7] full -> carry od[8];
   //        a1*a3 (4,5) a1*a5 (6,7) a1*a7 (8,9) -> ev[4..9], ev[8],ev[9] fresh
   od[8] = mad_row<3, 0>(od + 2, a + 2, a[1]);
@@ -296,6 +328,28 @@ FEC_DEV void sqr_wide_tok(u32 r[16], const u32 a[8], u32& tok_c) {
   mad_row<1, 1>(ev + 12, a + 7, a[5], z0);
   // row 6: a6*a7 (13,14) -> od[12..13], od[13] fresh
   mad_row<1, 1>(od + 12, a + 7, a[6], z0);
+#else
+  // Every row: first the chain whose top pair is new (fresh, no carry out), then the chain over a full span, whose carry-out
+  // is absorbed into the new pair's high word of the other parity -- the same position (see mad_row_absorb).
+  (void)z0;
+  // row 1: a1*a3 (4,5) a1*a5 (6,7) a1*a7 (8,9) -> ev[4..9], pair (8,9) new;  a1*a2 (3,4) a1*a4 (5,6) a1*a6 (7,8) -> od[2..7], carry at 9
+  mad_row<3, 2>(ev + 4, a + 3, a[1]);
+  mad_row_absorb<3>(od + 2, a + 2, a[1], ev[9]);
+  // row 2: a2*a3 (5,6) a2*a5 (7,8) a2*a7 (9,10) -> od[4..9], pair (9,10) new;  a2*a4 (6,7) a2*a6 (8,9) -> ev[6..9], carry at 10
+  mad_row<3, 2>(od + 4, a + 3, a[2]);
+  mad_row_absorb<2>(ev + 6, a + 4, a[2], od[9]);
+  // row 3: a3*a5 (8,9) a3*a7 (10,11) -> ev[8..11], pair (10,11) new;  a3*a4 (7,8) a3*a6 (9,10) -> od[6..9], carry at 11
+  mad_row<2, 2>(ev + 8, a + 5, a[3]);
+  mad_row_absorb<2>(od + 6, a + 4, a[3], ev[11]);
+  // row 4: a4*a5 (9,10) a4*a7 (11,12) -> od[8..11], pair (11,12) new;  a4*a6 (10,11) -> ev[10..11], carry at 12
+  mad_row<2, 2>(od + 8, a + 5, a[4]);
+  mad_row_absorb<1>(ev + 10, a + 6, a[4], od[11]);
+  // row 5: a5*a7 (12,13) -> ev[12..13] new;  a5*a6 (11,12) -> od[10..11], carry at 13
+  mad_row<1, 2>(ev + 12, a + 7, a[5]);
+  mad_row_absorb<1>(od + 10, a + 6, a[5], ev[13]);
+  // row 6: a6*a7 (13,14) -> od[12..13] new
+  mad_row<1, 2>(od + 12, a + 7, a[6]);
+#endif
   // merge off-diagonals: s[1..14] (s[0]=0, s[15] = 0); s fits in 15 words (sum < 2^480)
   u32 s[16];
   s[1] = od[0];

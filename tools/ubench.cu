@@ -165,6 +165,42 @@ __global__ void __launch_bounds__(1024, 1) k_phase(u32* sink, long long* cycles,
 static u32* g_sink;
 static long long* g_cyc;
 static int g_sms;
+template <class K> static double run(K kern, int warps, int trips, double ops_per_trip_per_warp);
+
+// The issue-port model in its cleanest form: a loop body of W IMAD.WIDE.U32 (independent accumulators, loop-invariant
+// multiplicands: no moves) and A LOP3 (independent registers), interleaved, NOTHING else but the loop branch; the table printed
+// from it compares clk per trip with 4 W + A + 3 (the three loop-control instructions).
+template <int W, int A>
+__global__ void __launch_bounds__(1024, 1) k_model(u32* sink, long long* cycles, u32 seed, int trips) {
+  u32 lo[8], hi[8], m[8], y[8];
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < 8; c++) { lo[c] = t + c; hi[c] = seed + c; m[c] = seed * (c + 3) + t; y[c] = t ^ (c * 77u); }
+  const u32 b = seed | 0x80000001u;
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < trips; it++) {
+    constexpr int N = W > A ? W : A;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+      if (c < W) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[c & 7]), "+r"(hi[c & 7]) : "r"(m[c & 7]), "r"(b));
+      if (c < A) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[c & 7]) : "r"(m[(c + 1) & 7]), "r"(b));
+    }
+  }
+  const long long t1 = clock64();
+  u32 acc = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) acc ^= lo[c] ^ hi[c] ^ y[c];
+  sink[t] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+#define MODEL(W, A)                                                                                              \
+  do {                                                                                                           \
+    const double per_clk = run(k_model<W, A>, 32, 4000, (double)((W) + (A)));                                    \
+    const double clk = ((W) + (A)) / per_clk;                                                                    \
+    printf("model W=%2d IMAD.WIDE + A=%2d LOP3 per trip: %7.1f clk per trip per sub-partition-warp slot; 4W + A + 3 = %3d; ratio %.3f\n", W, A, clk, 4 * (W) + (A) + 3, clk / (4 * (W) + (A) + 3)); \
+  } while (0)
+
 
 template <class K>
 static double run(K kern, int warps, int trips, double ops_per_trip_per_warp) {
@@ -254,6 +290,8 @@ int main() {
   CK(cudaMalloc(&g_sink, (size_t)g_sms * 8192 * 4));
   CK(cudaMalloc(&g_cyc, g_sms * 8 * sizeof(long long)));
   printf("SMs %d\n", g_sms);
+  printf("== issue-port model, 8 warps per sub-partition (clk per trip = (W + A) / (instructions per clk per sub-partition) x 8 warps ... reported per warp slot)\n");
+  MODEL(8, 0); MODEL(16, 0); MODEL(32, 0); MODEL(0, 32); MODEL(32, 8); MODEL(32, 16); MODEL(32, 32); MODEL(16, 32); MODEL(8, 32); MODEL(32, 64);
   // latencies (1 warp per SMSP)
   printf("lat IMAD.WIDE.X row of 4 (dependent rows): %.2f clk per instr\n", 1.0 / run(k_lat<0>, 4, 2000, 16.0));
   printf("lat IADD3.X chain of 8                   : %.2f clk per instr\n", 1.0 / run(k_lat<1>, 4, 2000, 32.0));
