@@ -127,6 +127,67 @@ struct FeK1 {
     u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     sub(o, z, a);
   }
+  // ---- chains of linear operations with ONE fold (r2).  A weak-form addition or subtraction is 8 instructions of arithmetic
+  // and ~16 of folding the carry back in; a chain a - b - c ... keeps the 256-bit value wrapped and counts the wraps in a small
+  // signed v instead (value = t + v 2^256), and folds once: o = t + v (2^32 + 977).
+  FEC_DEV static void fold_signed(u32 o[8], const u32 t[8], u32 v) {  // |v| < 2^20 (as a signed number)
+    const u32 s = (u32)((int)v >> 31);
+    u32 x[8];
+    x[0] = add_cc(t[0], v * C977);  // v (2^32 + 977) as a 256-bit two's-complement number: (v 977, v + s, s, s, s, s, s, s)
+    x[1] = addc_cc(t[1], v + s);
+#pragma unroll
+    for (int i = 2; i < 8; i++) x[i] = addc_cc(t[i], s);
+    const u32 corr = addc(s, 0u);   // carry + s: +1 wrapped above 2^256, -1 wrapped below 0 (the value is then within 2^37 of the wrap)
+    const u32 cs = (u32)((int)corr >> 31);
+    o[0] = add_cc(x[0], corr * C977);
+    o[1] = addc_cc(x[1], corr + cs);
+    o[2] = addc(x[2], cs);
+#pragma unroll
+    for (int i = 3; i < 8; i++) o[i] = x[i];
+  }
+  // t -= b, wraps counted in v (a borrow is -1)
+  FEC_DEV static void sub_acc(u32 t[8], u32& v, const u32 b[8]) {
+    t[0] = sub_cc(t[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(t[i], b[i]);
+    v += subc(0u, 0u);  // 0 or 0xFFFFFFFF
+  }
+  FEC_DEV static void sub2_dbl(u32 o[8], const u32 t[8], const u32 a[8], const u32 b[8]) {  // 2 (t - a - b)
+    u32 d[8], v = 0u;
+    copy8(d, t);
+    sub_acc(d, v, a);
+    sub_acc(d, v, b);
+    v = (v << 1) + (d[7] >> 31);
+#pragma unroll
+    for (int i = 7; i >= 1; i--) d[i] = funnel_l(d[i - 1], d[i], 1);
+    d[0] <<= 1;
+    fold_signed(o, d, v);
+  }
+  FEC_DEV static void sub_twice(u32 o[8], const u32 t[8], const u32 a[8]) {  // t - 2a
+    u32 d[8], v = 0u;
+    copy8(d, t);
+    sub_acc(d, v, a);
+    sub_acc(d, v, a);
+    fold_signed(o, d, v);
+  }
+  FEC_DEV static void sub3(u32 o[8], const u32 t[8], const u32 a[8], const u32 b[8]) {  // t - a - 2b
+    u32 d[8], v = 0u;
+    copy8(d, t);
+    sub_acc(d, v, a);
+    sub_acc(d, v, b);
+    sub_acc(d, v, b);
+    fold_signed(o, d, v);
+  }
+  FEC_DEV static void sub_mul8(u32 o[8], const u32 t[8], const u32 a[8]) {  // t - 8a
+    u32 e[8], d[8], v = 0u - (a[7] >> 29);
+#pragma unroll
+    for (int i = 7; i >= 1; i--) e[i] = funnel_l(a[i - 1], a[i], 3);
+    e[0] = a[0] << 3;
+    copy8(d, t);
+    sub_acc(d, v, e);
+    fold_signed(o, d, v);
+  }
+  static constexpr bool HAS_FUSED_LINEAR = true;
   // o = a * c for a small constant c (< 2^16): one 9-limb product + fold
   FEC_DEV static void mul_small(u32 o[8], const u32 a[8], u32 c) {
     u32 t[8];

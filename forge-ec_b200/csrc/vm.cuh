@@ -160,6 +160,57 @@ template <class F, int T> FEC_VMLIN fe vm_rsub(fe a, saddr p) {  // [p] - a
   F::sub(r.v, b, a.v);
   return r;
 }
+// Chains of linear operations.  Fields that provide them (FeK1: HAS_FUSED_LINEAR) run a chain with ONE fold of the wrapped
+// value (fields.cuh: fold_signed), the others as the operations they stand for.
+template <class F, class = void> struct has_fused_linear { static constexpr bool value = false; };
+template <class F> struct has_fused_linear<F, decltype((void)F::HAS_FUSED_LINEAR)> { static constexpr bool value = F::HAS_FUSED_LINEAR; };
+template <class F, int T> FEC_VMLIN fe vm_sub2_dbl(fe a, saddr p, saddr q) {  // 2 (a - [p] - [q])
+  u32 b[8], c[8];
+  Vm<F, T>::ldv(b, p);
+  Vm<F, T>::ldv(c, q);
+  fe r;
+  if constexpr (has_fused_linear<F>::value) {
+    F::sub2_dbl(r.v, a.v, b, c);
+  } else {
+    F::sub(r.v, a.v, b); F::sub(r.v, r.v, c); F::mul2(r.v, r.v);
+  }
+  return r;
+}
+template <class F, int T> FEC_VMLIN fe vm_sub_twice(fe a, saddr p) {  // a - 2 [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  if constexpr (has_fused_linear<F>::value) {
+    F::sub_twice(r.v, a.v, b);
+  } else {
+    F::sub(r.v, a.v, b); F::sub(r.v, r.v, b);
+  }
+  return r;
+}
+template <class F, int T> FEC_VMLIN fe vm_sub3(fe a, saddr p, saddr q) {  // a - [p] - 2 [q]
+  u32 b[8], c[8];
+  Vm<F, T>::ldv(b, p);
+  Vm<F, T>::ldv(c, q);
+  fe r;
+  if constexpr (has_fused_linear<F>::value) {
+    F::sub3(r.v, a.v, b, c);
+  } else {
+    F::sub(r.v, a.v, b); F::sub(r.v, r.v, c); F::sub(r.v, r.v, c);
+  }
+  return r;
+}
+template <class F, int T> FEC_VMLIN fe vm_sub_mul8(fe a, saddr p) {  // a - 8 [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  if constexpr (has_fused_linear<F>::value) {
+    F::sub_mul8(r.v, a.v, b);
+  } else {
+    u32 t[8];
+    F::mul8(t, b); F::sub(r.v, a.v, t);
+  }
+  return r;
+}
 template <class F, int K> FEC_VMLIN fe vm_small(fe a) {  // a * K, K in {2,3,4,8}
   fe r;
   if (K == 2) F::mul2(r.v, a.v);
@@ -255,15 +306,25 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = V::ld(X);
   a = vm_add<F, T>(a, B);
   a = vm_sqr<F>(a);
+#ifndef FEC_VM_NO_FUSED_LINEAR
+  a = vm_sub2_dbl<F, T>(a, A, Cs); V::st(D, a);  // D = 2((X+B)^2 - A - C), one fold
+#else
   a = vm_sub<F, T>(a, A);
   a = vm_sub<F, T>(a, Cs);
   a = vm_small<F, 2>(a); V::st(D, a);            // D = 2((X+B)^2 - A - C)
+#endif
   a = V::ld(Y);
   a = vm_mul<F, T>(a, Z);
   a = vm_small<F, 2>(a); V::st(Z, a);            // Z3 = 2YZ
   a = V::ld(A);
   a = vm_small<F, 3>(a); V::st(A, a);            // E = 3A
   a = vm_sqr<F>(a);
+#ifndef FEC_VM_NO_FUSED_LINEAR
+  a = vm_sub_twice<F, T>(a, D); V::st(X, a);     // X3 = E^2 - 2D, one fold
+  a = vm_rsub<F, T>(a, D);                       // D - X3
+  a = vm_mul<F, T>(a, A);                        // E (D - X3)
+  a = vm_sub_mul8<F, T>(a, Cs); V::st(Y, a);     // Y3 = E(D - X3) - 8C, one fold, nothing parked in a slot
+#else
   a = vm_sub<F, T>(a, D);
   a = vm_sub<F, T>(a, D); V::st(X, a);           // X3 = E^2 - 2D
   a = vm_rsub<F, T>(a, D);                       // D - X3
@@ -271,6 +332,7 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = V::ld(Cs);
   a = vm_small<F, 8>(a);
   a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
+#endif
 }
 
 // Q <- 2Q for a = -3 curves (P-256), in place: 4M + 4S with 2Y carried through (see jac_dbl in curves.cuh) -- the
@@ -434,9 +496,13 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
     a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 HH
     a = V::ld(R);
     a = vm_sqr<F>(a);
+#ifndef FEC_VM_NO_FUSED_LINEAR
+    a = vm_sub3<F, T>(a, H, A); V::st(X, a);       // X3 = r^2 - HHH - 2V, one fold where the field has it
+#else
     a = vm_sub<F, T>(a, H);
     a = vm_sub<F, T>(a, A);
     a = vm_sub<F, T>(a, A); V::st(X, a);           // X3 = r^2 - HHH - 2V
+#endif
     a = vm_rsub<F, T>(a, A);                       // V - X3
     a = vm_mul<F, T>(a, R); V::st(R, a);           // r (V - X3)
     a = V::ld(Y);

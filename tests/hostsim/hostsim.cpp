@@ -154,9 +154,24 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
   sec1_encode(out, ofmt, x, y, st ? 0xFFFFFFFFu : 0u);
   return (int)st;
 }
+// the fused chains of linear operations of FeK1 (fields.cuh: sub2_dbl, sub_twice, sub3, sub_mul8): operands are taken as they
+// are (weak representatives included), the result is canonicalised
+void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint8_t* o) {
+  u32 x[8], y[8], z[8], r[8], c[8];
+  load_le32(x, t); load_le32(y, a); load_le32(z, b);
+  switch (op) {
+    case 0: FeK1::sub2_dbl(r, x, y, z); break;
+    case 1: FeK1::sub_twice(r, x, y); break;
+    case 2: FeK1::sub3(r, x, y, z); break;
+    default: FeK1::sub_mul8(r, x, y); break;
+  }
+  FeK1::canon(c, r);
+  store_le32(o, c);
+}
 }  // namespace
 
 extern "C" {
+void hs_k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint8_t* o) { k1_fused(op, t, a, b, o); }
 void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
   if (prime == 0) field_op<FeK1>(op, a, b, o);
   else if (prime == 1) field_op<FeP256>(op, a, b, o);

@@ -114,6 +114,31 @@ def test_device_field_code_on_host_matches_model(hostsim, pm):
             assert int.from_bytes(o.raw, "little") == (1 if a % p == 0 else 0), (prime, hex(a))
 
 
+def test_fused_linear_chains_of_the_secp256k1_field(hostsim, pm):
+    """2 (t - a - b), t - 2a, t - a - 2b, t - 8a with ONE fold of the wrapped value (fields.cuh: fold_signed) against the integers,
+    on weak representatives (anything below 2^256) and on the operands that wrap the most often"""
+    import random
+    rnd = random.Random(23)
+    p = pm.PRIMES[0]
+    edge = [0, 1, 2, 976, 977, 978, 2**32 + 976, 2**32 + 977, 2**32 + 978, 2**33, p - 1, p, p + 1, 2**256 - 1, 2**256 - 2, 2**256 - 978,
+            2**256 - 2**32 - 978, 2**256 - 2**33, 2**255, 2**255 - 1, 2**253, 3 * 2**253, 7 * 2**253, (1 << 224) - 1]
+    vals = edge + [rnd.randrange(2**256) for _ in range(40)]
+    le = lambda v: v.to_bytes(32, "little")
+    exp = [lambda t, a, b: 2 * (t - a - b), lambda t, a, b: t - 2 * a, lambda t, a, b: t - a - 2 * b, lambda t, a, b: t - 8 * a]
+    o = ctypes.create_string_buffer(32)
+    for _ in range(6000):
+        t, a, b = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
+        for op in range(4):
+            hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
+            assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
+    for t in edge:
+        for a in edge:
+            for b in edge[:12]:
+                for op in range(4):
+                    hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
+                    assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
+
+
 def test_device_lane_code_on_host_matches_model(hostsim, pm):
     """recoding, table building, exceptional additions, encoders, ladder, SHA-512, Ed25519 comb"""
     import random

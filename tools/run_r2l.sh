@@ -1,0 +1,5 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+SWEEP_LG=22 SWEEP_STAGES=1 python tools/sweep_var.py 2>&1 | tail -2
+FORGE_EC_CUDA_LIB=$PWD/gpurun_ab/lib_nofused.so SWEEP_LG=22 SWEEP_STAGES=1 python tools/sweep_var.py 2>&1 | tail -2
+python tools/sweep_p256.py 2>&1 | tail -1
