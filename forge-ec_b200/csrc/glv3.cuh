@@ -30,14 +30,13 @@ FEC_DEV void glv_prepare(u32* tab, u32 zs[8], u32 KK[8], u32& flags, const u32 k
     F::mul(C3, C2, D.Z);
     F::mul(A.X, px, C2);
     F::mul(A.Y, py, C3);
-    set_small(A.Z, 1u);
     g_st8(tab, A.X); g_st8(tab + 16, A.Y);
 #pragma unroll 1
-    for (int j = 1; j < 8; j++) {
-      jac_madd_zr<C>(A, D.X, D.Y, zr[j - 1]);
+    for (int j = 1; j < 8; j++) {  // A = (2j+1) P and D = 2P kept at one common Z: co-Z additions, 4M + 2S each (lanes.cuh)
+      coz_addu<C>(A.X, A.Y, D.X, D.Y, zr[j - 1]);
       g_st8(tab + 24 * j, A.X); g_st8(tab + 24 * j + 16, A.Y);
     }
-    F::mul(zs, A.Z, D.Z);
+    copy8(zs, D.Z);  // Z(2P) of the doubling; the product of the ratios joins it below
     k1_beta(beta);
     // entry 7 is already affine on the final curve; entry j < 7 is scaled by s = zr[j] .. zr[6]
     {
@@ -59,6 +58,7 @@ FEC_DEV void glv_prepare(u32* tab, u32 zs[8], u32 KK[8], u32& flags, const u32 k
       g_st8(tab + 24 * j, x); g_st8(tab + 24 * j + 8, bx); g_st8(tab + 24 * j + 16, y);
       if (j > 0) F::mul(s, s, zr[j - 1]);
     }
+    F::mul(zs, zs, s);  // s is now the product of all seven ratios = Z(15 P) on the isomorphic curve
   }
   u32 s1[4], s2[4], neg1, neg2;
   glv_split(s1, neg1, s2, neg2, k);

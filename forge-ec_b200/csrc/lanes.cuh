@@ -103,6 +103,32 @@ FEC_DEV void jac_madd_zr(Jac& q, const u32 x2[8], const u32 y2[8], u32 zr[8]) {
   F::sub(q.Y, t, J);
 }
 
+// Co-Z addition with update (Meloni; Goundar-Joye-Miyaji ZADDU), for the tables of odd multiples: R = (rx, ry) and P = (px, py)
+// share one (implicit) Z.  R <- R + P, P <- the same point P rescaled to the Z of the new R, zr = Z_new / Z_old = px - rx.
+// 4M + 2S and 7 subtractions -- against 8M + 3S and 10 linear operations for the mixed addition that also tracks Z
+// (jac_madd_zr above): the table builders only need the RATIOS of consecutive Z (r2: -24 % of the secp256k1 prepare kernel).
+// No exceptional case for a point of prime order > 15: R = (2j-1) P and P = 2 P' never share an x.
+template <class C>
+FEC_DEV void coz_addu(u32 rx[8], u32 ry[8], u32 px[8], u32 py[8], u32 zr[8]) {
+  typedef typename C::F F;
+  u32 Cc[8], W1[8], W2[8], D[8], A1[8], t[8];
+  F::sub(zr, px, rx);                // X1 - X2
+  F::sqr(Cc, zr);
+  F::mul(W1, px, Cc);
+  F::mul(W2, rx, Cc);
+  F::sub(t, py, ry);                 // Y1 - Y2
+  F::sqr(D, t);
+  F::sub(Cc, W1, W2);
+  F::mul(A1, py, Cc);                // Y1 (W1 - W2)
+  F::sub(D, D, W1);
+  F::sub(rx, D, W2);                 // X3 = D - W1 - W2
+  F::sub(Cc, W1, rx);
+  F::mul(Cc, t, Cc);
+  F::sub(ry, Cc, A1);                // Y3 = (Y1 - Y2)(W1 - X3) - A1
+  copy8(px, W1);
+  copy8(py, A1);
+}
+
 // mixed addition with the two exceptional cases repaired under a warp-uniform branch:
 // Q == T -> 2T, Q == -T -> infinity.  (They need k = +-d (mod n) for a partial scalar, which the
 // recoding only produces for a handful of scalars next to n; see DESIGN.md.)
@@ -143,14 +169,14 @@ FEC_DEV void wmul_var_table(Tab& tab, const u32 px[8], const u32 py[8], Inv& inv
     F::mul(C3, C2, D.Z);
     F::mul(A.X, px, C2);
     F::mul(A.Y, py, C3);
-    F::one(A.Z);
     tab.store(0, px, py);
+    copy8(zt, D.Z);
 #pragma unroll 1
-    for (int j = 1; j < 8; j++) {
-      jac_madd_zr<C>(A, D.X, D.Y, zr[j - 1]);
+    for (int j = 1; j < 8; j++) {  // A = (2j+1) P and D = 2P kept at one common Z (co-Z additions)
+      coz_addu<C>(A.X, A.Y, D.X, D.Y, zr[j - 1]);
       tab.store(j, A.X, A.Y);
+      F::mul(zt, zt, zr[j - 1]);   // true Z of the newest entry: Z(2P) times the ratios so far
     }
-    F::mul(zt, A.Z, D.Z);  // true Z of 15P
     inv(zi, zt);
 #pragma unroll 1
     for (int j = 7; j >= 1; j--) {
