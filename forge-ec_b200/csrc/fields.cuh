@@ -130,10 +130,11 @@ struct FeK1 {
   // ---- chains of linear operations with ONE fold (r2).  A weak-form addition or subtraction is 8 instructions of arithmetic
   // and ~16 of folding the carry back in; a chain a - b - c ... keeps the 256-bit value wrapped and counts the wraps in a small
   // signed v instead (value = t + v 2^256), and folds once: o = t + v (2^32 + 977).
-  FEC_DEV static void fold_signed(u32 o[8], const u32 t[8], u32 v) {  // |v| < 2^20 (as a signed number)
+  // extra (0 or 1, and 0 when v == 0 ... or any v <= 0) rides in the low limb: o = t + v (2^32 + 977) + extra
+  FEC_DEV static void fold_signed(u32 o[8], const u32 t[8], u32 v, u32 extra = 0u) {  // |v| < 2^20 (as a signed number)
     const u32 s = (u32)((int)v >> 31);
     u32 x[8];
-    x[0] = add_cc(t[0], v * C977);  // v (2^32 + 977) as a 256-bit two's-complement number: (v 977, v + s, s, s, s, s, s, s)
+    x[0] = add_cc(t[0], v * C977 + extra);  // v (2^32 + 977) as a 256-bit two's-complement number: (v 977, v + s, s, s, s, s, s, s)
     x[1] = addc_cc(t[1], v + s);
 #pragma unroll
     for (int i = 2; i < 8; i++) x[i] = addc_cc(t[i], s);
@@ -187,6 +188,15 @@ struct FeK1 {
     sub_acc(d, v, e);
     fold_signed(o, d, v);
   }
+  // (m ? -a : a) - b for a full mask m.  -a = ~a + 1 - 2^256 == ~a + 1 - (2^32 + 977): the complement is one XOR per limb, and
+  // its "- (2^32 + 977)" joins the wrap count of the subtraction (v starts at -1), its "+ 1" the low limb of the fold.
+  FEC_DEV static void cneg_sub(u32 o[8], const u32 a[8], u32 m, const u32 b[8]) {
+    u32 d[8], v = m;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = a[i] ^ m;
+    sub_acc(d, v, b);
+    fold_signed(o, d, v, m & 1u);
+  }
   static constexpr bool HAS_FUSED_LINEAR = true;
   // o = a * c for a small constant c (< 2^16): one 9-limb product + fold
   FEC_DEV static void mul_small(u32 o[8], const u32 a[8], u32 c) {
@@ -238,7 +248,7 @@ struct FeK1 {
   FEC_DEV static void one(u32 o[8]) { o[0] = 1u; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = 0u; }
   FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) { copy8(o, a); }
   FEC_DEV static void to_plain(u32 o[8], const u32 a[8]) { canon(o, a); }
-  // o = a * 2^S (S = 1, 2, 3): one funnel-shift pass, the S bits shifted out are folded with 2^32 + 977
+  // o = a * 2^S (S = 1 .. 4): one funnel-shift pass, the S bits shifted out are folded with 2^32 + 977
   template <int S>
   FEC_DEV static void mul_pow2(u32 o[8], const u32 a[8]) {
     const u32 v = a[7] >> (32 - S);

@@ -128,7 +128,12 @@ FEC_DEV void glv_ladder(saddr S, const u32* tab, const u32 KK[8], u32 flags) {
   for (int i = 0; i < 32; i++) {
     if (i > 0) {
 #pragma unroll 1
+#ifndef FEC_K1_NO_LAZY_Z  // Z3 = Y Z in the four doublings and one Z <- 16 Z after them (r2: three folds fewer per window)
+      for (int d = 0; d < 4; d++) vm_jac_dbl_a0<F, T, true>(S);
+      vm_scale_z<F, T, 4>(S);
+#else
       for (int d = 0; d < 4; d++) vm_jac_dbl_a0<F, T>(S);
+#endif
     }
 #pragma unroll 1
     for (int h = (i == 0 ? 1 : 0); h < 2; h++) {
@@ -140,7 +145,12 @@ FEC_DEV void glv_ladder(saddr S, const u32* tab, const u32 KK[8], u32 flags) {
 #else
       constexpr bool LEAN = false;
 #endif
+#ifndef FEC_K1_EXACT_FLAGS  // a two-compare filter on the fast path, the exact tests only in a warp it flags (r2)
+      u32 fl = vm_jac_madd_1<F, T, LEAN, true>(S, neg_y);
+      if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+#else
       const u32 fl = vm_jac_madd_1<F, T, LEAN>(S, neg_y);
+#endif
       // the addend slots are free again: start fetching the next addend (none after the very last addition)
       if (!(i == 31 && h == 1)) {
         if (h == 0) next_digit4(K2r, idx, sgn); else next_digit4(K1r, idx, sgn);

@@ -39,6 +39,7 @@ typedef u32 saddr;  // byte address in the shared window
 #else
 #define FEC_VMLIN __device__ __forceinline__
 #endif
+#define FEC_VMRARE __device__ __noinline__  // rare paths: kept out of the loop body
 FEC_DEV void lds128(u32 r[4], saddr p) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(p) : "memory");
 }
@@ -55,6 +56,7 @@ FEC_DEV saddr sa_add(saddr p, int bytes) { return p + (u32)bytes; }
 typedef u32* saddr;
 #define FEC_VMOP inline
 #define FEC_VMLIN inline
+#define FEC_VMRARE inline
 FEC_DEV void lds128(u32 r[4], saddr p) { for (int i = 0; i < 4; i++) r[i] = p[i]; }
 FEC_DEV void sts128(saddr p, const u32 r[4]) { for (int i = 0; i < 4; i++) p[i] = r[i]; }
 FEC_DEV void cp_async16(saddr dst, const void* src) { for (int i = 0; i < 4; i++) dst[i] = static_cast<const u32*>(src)[i]; }
@@ -211,6 +213,25 @@ template <class F, int T> FEC_VMLIN fe vm_sub_mul8(fe a, saddr p) {  // a - 8 [p
   }
   return r;
 }
+#ifndef FEC_VM_NO_RELOAD
+#define VM_RELOAD(a, slot) a = V::ld(slot)
+#else
+#define VM_RELOAD(a, slot)
+#endif
+template <class F, int T> FEC_VMLIN fe vm_cneg_sub(fe a, u32 m, saddr p) {  // (m ? -a : a) - [p]
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  if constexpr (has_fused_linear<F>::value) {
+    F::cneg_sub(r.v, a.v, m, b);
+  } else {
+    u32 n[8], t[8];
+    F::neg(n, a.v);
+    select8(t, m, n, a.v);
+    F::sub(r.v, t, b);
+  }
+  return r;
+}
 template <class F, int K> FEC_VMLIN fe vm_small(fe a) {  // a * K, K in {2,3,4,8}
   fe r;
   if (K == 2) F::mul2(r.v, a.v);
@@ -218,6 +239,13 @@ template <class F, int K> FEC_VMLIN fe vm_small(fe a) {  // a * K, K in {2,3,4,8
   else if (K == 4) F::mul4(r.v, a.v);
   else F::mul8(r.v, a.v);
   return r;
+}
+template <class F, int T, int SH> FEC_VMLIN void vm_scale_z(saddr S) {  // Z <- 2^SH Z: the factors Z_LAZY doublings left out
+  typedef Vm<F, T> V;
+  fe a = V::ld(V::slot(S, 2));
+  fe r;
+  F::template mul_pow2<SH>(r.v, a.v);
+  V::st(V::slot(S, 2), r);
 }
 template <class F> FEC_VMLIN fe vm_half(fe a) {  // a / 2 (fields that provide it)
   fe r;
@@ -239,7 +267,9 @@ template <class F> FEC_VMLIN fe vm_cneg(fe a, u32 m) {  // m ? -a : a
 enum { VS_X = 0, VS_Y = 1, VS_Z = 2, VS_A = 3, VS_B = 4, VS_C = 5, VS_D = 6, VS_TX = 7, VS_TY = 8, VS_COUNT = 9 };
 
 // Q <- 2Q  (dbl-2009-l, 2M + 5S), in place
-template <class F, int T>
+// Z_LAZY: Z3 = Y Z without the factor 2 -- the caller owes Z a factor 2 per doubling and pays the run of them at once
+// (vm_scale_z); nothing else in a doubling reads Z.
+template <class F, int T, bool Z_LAZY = false>
 FEC_DEV void vm_jac_dbl_a0(saddr S) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), B = V::slot(S, VS_B),
@@ -298,8 +328,11 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
     return;
   }
 #endif
+  // (a routine returns its result in other registers than it takes its argument in: feeding one straight into the next costs
+  // 8 moves, reading the slot just written costs 2 loads -- VM_RELOAD)
   fe a = V::ld(Y);
   a = vm_sqr<F>(a); V::st(B, a);                 // B = Y^2
+  VM_RELOAD(a, B);
   a = vm_sqr<F>(a); V::st(Cs, a);                // C = B^2
   a = V::ld(X);
   a = vm_sqr<F>(a); V::st(A, a);                 // A = X^2
@@ -315,7 +348,8 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
 #endif
   a = V::ld(Y);
   a = vm_mul<F, T>(a, Z);
-  a = vm_small<F, 2>(a); V::st(Z, a);            // Z3 = 2YZ
+  if (!Z_LAZY) a = vm_small<F, 2>(a);
+  V::st(Z, a);                                   // Z3 = 2YZ
   a = V::ld(A);
   a = vm_small<F, 3>(a); V::st(A, a);            // E = 3A
   a = vm_sqr<F>(a);
@@ -382,6 +416,7 @@ FEC_DEV void vm_jac_dbl_am3(saddr S) {
   a = vm_mul<F, T>(a, Z); V::st(Z, a);           // Z3 = 2Y Z
   a = V::ld(B);
   a = vm_sqr<F>(a); V::st(B, a);                 // 4 gamma
+  VM_RELOAD(a, B);
   a = vm_mul<F, T>(a, X); V::st(Cs, a);          // 4 beta
   a = V::ld(D);
   a = vm_sqr<F>(a);
@@ -408,7 +443,7 @@ FEC_DEV void vm_prefetch_xy(saddr S, const u32* e) {
 // addend slots are no longer needed (the caller may start the next prefetch into them).
 // Returns the flag word of jac_madd_lean: bit0 formula does not apply, bit1 Q was at infinity, bit2 doubling.
 // SUBS_ONLY (fields bound by the ALU pipe): the 8M + 3S form of jac_madd_lean, r = S2 - Y1 undoubled.
-template <class F, int T, bool SUBS_ONLY = false>
+template <class F, int T, bool SUBS_ONLY = false, bool FILTER = false>
 FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   typedef Vm<F, T> V;
   const saddr X = V::slot(S, VS_X), Y = V::slot(S, VS_Y), Z = V::slot(S, VS_Z), A = V::slot(S, VS_A), H = V::slot(S, VS_B),
@@ -445,19 +480,54 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   }
 #endif
   fe a = V::ld(Z);
-  const u32 q_inf = F::is_zero(a.v);
+  // FILTER: a two-compare necessary condition instead of the three exact tests (a value that is 0 mod p has its top limb all
+  // zeros or all ones); when any lane of the warp passes it the caller gets the exact word from vm_madd_flags (the slots Z, H,
+  // R still hold what the tests read) -- a false alarm costs that warp ~60 instructions once in ~2^26 additions
+  u32 q_inf;
+  if (FILTER) q_inf = (a.v[7] + 1u <= 1u) ? 1u : 0u; else q_inf = F::is_zero(a.v);
   a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
+  VM_RELOAD(a, A);
   a = vm_mul<F, T>(a, TX);
   a = vm_sub<F, T>(a, X); V::st(H, a);           // H = U2 - X1
-  const u32 h_zero = F::is_zero(a.v);
+  u32 h_zero;
+  if (FILTER) h_zero = (a.v[7] + 1u <= 1u) ? 1u : 0u; else h_zero = F::is_zero(a.v);
   a = V::ld(Z);
   a = vm_mul<F, T>(a, A);
-  a = vm_mul<F, T>(a, TY);
+#ifndef FEC_VM_NO_RELOAD
+  if (SUBS_ONLY) {
+    V::st(A, a);                                 // Z1^3 through the slot of Z1Z1 (dead from here in the 8M + 3S form)
+    a = V::ld(TY);
+    a = vm_mul<F, T>(a, A);
+  } else
+#endif
+    a = vm_mul<F, T>(a, TY);
+#ifndef FEC_VM_NO_FUSED_LINEAR
+  a = vm_cneg_sub<F, T>(a, neg_y, Y);            // +-y2 Z1^3 - Y1, negation and subtraction under one fold
+#else
   a = vm_cneg<F>(a, neg_y);                      // S2 = +-y2 Z1^3
   a = vm_sub<F, T>(a, Y);
+#endif
+  if (FILTER) {
+    if (!SUBS_ONLY) a = vm_small<F, 2>(a);
+    V::st(R, a);
+    return q_inf | h_zero;
+  }
   const u32 r_zero = F::is_zero(a.v);
   if (!SUBS_ONLY) a = vm_small<F, 2>(a);
   V::st(R, a);                                   // r = 2(S2 - Y1), or S2 - Y1
+  return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+}
+// the exact flag word of vm_jac_madd_1, from the slots it left (Z1, H, r): the rare path behind its FILTER
+template <class F, int T>
+FEC_VMRARE u32 vm_madd_flags(saddr S) {
+  typedef Vm<F, T> V;
+  u32 t[8];
+  V::ldv(t, V::slot(S, VS_Z));
+  const u32 q_inf = F::is_zero(t);
+  V::ldv(t, V::slot(S, VS_B));
+  const u32 h_zero = F::is_zero(t);
+  V::ldv(t, V::slot(S, VS_C));
+  const u32 r_zero = F::is_zero(t);
   return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
 }
 template <class F, int T, bool SUBS_ONLY = false>
@@ -491,6 +561,7 @@ FEC_DEV void vm_jac_madd_2(saddr S) {
     a = vm_mul<F, T>(a, H); V::st(Z, a);           // Z3 = Z1 H
     a = V::ld(H);
     a = vm_sqr<F>(a); V::st(HH, a);                // HH
+    VM_RELOAD(a, HH);
     a = vm_mul<F, T>(a, H); V::st(H, a);           // HHH
     a = V::ld(X);
     a = vm_mul<F, T>(a, HH); V::st(A, a);          // V = X1 HH

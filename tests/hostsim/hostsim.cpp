@@ -154,7 +154,7 @@ int wmul(const uint8_t* k_be, const uint8_t* pt, int pfmt, int fixed, int ofmt, 
   sec1_encode(out, ofmt, x, y, st ? 0xFFFFFFFFu : 0u);
   return (int)st;
 }
-// the fused chains of linear operations of FeK1 (fields.cuh: sub2_dbl, sub_twice, sub3, sub_mul8): operands are taken as they
+// the fused chains of linear operations of FeK1 (fields.cuh: sub2_dbl, sub_twice, sub3, sub_mul8, cneg_sub; mul_pow2<4>): operands are taken as they
 // are (weak representatives included), the result is canonicalised
 void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint8_t* o) {
   u32 x[8], y[8], z[8], r[8], c[8];
@@ -163,7 +163,10 @@ void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint
     case 0: FeK1::sub2_dbl(r, x, y, z); break;
     case 1: FeK1::sub_twice(r, x, y); break;
     case 2: FeK1::sub3(r, x, y, z); break;
-    default: FeK1::sub_mul8(r, x, y); break;
+    case 3: FeK1::sub_mul8(r, x, y); break;
+    case 4: FeK1::cneg_sub(r, x, 0u, y); break;
+    case 5: FeK1::cneg_sub(r, x, 0xFFFFFFFFu, y); break;
+    default: FeK1::template mul_pow2<4>(r, x); break;
   }
   FeK1::canon(c, r);
   store_le32(o, c);

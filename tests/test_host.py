@@ -115,7 +115,7 @@ def test_device_field_code_on_host_matches_model(hostsim, pm):
 
 
 def test_fused_linear_chains_of_the_secp256k1_field(hostsim, pm):
-    """2 (t - a - b), t - 2a, t - a - 2b, t - 8a with ONE fold of the wrapped value (fields.cuh: fold_signed) against the integers,
+    """2 (t - a - b), t - 2a, t - a - 2b, t - 8a, +-t - a (and 16 t) with ONE fold of the wrapped value (fields.cuh: fold_signed) against the integers,
     on weak representatives (anything below 2^256) and on the operands that wrap the most often"""
     import random
     rnd = random.Random(23)
@@ -124,17 +124,18 @@ def test_fused_linear_chains_of_the_secp256k1_field(hostsim, pm):
             2**256 - 2**32 - 978, 2**256 - 2**33, 2**255, 2**255 - 1, 2**253, 3 * 2**253, 7 * 2**253, (1 << 224) - 1]
     vals = edge + [rnd.randrange(2**256) for _ in range(40)]
     le = lambda v: v.to_bytes(32, "little")
-    exp = [lambda t, a, b: 2 * (t - a - b), lambda t, a, b: t - 2 * a, lambda t, a, b: t - a - 2 * b, lambda t, a, b: t - 8 * a]
+    exp = [lambda t, a, b: 2 * (t - a - b), lambda t, a, b: t - 2 * a, lambda t, a, b: t - a - 2 * b, lambda t, a, b: t - 8 * a,
+           lambda t, a, b: t - a, lambda t, a, b: -t - a, lambda t, a, b: 16 * t]
     o = ctypes.create_string_buffer(32)
     for _ in range(6000):
         t, a, b = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
-        for op in range(4):
+        for op in range(7):
             hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
             assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
     for t in edge:
         for a in edge:
             for b in edge[:12]:
-                for op in range(4):
+                for op in range(7):
                     hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
                     assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
 
