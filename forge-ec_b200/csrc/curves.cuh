@@ -479,8 +479,12 @@ FEC_DEV void x25519_step(u32 xd[8], u32 zd[8], u32 xs[8], u32 zs[8], const u32 x
   F::sqr(BB, B);
   F::sub(E, AA, BB);
   F::mul(xd, AA, BB);
+#ifndef FEC_X25519_NO_FUSED_A24
+  F::mul_small_add(zd, E, 121665u, AA);  // AA + a24 E, one pass and one fold
+#else
   F::mul_small(zd, E, 121665u);
   F::add(zd, AA, zd);
+#endif
   F::mul(zd, E, zd);
 }
 

@@ -164,6 +164,31 @@ struct FeK1 {
     d[0] <<= 1;
     fold_signed(o, d, v);
   }
+  // the same with the fold left to the consumers: the value is d + v 2^256 (v in -4 .. 1), d goes to a slot and v stays in a
+  // register -- for a value that only enters further chains (the D of a doubling) this saves its fold
+  FEC_DEV static void sub2_dbl_raw(u32 d[8], u32& v, const u32 t[8], const u32 a[8], const u32 b[8]) {
+    v = 0u;
+    copy8(d, t);
+    sub_acc(d, v, a);
+    sub_acc(d, v, b);
+    v = (v << 1) + (d[7] >> 31);
+#pragma unroll
+    for (int i = 7; i >= 1; i--) d[i] = funnel_l(d[i - 1], d[i], 1);
+    d[0] <<= 1;
+  }
+  FEC_DEV static void sub_twice_raw(u32 o[8], const u32 t[8], const u32 a[8], u32 va) {  // t - 2 (a + va 2^256)
+    u32 d[8], v = 0u - (va << 1);
+    copy8(d, t);
+    sub_acc(d, v, a);
+    sub_acc(d, v, a);
+    fold_signed(o, d, v);
+  }
+  FEC_DEV static void rsub_raw(u32 o[8], const u32 a[8], u32 va, const u32 x[8]) {  // (a + va 2^256) - x
+    u32 d[8], v = va;
+    copy8(d, a);
+    sub_acc(d, v, x);
+    fold_signed(o, d, v);
+  }
   FEC_DEV static void sub_twice(u32 o[8], const u32 t[8], const u32 a[8]) {  // t - 2a
     u32 d[8], v = 0u;
     copy8(d, t);
@@ -415,6 +440,26 @@ struct Fe25519 {
       carry = m >> 32;
     }
     t[0] = add_cc(t[0], (u32)carry * 38u);  // carry < 2^26 -> < 2^32
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = addc_cc(t[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = t[0] + ((0u - c2) & 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = t[i];
+  }
+  // o = a * c + b (c < 2^26) in one pass: b rides as the addend of the eight products, so the sum has one fold instead of the
+  // two of mul_small + add (r2: the "AA + a24 E" of the X25519 step)
+  FEC_DEV static void mul_small_add(u32 o[8], const u32 a[8], u32 c, const u32 b[8]) {
+    u32 t[8];
+    u64 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 m = (u64)a[i] * c + b[i];  // < 2^58 + 2^32
+      m += carry;
+      t[i] = (u32)m;
+      carry = m >> 32;
+    }
+    t[0] = add_cc(t[0], (u32)carry * 38u);  // carry <= 2^26 -> < 2^32
 #pragma unroll
     for (int i = 1; i < 8; i++) t[i] = addc_cc(t[i], 0u);
     u32 c2 = addc(0u, 0u);

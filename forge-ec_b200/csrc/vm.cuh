@@ -178,6 +178,29 @@ template <class F, int T> FEC_VMLIN fe vm_sub2_dbl(fe a, saddr p, saddr q) {  //
   }
   return r;
 }
+// (raw forms: fields.cuh -- [p] holds the unfolded value, its wrap count v travels in a register)
+template <class F, int T> FEC_VMLIN fe vm_sub2_dbl_raw(fe a, saddr p, saddr q, u32& v) {
+  u32 b[8], c[8];
+  Vm<F, T>::ldv(b, p);
+  Vm<F, T>::ldv(c, q);
+  fe r;
+  F::sub2_dbl_raw(r.v, v, a.v, b, c);
+  return r;
+}
+template <class F, int T> FEC_VMLIN fe vm_sub_twice_raw(fe a, saddr p, u32 vp) {  // a - 2 ([p] + vp 2^256)
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::sub_twice_raw(r.v, a.v, b, vp);
+  return r;
+}
+template <class F, int T> FEC_VMLIN fe vm_rsub_raw(fe a, saddr p, u32 vp) {  // ([p] + vp 2^256) - a
+  u32 b[8];
+  Vm<F, T>::ldv(b, p);
+  fe r;
+  F::rsub_raw(r.v, b, vp, a.v);
+  return r;
+}
 template <class F, int T> FEC_VMLIN fe vm_sub_twice(fe a, saddr p) {  // a - 2 [p]
   u32 b[8];
   Vm<F, T>::ldv(b, p);
@@ -290,7 +313,9 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
     a1 = vm_small<F, 3>(a1); V::st(A, a1);         // E = 3A
     a0 = V::ld(Y);
     fe2 u = vm_mulsqr<F, T>(a0, Z, a1);            // Y Z, E^2
-    a0 = vm_small<F, 2>(u.a); V::st(Z, a0);        // Z3 = 2YZ
+    a0 = u.a;
+    if (!Z_LAZY) a0 = vm_small<F, 2>(a0);
+    V::st(Z, a0);                                  // Z3 = 2YZ
     a1 = vm_sub<F, T>(u.b, D);
     a1 = vm_sub<F, T>(a1, D); V::st(X, a1);        // X3 = E^2 - 2D
     a1 = vm_rsub<F, T>(a1, D);                     // D - X3
@@ -321,7 +346,8 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
     a = vm_mul<F, T>(a, A); V::st(B, a);           // E (D - X3)
     a = V::ld(Y);
     a = vm_mul<F, T>(a, Z);
-    a = vm_small<F, 2>(a); V::st(Z, a);            // Z3 = 2YZ
+    if (!Z_LAZY) a = vm_small<F, 2>(a);
+    V::st(Z, a);                                   // Z3 = 2YZ
     a = V::ld(Cs);
     a = vm_small<F, 8>(a);
     a = vm_rsub<F, T>(a, B); V::st(Y, a);          // Y3 = E(D - X3) - 8C
@@ -339,7 +365,15 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = V::ld(X);
   a = vm_add<F, T>(a, B);
   a = vm_sqr<F>(a);
-#ifndef FEC_VM_NO_FUSED_LINEAR
+#if !defined(FEC_VM_NO_FUSED_LINEAR) && !defined(FEC_VM_FOLD_D)
+  u32 vD = 0u;
+  if constexpr (has_fused_linear<F>::value) {
+    a = vm_sub2_dbl_raw<F, T>(a, A, Cs, vD);     // D = 2((X+B)^2 - A - C) UNFOLDED: it only enters the two chains below
+  } else {
+    a = vm_sub2_dbl<F, T>(a, A, Cs);
+  }
+  V::st(D, a);
+#elif !defined(FEC_VM_NO_FUSED_LINEAR)
   a = vm_sub2_dbl<F, T>(a, A, Cs); V::st(D, a);  // D = 2((X+B)^2 - A - C), one fold
 #else
   a = vm_sub<F, T>(a, A);
@@ -353,7 +387,17 @@ FEC_DEV void vm_jac_dbl_a0(saddr S) {
   a = V::ld(A);
   a = vm_small<F, 3>(a); V::st(A, a);            // E = 3A
   a = vm_sqr<F>(a);
-#ifndef FEC_VM_NO_FUSED_LINEAR
+#if !defined(FEC_VM_NO_FUSED_LINEAR) && !defined(FEC_VM_FOLD_D)
+  if constexpr (has_fused_linear<F>::value) {
+    a = vm_sub_twice_raw<F, T>(a, D, vD); V::st(X, a);  // X3 = E^2 - 2D
+    a = vm_rsub_raw<F, T>(a, D, vD);                    // D - X3
+  } else {
+    a = vm_sub_twice<F, T>(a, D); V::st(X, a);
+    a = vm_rsub<F, T>(a, D);
+  }
+  a = vm_mul<F, T>(a, A);                        // E (D - X3)
+  a = vm_sub_mul8<F, T>(a, Cs); V::st(Y, a);     // Y3 = E(D - X3) - 8C, one fold, nothing parked in a slot
+#elif !defined(FEC_VM_NO_FUSED_LINEAR)
   a = vm_sub_twice<F, T>(a, D); V::st(X, a);     // X3 = E^2 - 2D, one fold
   a = vm_rsub<F, T>(a, D);                       // D - X3
   a = vm_mul<F, T>(a, A);                        // E (D - X3)

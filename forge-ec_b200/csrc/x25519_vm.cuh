@@ -61,10 +61,11 @@ FEC_DEV void x25519_vm_step(saddr X1, saddr P, saddr Q, int off) {
   a = vm_sub<F, T>(a, P1); V::st(P2, a);           // E
   {
     fe t;
-    F::mul_small(t.v, a.v, 121665u);
+    u32 aa[8];
+    V::ldv(aa, P0);
+    F::mul_small_add(t.v, a.v, 121665u, aa);       // AA + a24 E
     a = t;
   }
-  a = vm_add<F, T>(a, P0);
   a = vm_mul<F, T>(a, P2); V::st(V::slot(Q, 1), a);  // z2' = E (AA + a24 E)
 }
 

@@ -166,7 +166,15 @@ void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint
     case 3: FeK1::sub_mul8(r, x, y); break;
     case 4: FeK1::cneg_sub(r, x, 0u, y); break;
     case 5: FeK1::cneg_sub(r, x, 0xFFFFFFFFu, y); break;
-    default: FeK1::template mul_pow2<4>(r, x); break;
+    case 6: FeK1::template mul_pow2<4>(r, x); break;
+    default: {  // D = 2 (t - a - b) kept unfolded, then (t - 2D) + (D - a) through the raw consumers = D + t - a ... checked as 2(t-a-b) + t - a
+      u32 d[8], v, x3[8], dm[8];
+      FeK1::sub2_dbl_raw(d, v, x, y, z);
+      FeK1::sub_twice_raw(x3, x, d, v);   // t - 2D
+      FeK1::rsub_raw(dm, d, v, y);        // D - a
+      FeK1::add(r, x3, dm);
+      break;
+    }
   }
   FeK1::canon(c, r);
   store_le32(o, c);

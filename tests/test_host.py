@@ -125,17 +125,18 @@ def test_fused_linear_chains_of_the_secp256k1_field(hostsim, pm):
     vals = edge + [rnd.randrange(2**256) for _ in range(40)]
     le = lambda v: v.to_bytes(32, "little")
     exp = [lambda t, a, b: 2 * (t - a - b), lambda t, a, b: t - 2 * a, lambda t, a, b: t - a - 2 * b, lambda t, a, b: t - 8 * a,
-           lambda t, a, b: t - a, lambda t, a, b: -t - a, lambda t, a, b: 16 * t]
+           lambda t, a, b: t - a, lambda t, a, b: -t - a, lambda t, a, b: 16 * t,
+           lambda t, a, b: (t - 2 * (2 * (t - a - b))) + (2 * (t - a - b) - a)]
     o = ctypes.create_string_buffer(32)
     for _ in range(6000):
         t, a, b = rnd.choice(vals), rnd.choice(vals), rnd.choice(vals)
-        for op in range(7):
+        for op in range(8):
             hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
             assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
     for t in edge:
         for a in edge:
             for b in edge[:12]:
-                for op in range(7):
+                for op in range(8):
                     hostsim.hs_k1_fused(op, le(t), le(a), le(b), o)
                     assert int.from_bytes(o.raw, "little") == exp[op](t, a, b) % p, (op, hex(t), hex(a), hex(b))
 
