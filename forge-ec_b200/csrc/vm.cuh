@@ -554,7 +554,11 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   if (FILTER) {
     if (!SUBS_ONLY) a = vm_small<F, 2>(a);
     V::st(R, a);
+#ifdef FEC_VM_FILTER_ALWAYS  // test builds: every addition takes the rare path (tests/test_host.py)
+    return 1u;
+#else
     return q_inf | h_zero;
+#endif
   }
   const u32 r_zero = F::is_zero(a.v);
   if (!SUBS_ONLY) a = vm_small<F, 2>(a);

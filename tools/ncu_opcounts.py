@@ -1,7 +1,9 @@
 """Executed-instruction counts per kernel from an Nsight Compute report (read here, no GPU needed), as the JSON artefact
 bench.py derives `roofline.frac_executed` and the issue-port model from (instead of constants in bench.py).
 
-  python tools/ncu_opcounts.py gpurun_out/prof.ncu-rep <lanes of the profiled calls> profiles/exec_counts.json [note]
+  python tools/ncu_opcounts.py gpurun_out/prof.ncu-rep[,second.ncu-rep...] <lanes of the profiled calls> profiles/exec_counts.json [note]
+
+(several reports, comma-separated: a capture of all kernels with sources is larger than one gpurun call brings back)
 
 The report must come from `ncu --set full --import-source on` (the source page carries "Instructions Executed" per SASS
 instruction).  Per kernel: warp instructions executed in total and by class, and the same per LANE as thread-level counts
@@ -27,14 +29,53 @@ def klass(op):
     return "alu"
 
 
-def main(rep, lanes, dst, note=""):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
+def kname(full):
+    """kernel name without its parameter list; template arguments kept, `(bool)0` / `0` spelled the same on every page"""
+    n = full.replace("fec::", "").replace("(bool)0", "0").replace("(bool)1", "1")
+    depth = 0
+    for i, ch in enumerate(n):
+        if ch == "<":
+            depth += 1
+        elif ch == ">":
+            depth -= 1
+        elif ch == "(" and depth == 0:
+            return n[:i]
+    return n
+
+
+def main(reps, lanes, dst, note=""):
+    rows = []
+    elapsed = collections.OrderedDict()
+    for rep in reps.split(","):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        rows += list(csv.reader(io.StringIO(out)))
+        # elapsed SM cycles, duration and DRAM bytes per launch from the raw page (units are chosen per report)
+        raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
+        if len(raw) <= 2:
+            continue
+        h = {n: i for i, n in enumerate(raw[0])}
+        for vals in raw[2:]:
+            kn = kname(vals[h["Kernel Name"]])
+            if kn in elapsed:
+                continue
+
+            def num(key):
+                try:
+                    return float(vals[h[key]].replace(",", ""))
+                except (KeyError, ValueError):
+                    return None
+
+            elapsed[kn] = {"sm_cycles_elapsed": num("sm__cycles_elapsed.max"), "duration": num("gpu__time_duration.sum"),
+                           "duration_unit": raw[1][h["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in h else None,
+                           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                           "dram_read": num("dram__bytes_read.sum"), "dram_read_unit": raw[1][h["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in h else "",
+                           "dram_write": num("dram__bytes_write.sum"), "dram_write_unit": raw[1][h["dram__bytes_write.sum"]] if "dram__bytes_write.sum" in h else ""}
+    rep = reps
     kernels = collections.OrderedDict()
     name, ix = None, None
     for r in rows:
         if r and r[0] == "Kernel Name":
-            name = re.sub(r"\(.*", "", r[1]).replace("fec::", "")
+            name = kname(r[1])
             while name in kernels:  # the same kernel launched again: keep the first launch
                 name += "'"
             kernels[name] = collections.Counter()
@@ -52,27 +93,6 @@ def main(rep, lanes, dst, note=""):
         op = m.group(2) if m else "?"
         kernels[name]["total"] += ex
         kernels[name][klass(op)] += ex
-    # elapsed SM cycles and duration per launch from the raw page (same launch order)
-    raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
-    elapsed = collections.OrderedDict()
-    if len(raw) > 2:
-        h = {n: i for i, n in enumerate(raw[0])}
-        for vals in raw[2:]:
-            kn = re.sub(r"\(.*", "", vals[h["Kernel Name"]]).replace("fec::", "")
-            if kn in elapsed:
-                continue
-
-            def num(key):
-                try:
-                    return float(vals[h[key]].replace(",", ""))
-                except (KeyError, ValueError):
-                    return None
-
-            elapsed[kn] = {"sm_cycles_elapsed": num("sm__cycles_elapsed.max"), "duration": num("gpu__time_duration.sum"),
-                           "duration_unit": raw[1][h["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in h else None,
-                           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                           "dram_read": num("dram__bytes_read.sum"), "dram_read_unit": raw[1][h["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in h else "",
-                           "dram_write": num("dram__bytes_write.sum"), "dram_write_unit": raw[1][h["dram__bytes_write.sum"]] if "dram__bytes_write.sum" in h else ""}
     res = {"source": f"{rep} (ncu --set full --import-source on, source page)", "lanes": lanes, "note": note, "smsps": 148 * 4, "kernels": {}}
     for k, c in kernels.items():
         if k.endswith("'") or c["total"] == 0:
