@@ -178,6 +178,52 @@ FEC_DEV u32 jac_madd_lean(Jac& q, const u32 x2[8], const u32 y2[8]) {
   F::sub(q.Y, A, H);
   return ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
 }
+// The same addition of (x2, neg_y ? -y2 : y2) with the zero tests behind a FILTER (r2): the exact flag word is computed only in a warp
+// where some lane's Z1 or H passes a one-compare necessary condition (F::maybe_zero, 2^-31 per value); the sign of the addend joins
+// the subtraction S2 - Y1 (one fold where the field has fused chains).  `any` is the caller's warp vote (lanes.cuh: warp_any).
+template <class C, class Any>
+FEC_DEV u32 jac_madd_lean_signed(Jac& q, const u32 x2[8], const u32 y2[8], u32 neg_y, Any any) {
+  typedef typename C::F F;
+  u32 A[8], H[8], r[8], D[8];
+  const u32 sus_z = F::maybe_zero(q.Z);
+  F::sqr(A, q.Z);                    // Z1Z1
+  F::mul(H, x2, A);                  // U2
+  F::sub(H, H, q.X);                 // H = U2 - X1
+  F::mul(r, q.Z, A);
+  F::mul(r, y2, r);                  // y2 Z1^3
+  if constexpr (has_fused_linear<F>::value) {
+    F::cneg_sub(r, r, neg_y, q.Y);   // +-y2 Z1^3 - Y1
+  } else {
+    u32 n[8];
+    F::neg(n, r);
+    select8(r, neg_y, n, r);
+    F::sub(r, r, q.Y);
+  }
+  u32 flags = 0u;
+  if (any(sus_z | F::maybe_zero(H))) {
+    const u32 q_inf = F::is_zero(q.Z), h_zero = F::is_zero(H), r_zero = F::is_zero(r);
+    flags = ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
+  }
+  F::mul2(r, r);                     // r = 2(S2 - Y1)
+  F::add(D, q.Z, H);
+  F::sqr(D, D);
+  F::sub(D, D, A);
+  F::sqr(A, H);                      // HH
+  F::sub(q.Z, D, A);                 // Z3 = (Z1+H)^2 - Z1Z1 - HH
+  F::mul4(A, A);                     // I = 4 HH
+  F::mul(H, H, A);                   // J = H I
+  F::mul(A, q.X, A);                 // V = X1 I
+  F::sqr(q.X, r);
+  F::sub(q.X, q.X, H);
+  F::sub(q.X, q.X, A);
+  F::sub(q.X, q.X, A);               // X3 = r^2 - J - 2V
+  F::sub(A, A, q.X);
+  F::mul(A, r, A);                   // r (V - X3)
+  F::mul(H, q.Y, H);
+  F::mul2(H, H);                     // 2 Y1 J
+  F::sub(q.Y, A, H);
+  return flags;
+}
 // repair of the lanes jac_madd_lean flagged: infinity + T = T, T + T = 2T, T + (-T) = infinity
 template <class C>
 FEC_DEV void jac_madd_fix(Jac& q, const u32 x2[8], const u32 y2[8], u32 flags) {

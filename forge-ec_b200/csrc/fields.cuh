@@ -269,6 +269,9 @@ struct FeK1 {
     P(p);
     return ~geq8(a, p);
   }
+  // a cheap NECESSARY condition for a == 0 (mod p): the representatives of zero below 2^256 are 0 and p, top word all zeros or all
+  // ones.  Non-zero where the exact test must be asked (2^-31 of all values).
+  FEC_DEV static u32 maybe_zero(const u32 a[8]) { return (a[7] + 1u <= 1u) ? 1u : 0u; }
   // byte records <-> the internal representation (here the integer itself; FeP256 works in the Montgomery domain)
   FEC_DEV static void one(u32 o[8]) { o[0] = 1u; o[1] = o[2] = o[3] = o[4] = o[5] = o[6] = o[7] = 0u; }
   FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) { copy8(o, a); }
@@ -355,6 +358,10 @@ struct FeK1 {
     copy8(o, t);
   }
 };
+
+// fields that provide chains of linear operations under one fold (FeK1: HAS_FUSED_LINEAR)
+template <class F, class = void> struct has_fused_linear { static constexpr bool value = false; };
+template <class F> struct has_fused_linear<F, decltype((void)F::HAS_FUSED_LINEAR)> { static constexpr bool value = F::HAS_FUSED_LINEAR; };
 
 // =====================================================================================
 // Curve25519 / Ed25519 base field
@@ -734,6 +741,7 @@ struct FeP256 {
   }
   FEC_DEV static void canon(u32 o[8], const u32 a[8]) { copy8(o, a); }
   FEC_DEV static u32 is_zero(const u32 a[8]) { return is_zero8(a); }
+  FEC_DEV static u32 maybe_zero(const u32 a[8]) { return a[7] == 0u ? 1u : 0u; }  // necessary condition (canonical form)
   FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) {  // a < p as an integer -> a * 2^256 mod p
     u32 rr[8];
     RR(rr);

@@ -138,6 +138,25 @@ FEC_DEV void jac_madd_safe(Jac& q, const u32 tx[8], const u32 ty[8]) {
   if (warp_any(flags)) jac_madd_fix<typename C::Cold>(q, tx, ty, flags);
 }
 
+// the same for the addend (tx, neg_y ? -ty : ty), zero tests behind the filter (curves.cuh: jac_madd_lean_signed)
+template <class C>
+FEC_DEV void jac_madd_safe_signed(Jac& q, const u32 tx[8], const u32 ty[8], u32 neg_y) {
+#ifndef FEC_MADD_EXACT_FLAGS
+  const u32 flags = jac_madd_lean_signed<C>(q, tx, ty, neg_y, [](u32 m) { return warp_any(m); });
+  if (warp_any(flags)) {
+    u32 ny[8], sy[8];
+    C::F::neg(ny, ty);
+    select8(sy, neg_y, ny, ty);
+    jac_madd_fix<typename C::Cold>(q, tx, sy, flags);
+  }
+#else
+  u32 ny[8], sy[8];
+  C::F::neg(ny, ty);
+  select8(sy, neg_y, ny, ty);
+  jac_madd_safe<C>(q, tx, sy);
+#endif
+}
+
 // P <- P + Q (Jacobian + Jacobian) including P == Q, which is repaired under a warp-uniform branch
 template <class C>
 FEC_DEV void jac_add_safe(Jac& p, const Jac& q) {
@@ -243,16 +262,14 @@ FEC_DEV void wmul_fixed_core(Jac& Q, u32 K[8], const Comb& comb) {
   comb(WINDOWS - 2, idx, nx, ny2);
 #pragma unroll 1
   for (int i = WINDOWS - 2; i >= 0; i--) {
-    u32 tx[8], ty[8], ny[8];
+    u32 tx[8], ty[8];
     const u32 sg = sgn;
     copy8(tx, nx); copy8(ty, ny2);
     if (i > 0) {  // fetch the next addend while this addition runs
       next_digit_w<W>(K, idx, sgn);
       comb(i - 1, idx, nx, ny2);
     }
-    F::neg(ny, ty);
-    select8(ty, sg, ny, ty);
-    jac_madd_safe<C>(Q, tx, ty);
+    jac_madd_safe_signed<C>(Q, tx, ty, sg);
   }
 }
 // The constant-time form of the same (FORGE_EC_CT_TABLE=1): 4-bit windows, 64 x 8 odd multiples = 32 KiB per curve, staged in

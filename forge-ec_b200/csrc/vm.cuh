@@ -164,8 +164,6 @@ template <class F, int T> FEC_VMLIN fe vm_rsub(fe a, saddr p) {  // [p] - a
 }
 // Chains of linear operations.  Fields that provide them (FeK1: HAS_FUSED_LINEAR) run a chain with ONE fold of the wrapped
 // value (fields.cuh: fold_signed), the others as the operations they stand for.
-template <class F, class = void> struct has_fused_linear { static constexpr bool value = false; };
-template <class F> struct has_fused_linear<F, decltype((void)F::HAS_FUSED_LINEAR)> { static constexpr bool value = F::HAS_FUSED_LINEAR; };
 template <class F, int T> FEC_VMLIN fe vm_sub2_dbl(fe a, saddr p, saddr q) {  // 2 (a - [p] - [q])
   u32 b[8], c[8];
   Vm<F, T>::ldv(b, p);
