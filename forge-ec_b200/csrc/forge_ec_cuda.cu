@@ -181,6 +181,7 @@ void device_free(Device& d) {
     if (d.streams[s]) cudaStreamDestroy(d.streams[s]);
   }
   cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels); cudaFree(d.comb_ct[0]); cudaFree(d.comb_ct[1]);
+  scratch_trim(d.id);  // the library's pool gives its cached scratch back to the driver
 }
 
 
@@ -576,7 +577,7 @@ int fec_batch_ecdh_dev(fec_ctx* ctx, int dev_index, fec_curve curve, const uint8
   AsyncBuf tmp;  // shared secrets (kdf != NONE) and lane status when the caller wants none; given back to the pool on return
   tmp.st = st;
   const size_t xbytes = kdf == FEC_KDF_NONE ? 0 : n * 32, sbytes = d_status == nullptr ? (n + 15) / 16 * 16 : 0;
-  if (xbytes + sbytes > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xbytes + sbytes, st));
+  if (xbytes + sbytes > 0) FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&tmp.p), xbytes + sbytes, st));
   uint8_t* dx = tmp.p;
   uint8_t* dst = d_status != nullptr ? d_status : tmp.p + xbytes;
   return launch_ecdh(ctx, *d, (int)curve, d_scalars, d_points, (int)points_fmt, n, (int)kdf, info, (int)info_len, (int)out_len,
@@ -592,7 +593,7 @@ static int msm_on_device(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, 
   if (n >= (curve == FEC_SECP256K1 ? MSM_PIPPENGER_MIN_K1 : MSM_PIPPENGER_MIN_P256) && n <= MSM_PIPPENGER_MAX && !no_pippenger) {
     AsyncBuf scratch;
     scratch.st = st;
-    FEC_CUDA(ctx, cudaMallocAsync(&scratch.p, msm_pippenger_scratch_bytes(n), st));
+    FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&scratch.p), msm_pippenger_scratch_bytes(n), st));
     int skewed = 0;
     const unsigned limit = (unsigned)(64 * (n >> 15) + 4096);
     FEC_CUDA(ctx, msm_pippenger_launch(curve, st, ds, dp, pfmt, n, scratch.p, ofmt, dout, dstatus, limit, &skewed));
@@ -603,7 +604,7 @@ static int msm_on_device(fec_ctx* ctx, Device& d, int curve, const uint8_t* ds, 
   const size_t xy_bytes = n * 64, st_bytes = (n + 15) / 16 * 16, sc_bytes = ((size_t)blocks * 24 + 4) * 4;
   AsyncBuf tmp;
   tmp.st = st;
-  FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xy_bytes + st_bytes + sc_bytes, st));
+  FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&tmp.p), xy_bytes + st_bytes + sc_bytes, st));
   int rc = launch_mul(ctx, d, curve, FEC_SEM_STD, ds, dp, pfmt, n, FEC_OUT_AFFINE_XY_BE, tmp.p, tmp.p + xy_bytes, st);
   if (rc) return rc;
   ctx->launches += 2;
@@ -646,7 +647,7 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
     AsyncBuf buf;
     buf.st = st;
     const size_t sb = count * 32, pb = (count * psz + 15) / 16 * 16;
-    FEC_CUDA(ctx, cudaMallocAsync(&buf.p, sb + pb + 128, st));
+    FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&buf.p), sb + pb + 128, st));
     FEC_CUDA(ctx, cudaMemcpyAsync(buf.p, scalars + first * 32, sb, cudaMemcpyHostToDevice, st));
     FEC_CUDA(ctx, cudaMemcpyAsync(buf.p + sb, points + first * psz, count * psz, cudaMemcpyHostToDevice, st));
     int rc = msm_on_device(ctx, d, (int)curve, buf.p, buf.p + sb, (int)points_fmt, count, FEC_OUT_AFFINE_XY_BE, buf.p + sb + pb,
@@ -673,7 +674,7 @@ int fec_msm(fec_ctx* ctx, fec_curve curve, const uint8_t* scalars, const uint8_t
   AsyncBuf buf;
   buf.st = st;
   const size_t sc_off = (G * 64 + G + 15) / 16 * 16;
-  FEC_CUDA(ctx, cudaMallocAsync(&buf.p, sc_off + (24 + 4) * 4 + 128, st));
+  FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&buf.p), sc_off + (24 + 4) * 4 + 128, st));
   FEC_CUDA(ctx, cudaMemcpyAsync(buf.p, part.data(), G * 64, cudaMemcpyHostToDevice, st));
   FEC_CUDA(ctx, cudaMemcpyAsync(buf.p + G * 64, pst.data(), G, cudaMemcpyHostToDevice, st));
   uint8_t* dres = buf.p + sc_off + (24 + 4) * 4;
@@ -741,7 +742,7 @@ int fec_batch_nonce_commit_dev(fec_ctx* ctx, int dev_index, fec_curve curve, fec
   AsyncBuf tmp;  // affine R and the lane status of the multiplication (Weierstrass modes)
   tmp.st = st;
   const size_t xyb = mode == FEC_NONCE_EDDSA ? 0 : n * 64, stb = mode == FEC_NONCE_EDDSA ? 0 : (n + 15) / 16 * 16;
-  if (xyb + stb > 0) FEC_CUDA(ctx, cudaMallocAsync(&tmp.p, xyb + stb, st));
+  if (xyb + stb > 0) FEC_CUDA(ctx, scratch_alloc(reinterpret_cast<void**>(&tmp.p), xyb + stb, st));
   return launch_nonce(ctx, *d, (int)curve, (int)mode, d_nonces, n, d_out_R, d_out_r, d_status, tmp.p, tmp.p + xyb, st);
 }
 

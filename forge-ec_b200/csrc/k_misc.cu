@@ -2,7 +2,49 @@
 #include "kernels.cuh"
 #include "kdf.cuh"
 
+#include <mutex>
+
 namespace fec {
+
+// ======================================================================================
+// The library's own stream-ordered memory pool, one per device (r2: the process-wide default pool is left as the application
+// configured it).  Scratch of earlier calls stays in the pool (release threshold = max) instead of going back to the driver at
+// every synchronisation; scratch_trim gives it back (fec_ctx_destroy).  Pools live as long as the process.
+// ======================================================================================
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[64] = {};
+static cudaError_t pool_of(int dev, cudaMemPool_t* out) {
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool[dev] == nullptr) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) { cudaMemPoolDestroy(pool); return e; }
+    g_pool[dev] = pool;
+  }
+  *out = g_pool[dev];
+  return cudaSuccess;
+}
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaMemPool_t pool;
+  if ((e = pool_of(dev, &pool)) != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+void scratch_trim(int dev) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (dev >= 0 && dev < 64 && g_pool[dev] != nullptr) cudaMemPoolTrimTo(g_pool[dev], 0);
+}
 
 // ======================================================================================
 // kernel: field microbenchmark (config 2) -- iters dependent operations per lane, in registers

@@ -226,14 +226,9 @@ cudaError_t wmul_glv_setup_k1() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_glv_ladder, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  // keep the scratch memory of earlier calls in the stream-ordered pool instead of returning it at every synchronisation
   int dev = 0;
-  cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-  unsigned long long keep = ~0ull;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
-  if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+  cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
   return cudaFuncSetAttribute(k_glv_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, GLV_FIN_SMEM);
 }
 
@@ -251,7 +246,7 @@ cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const ui
   if (n == 0) return cudaSuccess;
   const size_t cap = n < chunk ? n : chunk;
   uint8_t* base = nullptr;
-  cudaError_t e = cudaMallocAsync(&base, cap * GLV_SCRATCH_BYTES_PER_LANE + 256, st);
+  cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&base), cap * GLV_SCRATCH_BYTES_PER_LANE + 256, st);
   if (e != cudaSuccess) return e;
   GlvScratch sc;
   sc.tab = reinterpret_cast<u32*>(base);

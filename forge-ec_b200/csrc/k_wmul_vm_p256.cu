@@ -231,7 +231,7 @@ cudaError_t wmul_vm_launch_p256(cudaStream_t st, const uint8_t* scalars, const u
   if (n == 0) return cudaSuccess;
   const size_t cap = n < chunk ? n : chunk;
   uint8_t* base = nullptr;
-  cudaError_t e = cudaMallocAsync(&base, cap * P3_SCRATCH_BYTES_PER_LANE + 32 * P3_TAB_WORDS * 4 + 256, st);
+  cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&base), cap * P3_SCRATCH_BYTES_PER_LANE + 32 * P3_TAB_WORDS * 4 + 256, st);
   if (e != cudaSuccess) return e;
   P3Scratch sc;
   sc.tab = reinterpret_cast<u32*>(base);

@@ -172,6 +172,9 @@ inline size_t glv_chunk_lanes() {
   return v;
 }
 #define GLV_CHUNK_LANES (glv_chunk_lanes())
+// stream-ordered scratch from the library's own per-device pool (k_misc.cu); freed with cudaFreeAsync
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st);
+void scratch_trim(int dev);
 cudaError_t wmul_glv_setup_k1();
 cudaError_t wmul_glv_launch_k1(cudaStream_t st, const uint8_t* scalars, const uint8_t* points, int points_fmt, size_t n, int out_fmt,
                                uint8_t* out, uint8_t* status, size_t chunk, int* launches, StageEvents* se);

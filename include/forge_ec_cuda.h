@@ -41,8 +41,9 @@
  *     fec_ctx_stage_ms are single-threaded measurement aids and must not overlap other calls on the same context.
  *   - `*_dev` calls never synchronise, with one exception: fec_msm_dev with n >= 2^16 points waits once for the stream (the
  *     bucket method reads back its largest bucket size to decide on the fallback), so it cannot be captured in a CUDA graph.
- *   - Scratch memory comes from the device's default stream-ordered pool (cudaMallocAsync), whose release threshold the
- *     context raises so that the pool keeps its memory between calls.
+ *   - Scratch memory comes from a stream-ordered pool the library creates per device (cudaMallocFromPoolAsync; the
+ *     process-wide default pool and its attributes are not touched).  The pool keeps its memory between calls and gives
+ *     it back to the driver in fec_ctx_destroy.
  */
 #ifndef FORGE_EC_CUDA_H
 #define FORGE_EC_CUDA_H
