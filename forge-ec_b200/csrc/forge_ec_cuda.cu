@@ -38,6 +38,7 @@ struct Device {
   int sms = 0;
   u32* comb[2] = {nullptr, nullptr};  // secp256k1, P-256
   u32* comb_ct[2] = {nullptr, nullptr};  // the 4-bit combs of the constant-time table form (32 KiB each)
+  u32* niels_ct = nullptr;               // the same for Ed25519 (48 KiB)
   u32* niels = nullptr;
   cudaStream_t streams[N_PIPE] = {};
   uint8_t* buf_in_a[N_PIPE] = {};   // scalars / seeds / field a
@@ -127,7 +128,9 @@ int device_init(fec_ctx* ctx, Device& d) {
     FEC_CUDA(ctx, cudaMalloc(&d.comb_ct[c], (size_t)CT_TABLE_WORDS * 4));
     FEC_CUDA(ctx, build_comb_ct_launch(c, d.streams[0], d.comb_ct[c]));
   }
-  ctx->launches += 8;
+  FEC_CUDA(ctx, cudaMalloc(&d.niels_ct, (size_t)CT_NIELS_WORDS * 4));
+  FEC_CUDA(ctx, build_niels_ct_launch(d.streams[0], d.niels_ct));
+  ctx->launches += 9;
   FEC_CUDA(ctx, cudaStreamSynchronize(d.streams[0]));
   cudaFree(bases);
   return FEC_OK;
@@ -180,7 +183,7 @@ void device_free(Device& d) {
     cudaFree(d.buf_in_a[s]); cudaFree(d.buf_in_b[s]); cudaFree(d.buf_out[s]); cudaFree(d.buf_st[s]); cudaFree(d.buf_x[s]);
     if (d.streams[s]) cudaStreamDestroy(d.streams[s]);
   }
-  cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels); cudaFree(d.comb_ct[0]); cudaFree(d.comb_ct[1]);
+  cudaFree(d.comb[0]); cudaFree(d.comb[1]); cudaFree(d.niels); cudaFree(d.comb_ct[0]); cudaFree(d.comb_ct[1]); cudaFree(d.niels_ct);
   scratch_trim(d.id);  // the library's pool gives its cached scratch back to the driver
 }
 
@@ -243,7 +246,7 @@ int launch_x25519(fec_ctx* ctx, Device& d, int sem, const uint8_t* ds, const uin
   if (sem == FEC_SEM_FORGE_QUIRK)  // the reference's literal x25519(), one lane per thread (k_quirk_k1.cu)
     FEC_CUDA(ctx, quirk_x25519_launch(st, ds, du, n, dout));
   else if (du == nullptr)  // base point u = 9: fixed-base path on the Edwards form of the curve (k_ed25519.cu, mode 2)
-    FEC_CUDA(ctx, ed25519_launch(d.sms, st, ds, 2, d.niels, n, dout));
+    FEC_CUDA(ctx, fixed_ct_table() ? ed25519_ct_launch(d.sms, st, ds, 2, d.niels_ct, n, dout) : ed25519_launch(d.sms, st, ds, 2, d.niels, n, dout));
   else if (x_use_vm())
     FEC_CUDA(ctx, x25519_vm_launch(d.sms, st, ds, du, n, dout));
   else
@@ -256,7 +259,8 @@ int launch_ed(fec_ctx* ctx, Device& d, int sem, const uint8_t* din, int is_seed,
   if (sem == FEC_SEM_FORGE_QUIRK)  // the reference's literal derive_public_key (seeds only), one lane per thread
     FEC_CUDA(ctx, quirk_ed25519_launch(st, din, n, dout));
   else
-    FEC_CUDA(ctx, ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
+    FEC_CUDA(ctx, fixed_ct_table() ? ed25519_ct_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels_ct, n, dout)
+                                   : ed25519_launch(d.sms, st, din, is_seed ? 1 : 0, d.niels, n, dout));
   return FEC_OK;
 }
 // signing-side nonce commitment (k_nonce.cu).  Weierstrass modes: R = k G as affine X || Y into `dxy` with its lane status into

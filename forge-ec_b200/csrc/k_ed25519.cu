@@ -7,7 +7,10 @@ namespace fec {
 // kernel: Ed25519 public keys  (config 5b)
 // ======================================================================================
 // Warp-independent tiles with a deferred warp-level inversion, as k_wmul_fixed (k_wmul_fixed.cuh).
+// CT = true (FORGE_EC_CT_TABLE=1): the constant-time table form -- niels_g is the 48 KiB 4-bit comb (lanes.cuh: ScanNiels), copied
+// to shared memory by every block; 64 additions with masked scans instead of 16 with gathers by secret digits.
 constexpr int ED_DEFER = 16;
+template <bool CT>
 __global__ void __launch_bounds__(ED_THREADS, ED_BLOCKS_PER_SM)
 k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict__ niels_g, size_t n,
                  uint8_t* __restrict__ out) {
@@ -17,7 +20,13 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict
   //         clamped scalar is never a multiple of the group order.
   const int input_is_seed = mode == 1;
   typedef Fe25519 F;
-  GlobalNiels niels{niels_g};
+  typename std::conditional<CT, ScanNiels, GlobalNiels>::type niels{niels_g};
+  if (CT) {
+    extern __shared__ __align__(16) u32 ct_tab[];
+    for (int i = threadIdx.x; i < CT_NIELS_WORDS; i += ED_THREADS) ct_tab[i] = niels_g[i];
+    __syncthreads();
+    niels.base = ct_tab;
+  }
   const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const size_t ntiles = (n + 31) / 32;
   const size_t gwarp = (size_t)blockIdx.x * (ED_THREADS / 32) + warp, nwarps = (size_t)gridDim.x * (ED_THREADS / 32);
@@ -53,7 +62,8 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict
       }
       ed_scalar_prepare(K, s);
       EdExt Q;
-      ed_comb_core(Q, K, niels);  // Z != 0 always (complete formulas)
+      if (CT) ed_comb_core<decltype(niels), CT_W>(Q, K, niels);
+      else ed_comb_core(Q, K, niels);  // Z != 0 always (complete formulas)
       if (mode == 2) {            // (Y, Z) <- (Z + Y, Z - Y): the unwinding multiplies Y by 1 / Z
         u32 t[8];
         F::add(t, Q.Z, Q.Y);
@@ -120,11 +130,35 @@ __global__ void __launch_bounds__(128) k_build_niels(u32* __restrict__ niels_g, 
 }
 
 
-cudaError_t ed25519_setup() { return cudaSuccess; }
+// the 4-bit Niels comb of the constant-time form: one thread per entry (i, j) = (2j+1) 2^(4i) B
+__global__ void __launch_bounds__(128) k_build_niels_ct(u32* __restrict__ niels4) {
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  const int i = e / CT_ENTRIES, j = e % CT_ENTRIES;
+  EdExt Bi;
+  ed_comb_base<CT_W>(Bi, i);
+  u32 a[8], b[8], c[8];
+  ed_comb_entry<CT_W>(a, b, c, Bi, j);
+  u32* o = niels4 + (size_t)e * 24;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { o[w] = a[w]; o[8 + w] = b[w]; o[16 + w] = c[w]; }
+}
+
+cudaError_t ed25519_setup() {
+  return cudaFuncSetAttribute(k_ed25519_pubkey<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_NIELS_WORDS * 4);
+}
+cudaError_t ed25519_ct_launch(int sms, cudaStream_t st, const uint8_t* in, int mode, const u32* niels4, size_t n, uint8_t* out) {
+  const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS - 1) / ED_THREADS);
+  k_ed25519_pubkey<true><<<g, ED_THREADS, CT_NIELS_WORDS * 4, st>>>(in, mode, niels4, n, out);
+  return cudaGetLastError();
+}
+cudaError_t build_niels_ct_launch(cudaStream_t st, u32* niels4) {
+  k_build_niels_ct<<<CT_WINDOWS * CT_ENTRIES / 128, 128, 0, st>>>(niels4);
+  return cudaGetLastError();
+}
 cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode, const u32* niels, size_t n,
                            uint8_t* out) {
   const int g = persistent_grid(sms, ED_BLOCKS_PER_SM, (n + ED_THREADS - 1) / ED_THREADS);
-  k_ed25519_pubkey<<<g, ED_THREADS, 0, st>>>(in, mode, niels, n, out);
+  k_ed25519_pubkey<false><<<g, ED_THREADS, 0, st>>>(in, mode, niels, n, out);
   return cudaGetLastError();
 }
 cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases) {

@@ -227,6 +227,9 @@ cudaError_t ed25519_launch(int sms, cudaStream_t st, const uint8_t* in, int mode
                            uint8_t* out);
 cudaError_t build_comb_launch(int curve, cudaStream_t st, u32* comb, u32* bases /* COMB_WINDOWS x 16 words scratch */);
 cudaError_t build_niels_launch(cudaStream_t st, u32* niels, u32* bases /* COMB_WINDOWS x 32 words scratch */);
+// constant-time table form of the Ed25519 / X25519 base-point multiplication (FORGE_EC_CT_TABLE=1): 64 x 8 Niels triples (48 KiB)
+cudaError_t build_niels_ct_launch(cudaStream_t st, u32* niels4 /* CT_NIELS_WORDS words */);
+cudaError_t ed25519_ct_launch(int sms, cudaStream_t st, const uint8_t* in, int mode, const u32* niels4, size_t n, uint8_t* out);
 cudaError_t field_bench_launch(int sms, cudaStream_t st, int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
                                size_t lanes, int iters);
 cudaError_t imad_peak_launch(int variant, int blocks, cudaStream_t st, u32* sink, u32 seed, int trips);

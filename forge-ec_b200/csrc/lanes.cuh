@@ -295,6 +295,23 @@ struct ScanComb {
   }
 };
 
+// the Ed25519 / X25519-base-point counterpart: 64 x 8 Niels triples = 48 KiB in shared memory, every triple of a window scanned
+constexpr int CT_NIELS_WORDS = CT_WINDOWS * CT_ENTRIES * 24;
+struct ScanNiels {
+  const u32* base;  // shared memory: entry (i, j) at word (i * 8 + j) * 24
+  FEC_DEV void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const {
+#pragma unroll
+    for (int w = 0; w < 8; w++) { a[w] = 0u; b[w] = 0u; c[w] = 0u; }
+#pragma unroll
+    for (u32 j = 0; j < (u32)CT_ENTRIES; j++) {
+      const u32* e = base + ((size_t)i * CT_ENTRIES + j) * 24;  // the same address in every lane: a broadcast read
+      const u32 m = (j == idx) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { a[w] |= e[w] & m; b[w] |= e[8 + w] & m; c[w] |= e[16 + w] & m; }
+    }
+  }
+};
+
 // -------------------------------------------------------------------------------------
 // secp256k1 only: GLV endomorphism phi(x,y) = (beta x, y) = lambda (x,y).
 // k = k1 + k2 lambda (mod n) with |k1|, |k2| < 2^128 (lattice basis and rounding constants g1, g2 as
@@ -722,20 +739,21 @@ FEC_DEV void ed_scalar_prepare(u32 K[8], const u32 s[8]) {
   recode_reg(K, t);
 }
 // Q = sum of COMB_WINDOWS signed odd digits times the Niels comb: niels(i, idx, ypx, ymx, t2d) = (2 idx+1) 2^(W i) B
-template <class Comb>
+template <class Comb, int W = COMB_W>
 FEC_DEV void ed_comb_core(EdExt& Q, u32 K[8], const Comb& niels) {
   typedef Fe25519 F;
+  constexpr int WINDOWS = 256 / W;
   ed_set_identity(Q);
   u32 idx, sgn, na[8], nb[8], nc[8];
-  next_digit_w<COMB_W>(K, idx, sgn);
-  niels(COMB_WINDOWS - 1, idx, na, nb, nc);
+  next_digit_w<W>(K, idx, sgn);
+  niels(WINDOWS - 1, idx, na, nb, nc);
 #pragma unroll 1
-  for (int i = COMB_WINDOWS - 1; i >= 0; i--) {
+  for (int i = WINDOWS - 1; i >= 0; i--) {
     u32 ypx[8], ymx[8], t2d[8], nt[8];
     const u32 sg = sgn;
     copy8(ypx, na); copy8(ymx, nb); copy8(t2d, nc);
     if (i > 0) {  // fetch the next addend while this addition runs
-      next_digit_w<COMB_W>(K, idx, sgn);
+      next_digit_w<W>(K, idx, sgn);
       niels(i - 1, idx, na, nb, nc);
     }
     cswap8(ypx, ymx, sg);
@@ -785,12 +803,13 @@ FEC_DEV void comb_entry_jac(Jac& R, const u32 bx[8], const u32 by[8], int j) {
   }
 }
 // Ed25519 window base 2^(W i) B in extended coordinates with Z = 1
+template <int W = COMB_W>
 FEC_DEV void ed_comb_base(EdExt& Bi, int i) {
   typedef Fe25519 F;
   ed_base(Bi.X, Bi.Y);
   set_small(Bi.Z, 1u);
   F::mul(Bi.T, Bi.X, Bi.Y);
-  for (int d = 0; d < COMB_W * i; d++) {
+  for (int d = 0; d < W * i; d++) {
     EdExt c = Bi;
     ed_add(Bi, c);
   }
@@ -804,11 +823,12 @@ FEC_DEV void ed_comb_base(EdExt& Bi, int i) {
   F::mul(Bi.T, Bi.X, Bi.Y);
 }
 // (2j+1) Bi as a Niels triple (y+x, y-x, 2dxy), canonical limbs
+template <int W = COMB_W>
 FEC_DEV void ed_comb_entry(u32 ypx[8], u32 ymx[8], u32 t2d[8], const EdExt& Bi, int j) {
   typedef Fe25519 F;
   EdExt R = Bi;
   const int m = 2 * j + 1;
-  int top = COMB_W - 1;
+  int top = W - 1;
   while (top > 0 && !((m >> top) & 1)) top--;
   for (int b = top - 1; b >= 0; b--) {
     EdExt c = R;

@@ -44,6 +44,10 @@
  *   - Scratch memory comes from a stream-ordered pool the library creates per device (cudaMallocFromPoolAsync; the
  *     process-wide default pool and its attributes are not touched).  The pool keeps its memory between calls and gives
  *     it back to the driver in fec_ctx_destroy.
+ *   - Side channels: control flow never depends on secrets.  By default the fixed-base entry points (k*G, Ed25519 key
+ *     generation, X25519 with the base point, nonce commitments) gather table entries by secret digits; the environment
+ *     variable FORGE_EC_CT_TABLE=1 (read once per process) selects scanned 4-bit tables in shared memory for all of them
+ *     at about a quarter of the throughput.
  */
 #ifndef FORGE_EC_CUDA_H
 #define FORGE_EC_CUDA_H

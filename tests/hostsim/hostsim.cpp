@@ -63,6 +63,25 @@ struct HostNiels {
   void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const { ed_comb_entry(a, b, c, bases[i], (int)idx); }
 };
 
+// the 4-bit Niels comb of the constant-time form, entries built as k_build_niels_ct does and read through ScanNiels
+struct HostNiels4 {
+  u32* tab;
+  ScanNiels scan;
+  HostNiels4() {
+    tab = new u32[CT_NIELS_WORDS];
+    for (int i = 0; i < CT_WINDOWS; i++) {
+      EdExt Bi;
+      ed_comb_base<CT_W>(Bi, i);
+      for (int j = 0; j < CT_ENTRIES; j++) {
+        u32* o = tab + ((size_t)i * CT_ENTRIES + j) * 24;
+        ed_comb_entry<CT_W>(o, o + 8, o + 16, Bi, j);
+      }
+    }
+    scan.base = tab;
+  }
+  void operator()(int i, u32 idx, u32 a[8], u32 b[8], u32 c[8]) const { scan(i, idx, a, b, c); }
+};
+
 template <class F> void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
   u32 x[8], y[8], r[8], t[8];
   load_le32(x, a); load_le32(y, b);
@@ -241,6 +260,17 @@ void hs_ed25519_pubkey(const uint8_t* in, int is_seed, uint8_t* out) {
   ed_scalar_prepare(K, s);
   EdExt Q;
   ed_comb_core(Q, K, niels);
+  Fe25519::inv(zi, Q.Z);
+  ed_encode(o, Q, zi);
+  store_le32(out, o);
+}
+void hs_ed25519_pubkey_ct(const uint8_t* in, int is_seed, uint8_t* out) {  // constant-time table form (FORGE_EC_CT_TABLE=1)
+  static HostNiels4 niels;
+  u32 s[8], K[8], zi[8], o[8];
+  if (is_seed) ed25519_expand_seed(s, in); else load_le32(s, in);
+  ed_scalar_prepare(K, s);
+  EdExt Q;
+  ed_comb_core<HostNiels4, CT_W>(Q, K, niels);
   Fe25519::inv(zi, Q.Z);
   ed_encode(o, Q, zi);
   store_le32(out, o);

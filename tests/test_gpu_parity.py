@@ -698,6 +698,11 @@ us = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
 us[0] = 0
 us[1] = 255
 h.update(np.ascontiguousarray(eng.batch_x25519(ks, us)).tobytes())
+ks[2] = 0
+ks[3] = 255
+h.update(np.ascontiguousarray(eng.batch_x25519(ks, None)).tobytes())              # base point: the Ed25519 fixed-base route
+h.update(np.ascontiguousarray(eng.batch_ed25519_pubkey(ks, True)).tobytes())      # seeds
+h.update(np.ascontiguousarray(eng.batch_ed25519_pubkey(ks, False)).tobytes())     # scalars as they are
 print("DIGEST", h.hexdigest())
 """
 
@@ -705,7 +710,8 @@ print("DIGEST", h.hexdigest())
 def test_every_kernel_form_returns_the_same_bytes(tmp_path):
     """The forms kept for A/B measurements (single-kernel k*P, register-resident / accumulator-machine fixed base, the
     accumulator-machine X25519 ladder) against the default kernels on 4096 seeded lanes per entry point, edge scalars included.
-    The switches are read once per process, so each form runs in a child process and reports a digest of all outputs."""
+    The switches are read once per process, so each form runs in a child process and reports a digest of all outputs.
+    FORGE_EC_CT_TABLE=1 covers k*G of both Weierstrass curves AND the Ed25519 / X25519-base-point comb (scanned 4-bit tables)."""
     import os
     import subprocess
     import sys

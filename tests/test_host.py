@@ -188,6 +188,10 @@ def test_device_lane_code_on_host_matches_model(hostsim, pm):
         assert o.raw == pm.ed25519_pubkey(k)
         hostsim.hs_ed25519_pubkey(k, 0, o)
         assert o.raw == pm.ed25519_pubkey(k, False)
+        hostsim.hs_ed25519_pubkey_ct(k, 1, o)    # the 4-bit scanned comb of FORGE_EC_CT_TABLE=1
+        assert o.raw == pm.ed25519_pubkey(k)
+        hostsim.hs_ed25519_pubkey_ct(k, 0, o)
+        assert o.raw == pm.ed25519_pubkey(k, False)
 
 
 def test_dual_operation_programs_of_the_accumulator_machine(pm):
