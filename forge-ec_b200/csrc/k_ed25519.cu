@@ -9,7 +9,10 @@ namespace fec {
 // Warp-independent tiles with a deferred warp-level inversion, as k_wmul_fixed (k_wmul_fixed.cuh).
 // CT = true (FORGE_EC_CT_TABLE=1): the constant-time table form -- niels_g is the 48 KiB 4-bit comb (lanes.cuh: ScanNiels), copied
 // to shared memory by every block; 64 additions with masked scans instead of 16 with gathers by secret digits.
-constexpr int ED_DEFER = 16;
+#ifndef FEC_ED_DEFER
+#define FEC_ED_DEFER 64
+#endif
+constexpr int ED_DEFER = FEC_ED_DEFER;
 template <bool CT>
 __global__ void __launch_bounds__(ED_THREADS, ED_BLOCKS_PER_SM)
 k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict__ niels_g, size_t n,
@@ -35,7 +38,7 @@ k_ed25519_pubkey(const uint8_t* __restrict__ in, int mode, const u32* __restrict
   int cnt = 0;
   size_t first_tile_of_batch = 0;
   __shared__ u32 inv_scratch[INV_SCRATCH_WORDS];
-  const bool small = small_batch_mode(ntiles, nwarps, ED_DEFER);  // kernel-uniform
+  const bool small = small_batch_mode(ntiles, nwarps, 16);  // kernel-uniform
   set_small(acc, 1u);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform

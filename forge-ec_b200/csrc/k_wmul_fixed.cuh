@@ -13,7 +13,13 @@ namespace fec {
 // FIX_DEFER tiles in thread-local memory together with the running product of their Z, then performs ONE warp-level
 // inversion for all 32 x FIX_DEFER results (Montgomery's trick along the tile axis), normalises, encodes and writes
 // them.  With 15 additions per scalar the inversion would otherwise be a third of the work.
-constexpr int FIX_DEFER = 16;
+// r2: 64 tiles per inversion instead of 16 (the Fermat chain is 270 field operations per WARP: 17 per tile at 16, 4 at 64 against the
+// ~170 of a tile's additions): k*G 511 -> 543 M/s, Ed25519 keygen 588 -> 622 M/s at 2^22 lanes, nothing lost at 2^18
+// (profiles/r2v_defer_ab.log).  The price is thread-local memory: 64 x 36 words = 9 KiB per thread.
+#ifndef FEC_FIX_DEFER
+#define FEC_FIX_DEFER 64
+#endif
+constexpr int FIX_DEFER = FEC_FIX_DEFER;
 constexpr int FIX_SLOT_WORDS = 36;  // X, Y, Z, prefix (8 words each) + status + padding
 
 // CT = true: the constant-time table form (ScanComb, lanes.cuh): comb_g is the 32 KiB 4-bit comb, copied to shared memory first
@@ -39,7 +45,7 @@ k_wmul_fixed(const uint8_t* __restrict__ scalars, const u32* __restrict__ comb_g
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
-  const bool small = small_batch_mode(ntiles, nwarps, FIX_DEFER);  // kernel-uniform
+  const bool small = small_batch_mode(ntiles, nwarps, 16);  // kernel-uniform
   u32* inv_scratch = smem + (FIX_THREADS / 32) * FIX_IO_BYTES_PER_WARP / 4;
   F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {

@@ -12,7 +12,10 @@ constexpr int FIXVM_THREADS = 128;
 #define FEC_FIXVM_BLOCKS 5
 #endif
 constexpr int FIXVM_BLOCKS = FEC_FIXVM_BLOCKS;
-constexpr int FIXVM_DEFER = 16;
+#ifndef FEC_FIXVM_DEFER
+#define FEC_FIXVM_DEFER 64
+#endif
+constexpr int FIXVM_DEFER = FEC_FIXVM_DEFER;
 constexpr int FIXVM_SLOT_BYTES = VS_COUNT * 32 * FIXVM_THREADS;
 constexpr int FIXVM_IO_BYTES = (FIXVM_THREADS / 32) * 65 * 32;
 constexpr int FIXVM_SMEM = FIXVM_SLOT_BYTES + FIXVM_IO_BYTES;  // slots + staging: 45 184 B, five blocks per SM (one more KB would leave four)
@@ -40,7 +43,7 @@ k_wmul_fixed_vm(const uint8_t* __restrict__ scalars, const u32* __restrict__ com
   u32 acc[8];
   int cnt = 0;
   size_t first_tile_of_batch = 0;
-  const bool small = small_batch_mode(ntiles, nwarps, FIXVM_DEFER);  // kernel-uniform
+  const bool small = small_batch_mode(ntiles, nwarps, 16);  // kernel-uniform
   u32* inv_scratch = smem;  // the slot area: free once every warp of the block has left its last tile (barrier below)
   F::one(acc);
   for (size_t tile = gwarp;; tile += nwarps) {

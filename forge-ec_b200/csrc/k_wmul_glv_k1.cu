@@ -29,7 +29,10 @@ constexpr int GLV_FIN_THREADS = 128;
 #define FEC_GLV_FIN_BLOCKS 5
 #endif
 constexpr int GLV_FIN_BLOCKS = FEC_GLV_FIN_BLOCKS;
-constexpr int GLV_FIN_DEFER = 16;
+#ifndef FEC_GLV_FIN_DEFER
+#define FEC_GLV_FIN_DEFER 48
+#endif
+constexpr int GLV_FIN_DEFER = FEC_GLV_FIN_DEFER;
 constexpr int GLV_FIN_SMEM = (GLV_FIN_THREADS / 32) * 65 * 32;
 
 struct GlvScratch {

@@ -35,7 +35,10 @@ constexpr int P3_FIN_THREADS = 128;
 #define FEC_P3_FIN_BLOCKS 5
 #endif
 constexpr int P3_FIN_BLOCKS = FEC_P3_FIN_BLOCKS;
-constexpr int P3_FIN_DEFER = 16;
+#ifndef FEC_P3_FIN_DEFER
+#define FEC_P3_FIN_DEFER 48
+#endif
+constexpr int P3_FIN_DEFER = FEC_P3_FIN_DEFER;
 constexpr int P3_FIN_SMEM = (P3_FIN_THREADS / 32) * 65 * 32;
 
 struct P3Scratch {

@@ -8,7 +8,10 @@ namespace fec {
 // ======================================================================================
 // Warp-independent tiles of 32 lanes; the final x2 / z2 of X_DEFER tiles share ONE warp-level inversion (Montgomery's
 // trick along the tile axis), so no warp ever waits at a barrier while another one runs the Fermat chain.
-constexpr int X_DEFER = 8;
+#ifndef FEC_X_DEFER
+#define FEC_X_DEFER 32
+#endif
+constexpr int X_DEFER = FEC_X_DEFER;
 __global__ void __launch_bounds__(X_THREADS, X_BLOCKS_PER_SM)
 k_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, size_t n, uint8_t* __restrict__ out) {
   typedef Fe25519 F;
@@ -20,7 +23,7 @@ k_x25519(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ us, si
   int cnt = 0;
   size_t first_tile_of_batch = 0;
   __shared__ u32 inv_scratch[INV_SCRATCH_WORDS];
-  const bool small = small_batch_mode(ntiles, nwarps, X_DEFER);  // kernel-uniform
+  const bool small = small_batch_mode(ntiles, nwarps, 8);  // kernel-uniform
   set_small(acc, 1u);
   for (size_t tile = gwarp;; tile += nwarps) {
     const bool have = tile < ntiles;  // warp-uniform

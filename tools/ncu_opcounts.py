@@ -61,11 +61,20 @@ def main(reps, lanes, dst, note=""):
 
             def num(key):
                 try:
-                    return float(vals[h[key]].replace(",", ""))
+                    x = float(vals[h[key]].replace(",", ""))
+                    return None if x != x else x  # ncu prints -nan for a counter it could not collect
                 except (KeyError, ValueError):
                     return None
 
-            elapsed[kn] = {"sm_cycles_elapsed": num("sm__cycles_elapsed.max"), "duration": num("gpu__time_duration.sum"),
+            cyc = num("sm__cycles_elapsed.max")
+            cyc_src = "sm__cycles_elapsed.max"
+            if cyc is None and num("gpu__time_duration.sum") is not None and num("device__attribute_clock_rate") is not None:
+                # (seen on persistent-grid kernels: every *_cycles_elapsed counter of the launch is -nan) duration x SM clock
+                unit = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0}.get(raw[1][h["gpu__time_duration.sum"]].replace("μ", "u"), None)
+                if unit is not None:
+                    cyc = num("gpu__time_duration.sum") * unit * num("device__attribute_clock_rate") * 1e3
+                    cyc_src = "gpu__time_duration.sum x device__attribute_clock_rate"
+            elapsed[kn] = {"sm_cycles_elapsed": cyc, "cycles_source": cyc_src, "duration": num("gpu__time_duration.sum"),
                            "duration_unit": raw[1][h["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in h else None,
                            "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                            "dram_read": num("dram__bytes_read.sum"), "dram_read_unit": raw[1][h["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in h else "",
@@ -106,7 +115,7 @@ def main(reps, lanes, dst, note=""):
         if e and e["sm_cycles_elapsed"]:
             # cycles the model predicts for this launch on 592 SMSPs against the cycles it took
             pred = (4 * c["imad_wide"] + c["total"] - c["imad_wide"]) / (148 * 4)
-            res["kernels"][k].update({"sm_cycles_elapsed": e["sm_cycles_elapsed"], "issue_model_cycles": pred,
+            res["kernels"][k].update({"sm_cycles_elapsed": e["sm_cycles_elapsed"], "cycles_source": e["cycles_source"], "issue_model_cycles": pred,
                                       "issue_port_utilisation": pred / e["sm_cycles_elapsed"], "ncu_issue_active_pct": e["issue_active_pct"],
                                       "duration": e["duration"], "duration_unit": e["duration_unit"]})
         if e and e.get("dram_read") is not None and e.get("dram_write") is not None:
