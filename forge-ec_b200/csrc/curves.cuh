@@ -204,6 +204,22 @@ FEC_DEV u32 jac_madd_lean_signed(Jac& q, const u32 x2[8], const u32 y2[8], u32 n
     const u32 q_inf = F::is_zero(q.Z), h_zero = F::is_zero(H), r_zero = F::is_zero(r);
     flags = ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
   }
+#ifndef FEC_FIXED_MADD_7M4S
+  if constexpr (has_fused_linear<F>::value) {
+    // 8M + 3S with r = S2 - Y1 undoubled (r2): 5 linear operations instead of 14 for one multiplication more than a squaring
+    F::mul(q.Z, q.Z, H);             // Z3 = Z1 H
+    F::sqr(A, H);                    // HH
+    F::mul(H, H, A);                 // HHH
+    F::mul(A, q.X, A);               // V = X1 HH
+    F::sqr(D, r);
+    F::sub3(q.X, D, H, A);           // X3 = r^2 - HHH - 2V, one fold
+    F::sub(A, A, q.X);
+    F::mul(A, r, A);                 // r (V - X3)
+    F::mul(H, q.Y, H);               // Y1 HHH
+    F::sub(q.Y, A, H);
+    return flags;
+  }
+#endif
   F::mul2(r, r);                     // r = 2(S2 - Y1)
   F::add(D, q.Z, H);
   F::sqr(D, D);
