@@ -471,6 +471,31 @@ FEC_DEV void ed_set_identity(EdExt& q) {
   q.Y[0] = 1; q.Z[0] = 1;
 }
 // Q <- Q + N  (madd-2008-hwcd-3, 7M; complete: no exceptional cases, identity = (1,1,0))
+// the same for the addend or its negative (neg: full mask).  -(y+x, y-x, 2dxy) = (y-x, y+x, -2dxy): the first two trade places
+// as multipliers, and instead of negating the third, F = D - C and G = D + C trade places after it (32 selections instead of a
+// conditional swap, a field negation and a selection)
+FEC_DEV void ed_madd_signed(EdExt& q, const u32 ypx[8], const u32 ymx[8], const u32 t2d[8], u32 neg) {
+  typedef Fe25519 F;
+  u32 A[8], B[8], Cc[8], D[8], E[8], Fv[8], G[8], H[8], m[8];
+  F::sub(A, q.Y, q.X);
+  select8(m, neg, ypx, ymx);
+  F::mul(A, A, m);
+  F::add(B, q.Y, q.X);
+  select8(m, neg, ymx, ypx);
+  F::mul(B, B, m);
+  F::mul(Cc, q.T, t2d);
+  F::dbl(D, q.Z);
+  F::sub(E, B, A);
+  F::sub(m, D, Cc);
+  F::add(H, D, Cc);
+  select8(Fv, neg, H, m);
+  select8(G, neg, m, H);
+  F::add(H, B, A);
+  F::mul(q.X, E, Fv);
+  F::mul(q.Y, G, H);
+  F::mul(q.T, E, H);
+  F::mul(q.Z, Fv, G);
+}
 FEC_DEV void ed_madd(EdExt& q, const u32 ypx[8], const u32 ymx[8], const u32 t2d[8]) {
   typedef Fe25519 F;
   u32 A[8], B[8], Cc[8], D[8], E[8], Fv[8], G[8], H[8];

@@ -749,17 +749,24 @@ FEC_DEV void ed_comb_core(EdExt& Q, u32 K[8], const Comb& niels) {
   niels(WINDOWS - 1, idx, na, nb, nc);
 #pragma unroll 1
   for (int i = WINDOWS - 1; i >= 0; i--) {
-    u32 ypx[8], ymx[8], t2d[8], nt[8];
+    u32 ypx[8], ymx[8], t2d[8];
+#ifdef FEC_ED_SIGN_BY_NEGATION
+    u32 nt[8];
+#endif
     const u32 sg = sgn;
     copy8(ypx, na); copy8(ymx, nb); copy8(t2d, nc);
     if (i > 0) {  // fetch the next addend while this addition runs
       next_digit_w<W>(K, idx, sgn);
       niels(i - 1, idx, na, nb, nc);
     }
+#ifndef FEC_ED_SIGN_BY_NEGATION
+    ed_madd_signed(Q, ypx, ymx, t2d, sg);
+#else
     cswap8(ypx, ymx, sg);
     F::neg(nt, t2d);
     select8(t2d, sg, nt, t2d);
     ed_madd(Q, ypx, ymx, t2d);
+#endif
   }
 }
 // RFC 8032 5.1.2 encoding with a supplied 1/Z: y little-endian, bit 255 = x & 1

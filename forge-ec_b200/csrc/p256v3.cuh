@@ -51,7 +51,12 @@ FEC_DEV void p3_ladder(saddr S, const u32* tab, const u32 Kin[8]) {
     for (int d = 0; d < 4; d++) vm_jac_dbl_am3<F, T>(S);
     const u32 cur = idx, neg_y = sgn;
     cp_async_wait();
+#ifndef FEC_VM_EXACT_FLAGS  // the zero tests of the addition behind a one-compare filter (vm.cuh), exact flags only in a flagged warp
+    u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND, true>(S, neg_y);
+    if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+#else
     const u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND>(S, neg_y);
+#endif
     // the addend slots are free again: start fetching the next addend (none after the last addition)
     if (i < 62) {
       next_digit(K, idx, sgn);

@@ -526,13 +526,13 @@ FEC_DEV u32 vm_jac_madd_1(saddr S, u32 neg_y) {
   // zeros or all ones); when any lane of the warp passes it the caller gets the exact word from vm_madd_flags (the slots Z, H,
   // R still hold what the tests read) -- a false alarm costs that warp ~60 instructions once in ~2^26 additions
   u32 q_inf;
-  if (FILTER) q_inf = (a.v[7] + 1u <= 1u) ? 1u : 0u; else q_inf = F::is_zero(a.v);
+  if (FILTER) q_inf = F::maybe_zero(a.v); else q_inf = F::is_zero(a.v);
   a = vm_sqr<F>(a); V::st(A, a);                 // Z1Z1
   VM_RELOAD(a, A);
   a = vm_mul<F, T>(a, TX);
   a = vm_sub<F, T>(a, X); V::st(H, a);           // H = U2 - X1
   u32 h_zero;
-  if (FILTER) h_zero = (a.v[7] + 1u <= 1u) ? 1u : 0u; else h_zero = F::is_zero(a.v);
+  if (FILTER) h_zero = F::maybe_zero(a.v); else h_zero = F::is_zero(a.v);
   a = V::ld(Z);
   a = vm_mul<F, T>(a, A);
 #ifndef FEC_VM_NO_RELOAD

@@ -55,7 +55,12 @@ FEC_DEV void wmul_fixed_vm_core(saddr S, u32 K[8], const Entry& entry) {
     const u32* cur = e;
     const u32 neg_y = sgn;
     cp_async_wait();
+#ifndef FEC_VM_EXACT_FLAGS  // the zero tests of the addition behind a one-compare filter (vm.cuh), exact flags only in a flagged warp
+    u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND, true>(S, neg_y);
+    if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+#else
     const u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND>(S, neg_y);
+#endif
     if (i > 0) {  // the addend slots are free again: fetch the next addend while this addition runs
       next_digit_w<COMB_W>(K, idx, sgn);
       e = entry(i - 1, idx);

@@ -235,13 +235,16 @@ def test_zero_test_filter_of_the_secp256k1_ladder_rare_path(pm):
     be = lambda v: v.to_bytes(32, "big")
     hs.hs_set_var_impl(1)
     o = ctypes.create_string_buffer(33)
-    c = pm.CURVES[0]
-    ks = [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, (30 << 252) - c.n, 15 << 252] + [rnd.randrange(c.n) for _ in range(12)]
-    for k in ks:
-        P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
-        for pt in (be(P[0]) + be(P[1]), be(c.gx) + be(c.gy)):
-            st = hs.hs_wmul(0, be(k), pt, 0, 0, 0, o)
-            assert (o.raw, bytes([st])) == pm.batch_mul(0, be(k), pt, 1, 0, 0), hex(k)
+    for curve in (0, 1):  # the P-256 ladder and the accumulator-machine fixed-base loop use the same filter
+        c = pm.CURVES[curve]
+        ks = [0, 1, 2, 3, c.n - 1, c.n - 2, (c.n + 1) // 2, (30 << 252) - c.n, 15 << 252] + [rnd.randrange(c.n) for _ in range(12)]
+        for k in ks:
+            P = pm.w_mul(c, rnd.randrange(1, c.n), (c.gx, c.gy))
+            for pt in (be(P[0]) + be(P[1]), be(c.gx) + be(c.gy)):
+                st = hs.hs_wmul(curve, be(k), pt, 0, 0, 0, o)
+                assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), pt, 1, 0, 0), (curve, hex(k))
+            st = hs.hs_wmul(curve, be(k), None, 0, 1, 0, o)
+            assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), (curve, hex(k))
 
 
 def test_karatsuba_variant_of_the_multiplier(pm):
