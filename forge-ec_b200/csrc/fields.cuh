@@ -397,10 +397,39 @@ struct Fe25519 {
 #pragma unroll
     for (int i = 1; i < 8; i++) o[i] = acc[i];
   }
+  // r2: the product is reduced from its UNMERGED column-parity accumulators (u256.cuh: mul_wide_evod).  With
+  // a b = EV + OD 2^32 and h = the limbs of weight >= 2^256 (ev[8..16) + od[7..14), one 8-word chain), the even-indexed words
+  // of h times 38 land on the pairs of EV's low half and the odd-indexed ones on the pairs of OD's low half (which sit one limb
+  // higher): both folds are IMAD.WIDE chains with the accumulators as their own addends, and ONE merge of the two low halves
+  // follows -- 16 additions instead of 23, and no moves to re-align pairs (88 MOV per X25519 ladder step were such moves).
   FEC_DEV static void mul_inl(u32 o[8], const u32 a[8], const u32 b[8]) {
+#ifndef FEC_25519_EVOD_REDUCE  // set by k_x25519.cu: the ladder gains 0.8 %, the Ed25519 comb loses 1.6 % (profiles/r2z_25519_evod_ab.log)
     u32 r[16];
     mul_wide(r, a, b);
     reduce512(o, r);
+#else
+    u32 ev[16], od[14], h[8];
+    mul_wide_evod(ev, od, a, b);
+    h[0] = add_cc(ev[8], od[7]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) h[i] = addc_cc(ev[8 + i], od[7 + i]);
+    h[7] = addc(ev[15], 0u);                         // a b < 2^512: no carry out
+    const u32 ca = mad_row<4, 0>(ev, h, 38u);        // ev[0..8) += {h0,h2,h4,h6} * 38
+    mad_row<4, 1>(od, h + 1, 38u);                   // (od0,od1) .. (od6, 0) += {h1,h3,h5,h7} * 38: limbs 1 .. 8, cannot carry out
+    u32 acc[8];
+    acc[0] = ev[0];
+    acc[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+    for (int i = 2; i < 8; i++) acc[i] = addc_cc(ev[i], od[i - 1]);
+    const u32 v = addc(od[7], ca);                   // limb 8: < 2^7
+    acc[0] = add_cc(acc[0], v * 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
+    const u32 c2 = addc(0u, 0u);
+    o[0] = acc[0] + ((0u - c2) & 38u);               // wrapped value < 2^13: no further carry
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = acc[i];
+#endif
   }
   FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {
     u32 r[16];

@@ -1,4 +1,5 @@
 // k_x25519.cu -- X25519 ladder kernel (config 4)
+#define FEC_25519_EVOD_REDUCE  // Fe25519::mul_inl reduces the product from its unmerged accumulators (fields.cuh)
 #include "kernels.cuh"
 
 namespace fec {

@@ -181,6 +181,25 @@ FEC_DEV void mul_wide_school_tok(u32 r[16], const u32 a[8], const u32 b[8], u32&
   }
   tok_e = ev[15]; tok_o = od[14];
 }
+// The product left in its two column-parity accumulators, NOT merged: a * b = sum ev[k] 2^(32k) + sum od[k] 2^(32(k+1)), ev[0..16),
+// od[0..14), every (x[2j], x[2j+1]) an aligned register pair.  For reductions that fold the high half back as the addends of
+// IMAD.WIDE chains on these very pairs (Fe25519::mul_inl): merging first costs 8 additions more and moves to re-align pairs.
+FEC_DEV void mul_wide_evod(u32 ev[16], u32 od[14], const u32 a[8], const u32 b[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    ev[j] = mul_lo(a[j], b[0]);
+    ev[j + 1] = mul_hi(a[j], b[0]);
+    od[j] = mul_lo(a[j + 1], b[0]);
+    od[j + 1] = mul_hi(a[j + 1], b[0]);
+  }
+  mad_row<4, 2>(ev + 2, a + 1, b[1]);  mad_row_absorb<4>(od + 0, a, b[1], ev[9]);
+  mad_row<4, 2>(od + 2, a + 1, b[2]);  mad_row_absorb<4>(ev + 2, a, b[2], od[9]);
+  mad_row<4, 2>(ev + 4, a + 1, b[3]);  mad_row_absorb<4>(od + 2, a, b[3], ev[11]);
+  mad_row<4, 2>(od + 4, a + 1, b[4]);  mad_row_absorb<4>(ev + 4, a, b[4], od[11]);
+  mad_row<4, 2>(ev + 6, a + 1, b[5]);  mad_row_absorb<4>(od + 4, a, b[5], ev[13]);
+  mad_row<4, 2>(od + 6, a + 1, b[6]);  mad_row_absorb<4>(ev + 6, a, b[6], od[13]);
+  mad_row<4, 2>(ev + 8, a + 1, b[7]);  mad_row_absorb<4>(od + 6, a, b[7], ev[15]);
+}
 FEC_DEV void mul_wide_school(u32 r[16], const u32 a[8], const u32 b[8]) {
   u32 te, to, tc;
   mul_wide_school_tok<false>(r, a, b, te, to, tc);
