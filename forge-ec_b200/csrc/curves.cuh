@@ -548,23 +548,30 @@ FEC_DEV void ed_add(EdExt& q, const EdExt& r) {
 // selection of the doubling's operand: sel = all-ones -> double S, else D.  (16 instead of 48 logic operations per bit.)
 FEC_DEV void x25519_step(u32 xd[8], u32 zd[8], u32 xs[8], u32 zs[8], const u32 x1[8], u32 sel) {
   typedef Fe25519 F;
+#ifdef FEC_25519_FOLD255  // every operand of the additions / subtractions below is a result of mul / sqr (or the masked u, 1, 0)
+#define X_ADD F::add_r1
+#define X_SUB F::sub_r1
+#else
+#define X_ADD F::add
+#define X_SUB F::sub
+#endif
   u32 A[8], AA[8], B[8], BB[8], E[8], Cc[8], D[8], DA[8], CB[8];
-  F::add(A, xd, zd);
-  F::sub(B, xd, zd);
-  F::add(Cc, xs, zs);
-  F::sub(D, xs, zs);
+  X_ADD(A, xd, zd);
+  X_SUB(B, xd, zd);
+  X_ADD(Cc, xs, zs);
+  X_SUB(D, xs, zs);
   F::mul(DA, D, A);
   F::mul(CB, Cc, B);
-  F::add(xs, DA, CB);
+  X_ADD(xs, DA, CB);
   F::sqr(xs, xs);
-  F::sub(zs, DA, CB);
+  X_SUB(zs, DA, CB);
   F::sqr(zs, zs);
   F::mul(zs, x1, zs);
   select8(A, sel, Cc, A);
   select8(B, sel, D, B);
   F::sqr(AA, A);
   F::sqr(BB, B);
-  F::sub(E, AA, BB);
+  X_SUB(E, AA, BB);
   F::mul(xd, AA, BB);
 #ifndef FEC_X25519_NO_FUSED_A24
   F::mul_small_add(zd, E, 121665u, AA);  // AA + a24 E, one pass and one fold
@@ -573,6 +580,8 @@ FEC_DEV void x25519_step(u32 xd[8], u32 zd[8], u32 xs[8], u32 zs[8], const u32 x
   F::add(zd, AA, zd);
 #endif
   F::mul(zd, E, zd);
+#undef X_ADD
+#undef X_SUB
 }
 
 }  // namespace fec

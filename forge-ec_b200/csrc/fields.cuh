@@ -374,6 +374,54 @@ struct Fe25519 {
     for (int i = 1; i < 7; i++) p[i] = 0xFFFFFFFFu;
     p[7] = 0x7FFFFFFFu;
   }
+  // The last step of both reductions: acc (< 2^256) + v 2^256 with v < 2^7.
+  // Default: fold v at 2^256 (x 38) and the rare wrap once more: any value below 2^256 comes out.
+  // FEC_25519_FOLD255 (the X25519 ladder, k_x25519.cu): fold at 2^255 instead (bit 255 and v, x 19): the result is below
+  // 2^255 + 2^11, so the SUM of two results cannot leave 2^256 except when both are within 2^12 of 2^255 -- add_r1 / sub_r1 below
+  // use that (an addition without a fold, a subtraction with one fold and no second level).
+  FEC_DEV static void fold_tail(u32 o[8], u32 acc[8], u32 v) {
+#ifdef FEC_25519_FOLD255
+    const u32 t = (v << 1) | (acc[7] >> 31);  // < 2^8
+    o[0] = add_cc(acc[0], t * 19u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) o[i] = addc_cc(acc[i], 0u);
+    o[7] = addc(acc[7] & 0x7FFFFFFFu, 0u);
+#else
+    acc[0] = add_cc(acc[0], v * 38u);
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
+    u32 c2 = addc(0u, 0u);
+    o[0] = acc[0] + ((0u - c2) & 38u);  // wrapped value < 2^13: no further carry
+#pragma unroll
+    for (int i = 1; i < 8; i++) o[i] = acc[i];
+#endif
+  }
+  FEC_DEV static bool any_lane(u32 m) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xFFFFFFFFu, m != 0u) != 0;
+#else
+    return m != 0u;
+#endif
+  }
+  // a + b for a, b < 2^255 + 2^11 (results of mul / sqr under FEC_25519_FOLD255): eight additions.  The sum leaves 2^256 only when
+  // both operands are within 2^12 of 2^255 -- no ladder intermediate ever is, and the warp-uniform branch keeps that case exact.
+  FEC_DEV static void add_r1(u32 o[8], const u32 a[8], const u32 b[8]) {
+    const u32 c = add8(o, a, b);
+    if (any_lane(c)) {
+      o[0] = add_cc(o[0], (0u - c) & 38u);  // the wrapped sum is below 2^13: no further carry out of the top
+#pragma unroll
+      for (int i = 1; i < 8; i++) o[i] = addc_cc(o[i], 0u);
+    }
+  }
+  // a - b for the same operands: a borrow means the difference is above 2^256 - 2^255 - 2^11, so "- 38" cannot borrow again
+  FEC_DEV static void sub_r1(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 d[8];
+    const u32 bw = sub8(d, a, b);
+    o[0] = sub_cc(d[0], (0u - bw) & 38u);
+#pragma unroll
+    for (int i = 1; i < 7; i++) o[i] = subc_cc(d[i], 0u);
+    o[7] = subc(d[7], 0u);
+  }
   FEC_DEV static void reduce512(u32 o[8], const u32 r[16]) {
     const u32* h = r + 8;
     u32 acc[8];
@@ -389,13 +437,7 @@ struct Fe25519 {
 #pragma unroll
     for (int i = 2; i < 8; i++) acc[i] = addc_cc(acc[i], od[i - 1]);
     u32 v = addc(od[7], ca);  // < 40
-    acc[0] = add_cc(acc[0], v * 38u);
-#pragma unroll
-    for (int i = 1; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
-    u32 c2 = addc(0u, 0u);
-    o[0] = acc[0] + ((0u - c2) & 38u);  // wrapped value < 1520: no further carry
-#pragma unroll
-    for (int i = 1; i < 8; i++) o[i] = acc[i];
+    fold_tail(o, acc, v);
   }
   // r2: the product is reduced from its UNMERGED column-parity accumulators (u256.cuh: mul_wide_evod).  With
   // a b = EV + OD 2^32 and h = the limbs of weight >= 2^256 (ev[8..16) + od[7..14), one 8-word chain), the even-indexed words
@@ -422,13 +464,7 @@ struct Fe25519 {
 #pragma unroll
     for (int i = 2; i < 8; i++) acc[i] = addc_cc(ev[i], od[i - 1]);
     const u32 v = addc(od[7], ca);                   // limb 8: < 2^7
-    acc[0] = add_cc(acc[0], v * 38u);
-#pragma unroll
-    for (int i = 1; i < 8; i++) acc[i] = addc_cc(acc[i], 0u);
-    const u32 c2 = addc(0u, 0u);
-    o[0] = acc[0] + ((0u - c2) & 38u);               // wrapped value < 2^13: no further carry
-#pragma unroll
-    for (int i = 1; i < 8; i++) o[i] = acc[i];
+    fold_tail(o, acc, v);
 #endif
   }
   FEC_DEV static void sqr_inl(u32 o[8], const u32 a[8]) {

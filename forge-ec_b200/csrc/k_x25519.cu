@@ -1,5 +1,8 @@
 // k_x25519.cu -- X25519 ladder kernel (config 4)
 #define FEC_25519_EVOD_REDUCE  // Fe25519::mul_inl reduces the product from its unmerged accumulators (fields.cuh)
+#ifndef FEC_25519_NO_FOLD255
+#define FEC_25519_FOLD255      // results of mul / sqr below 2^255 + 2^11: the ladder's additions need no fold (fields.cuh, curves.cuh)
+#endif
 #include "kernels.cuh"
 
 namespace fec {

@@ -202,6 +202,17 @@ void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint
 
 extern "C" {
 void hs_k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint8_t* o) { k1_fused(op, t, a, b, o); }
+// Fe25519 under FEC_25519_FOLD255 (the X25519 ladder kernel): op 0 / 1 = add_r1 / sub_r1 (canonicalised result), op 2 / 3 =
+// mul / sqr with the RAW result (the caller checks its range: below 2^255 + 2^11 in that build)
+void hs_f25519_r1(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
+  u32 x[8], y[8], r[8], c[8];
+  load_le32(x, a); load_le32(y, b);
+  if (op == 0) { Fe25519::add_r1(r, x, y); Fe25519::canon(c, r); }
+  else if (op == 1) { Fe25519::sub_r1(r, x, y); Fe25519::canon(c, r); }
+  else if (op == 2) { Fe25519::mul_inl(c, x, y); }
+  else { Fe25519::sqr_inl(c, x); }
+  store_le32(o, c);
+}
 void hs_field_op(int prime, int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
   if (prime == 0) field_op<FeK1>(op, a, b, o);
   else if (prime == 1) field_op<FeP256>(op, a, b, o);

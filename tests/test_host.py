@@ -247,6 +247,49 @@ def test_zero_test_filter_of_the_secp256k1_ladder_rare_path(pm):
             assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), (curve, hex(k))
 
 
+def test_x25519_ladder_field_forms(pm):
+    """k_x25519.cu builds Fe25519 with FEC_25519_EVOD_REDUCE (products reduced from their unmerged accumulators) and
+    FEC_25519_FOLD255 (results of mul / sqr folded at 2^255, below 2^255 + 2^11; the ladder's additions then need no fold and its
+    subtractions one): the same device code on the host -- raw result ranges, add_r1 / sub_r1 on operands at the edges of that range
+    (including the pair that makes the addition leave 2^256: the branch no ladder ever takes), and the ladder on the RFC 7748 edge inputs."""
+    import random
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libhostsim_x255.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DFEC_25519_EVOD_REDUCE", "-DFEC_25519_FOLD255", "-x", "c++", "-shared", "-fPIC", "-o", so, src], check=True)
+    hs = ctypes.CDLL(so)
+    rnd = random.Random(31)
+    p = 2**255 - 19
+    le = lambda v: v.to_bytes(32, "little")
+    o = ctypes.create_string_buffer(32)
+    top = 2**255 + 2**11 - 1
+    edge = [0, 1, 2, 18, 19, 20, p - 1, p, p + 1, 2**255 - 1, 2**255, 2**255 + 1, top, top - 1, 2**254, 2**255 - 2**12, 2**255 - 2**12 + 1]
+    weak = [2**256 - 1, 2**256 - 38, 2**256 - 39, 2 * p, 2 * p + 1] + [rnd.randrange(2**256) for _ in range(40)]
+    for a in edge + weak:                              # mul / sqr: any weak operand in, range and value out
+        for b in edge + weak[:12]:
+            hs.hs_f25519_r1(2, le(a), le(b), o)
+            r = int.from_bytes(o.raw, "little")
+            assert r <= top and r % p == (a * b) % p, (hex(a), hex(b), hex(r))
+        hs.hs_f25519_r1(3, le(a), le(a), o)
+        r = int.from_bytes(o.raw, "little")
+        assert r <= top and r % p == (a * a) % p, (hex(a), hex(r))
+    r1 = edge + [rnd.randrange(top + 1) for _ in range(60)]
+    for a in r1:                                       # add_r1 / sub_r1 on operands of that range
+        for b in r1:
+            hs.hs_f25519_r1(0, le(a), le(b), o)
+            assert int.from_bytes(o.raw, "little") == (a + b) % p, ("add", hex(a), hex(b))
+            hs.hs_f25519_r1(1, le(a), le(b), o)
+            assert int.from_bytes(o.raw, "little") == (a - b) % p, ("sub", hex(a), hex(b))
+    p25519 = p
+    us = [0, 1, p25519 - 1, p25519, p25519 + 1, 2**255 - 1, 2**256 - 1, 9,
+          0x00b8495f16056286fdb1329ceb8d09da6ac49ff1fae35616aeb8413b7c7aebe0]
+    for uv in us + [rnd.randrange(2**256) for _ in range(6)]:
+        for k in (bytes(32), b"\xff" * 32, bytes(range(32)), bytes([rnd.randrange(256) for _ in range(32)])):
+            hs.hs_x25519(k, le(uv), o)
+            assert o.raw == pm.x25519(k, le(uv)), (hex(uv), k.hex())
+
+
 def test_karatsuba_variant_of_the_multiplier(pm):
     """u256.cuh keeps a one-level Karatsuba 8x8 multiplier behind FEC_KARATSUBA (measured slower on B200: it trades 16
     IMAD.WIDE for ~70 additions); it must stay correct, including equal and extreme halves."""
