@@ -477,6 +477,22 @@ FEC_DEV void ed_set_identity(EdExt& q) {
 FEC_DEV void ed_madd_signed(EdExt& q, const u32 ypx[8], const u32 ymx[8], const u32 t2d[8], u32 neg) {
   typedef Fe25519 F;
   u32 A[8], B[8], Cc[8], D[8], E[8], Fv[8], G[8], H[8], m[8];
+#ifdef FEC_25519_FOLD255  // (k_ed25519.cu) X, Y, Z, T and A, B, C are results of multiplications: below 2^255 + 2^11 (fields.cuh)
+  F::sub_r1(A, q.Y, q.X);
+  select8(m, neg, ypx, ymx);
+  F::mul(A, A, m);
+  F::add_r1(B, q.Y, q.X);
+  select8(m, neg, ymx, ypx);
+  F::mul(B, B, m);
+  F::mul(Cc, q.T, t2d);
+  F::add_r1(D, q.Z, q.Z);          // 2Z: leaves 2^256 only for Z >= 2^255
+  F::sub_r1(E, B, A);
+  F::sub_r1(m, D, Cc);             // (sub_r1 needs only its SUBTRAHEND in the range)
+  F::add(H, D, Cc);                // D is anywhere below 2^256: the general addition
+  select8(Fv, neg, H, m);
+  select8(G, neg, m, H);
+  F::add_r1(H, B, A);
+#else
   F::sub(A, q.Y, q.X);
   select8(m, neg, ypx, ymx);
   F::mul(A, A, m);
@@ -491,6 +507,7 @@ FEC_DEV void ed_madd_signed(EdExt& q, const u32 ypx[8], const u32 ymx[8], const 
   select8(Fv, neg, H, m);
   select8(G, neg, m, H);
   F::add(H, B, A);
+#endif
   F::mul(q.X, E, Fv);
   F::mul(q.Y, G, H);
   F::mul(q.T, E, H);

@@ -413,7 +413,8 @@ struct Fe25519 {
       for (int i = 1; i < 8; i++) o[i] = addc_cc(o[i], 0u);
     }
   }
-  // a - b for the same operands: a borrow means the difference is above 2^256 - 2^255 - 2^11, so "- 38" cannot borrow again
+  // a - b for b in that range (a anywhere below 2^256): a borrow means the difference is above 2^256 - 2^255 - 2^11, so "- 38"
+  // cannot borrow again
   FEC_DEV static void sub_r1(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 d[8];
     const u32 bw = sub8(d, a, b);

@@ -1,4 +1,7 @@
 // k_ed25519.cu -- Ed25519 public-key kernel (config 5b) and its Niels comb builder
+#ifndef FEC_25519_NO_FOLD255
+#define FEC_25519_FOLD255  // results of mul / sqr below 2^255 + 2^11: most additions of ed_madd_signed need no fold (fields.cuh, curves.cuh)
+#endif
 #include "kernels.cuh"
 
 namespace fec {

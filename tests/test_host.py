@@ -288,6 +288,13 @@ def test_x25519_ladder_field_forms(pm):
         for k in (bytes(32), b"\xff" * 32, bytes(range(32)), bytes([rnd.randrange(256) for _ in range(32)])):
             hs.hs_x25519(k, le(uv), o)
             assert o.raw == pm.x25519(k, le(uv)), (hex(uv), k.hex())
+    # the Ed25519 comb (k_ed25519.cu builds with FEC_25519_FOLD255 too: ed_madd_signed uses add_r1 / sub_r1), both table forms
+    for k in [bytes(32), b"\xff" * 32, bytes(range(32))] + [bytes(rnd.randrange(256) for _ in range(32)) for _ in range(8)]:
+        for seed in (1, 0):
+            hs.hs_ed25519_pubkey(k, seed, o)
+            assert o.raw == pm.ed25519_pubkey(k, bool(seed)), (k.hex(), seed)
+            hs.hs_ed25519_pubkey_ct(k, seed, o)
+            assert o.raw == pm.ed25519_pubkey(k, bool(seed)), (k.hex(), seed)
 
 
 def test_karatsuba_variant_of_the_multiplier(pm):
