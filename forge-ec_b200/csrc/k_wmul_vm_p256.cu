@@ -117,6 +117,94 @@ k_p3_prep(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ point
   }
 }
 
+// r2: the same with the inversion DEFERRED over P3_PREP_DEFER consecutive tiles of a warp (as the finish kernels do): the first
+// half of every tile's table (co-Z chain, un-normalised entries in the scratch area) runs first, the common denominators are
+// multiplied together, ONE warp-level inversion follows, and the tables are normalised on the way back (Montgomery's trick along
+// the tile axis: 2 multiplications per tile).  The Fermat chain costs 270 field operations per warp whatever it inverts: a share of
+// 67 per tile with one inversion per block of four tiles (three of whose warps wait at the barrier meanwhile), 34 + 2 at 8 tiles.
+#ifndef FEC_P3_PREP_DEFER
+#define FEC_P3_PREP_DEFER 16  // most tiles per inversion (0: always k_p3_prep above); the launcher takes fewer when the batch is small
+#endif
+constexpr int P3_PREP_DEFER = FEC_P3_PREP_DEFER > 0 ? FEC_P3_PREP_DEFER : 1;
+__global__ void __launch_bounds__(P3_PREP_THREADS, FEC_P3_PREP_BLOCKS)
+k_p3_prep_defer(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ points, int points_fmt, size_t n, P3Scratch sc,
+                int tiles_per_warp /* 1 .. P3_PREP_DEFER */) {
+  typedef CurveP256 C;
+  typedef FeP256 F;
+  __shared__ __align__(16) uint8_t io_all[(P3_PREP_THREADS / 32) * 33 * 32 + 16];
+  const unsigned lane_in_warp = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* io = io_all + warp * (33 * 32);
+  const size_t ntiles = (n + 31) / 32;
+  const size_t tile0 = ((size_t)blockIdx.x * (P3_PREP_THREADS / 32) + warp) * (size_t)tiles_per_warp;
+  if (tile0 >= ntiles) return;  // warp-uniform; no block-level barrier in this kernel
+  u32 zr[P3_PREP_DEFER][7][8];  // thread-local memory
+  u32 zts[P3_PREP_DEFER][8], pre[P3_PREP_DEFER][8];
+  u32 acc[8];
+  F::one(acc);
+  int cnt = 0;
+#pragma unroll 1
+  for (int t = 0; t < tiles_per_warp; t++) {
+    const size_t first = (tile0 + t) * 32;
+    if (first >= n) break;  // warp-uniform
+    const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+    const bool live = (int)lane_in_warp < cnt_lanes;
+    // lanes past the end recompute the last lane (the whole warp takes part in the inversion) into 32 spare table rows
+    const size_t lane = live ? first + lane_in_warp : n - 1;
+    const size_t row = live ? lane : n + lane_in_warp;
+    u32 k[8], px[8], py[8], ok, idn = 0u;
+    if (points_fmt == FEC_PT_SEC1_COMPRESSED) {
+      __syncwarp();
+      warp_copy(io, points + first * 33, (size_t)cnt_lanes * 33);
+      __syncwarp();
+      if (live) {
+        ok = sec1_decompress_id<C>(px, py, io + lane_in_warp * 33, idn);
+      } else {
+        uint8_t rec[33];
+        for (int i = 0; i < 33; i++) rec[i] = points[lane * 33 + i];
+        ok = sec1_decompress_id<C>(px, py, rec, idn);
+      }
+    } else {
+      load_rec32_be(px, points + lane * 64);
+      load_rec32_be(py, points + lane * 64 + 32);
+      ok = affine_from_plain_id<C>(px, py, idn);
+    }
+    load_rec32_be(k, scalars + lane * 32);
+    {
+      u32 gx[8], gy[8];
+      C::G(gx, gy);
+      select8(px, ok, px, gx);
+      select8(py, ok, py, gy);
+    }
+    u32 K[8], negm, st;
+    scalar_prepare<C>(K, negm, st, k);
+    st = lane_status(st, ok, idn);  // range > invalid point > identity (k = 0, or the identity as the input point)
+    GlobalLaneTab tab{sc.tab + row * P3_TAB_WORDS};
+    u32 zt[8];
+    wmul_var_table_build<C>(tab, px, py, zt, zr[t]);
+    if (live) {
+      g_st8(sc.kk + lane * 8, K);
+      sc.flags[lane] = (negm & 1u) | (st << 8);
+    }
+    copy8(zts[t], zt);
+    copy8(pre[t], acc);
+    if (t == 0) copy8(acc, zt); else F::mul(acc, acc, zt);
+    cnt++;
+  }
+  u32 inv[8];
+  warp_batch_inv<F>(inv, acc);
+#pragma unroll 1
+  for (int t = cnt - 1; t >= 0; t--) {
+    u32 zi[8];
+    if (t > 0) { F::mul(zi, inv, pre[t]); F::mul(inv, inv, zts[t]); } else { copy8(zi, inv); }
+    const size_t first = (tile0 + t) * 32;
+    const int cnt_lanes = (int)((n - first) < 32 ? (n - first) : 32);
+    const bool live = (int)lane_in_warp < cnt_lanes;
+    const size_t row = live ? first + lane_in_warp : n + lane_in_warp;
+    GlobalLaneTab tab{sc.tab + row * P3_TAB_WORDS};
+    wmul_var_table_finish<C>(tab, zi, zr[t]);
+  }
+}
+
 #ifdef FEC_P3_LAD_MAXNREG  // A/B: an explicit register cap instead of a resident-block count
 __global__ void __maxnreg__(FEC_P3_LAD_MAXNREG)
 #else
@@ -249,8 +337,20 @@ cudaError_t wmul_vm_launch_p256(cudaStream_t st, const uint8_t* scalars, const u
   for (size_t off = 0; off < n; off += cap) {
     const size_t m = (n - off) < cap ? (n - off) : cap;
     mark();
-    k_p3_prep<<<(unsigned)((m + P3_PREP_THREADS - 1) / P3_PREP_THREADS), P3_PREP_THREADS, 0, st>>>(
-        scalars + off * 32, points + off * psz, points_fmt, m, sc);
+    // tiles per inversion: as many as leave every resident warp of the device something to do; below two tiles per warp the
+    // block-level inversion of k_p3_prep is the better deal (four tiles per inversion, all of them in flight at once)
+    const size_t warps_resident = (size_t)(g_sms_p3 > 0 ? g_sms_p3 : 148) * FEC_P3_PREP_BLOCKS * (P3_PREP_THREADS / 32);
+    const size_t tiles = (m + 31) / 32;
+    size_t tpw = FEC_P3_PREP_DEFER > 0 ? tiles / warps_resident : 0;
+    if (tpw > (size_t)P3_PREP_DEFER) tpw = P3_PREP_DEFER;
+    if (tpw >= 2) {
+      const size_t lanes_per_block = (size_t)P3_PREP_THREADS * tpw;
+      k_p3_prep_defer<<<(unsigned)((m + lanes_per_block - 1) / lanes_per_block), P3_PREP_THREADS, 0, st>>>(
+          scalars + off * 32, points + off * psz, points_fmt, m, sc, (int)tpw);
+    } else {
+      k_p3_prep<<<(unsigned)((m + P3_PREP_THREADS - 1) / P3_PREP_THREADS), P3_PREP_THREADS, 0, st>>>(
+          scalars + off * 32, points + off * psz, points_fmt, m, sc);
+    }
     mark();
     k_p3_ladder<<<(unsigned)((m + P3_LAD_THREADS - 1) / P3_LAD_THREADS), P3_LAD_THREADS, P3_LAD_SMEM, st>>>(m, sc);
     mark();

@@ -174,41 +174,54 @@ FEC_DEV void jac_add_safe(Jac& p, const Jac& q) {
 // Cost: table 1 dbl + 7 madd + 7 x (4M+1S) + shared inversion; loop 252 dbl + 63 madd.
 // -------------------------------------------------------------------------------------
 // the table: affine odd multiples P, 3P, .., 15P (entry j = (2j+1) P), ONE shared inversion
+// the table in two halves, so that a caller may put ONE inversion between the halves of several tables (k_p3_prep):
+// build: entries 1..7 on the curve isomorphic by zt (entry 0 is P itself), zt = their common true Z, zr = the co-Z ratios
+template <class C, class Tab>
+FEC_DEV void wmul_var_table_build(Tab& tab, const u32 px[8], const u32 py[8], u32 zt[8], u32 zr[7][8]) {
+  typedef typename C::F F;
+  // odd multiples P, 3P, .., 15P on the curve isomorphic by C = Z(2P), where 2P is affine
+  Jac D, A;
+  u32 C2[8], C3[8];
+  copy8(D.X, px); copy8(D.Y, py); F::one(D.Z);
+  jac_dbl<C>(D);
+  F::sqr(C2, D.Z);
+  F::mul(C3, C2, D.Z);
+  F::mul(A.X, px, C2);
+  F::mul(A.Y, py, C3);
+  tab.store(0, px, py);
+  copy8(zt, D.Z);
+#pragma unroll 1
+  for (int j = 1; j < 8; j++) {  // A = (2j+1) P and D = 2P kept at one common Z (co-Z additions)
+    coz_addu<C>(A.X, A.Y, D.X, D.Y, zr[j - 1]);
+    tab.store(j, A.X, A.Y);
+    F::mul(zt, zt, zr[j - 1]);   // true Z of the newest entry: Z(2P) times the ratios so far
+  }
+}
+// finish: zi = 1 / zt; every entry back to the curve itself (affine)
+template <class C, class Tab>
+FEC_DEV void wmul_var_table_finish(Tab& tab, const u32 zi_in[8], const u32 zr[7][8]) {
+  typedef typename C::F F;
+  u32 zi[8];
+  copy8(zi, zi_in);
+#pragma unroll 1
+  for (int j = 7; j >= 1; j--) {
+    u32 x[8], y[8], z2[8];
+    tab.load(j, x, y);
+    F::sqr(z2, zi);
+    F::mul(x, x, z2);
+    F::mul(z2, z2, zi);
+    F::mul(y, y, z2);
+    tab.store(j, x, y);
+    F::mul(zi, zi, zr[j - 1]);
+  }
+}
 template <class C, class Tab, class Inv>
 FEC_DEV void wmul_var_table(Tab& tab, const u32 px[8], const u32 py[8], Inv& inv) {
-  typedef typename C::F F;
-  {
-    // odd multiples P, 3P, .., 15P on the curve isomorphic by C = Z(2P), where 2P is affine
-    Jac D, A;
-    u32 C2[8], C3[8], zt[8], zi[8];
-    u32 zr[7][8];
-    copy8(D.X, px); copy8(D.Y, py); F::one(D.Z);
-    jac_dbl<C>(D);
-    F::sqr(C2, D.Z);
-    F::mul(C3, C2, D.Z);
-    F::mul(A.X, px, C2);
-    F::mul(A.Y, py, C3);
-    tab.store(0, px, py);
-    copy8(zt, D.Z);
-#pragma unroll 1
-    for (int j = 1; j < 8; j++) {  // A = (2j+1) P and D = 2P kept at one common Z (co-Z additions)
-      coz_addu<C>(A.X, A.Y, D.X, D.Y, zr[j - 1]);
-      tab.store(j, A.X, A.Y);
-      F::mul(zt, zt, zr[j - 1]);   // true Z of the newest entry: Z(2P) times the ratios so far
-    }
-    inv(zi, zt);
-#pragma unroll 1
-    for (int j = 7; j >= 1; j--) {
-      u32 x[8], y[8], z2[8];
-      tab.load(j, x, y);
-      F::sqr(z2, zi);
-      F::mul(x, x, z2);
-      F::mul(z2, z2, zi);
-      F::mul(y, y, z2);
-      tab.store(j, x, y);
-      F::mul(zi, zi, zr[j - 1]);
-    }
-  }
+  u32 zt[8], zi[8];
+  u32 zr[7][8];
+  wmul_var_table_build<C>(tab, px, py, zt, zr);
+  inv(zi, zt);
+  wmul_var_table_finish<C>(tab, zi, zr);
 }
 template <class C, class Tab, class Inv>
 FEC_DEV void wmul_var_core(Jac& Q, u32 K[8], const u32 px[8], const u32 py[8], Tab& tab, Inv& inv) {
