@@ -200,7 +200,7 @@ FEC_DEV u32 jac_madd_lean_signed(Jac& q, const u32 x2[8], const u32 y2[8], u32 n
     F::sub(r, r, q.Y);
   }
   u32 flags = 0u;
-  if (any(sus_z | F::maybe_zero(H))) {
+  if (FEC_UNLIKELY(any(sus_z | F::maybe_zero(H)))) {
     const u32 q_inf = F::is_zero(q.Z), h_zero = F::is_zero(H), r_zero = F::is_zero(r);
     flags = ((q_inf | h_zero) & 1u) | (q_inf & 2u) | (h_zero & r_zero & 4u);
   }

@@ -9,8 +9,10 @@
 //   FeK1 / Fe25519: "weak" form -- any value in [0, 2^256) stands for its residue; add/sub/mul
 //     fold the overflow with 2^256 = 2^32+977 (resp. 38) and never need a comparison with p.
 //     canon() produces the unique representative in [0,p) for output / equality.
-//   FeP256: Montgomery domain (x held as x 2^256 mod p), always canonical in [0,p) (2^256 mod p is a 225-bit
-//     number, so weak form buys nothing).  from_plain / to_plain convert at the byte-record boundary.
+//   FeP256: Montgomery domain (x held as x 2^256 mod p); weak since r2 -- any representative below 2^256, which only the residues
+//     below 2^256 - p have two of: what the form buys is the end of the Montgomery reduction (a masked subtraction instead of
+//     compare-and-select), at the price of a second correction in add / sub that sits under a warp-uniform branch (2^-32 per
+//     operation).  FEC_P256_CANONICAL restores [0,p).  from_plain / to_plain convert at the byte-record boundary.
 // All functions are branch-free (masks only): control flow never depends on data.
 //
 // IMAD.WIDE count per op (the canonical IMUL32 figures of SURVEY.md section 8d):
@@ -398,7 +400,7 @@ struct Fe25519 {
   }
   FEC_DEV static bool any_lane(u32 m) {
 #if defined(__CUDA_ARCH__)
-    return __any_sync(0xFFFFFFFFu, m != 0u) != 0;
+    return __any_sync(__activemask(), m != 0u) != 0;  // among the lanes that are here together: the callers may be in divergent code
 #else
     return m != 0u;
 #endif
@@ -407,7 +409,7 @@ struct Fe25519 {
   // both operands are within 2^12 of 2^255 -- no ladder intermediate ever is, and the warp-uniform branch keeps that case exact.
   FEC_DEV static void add_r1(u32 o[8], const u32 a[8], const u32 b[8]) {
     const u32 c = add8(o, a, b);
-    if (any_lane(c)) {
+    if (FEC_UNLIKELY(any_lane(c))) {
       o[0] = add_cc(o[0], (0u - c) & 38u);  // the wrapped sum is below 2^13: no further carry out of the top
 #pragma unroll
       for (int i = 1; i < 8; i++) o[i] = addc_cc(o[i], 0u);
@@ -649,11 +651,44 @@ struct FeP256 {
       t[b + 9] = addc_cc(t[b + 9], m3);
       cy = addc(0u, 0u);
     }
-    // (cy, t[8..16)) < 2p: one conditional subtraction
+    red_final(o, t, cy);
+  }
+  // The last step.  Canonical form (FEC_P256_CANONICAL, and always for to_plain / canon): (cy, t[8..16)) < 2p for operands below
+  // p, one compare-and-select.  WEAK form (r2, the default): operands are anywhere below 2^256, so (cy, t[8..16)) < 2^256 + p, and
+  // subtracting p exactly when cy is set leaves a value below 2^256 -- a masked subtraction whose borrow cancels cy: 10
+  // instructions instead of 18, on the pipe that bounds this field.  (The four rounds are exact for any c < 2^512.)
+  FEC_DEV static void red_final_canon(u32 o[8], const u32 t[16], u32 cy) {
     u32 p[8], d[8];
     P(p);
     const u32 bw = sub8(d, t + 8, p);
     select8(o, (0u - cy) | (bw - 1u), d, t + 8);
+  }
+  FEC_DEV static void sub_p_masked(u32 o[8], const u32 a[8], u32 m) {  // a - (p & m) mod 2^256, p = {~0,~0,~0,0,0,0,1,~0}
+    o[0] = sub_cc(a[0], m);
+    o[1] = subc_cc(a[1], m);
+    o[2] = subc_cc(a[2], m);
+    o[3] = subc_cc(a[3], 0u);
+    o[4] = subc_cc(a[4], 0u);
+    o[5] = subc_cc(a[5], 0u);
+    o[6] = subc_cc(a[6], m & 1u);
+    o[7] = subc_cc(a[7], m);
+  }
+  FEC_DEV static void add_p_masked(u32 o[8], const u32 a[8], u32 m) {  // a + (p & m) mod 2^256
+    o[0] = add_cc(a[0], m);
+    o[1] = addc_cc(a[1], m);
+    o[2] = addc_cc(a[2], m);
+    o[3] = addc_cc(a[3], 0u);
+    o[4] = addc_cc(a[4], 0u);
+    o[5] = addc_cc(a[5], 0u);
+    o[6] = addc_cc(a[6], m & 1u);
+    o[7] = addc_cc(a[7], m);
+  }
+  FEC_DEV static bool any_lane(u32 m) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), m != 0u) != 0;  // among the lanes that are here together: the callers may be in divergent code
+#else
+    return m != 0u;
+#endif
   }
   // reduce512 in stages (see mul2_inl): one 64-bit round, and the conditional subtraction
   template <int R>
@@ -675,10 +710,11 @@ struct FeP256 {
     cy = addc(0u, 0u);
   }
   FEC_DEV static void red_final(u32 o[8], const u32 t[16], u32 cy) {
-    u32 p[8], d[8];
-    P(p);
-    const u32 bw = sub8(d, t + 8, p);
-    select8(o, (0u - cy) | (bw - 1u), d, t + 8);
+#ifdef FEC_P256_CANONICAL
+    red_final_canon(o, t, cy);
+#else
+    sub_p_masked(o, t + 8, 0u - cy);
+#endif
   }
   // Two independent multiplications, INTERLEAVED at carry-chain granularity (FEC_VM_DUAL): all rows of
   // the first product, then the rows of the second one between the merge, the four reduction rounds and the final
@@ -767,6 +803,7 @@ struct FeP256 {
   // mul / sqr: inlined, or (FEC_NOINLINE_FIELD, the big kernels) one shared subroutine per kernel image
   FEC_DEV static void mul(u32 o[8], const u32 a[8], const u32 b[8]) { field_mul<FeP256>(o, a, b); }
   FEC_DEV static void sqr(u32 o[8], const u32 a[8]) { field_sqr<FeP256>(o, a); }
+#ifdef FEC_P256_CANONICAL
   FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 s[8], d[8], p[8];
     P(p);
@@ -778,17 +815,37 @@ struct FeP256 {
   FEC_DEV static void sub(u32 o[8], const u32 a[8], const u32 b[8]) {
     u32 d[8];
     u32 bw = sub8(d, a, b);
-    u32 m = 0u - bw;
-    // + (p & m): p = {~0,~0,~0,0,0,0,1,~0}
-    o[0] = add_cc(d[0], m);
-    o[1] = addc_cc(d[1], m);
-    o[2] = addc_cc(d[2], m);
-    o[3] = addc_cc(d[3], 0u);
-    o[4] = addc_cc(d[4], 0u);
-    o[5] = addc_cc(d[5], 0u);
-    o[6] = addc_cc(d[6], m & 1u);
-    o[7] = addc(d[7], m);
+    add_p_masked(o, d, 0u - bw);
   }
+#else
+  // Weak form: operands and results anywhere below 2^256.  A carry out of a + b takes one p away (the borrow of that subtraction
+  // cancels the carry); the sum is still above 2^256 only when a + b >= 2^256 + p, i.e. both operands above p -- the top 2^-32 of the
+  // range -- and that second correction sits under a warp-uniform branch.  The same for a borrow of a - b and b - a > p.
+  FEC_DEV static void add(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 s[8];
+    const u32 c = add8(s, a, b);
+    sub_p_masked(o, s, 0u - c);
+    const u32 bw = subc(0u, 0u) & 1u;
+    const u32 still = c & (bw ^ 1u);
+    if (FEC_UNLIKELY(any_lane(still))) {
+      u32 t[8];
+      copy8(t, o);
+      sub_p_masked(o, t, 0u - still);
+    }
+  }
+  FEC_DEV static void sub(u32 o[8], const u32 a[8], const u32 b[8]) {
+    u32 d[8];
+    const u32 bw = sub8(d, a, b);
+    add_p_masked(o, d, 0u - bw);
+    const u32 cy = addc(0u, 0u);
+    const u32 still = bw & (cy ^ 1u);
+    if (FEC_UNLIKELY(any_lane(still))) {
+      u32 t[8];
+      copy8(t, o);
+      add_p_masked(o, t, 0u - still);
+    }
+  }
+#endif
   FEC_DEV static void neg(u32 o[8], const u32 a[8]) {
     u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     sub(o, z, a);
@@ -805,9 +862,24 @@ struct FeP256 {
     }
     copy8(o, acc);
   }
+#ifdef FEC_P256_CANONICAL
   FEC_DEV static void canon(u32 o[8], const u32 a[8]) { copy8(o, a); }
   FEC_DEV static u32 is_zero(const u32 a[8]) { return is_zero8(a); }
   FEC_DEV static u32 maybe_zero(const u32 a[8]) { return a[7] == 0u ? 1u : 0u; }  // necessary condition (canonical form)
+#else
+  FEC_DEV static void canon(u32 o[8], const u32 a[8]) {  // the representative below p
+    u32 p[8], d[8];
+    P(p);
+    const u32 bw = sub8(d, a, p);
+    select8(o, bw - 1u, d, a);
+  }
+  FEC_DEV static u32 is_zero(const u32 a[8]) {  // mask; the representatives of zero below 2^256 are 0 and p
+    const u32 z = a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+    const u32 q = ~(a[0] & a[1] & a[2] & a[7]) | a[3] | a[4] | a[5] | (a[6] ^ 1u);
+    return ((z == 0u) | (q == 0u)) ? 0xFFFFFFFFu : 0u;
+  }
+  FEC_DEV static u32 maybe_zero(const u32 a[8]) { return (a[7] + 1u <= 1u) ? 1u : 0u; }  // necessary: top word of 0 or of p
+#endif
   FEC_DEV static void from_plain(u32 o[8], const u32 a[8]) {  // a < p as an integer -> a * 2^256 mod p
     u32 rr[8];
     RR(rr);
@@ -817,7 +889,9 @@ struct FeP256 {
     u32 t[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) { t[i] = a[i]; t[8 + i] = 0u; }
-    reduce512(o, t);
+    u32 cy = 0u;
+    red_round<0>(t, cy); red_round<1>(t, cy); red_round<2>(t, cy); red_round<3>(t, cy);
+    red_final_canon(o, t, cy);  // a / 2^256 < p + 1: canonical after one compare-and-select, whatever form a came in
   }
   FEC_DEV static void mul2(u32 o[8], const u32 a[8]) { add(o, a, a); }
   FEC_DEV static void mul3(u32 o[8], const u32 a[8]) { u32 t[8]; add(t, a, a); add(o, t, a); }
@@ -828,7 +902,7 @@ struct FeP256 {
     P(p);
     return ~geq8(a, p);
   }
-  // a / 2: (a + (a odd ? p : 0)) >> 1; canonical in, canonical out
+  // a / 2: (a + (a odd ? p : 0)) >> 1; any representative in (a + p is even for either), below 2^256 out
   FEC_DEV static void half(u32 o[8], const u32 a[8]) {
     const u32 m = 0u - (a[0] & 1u);
     u32 t[8];

@@ -147,7 +147,7 @@ FEC_DEV void glv_ladder(saddr S, const u32* tab, const u32 KK[8], u32 flags) {
 #endif
 #ifndef FEC_K1_EXACT_FLAGS  // a two-compare filter on the fast path, the exact tests only in a warp it flags (r2)
       u32 fl = vm_jac_madd_1<F, T, LEAN, true>(S, neg_y);
-      if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+      if (FEC_UNLIKELY(warp_any(fl))) fl = vm_madd_flags<F, T>(S);
 #else
       const u32 fl = vm_jac_madd_1<F, T, LEAN>(S, neg_y);
 #endif
@@ -157,7 +157,7 @@ FEC_DEV void glv_ladder(saddr S, const u32* tab, const u32 KK[8], u32 flags) {
         glv_prefetch<T>(S, tab, idx, h ^ 1);
       }
       vm_jac_madd_2<F, T, LEAN>(S);
-      if (warp_any(fl)) glv_madd_fix<T>(S, tab, cur, h, neg_y, fl);
+      if (FEC_UNLIKELY(warp_any(fl))) glv_madd_fix<T>(S, tab, cur, h, neg_y, fl);
     }
   }
 }
@@ -208,7 +208,7 @@ FEC_DEV void glv_ladder_regs(Jac& Q, const u32* tab, const u32 KK[8], u32 flags)
         g_ld8(ty, tab + idx * 24 + 16);
       }
       const u32 fl = jac_madd_lean<CH>(Q, cx, cy);
-      if (warp_any(fl)) jac_madd_fix<CurveK1>(Q, cx, cy, fl);
+      if (FEC_UNLIKELY(warp_any(fl))) jac_madd_fix<CurveK1>(Q, cx, cy, fl);
     }
   }
 }

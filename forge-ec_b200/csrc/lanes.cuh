@@ -135,7 +135,7 @@ FEC_DEV void coz_addu(u32 rx[8], u32 ry[8], u32 px[8], u32 py[8], u32 zr[8]) {
 template <class C>
 FEC_DEV void jac_madd_safe(Jac& q, const u32 tx[8], const u32 ty[8]) {
   const u32 flags = jac_madd_lean<C>(q, tx, ty);
-  if (warp_any(flags)) jac_madd_fix<typename C::Cold>(q, tx, ty, flags);
+  if (FEC_UNLIKELY(warp_any(flags))) jac_madd_fix<typename C::Cold>(q, tx, ty, flags);
 }
 
 // the same for the addend (tx, neg_y ? -ty : ty), zero tests behind the filter (curves.cuh: jac_madd_lean_signed)
@@ -143,7 +143,7 @@ template <class C>
 FEC_DEV void jac_madd_safe_signed(Jac& q, const u32 tx[8], const u32 ty[8], u32 neg_y) {
 #ifndef FEC_MADD_EXACT_FLAGS
   const u32 flags = jac_madd_lean_signed<C>(q, tx, ty, neg_y, [](u32 m) { return warp_any(m); });
-  if (warp_any(flags)) {
+  if (FEC_UNLIKELY(warp_any(flags))) {
     u32 ny[8], sy[8];
     C::F::neg(ny, ty);
     select8(sy, neg_y, ny, ty);
@@ -411,7 +411,7 @@ FEC_DEV void next_digit4(u32 K[4], u32& idx, u32& sgn) {
 template <class C>
 FEC_DEV void jac_madd_safe_skip(Jac& q, const u32 tx[8], const u32 ty[8], u32 skip) {
   u32 exc = jac_madd<C>(q, tx, ty, skip);
-  if (warp_any(exc)) {
+  if (FEC_UNLIKELY(warp_any(exc))) {
     Jac d;
     copy8(d.X, tx); copy8(d.Y, ty); C::F::one(d.Z);
     jac_dbl<C>(d);

@@ -53,7 +53,7 @@ FEC_DEV void p3_ladder(saddr S, const u32* tab, const u32 Kin[8]) {
     cp_async_wait();
 #ifndef FEC_VM_EXACT_FLAGS  // the zero tests of the addition behind a one-compare filter (vm.cuh), exact flags only in a flagged warp
     u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND, true>(S, neg_y);
-    if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+    if (FEC_UNLIKELY(warp_any(fl))) fl = vm_madd_flags<F, T>(S);
 #else
     const u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND>(S, neg_y);
 #endif
@@ -63,7 +63,7 @@ FEC_DEV void p3_ladder(saddr S, const u32* tab, const u32 Kin[8]) {
       vm_prefetch_xy<F, T>(S, tab + idx * 16);
     }
     vm_jac_madd_2<F, T, C::ALU_BOUND>(S);
-    if (warp_any(fl)) vm_madd_fix<C, T>(S, tab + cur * 16, neg_y, fl);
+    if (FEC_UNLIKELY(warp_any(fl))) vm_madd_fix<C, T>(S, tab + cur * 16, neg_y, fl);
   }
 }
 

@@ -23,6 +23,8 @@ typedef uint64_t u64;
 #else
 #define FEC_DEV inline
 #endif
+// a warp-uniform branch that (almost) never runs: its body belongs out of the instruction stream of the hot path
+#define FEC_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 #if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 // ---- carry-flag primitives (one PTX instruction each; `volatile` keeps their order, the

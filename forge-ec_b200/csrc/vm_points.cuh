@@ -57,7 +57,7 @@ FEC_DEV void wmul_fixed_vm_core(saddr S, u32 K[8], const Entry& entry) {
     cp_async_wait();
 #ifndef FEC_VM_EXACT_FLAGS  // the zero tests of the addition behind a one-compare filter (vm.cuh), exact flags only in a flagged warp
     u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND, true>(S, neg_y);
-    if (warp_any(fl)) fl = vm_madd_flags<F, T>(S);
+    if (FEC_UNLIKELY(warp_any(fl))) fl = vm_madd_flags<F, T>(S);
 #else
     const u32 fl = vm_jac_madd_1<F, T, C::ALU_BOUND>(S, neg_y);
 #endif
@@ -67,7 +67,7 @@ FEC_DEV void wmul_fixed_vm_core(saddr S, u32 K[8], const Entry& entry) {
       vm_prefetch_xy<F, T>(S, e);
     }
     vm_jac_madd_2<F, T, C::ALU_BOUND>(S);
-    if (warp_any(fl)) vm_madd_fix<C, T>(S, cur, neg_y, fl);
+    if (FEC_UNLIKELY(warp_any(fl))) vm_madd_fix<C, T>(S, cur, neg_y, fl);
   }
 }
 

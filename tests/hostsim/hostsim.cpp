@@ -202,6 +202,26 @@ void k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint
 
 extern "C" {
 void hs_k1_fused(int op, const uint8_t* t, const uint8_t* a, const uint8_t* b, uint8_t* o) { k1_fused(op, t, a, b, o); }
+// FeP256 on RAW Montgomery-domain limbs (weak representatives included), raw result: op 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 half,
+// 6 canon, 7 is_zero (0 / 1), 8 to_plain, 9 mul3, 10 mul8
+void hs_p256_raw(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {
+  u32 x[8], y[8], r[8];
+  load_le32(x, a); load_le32(y, b);
+  switch (op) {
+    case 0: FeP256::mul_inl(r, x, y); break;
+    case 1: FeP256::sqr_inl(r, x); break;
+    case 2: FeP256::add(r, x, y); break;
+    case 3: FeP256::sub(r, x, y); break;
+    case 4: FeP256::neg(r, x); break;
+    case 5: FeP256::half(r, x); break;
+    case 6: FeP256::canon(r, x); break;
+    case 7: set_small(r, FeP256::is_zero(x) & 1u); break;
+    case 8: FeP256::to_plain(r, x); break;
+    case 9: FeP256::mul3(r, x); break;
+    default: FeP256::mul8(r, x); break;
+  }
+  store_le32(o, r);
+}
 // Fe25519 under FEC_25519_FOLD255 (the X25519 ladder kernel): op 0 / 1 = add_r1 / sub_r1 (canonicalised result), op 2 / 3 =
 // mul / sqr with the RAW result (the caller checks its range: below 2^255 + 2^11 in that build)
 void hs_f25519_r1(int op, const uint8_t* a, const uint8_t* b, uint8_t* o) {

@@ -247,6 +247,39 @@ def test_zero_test_filter_of_the_secp256k1_ladder_rare_path(pm):
             assert (o.raw, bytes([st])) == pm.batch_mul(curve, be(k), None, 1, 0), (curve, hex(k))
 
 
+def test_p256_weak_form_on_raw_limbs(hostsim, pm):
+    """FeP256 (r2) keeps any representative below 2^256: every operation on raw Montgomery-domain limbs, with operands at the edges
+    -- 0, p, p + 1, 2^256 - 1, the pairs that trigger the second correction of add / sub (both operands above p; b - a > p) --
+    against the integers: result below 2^256 and congruent; mul / sqr results times 2^256 congruent to the product; canon and to_plain
+    below p; is_zero true exactly for 0 and p."""
+    import random
+    rnd = random.Random(37)
+    p = pm.PRIMES[1]
+    R = 2**256
+    Rinv = pow(R, -1, p)
+    le = lambda v: v.to_bytes(32, "little")
+    o = ctypes.create_string_buffer(32)
+
+    def run(op, a, b=0):
+        hostsim.hs_p256_raw(op, le(a), le(b), o)
+        return int.from_bytes(o.raw, "little")
+
+    edge = [0, 1, 2, p - 2, p - 1, p, p + 1, p + 2, R - 1, R - 2, R - p, R - p - 1, R - p + 1, 2**255, 2**224, 2**224 - 1, (p + 1) // 2, p // 2]
+    vals = edge + [rnd.randrange(R) for _ in range(50)] + [rnd.randrange(p, R) for _ in range(10)]
+    for a in vals:
+        for b in vals:
+            assert run(0, a, b) % p == a * b * Rinv % p, ("mul", hex(a), hex(b))
+            assert run(2, a, b) % p == (a + b) % p, ("add", hex(a), hex(b))
+            assert run(3, a, b) % p == (a - b) % p, ("sub", hex(a), hex(b))
+        assert run(1, a) % p == a * a * Rinv % p, ("sqr", hex(a))
+        assert run(4, a) % p == (-a) % p, ("neg", hex(a))
+        assert run(5, a) % p == a * pow(2, -1, p) % p, ("half", hex(a))
+        assert run(6, a) == a % p, ("canon", hex(a))
+        assert run(7, a) == (1 if a % p == 0 else 0), ("is_zero", hex(a))
+        assert run(8, a) == a * Rinv % p, ("to_plain", hex(a))
+        assert run(9, a) % p == 3 * a % p and run(10, a) % p == 8 * a % p, ("small", hex(a))
+
+
 def test_x25519_ladder_field_forms(pm):
     """k_x25519.cu builds Fe25519 with FEC_25519_EVOD_REDUCE (products reduced from their unmerged accumulators) and
     FEC_25519_FOLD255 (results of mul / sqr folded at 2^255, below 2^255 + 2^11; the ladder's additions then need no fold and its
