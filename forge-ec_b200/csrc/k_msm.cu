@@ -9,6 +9,10 @@
 // contribute nothing; a lane with an out-of-range scalar or an invalid point makes the whole call fail
 // (status byte), exactly as a caller of the reference could not have built such a Scalar / PointAffine.
 #define FEC_NOINLINE_FIELD 1
+// (P-256 stays canonical in this translation unit: its kernels are dominated by general additions with masks, where the weak form's
+// rare-branch bodies cost more than the shorter reduction saves -- 288 against 277 M points/s; every value crossing to other kernels is
+// a byte record)
+#define FEC_P256_CANONICAL
 #include "kernels.cuh"
 
 namespace fec {

@@ -20,6 +20,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include "glv3.cuh"
+// (P-256 stays canonical in this translation unit: its kernels are dominated by general additions with masks, where the weak form's
+// rare-branch bodies cost more than the shorter reduction saves -- 288 against 277 M points/s; every value crossing to other kernels is
+// a byte record)
+#define FEC_P256_CANONICAL
 #include "kernels.cuh"
 
 namespace fec {
