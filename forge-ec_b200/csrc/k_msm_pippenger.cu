@@ -17,13 +17,13 @@
 // The bucket a lane falls into depends on the scalar (like the table index of the fixed-base kernels); control flow
 // within a warp does not.
 #define FEC_NOINLINE_FIELD 1
-#include <cub/device/device_scan.cuh>
-
-#include "glv3.cuh"
 // (P-256 stays canonical in this translation unit: its kernels are dominated by general additions with masks, where the weak form's
 // rare-branch bodies cost more than the shorter reduction saves -- 288 against 277 M points/s; every value crossing to other kernels is
 // a byte record)
 #define FEC_P256_CANONICAL
+#include <cub/device/device_scan.cuh>
+
+#include "glv3.cuh"
 #include "kernels.cuh"
 
 namespace fec {

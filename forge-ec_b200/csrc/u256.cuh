@@ -24,7 +24,11 @@ typedef uint64_t u64;
 #define FEC_DEV inline
 #endif
 // a warp-uniform branch that (almost) never runs: its body belongs out of the instruction stream of the hot path
+#ifdef FEC_NO_BRANCH_HINTS
+#define FEC_UNLIKELY(x) (x)
+#else
 #define FEC_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
 
 #if defined(__CUDA_ARCH__) || defined(__CUDACC__)
 // ---- carry-flag primitives (one PTX instruction each; `volatile` keeps their order, the
