@@ -26,11 +26,19 @@ static size_t chunk_lanes() {
   static const size_t v = [] {
     const char* e = getenv("FORGE_EC_CHUNK_LG");
     const int lg = e != nullptr ? atoi(e) : 0;
-    return size_t(1) << ((lg >= 16 && lg <= 22) ? lg : 19);  // 2^19: 58.3 -> 59.3 M/s end to end against 2^18 (fewer partial waves)
+    // capacity of a pipeline slot.  2^19 against 2^18: 58.3 -> 59.3 M/s end to end (fewer partial waves); r2: 2^20 for calls of
+    // 2^21 lanes and more, 64.1 -> 64.6 M/s (profiles/r2al_e2e_chunk.log); smaller calls keep 2^19-lane chunks (chunk_step)
+    return size_t(1) << ((lg >= 16 && lg <= 22) ? lg : 20);
   }();
   return v;
 }
 #define CHUNK_LANES (chunk_lanes())
+// lanes per chunk of one call on one device: the slot capacity for large calls, at most 2^19 below 2^21 lanes (so that a call of
+// 2^20 lanes still overlaps its copies with its kernels)
+static size_t chunk_step(size_t count) {
+  const size_t cap = CHUNK_LANES, small = size_t(1) << 19;
+  return (count >= (size_t(1) << 21) || cap <= small) ? cap : small;
+}
 constexpr int N_PIPE = 3;                        // in-flight chunks per device
 
 struct Device {
@@ -325,8 +333,9 @@ int run_shard(fec_ctx* ctx, Device& d, const HostJob& job, size_t first, size_t 
     pend[s].live = false;
   };
   int slot = 0;
-  for (size_t off = 0; off < count; off += CHUNK_LANES, slot = (slot + 1) % N_PIPE) {
-    const size_t m = (count - off) < CHUNK_LANES ? (count - off) : CHUNK_LANES;
+  const size_t step = chunk_step(count);
+  for (size_t off = 0; off < count; off += step, slot = (slot + 1) % N_PIPE) {
+    const size_t m = (count - off) < step ? (count - off) : step;
     const size_t g0 = first + off;
     cudaStream_t st = d.streams[slot];
     FEC_CUDA(ctx, cudaStreamSynchronize(st));  // slot's previous chunk fully drained
